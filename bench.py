@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py -- standalone quantize sweep (BASELINE.json configs[2]) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log2-numel L]
+
+A step = one pass of the fake-quant hot path over one batch: a resident bf16 tensor of 2^L
+elements per GPU (default 2^30 = 2 GiB in + 2 GiB out, far larger than the 126 MB L2) is
+quantized once with every spec of the sweep (int4, int8, e4m3, e5m2, fp6_e3m2, fp4_e2m1,
+posit8_1, posit8_2: 8 launches of the same kernel family).  Algorithmic bytes per launch
+= 2 * 2 B * 2^L.  `value` is whole-job algorithmic GB/s with inputs resident
+in HBM; `e2e` runs the same sweep through the public module API from pinned HOST buffers
+(H2D + kernels + D2H inside the timed region); `roofline` compares the kernel with the
+measured HBM copy peak; `cpu_baseline` times the CPU oracle port on the box's host cores.
+`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "quantized-training_b200"))
+sys.path.insert(0, ROOT)
+
+SWEEP = ["int4", "int8", "e4m3", "e5m2", "fp6_e3m2", "fp4_e2m1", "posit8_1", "posit8_2"]
+METRIC = "quantize GB/s vs HBM peak (standalone fake-quant sweep, algorithmic read+write bytes)"
+UNIT = "GB/s"
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_gbs(log2_numel, reps, specs=SWEEP):
+    """The CPU oracle port (table build once, then divide/index/lookup/multiply per call) on all host threads."""
+    import numpy as np
+    from oracle import oracle as O
+
+    n = 1 << log2_numel
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(n, dtype=np.float32) * 4.0)
+    xb = (x.view(np.uint32) >> 16).astype(np.uint16)  # bf16 bits (truncation is fine for a timing input)
+    mods = [O.FakeQuant(s) for s in specs]
+    for m in mods[:1]:
+        m(xb, (n,))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        for m in mods:
+            m(xb, (n,))
+    dt = time.perf_counter() - t0
+    return 4.0 * n * len(mods) * reps / dt / 1e9, O.num_threads(), dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path, as ported in oracle/ (OpenMP, all cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L = min(args.log2_numel, 24)
+    for _ in range(args.warmup):
+        cpu_port_gbs(L, 1, SWEEP[:1])
+    t0 = time.perf_counter()
+    gbs, threads, dt = cpu_port_gbs(L, args.steps)
+    sample = f"{args.steps} steps x {len(SWEEP)} specs x 2^{L} bf16 elements (bounded sample of the GPU workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "standalone quantize sweep (configs[2]) -- CPU port of the reference path",
+                   "specs": SWEEP, "log2_numel_per_step": L},
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import quantized_training as qt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = 1 << args.log2_numel
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    chunk = 1 << 26
+    for i in range(0, n, chunk):  # randn * 4: exercises normal, subnormal and (for fp4/int4) saturating branches
+        x[i:i + chunk] = (torch.randn(min(chunk, n - i), device=dev, generator=gen) * 4.0).to(torch.bfloat16)
+    mods = [qt.FusedAmaxObsFakeQuantize(s, device=dev) for s in SWEEP]
+    y = torch.empty_like(x)
+    fmts = [m._fmt for m in mods]
+    unit = torch.ones(1, device=dev)
+
+    def step():
+        for f in fmts:  # straight through the C ABI: y = fq(x), output buffer reused
+            qt._C.fq_forward(x, y, 1, 1, n, f, unit, None)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in SWEEP]
+          for _ in range(args.steps)]
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(args.steps):
+        for i, f in enumerate(fmts):
+            ev[k][i][0].record()
+            qt._C.fq_forward(x, y, 1, 1, n, f, unit, None)
+            ev[k][i][1].record()
+    t1.record()
+    barrier()
+    elapsed_ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    bytes_per_launch = 4.0 * n  # 2 B read + 2 B written per element
+    launches = args.steps * len(SWEEP)
+    value = bytes_per_launch * launches * world / (elapsed_ms * 1e-3) / 1e9
+    per_spec_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps
+                   for i in range(len(SWEEP))]
+    kernel_ms = sum(per_spec_ms) / len(SWEEP)
+    peak, peak_src = peaks()
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public module API, host buffers, copies inside the timed region
+    ne = 1 << min(args.log2_numel, args.e2e_log2_numel)
+    xh = torch.empty(ne, dtype=torch.bfloat16).pin_memory()
+    xh.copy_(x[:ne])
+    yh = torch.empty(ne, dtype=torch.bfloat16).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        for m in mods:
+            xd = xh.to(dev, non_blocking=True)
+            yh.copy_(m(xd), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = 4.0 * ne * len(SWEEP) * e2e_steps * world / e2e_s / 1e9
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            gbs, threads, dt = cpu_port_gbs(24, 2)
+            reps = max(1, min(40, int(15.0 / max(dt / 2, 1e-3))))  # about 15 s of CPU work
+            gbs, threads, dt = cpu_port_gbs(24, reps)
+            cpu = {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{reps} x {len(SWEEP)} specs x 2^24 bf16 elements, {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "standalone quantize sweep (BASELINE configs[2]): bf16 tensor resident in HBM, "
+                                   "bare specs " + "/".join(SWEEP),
+                       "log2_numel_per_gpu": args.log2_numel, "launches_per_step": len(SWEEP),
+                       "l2": "input+output 4*2^L bytes per launch >> 126 MB L2 (no flush needed)",
+                       "parallelism": f"dp{world} (independent shards, no collective)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "fq_flat_kernel",
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": kernel_ms,
+                         "per_spec_GBps": {s: bytes_per_launch / (ms * 1e-3) / 1e9 for s, ms in zip(SWEEP, per_spec_ms)}},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * ne * len(SWEEP),
+                    "d2h_bytes_per_step": 2 * ne * len(SWEEP), "log2_numel": ne.bit_length() - 1,
+                    "api": "FusedAmaxObsFakeQuantize.forward on pinned-host -> device -> pinned-host"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-numel", type=int, default=30)
+    ap.add_argument("--e2e-log2-numel", type=int, default=26)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+/*
+ * qt_b200.h -- C ABI of the B200-native fake-quant hot path (libqt_b200.so).
+ *
+ * Drop-in boundary for jeffreyyu0602/quantized-training.  The reference has no
+ * native code; its hot path is the torch op sequence below, and these entry
+ * points are what a binding for that path calls instead (reference file:line
+ * cited per function; paths relative to src/quantized_training/).
+ *
+ * Conventions: plain pointers and sizes, no torch types.  All data pointers are
+ * DEVICE pointers unless the name ends in _host.  Kernels are asynchronous on
+ * `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ * Every function returns 0 (QT_OK) or a QT_ERR_* code; the message for the last
+ * error on the calling thread is available from qt_last_error().  The caller
+ * owns all memory.  No global mutable state: calls on distinct streams are
+ * independent.  There is NO CPU fallback: compute entry points need a CUDA
+ * device and fail with QT_ERR_CUDA otherwise.
+ */
+#ifndef QT_B200_H
+#define QT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QT_OK 0
+#define QT_ERR_UNSUPPORTED_DTYPE 1 /* reference: ValueError("Unsupported dtype: ...") fake_quantize.py:95 */
+#define QT_ERR_INVALID_ARGUMENT 2
+#define QT_ERR_CUDA 3
+#define QT_ERR_UNALIGNED 4
+
+/* element type of x / y */
+#define QT_BF16 0
+#define QT_F32 1
+
+/* format families */
+#define QT_KIND_IDENTITY 0 /* "float32", "bfloat16": table is the identity */
+#define QT_KIND_INT 1      /* intN / uintN            fake_quantize.py:43-52 */
+#define QT_KIND_FP 2       /* e4m3/e5m2 and fpN_eXmY  fake_quantize.py:55-80, fp8.py */
+#define QT_KIND_POSIT 3    /* positN_ES               fake_quantize.py:84-86, posit.py */
+
+/* QT_KIND_FP flavours */
+#define QT_FP_CUSTOM 0 /* "e4m3", "e5m2", "fp8.e4m3": fp8.py:10-67  (non-finite -> NaN, zero results are +0) */
+#define QT_FP_MX 1     /* "fpN_eXmY": fp8.py:147-203 evaluated in bf16 (Inf passes, NaN band, below-half-min quirk) */
+
+/* A parsed dtype string.  Plain data; fill it with qt_format_from_string(). */
+typedef struct qt_format {
+    int32_t kind;        /* QT_KIND_* */
+    int32_t flavour;     /* QT_FP_* for QT_KIND_FP, else 0 */
+    int32_t nbits;       /* total bits (int, posit, fpN) */
+    int32_t ebits;       /* fp: exponent bits; posit: es */
+    int32_t mbits;       /* fp: explicit mantissa bits */
+    int32_t is_unsigned; /* uintN, or fpN_eXmY with N == X + Y (scale formats) */
+    float max_value;     /* largest magnitude of the format: qmax / max_norm / maxpos */
+    float min_value;     /* int: qmin (negative); others: -max_value */
+} qt_format_t;
+
+/* Library identification, e.g. "qt_b200 0.1 sm_100a". */
+const char *qt_version(void);
+const char *qt_last_error(void);
+
+/* Replaces the regex dispatch of get_quantization_map(dtype) (fake_quantize.py:31-95):
+ * "int8", "uint4", "e4m3", "E5M2", "fp8.e4m3", "fp8_e4m3", "fp6_e3m2", "fp4_e2m1",
+ * "posit8_1", "float32", "bfloat16".  "nfK" is outside this path -> QT_ERR_UNSUPPORTED_DTYPE. */
+int qt_format_from_string(const char *dtype, qt_format_t *fmt);
+
+/* get_quant_min_max(dtype) (quantizer/quantizer.py:53-94). */
+int qt_format_min_max(const char *dtype, double *qmin, double *qmax);
+
+/* HOST evaluation of the device rounding logic on all 65 536 bf16 bit patterns:
+ * table_host[i] = bf16 bits of round(bf16 value with bits i).  This is the same
+ * total function the reference stores in the `qmap` buffer (fake_quantize.py:304);
+ * the kernels never read such a table -- this is for API parity and for tests. */
+int qt_table_host(const qt_format_t *fmt, uint16_t *table_host);
+
+/* The observer half of FusedAmaxObsFakeQuantFunction.forward, minus the amax of the
+ * current tensor (fake_quantize.py:225-242).  Per channel c of `channels`:
+ *   amax = max_i history[i][c]  (read BEFORE the insert -> delayed scaling, NaN propagates)
+ *   history = roll(history, -1, 0);  history[0][c] = 0   (slot the next kernel max-accumulates into)
+ *   sf = amax / quant_max, kept only if amax > 0 and finite; optional 2^ceil(log2 sf)
+ *   scale[c] = sf
+ * Call it before qt_fq_forward / qt_amax with amax_out = history (slot 0). */
+int qt_scale_update(float *history, int amax_history_len, size_t channels, float *scale,
+                    float quant_max, int force_scale_power_of_two, void *stream);
+
+/* The fused quantize-dequantize pass (fake_quantize.py:244-246 + decomposed.py:146-163):
+ *   s = scale.to(x.dtype);  y = round_fmt(x / s) * s     (each op rounded to x's dtype;
+ *   fp32 inputs are first truncated to bf16 with round-to-odd, as vmap does)
+ * and, in the same pass, amax_out[c] = max(amax_out[c], max|x|) (fake_quantize.py:217-223).
+ * x, y: contiguous, viewed as [outer, channels, inner]; per-tensor / unobserved: channels = 1.
+ * scale:    `channels` floats on the device, or NULL for an exact scale of 1 (bare specs).
+ * amax_out: `channels` floats on the device (non-negative; NaN sticks), or NULL.
+ * y may alias x. */
+int qt_fq_forward(const void *x, void *y, size_t outer, size_t channels, size_t inner, int elem_type,
+                  const qt_format_t *fmt, const float *scale, float *amax_out, void *stream);
+
+/* Observer only (fake quant disabled, e.g. calibration): amax_out[c] = max(amax_out[c], max|x|). */
+int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type,
+            float *amax_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QT_B200_H */

@@ -397,34 +397,37 @@ void qto_scale_update(float *history, int ahl, size_t C, const float *amax_cur,
 void qto_fake_quant_bf16(const uint16_t *x, uint16_t *y, size_t outer, size_t C, size_t inner,
                          const float *scale, const uint16_t *qmap)
 {
-    size_t rows = outer * C;
+    if (C == 1) { /* per tensor / bare spec: one scale, parallel over elements */
+        const float s = bfr(scale[0]); /* scale.to(bf16) */
+        const size_t n = outer * inner;
 #pragma omp parallel for schedule(static)
-    for (size_t rc = 0; rc < rows; rc++) {
-        float s = bfr(scale[C == 1 ? 0 : rc % C]); /* scale.to(bf16) */
-        const uint16_t *xr = x + rc * inner;
-        uint16_t *yr = y + rc * inner;
-        for (size_t i = 0; i < inner; i++) {
-            uint16_t u = f2bf(bf2f(xr[i]) / s);  /* input / scale, bf16 */
-            float q = bf2f(qmap[u]);             /* vmap */
-            yr[i] = f2bf(q * s);                 /* * scale, bf16 */
+        for (size_t i = 0; i < n; i++) {
+            uint16_t u = f2bf(bf2f(x[i]) / s); /* input / scale, bf16 */
+            float q = bf2f(qmap[u]);           /* vmap */
+            y[i] = f2bf(q * s);                /* * scale, bf16 */
         }
+        return;
+    }
+    const size_t n = outer * C * inner;
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        const float s = bfr(scale[(i / inner) % C]);
+        uint16_t u = f2bf(bf2f(x[i]) / s);
+        float q = bf2f(qmap[u]);
+        y[i] = f2bf(q * s);
     }
 }
 
 void qto_fake_quant_f32(const float *x, float *y, size_t outer, size_t C, size_t inner,
                         const float *scale, const uint16_t *qmap)
 {
-    size_t rows = outer * C;
+    const size_t n = outer * C * inner;
 #pragma omp parallel for schedule(static)
-    for (size_t rc = 0; rc < rows; rc++) {
-        float s = scale[C == 1 ? 0 : rc % C];
-        const float *xr = x + rc * inner;
-        float *yr = y + rc * inner;
-        for (size_t i = 0; i < inner; i++) {
-            float u = xr[i] / s;
-            float q = bf2f(qmap[rto_index(u)]);
-            yr[i] = q * s;
-        }
+    for (size_t i = 0; i < n; i++) {
+        const float s = scale[C == 1 ? 0 : (i / inner) % C];
+        float u = x[i] / s;
+        float q = bf2f(qmap[rto_index(u)]);
+        y[i] = q * s;
     }
 }
 

@@ -1,0 +1,48 @@
+"""Build libqt_b200.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
+
+    python quantized-training_b200/build.py [--force]
+
+The .so lands next to the Python package (quantized_training/_lib/) so that it travels
+with the repo snapshot to the GPU box; it is git-ignored.  nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "quantized_training", "_lib")
+LIB = os.path.join(OUT_DIR, "libqt_b200.so")
+SOURCES = ["qt_format.cc", "qt_fq.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++",
+]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "qt_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_extension(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+          [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libqt_b200.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_extension(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,553 @@
+// qt_fq.cu -- fused quantize-dequantize + amax kernels for sm_100a, and their C-ABI launchers.
+//
+// One pass over HBM per call: 128-bit coalesced streaming loads -> (x / s) -> bitwise round to
+// the format (qt_round.h, no table) -> (* s) -> 128-bit streaming stores, while max|x| of the
+// UNSCALED input is reduced warp-wide (redux.sync) and block-wide and merged with one atomicMax
+// per CTA.  The reference's scaling is delayed (the scale applied now comes from earlier calls,
+// fake_quantize.py:230-242), so no grid-wide dependency exists and one pass suffices.
+//
+// Replaces (reference, src/quantized_training/): fake_quantize.py:217-223 (amax),
+// :244-246 (divide, vmap, multiply), decomposed.py:146-163 (vmap's Python chunk loop).
+//
+// Layouts:  x, y contiguous [outer, channels, inner].
+//   flat  kernel: channels == 1 (per-tensor or bare spec); persistent grid-stride over 16-byte vectors.
+//   rows  kernel: inner > 1 per-channel (e.g. weights [out, in], ax=0): one scale per row segment.
+//   cols  kernel: inner == 1 per-channel (ax = last dim): one scale per column, register-resident.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "qt_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;  // 16-byte vectors in flight per thread
+
+// ----------------------------------------------------------------------------- small helpers
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(uint4 *p, const uint4 &v) { __stcs(p, v); }
+
+// float -> bf16 (RNE, NaN canonical) returned as fp32 bits with the low half zero
+__device__ __forceinline__ uint32_t bf16_rne_hi(float f)
+{
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)) << 16;
+}
+
+// round-to-odd truncation of an fp32 to the bf16 grid: what vmap's index derivation does
+// (decomposed.py:151-153); returns fp32 bits with the low half zero
+__device__ __forceinline__ uint32_t f32_to_bf16_rto_hi(uint32_t b)
+{
+    return (b & 0xFFFF0000u) | (((b & 0xFFFFu) != 0u) ? 0x10000u : 0u);
+}
+
+// one bf16 element held as fp32 bits (low half zero): returns result in the same form
+template <int KIND, bool UNIT>
+__device__ __forceinline__ uint32_t fq_bf16(const QtRound &P, uint32_t xh, float s)
+{
+    if (UNIT) return qt_round<KIND>(P, xh);
+    const uint32_t uh = bf16_rne_hi(__fdiv_rn(__uint_as_float(xh), s));  // x / s, rounded to bf16
+    const uint32_t q = qt_round<KIND>(P, uh);
+    return bf16_rne_hi(__fmul_rn(__uint_as_float(q), s));  // q * s, rounded to bf16
+}
+
+template <int KIND, bool UNIT>
+__device__ __forceinline__ uint32_t fq_f32(const QtRound &P, uint32_t xb, float s)
+{
+    if (UNIT) return qt_round<KIND>(P, f32_to_bf16_rto_hi(xb));
+    const float u = __fdiv_rn(__uint_as_float(xb), s);
+    const uint32_t q = qt_round<KIND>(P, f32_to_bf16_rto_hi(__float_as_uint(u)));
+    return __float_as_uint(__fmul_rn(__uint_as_float(q), s));
+}
+
+// a 32-bit word holding two bf16 values
+template <int KIND, bool UNIT, bool AMAX>
+__device__ __forceinline__ uint32_t fq_word_bf16(const QtRound &P, uint32_t w, float s, uint32_t &amax)
+{
+    const uint32_t lo = w << 16, hi = w & 0xFFFF0000u;
+    if (AMAX) amax = max(amax, max(lo & 0x7FFFFFFFu, hi & 0x7FFFFFFFu));
+    const uint32_t qlo = fq_bf16<KIND, UNIT>(P, lo, s);
+    const uint32_t qhi = fq_bf16<KIND, UNIT>(P, hi, s);
+    return __byte_perm(qlo, qhi, 0x7632);  // {qhi[31:16], qlo[31:16]}
+}
+
+template <int KIND, bool F32, bool UNIT, bool AMAX>
+__device__ __forceinline__ uint4 fq_vec(const QtRound &P, uint4 v, float s, uint32_t &amax)
+{
+    uint4 r;
+    if (F32) {
+        if (AMAX)
+            amax = max(max(amax, v.x & 0x7FFFFFFFu),
+                       max(max(v.y & 0x7FFFFFFFu, v.z & 0x7FFFFFFFu), v.w & 0x7FFFFFFFu));
+        r.x = fq_f32<KIND, UNIT>(P, v.x, s);
+        r.y = fq_f32<KIND, UNIT>(P, v.y, s);
+        r.z = fq_f32<KIND, UNIT>(P, v.z, s);
+        r.w = fq_f32<KIND, UNIT>(P, v.w, s);
+    } else {
+        r.x = fq_word_bf16<KIND, UNIT, AMAX>(P, v.x, s, amax);
+        r.y = fq_word_bf16<KIND, UNIT, AMAX>(P, v.y, s, amax);
+        r.z = fq_word_bf16<KIND, UNIT, AMAX>(P, v.z, s, amax);
+        r.w = fq_word_bf16<KIND, UNIT, AMAX>(P, v.w, s, amax);
+    }
+    return r;
+}
+
+// scale.to(x.dtype): bf16 inputs see the scale rounded to bf16 (fake_quantize.py:245)
+template <bool F32>
+__device__ __forceinline__ float load_scale(const float *scale, size_t c)
+{
+    const float s = scale[c];
+    return F32 ? s : __uint_as_float(bf16_rne_hi(s));
+}
+
+// block-wide max of |x| bit patterns, then ONE atomicMax.  Non-negative floats order like
+// unsigned ints and NaN patterns sit above Inf, so NaN propagates exactly like torch.amax.
+__device__ __forceinline__ void block_amax_commit(uint32_t amax, float *amax_out)
+{
+    __shared__ uint32_t warp_max[kThreads / 32];
+    amax = __reduce_max_sync(0xFFFFFFFFu, amax);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) warp_max[warp] = amax;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = lane < (int)(blockDim.x >> 5) ? warp_max[lane] : 0u;
+        v = __reduce_max_sync(0xFFFFFFFFu, v);
+        if (lane == 0 && v != 0u) atomicMax(reinterpret_cast<unsigned int *>(amax_out), v);
+    }
+}
+
+// ----------------------------------------------------------------------------- flat kernel
+// channels == 1.  nvec 16-byte vectors; tile = kThreads * kUnroll vectors; persistent grid.
+template <int KIND, bool F32, bool UNIT, bool AMAX, bool WRITE>
+__device__ __forceinline__ void fq_flat_body(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
+                                             const QtRound &P, float s, float *__restrict__ amax_out)
+{
+    uint32_t amax = 0u;
+    const size_t tile = (size_t)kThreads * kUnroll;
+    const size_t ntiles = (nvec + tile - 1) / tile;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t base = t * tile + threadIdx.x;
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * kThreads;
+            v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * kThreads;
+            if (WRITE) {
+                const uint4 r = fq_vec<KIND, F32, UNIT, AMAX>(P, v[j], s, amax);
+                if (i < nvec) st_stream(y + i, r);
+            } else {
+                // observer only
+                if (F32)
+                    amax = max(max(amax, v[j].x & 0x7FFFFFFFu),
+                               max(max(v[j].y & 0x7FFFFFFFu, v[j].z & 0x7FFFFFFFu), v[j].w & 0x7FFFFFFFu));
+                else {
+                    const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        amax = max(amax, max((w[k] << 16) & 0x7FFFFFFFu, w[k] & 0x7FFF0000u));
+                }
+            }
+        }
+    }
+    if (AMAX) block_amax_commit(amax, amax_out);
+}
+
+// The scale is one number for the whole launch.  When it is exactly 1 (bare specs such as "e4m3" or
+// "posit8_1", whose `scale` buffer is never written) x / 1 and q * 1 are identities, so the CTA takes
+// a path without the divide / multiply / bf16 re-rounding.  The branch is grid-uniform.
+template <int KIND, bool F32, bool AMAX, bool WRITE>
+__global__ void __launch_bounds__(kThreads)
+fq_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec, const __grid_constant__ QtRound P,
+               const float *__restrict__ scale, float *__restrict__ amax_out)
+{
+    const float s = scale ? load_scale<F32>(scale, 0) : 1.0f;
+    if (!WRITE || s == 1.0f)
+        fq_flat_body<KIND, F32, true, AMAX, WRITE>(x, y, nvec, P, 1.0f, amax_out);
+    else
+        fq_flat_body<KIND, F32, false, AMAX, WRITE>(x, y, nvec, P, s, amax_out);
+}
+
+// ----------------------------------------------------------------------------- scalar kernel
+// Any layout, any alignment: element i belongs to channel (i / inner) % channels.  Used for tails,
+// misaligned views and odd per-channel shapes.  Elements [first, first + count).
+template <int KIND, bool F32, bool AMAX, bool WRITE>
+__global__ void __launch_bounds__(kThreads)
+fq_scalar_kernel(const void *__restrict__ xv, void *__restrict__ yv, size_t first, size_t count, size_t channels,
+                 size_t inner, const __grid_constant__ QtRound P, const float *__restrict__ scale,
+                 float *__restrict__ amax_out)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint32_t amax1 = 0u;  // channels == 1: reduce in registers, one atomic per CTA
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        const size_t i = first + j;
+        const size_t c = channels == 1 ? 0 : (i / inner) % channels;
+        const float s = scale ? load_scale<F32>(scale, c) : 1.0f;
+        uint32_t bits, ab;
+        if (F32) {
+            bits = static_cast<const uint32_t *>(xv)[i];
+            ab = bits & 0x7FFFFFFFu;
+            if (WRITE) static_cast<uint32_t *>(yv)[i] = fq_f32<KIND, false>(P, bits, s);
+        } else {
+            bits = (uint32_t) static_cast<const uint16_t *>(xv)[i] << 16;
+            ab = bits & 0x7FFFFFFFu;
+            if (WRITE) static_cast<uint16_t *>(yv)[i] = (uint16_t)(fq_bf16<KIND, false>(P, bits, s) >> 16);
+        }
+        if (AMAX) {
+            if (channels == 1)
+                amax1 = max(amax1, ab);
+            else if (ab != 0u)
+                atomicMax(reinterpret_cast<unsigned int *>(amax_out) + c, ab);
+        }
+    }
+    if (AMAX && channels == 1) block_amax_commit(amax1, amax_out);
+}
+
+// ----------------------------------------------------------------------------- rows kernel
+// inner > 1 per-channel, inner % VEC == 0, 16-byte aligned.  blockIdx.x enumerates (row, segment):
+// row = o * channels + c, a segment is kThreads * kUnroll vectors of that row.
+template <int KIND, bool F32, bool AMAX, bool WRITE>
+__global__ void __launch_bounds__(kThreads)
+fq_rows_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, size_t channels, size_t vec_per_row,
+               size_t segs_per_row, const __grid_constant__ QtRound P, const float *__restrict__ scale,
+               float *__restrict__ amax_out)
+{
+    const size_t tile = (size_t)kThreads * kUnroll;
+    const size_t work = rows * segs_per_row;
+    for (size_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
+        const size_t row = wi / segs_per_row, seg = wi - row * segs_per_row;
+        const size_t c = row % channels;
+        const float s = load_scale<F32>(scale, c);
+        const uint4 *xr = x + row * vec_per_row;
+        uint4 *yr = y + row * vec_per_row;
+        uint32_t amax = 0u;
+        const size_t base = seg * tile + threadIdx.x;
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * kThreads;
+            v[j] = i < vec_per_row ? ld_stream(xr + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * kThreads;
+            uint4 r = fq_vec<KIND, F32, false, AMAX>(P, v[j], s, amax);
+            if (WRITE && i < vec_per_row) st_stream(yr + i, r);
+        }
+        if (AMAX) {
+            __syncthreads();  // warp_max reuse across loop iterations
+            block_amax_commit(amax, amax_out + c);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- cols kernel
+// inner == 1 per-channel (channel = last dim), channels % VEC == 0, 16-byte aligned rows.
+// blockDim = (32, 8): threadIdx.x -> a 16-byte column group, threadIdx.y -> row phase.
+// Scales and running maxima for the thread's VEC columns stay in registers over all rows.
+template <int KIND, bool F32, bool AMAX, bool WRITE>
+__global__ void __launch_bounds__(kThreads)
+fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, size_t vec_per_row,
+               const __grid_constant__ QtRound P, const float *__restrict__ scale, float *__restrict__ amax_out)
+{
+    constexpr int VEC = F32 ? 4 : 8;
+    const size_t cg = (size_t)blockIdx.x * 32 + threadIdx.x;  // column group
+    const bool active = cg < vec_per_row;
+    float s[VEC];
+    uint32_t am[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        s[k] = active ? load_scale<F32>(scale, cg * VEC + k) : 1.0f;
+        am[k] = 0u;
+    }
+    if (active) {
+        for (size_t r = (size_t)blockIdx.y * blockDim.y + threadIdx.y; r < rows; r += (size_t)gridDim.y * blockDim.y) {
+            const uint4 v = ld_stream(x + r * vec_per_row + cg);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (F32) {
+                    if (AMAX) am[k] = max(am[k], w[k] & 0x7FFFFFFFu);
+                    o[k] = fq_f32<KIND, false>(P, w[k], s[k]);
+                } else {
+                    const uint32_t lo = w[k] << 16, hi = w[k] & 0xFFFF0000u;
+                    if (AMAX) {
+                        am[2 * k] = max(am[2 * k], lo & 0x7FFFFFFFu);
+                        am[2 * k + 1] = max(am[2 * k + 1], hi & 0x7FFFFFFFu);
+                    }
+                    o[k] = __byte_perm(fq_bf16<KIND, false>(P, lo, s[2 * k]), fq_bf16<KIND, false>(P, hi, s[2 * k + 1]),
+                                       0x7632);
+                }
+            }
+            if (WRITE) st_stream(y + r * vec_per_row + cg, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+    }
+    if (AMAX) {
+        __shared__ uint32_t red[8][32][VEC + 1];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) red[threadIdx.y][threadIdx.x][k] = am[k];
+        __syncthreads();
+        if (threadIdx.y == 0 && active) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                uint32_t m = 0u;
+                for (int yy = 0; yy < 8; ++yy) m = max(m, red[yy][threadIdx.x][k]);
+                if (m != 0u) atomicMax(reinterpret_cast<unsigned int *>(amax_out) + cg * VEC + k, m);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- scale update
+__global__ void scale_update_kernel(float *__restrict__ history, int ahl, size_t channels, float *__restrict__ scale,
+                                    float quant_max, int pow2)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    // history entries are max|x| bit patterns: non-negative or NaN, so an unsigned max is torch.amax
+    uint32_t m = 0u;
+    for (int i = 0; i < ahl; ++i) m = max(m, __float_as_uint(history[(size_t)i * channels + c]) & 0x7FFFFFFFu);
+    const float amax = __uint_as_float(m);
+    if (ahl > 1) {  // torch.roll(history, -1, 0)
+        const float first = history[c];
+        for (int i = 0; i + 1 < ahl; ++i) history[(size_t)i * channels + c] = history[(size_t)(i + 1) * channels + c];
+        history[(size_t)(ahl - 1) * channels + c] = first;
+    }
+    history[c] = 0.0f;  // slot 0 <- amax of the current tensor, max-accumulated by the next kernel
+    float sf = __fdiv_rn(amax, quant_max);
+    const bool keep = (amax > 0.0f) && (m < 0x7F800000u);
+    if (!keep) sf = scale[c];
+    if (pow2) sf = exp2f(ceilf(log2f(sf)));
+    scale[c] = sf;
+}
+
+// ----------------------------------------------------------------------------- launch plumbing
+
+int g_num_sms = 0;
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    qt_set_error("%s: %s", what, cudaGetErrorString(e));
+    return QT_ERR_CUDA;
+}
+
+int num_sms()
+{
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        g_num_sms = n;
+    }
+    return g_num_sms;
+}
+
+struct Job {
+    const void *x;
+    void *y;
+    size_t outer, channels, inner;
+    bool f32;
+    QtRound P;
+    const float *scale;
+    float *amax;
+    cudaStream_t stream;
+    bool write;
+};
+
+inline unsigned grid_for(size_t work_items, int ctas_per_sm)
+{
+    size_t cap = (size_t)num_sms() * ctas_per_sm;
+    if (cap == 0) cap = 148u * ctas_per_sm;
+    return (unsigned)(work_items < cap ? (work_items ? work_items : 1) : cap);
+}
+
+template <int KIND, bool F32, bool AMAX, bool WRITE>
+void launch_scalar(const Job &j, size_t first, size_t count)
+{
+    if (count == 0) return;
+    const unsigned grid = grid_for((count + kThreads - 1) / kThreads, 16);
+    fq_scalar_kernel<KIND, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(j.x, j.y, first, count, j.channels,
+                                                                              j.inner, j.P, j.scale, j.amax);
+}
+
+template <int KIND, bool F32, bool AMAX, bool WRITE>
+void launch_kind(const Job &j)
+{
+    constexpr size_t VEC = F32 ? 4 : 8;
+    const size_t n = j.outer * j.channels * j.inner;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(j.x) | reinterpret_cast<uintptr_t>(j.y)) & 15u) == 0;
+    const uint4 *xv = static_cast<const uint4 *>(j.x);
+    uint4 *yv = static_cast<uint4 *>(j.y);
+
+    if (j.channels == 1) {
+        const size_t nvec = aligned ? n / VEC : 0;
+        if (nvec) {
+            const size_t tile = (size_t)kThreads * kUnroll;
+            const unsigned grid = grid_for((nvec + tile - 1) / tile, 8);
+            fq_flat_kernel<KIND, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(xv, yv, nvec, j.P, j.scale, j.amax);
+        }
+        launch_scalar<KIND, F32, AMAX, WRITE>(j, nvec * VEC, n - nvec * VEC);
+        return;
+    }
+    // per channel (scale is never NULL here)
+    if (aligned && j.inner == 1 && j.channels % VEC == 0) {
+        const size_t rows = j.outer, vec_per_row = j.channels / VEC;
+        const unsigned gx = (unsigned)((vec_per_row + 31) / 32);
+        size_t want_y = ((size_t)num_sms() * 8 + gx - 1) / gx;
+        const size_t max_y = (rows + 7) / 8;
+        if (want_y > max_y) want_y = max_y;
+        if (want_y < 1) want_y = 1;
+        if (want_y > 65535) want_y = 65535;
+        fq_cols_kernel<KIND, F32, AMAX, WRITE><<<dim3(gx, (unsigned)want_y), dim3(32, 8), 0, j.stream>>>(
+            xv, yv, rows, vec_per_row, j.P, j.scale, j.amax);
+        return;
+    }
+    if (aligned && j.inner % VEC == 0 && j.inner >= 32 * VEC) {
+        const size_t rows = j.outer * j.channels, vec_per_row = j.inner / VEC;
+        const size_t tile = (size_t)kThreads * kUnroll;
+        const size_t segs = (vec_per_row + tile - 1) / tile;
+        const unsigned grid = grid_for(rows * segs, 8);
+        fq_rows_kernel<KIND, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(xv, yv, rows, j.channels, vec_per_row,
+                                                                                segs, j.P, j.scale, j.amax);
+        return;
+    }
+    launch_scalar<KIND, F32, AMAX, WRITE>(j, 0, n);
+}
+
+template <int KIND>
+void launch_flags(const Job &j)
+{
+    const bool amax = j.amax != nullptr;
+    if (!j.write) {  // observer only: the format is irrelevant, instantiate once
+        if constexpr (KIND == QTR_IDENTITY) {
+            j.f32 ? launch_kind<KIND, true, true, false>(j) : launch_kind<KIND, false, true, false>(j);
+        }
+        return;
+    }
+    if (j.f32)
+        amax ? launch_kind<KIND, true, true, true>(j) : launch_kind<KIND, true, false, true>(j);
+    else
+        amax ? launch_kind<KIND, false, true, true>(j) : launch_kind<KIND, false, false, true>(j);
+}
+
+int run_job(const Job &j)
+{
+    if (num_sms() == 0) {
+        cudaError_t e = cudaGetLastError();
+        return cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "qt_b200: no usable CUDA device (there is no CPU fallback)");
+    }
+    switch (j.P.kind) {
+    case QTR_IDENTITY: launch_flags<QTR_IDENTITY>(j); break;
+    case QTR_INT: launch_flags<QTR_INT>(j); break;
+    case QTR_FP_CUSTOM: launch_flags<QTR_FP_CUSTOM>(j); break;
+    case QTR_FP_MX: launch_flags<QTR_FP_MX>(j); break;
+    case QTR_POSIT: launch_flags<QTR_POSIT>(j); break;
+    default: qt_set_error("bad format kind %d", j.P.kind); return QT_ERR_INVALID_ARGUMENT;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fake-quant kernel launch");
+    return QT_OK;
+}
+
+int check_layout(const char *fn, const void *x, size_t outer, size_t channels, size_t inner, int elem_type)
+{
+    if (elem_type != QT_BF16 && elem_type != QT_F32) {
+        qt_set_error("%s: elem_type must be QT_BF16 or QT_F32, got %d", fn, elem_type);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (channels == 0) {
+        qt_set_error("%s: channels must be >= 1", fn);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    const size_t esz = elem_type == QT_F32 ? 4 : 2;
+    if (outer * channels * inner != 0 && (x == nullptr || (reinterpret_cast<uintptr_t>(x) % esz) != 0)) {
+        qt_set_error("%s: x is NULL or not aligned to its element size", fn);
+        return x ? QT_ERR_UNALIGNED : QT_ERR_INVALID_ARGUMENT;
+    }
+    return QT_OK;
+}
+
+}  // namespace
+
+extern "C" int qt_fq_forward(const void *x, void *y, size_t outer, size_t channels, size_t inner, int elem_type,
+                             const qt_format_t *fmt, const float *scale, float *amax_out, void *stream)
+{
+    int rc = check_layout("qt_fq_forward", x, outer, channels, inner, elem_type);
+    if (rc != QT_OK) return rc;
+    if (!fmt) {
+        qt_set_error("qt_fq_forward: fmt is NULL");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (channels > 1 && !scale) {
+        qt_set_error("qt_fq_forward: per-channel call (channels=%zu) needs a scale array", channels);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    Job j;
+    rc = qt_make_round(fmt, &j.P);
+    if (rc != QT_OK) return rc;
+    const size_t n = outer * channels * inner;
+    if (n == 0) return QT_OK;
+    if (!y) {
+        qt_set_error("qt_fq_forward: y is NULL");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    j.x = x;
+    j.y = y;
+    j.outer = outer;
+    j.channels = channels;
+    j.inner = inner;
+    j.f32 = elem_type == QT_F32;
+    j.scale = scale;
+    j.amax = amax_out;
+    j.stream = static_cast<cudaStream_t>(stream);
+    j.write = true;
+    return run_job(j);
+}
+
+extern "C" int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type, float *amax_out,
+                       void *stream)
+{
+    int rc = check_layout("qt_amax", x, outer, channels, inner, elem_type);
+    if (rc != QT_OK) return rc;
+    if (!amax_out) {
+        qt_set_error("qt_amax: amax_out is NULL");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (outer * channels * inner == 0) return QT_OK;
+    Job j;
+    memset(&j.P, 0, sizeof(j.P));
+    j.P.kind = QTR_IDENTITY;
+    j.x = x;
+    j.y = nullptr;
+    j.outer = outer;
+    j.channels = channels;
+    j.inner = inner;
+    j.f32 = elem_type == QT_F32;
+    // the rows/cols kernels read scales even when they only observe: give them any valid pointer
+    j.scale = channels > 1 ? amax_out : nullptr;
+    j.amax = amax_out;
+    j.stream = static_cast<cudaStream_t>(stream);
+    j.write = false;
+    return run_job(j);
+}
+
+extern "C" int qt_scale_update(float *history, int amax_history_len, size_t channels, float *scale, float quant_max,
+                               int force_scale_power_of_two, void *stream)
+{
+    if (!history || !scale || amax_history_len < 1 || channels == 0) {
+        qt_set_error("qt_scale_update: invalid argument (history=%p scale=%p ahl=%d channels=%zu)", (void *)history,
+                     (void *)scale, amax_history_len, channels);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (num_sms() == 0) return cuda_fail(cudaErrorNoDevice, "qt_b200: no usable CUDA device (there is no CPU fallback)");
+    const unsigned grid = (unsigned)((channels + 127) / 128);
+    scale_update_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(history, amax_history_len, channels, scale,
+                                                                             quant_max, force_scale_power_of_two);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "scale_update kernel launch");
+    return QT_OK;
+}

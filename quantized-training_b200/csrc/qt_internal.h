@@ -1,0 +1,12 @@
+// qt_internal.h -- shared by the translation units of libqt_b200.so (not installed).
+#pragma once
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/qt_b200.h"
+#include "qt_round.h"
+
+void qt_set_error(const char *fmt, ...);
+// qt_format_t -> kernel parameters; QT_ERR_INVALID_ARGUMENT if the struct is inconsistent
+int qt_make_round(const qt_format_t *fmt, QtRound *P);

@@ -1,0 +1,218 @@
+"""Fake-quantize module backed by the sm_100a kernels.
+
+Interface mirror of the reference's ``fake_quantize.py``: ``get_quantization_map`` (:31-95),
+``FusedAmaxObsFakeQuantFunction`` (:197-252) and ``FusedAmaxObsFakeQuantize`` (:255-435) --
+same constructor, buffers, state-dict keys, lazily shaped ``scale`` / ``amax_history``,
+straight-through backward.  What differs is the engine: one fused CUDA pass
+(``qt_scale_update`` + ``qt_fq_forward``) instead of ~15 ATen launches, a Python chunk loop
+over a 65 536-entry table and two host synchronisations per call.
+"""
+import logging
+from typing import Optional
+
+import torch
+from torch.ao.quantization import FakeQuantizeBase
+
+from . import _C
+from .quantizer.quantizer import QScheme
+
+__all__ = ["FusedAmaxObsFakeQuantize", "get_quantization_map"]
+
+logger = logging.getLogger(__name__)
+
+
+def get_quantization_map(dtype, device=None):
+    """bf16[65536]: value every bf16 bit pattern rounds to.  The kernels do not use this table
+    (they round bitwise); it is produced from the same rounding code for API parity."""
+    if dtype is None:
+        t = torch.arange(2 ** 16, dtype=torch.int32).to(torch.int16).view(torch.bfloat16)
+    else:
+        t = _C.table_host(_C.format_from_string(dtype))
+    return t.to(device) if device is not None else t
+
+
+def _channel_view(shape, ch_axis):
+    """Contiguous tensor of `shape` seen as [outer, channels, inner] around ch_axis."""
+    if ch_axis is None or isinstance(ch_axis, (tuple, list)):
+        raise TypeError("per_channel_symmetric needs an integer ch_axis (qspec key 'ax')")
+    nd = len(shape)
+    ax = ch_axis + nd if ch_axis < 0 else ch_axis
+    if not 0 <= ax < nd:
+        raise IndexError(f"ch_axis {ch_axis} out of range for a {nd}-d tensor")
+    outer = inner = 1
+    for d in shape[:ax]:
+        outer *= d
+    for d in shape[ax + 1:]:
+        inner *= d
+    keep = tuple(shape[i] if i == ax else 1 for i in range(nd))
+    return outer, shape[ax], inner, keep
+
+
+class FusedAmaxObsFakeQuantFunction(torch.autograd.Function):
+    """Delayed-scaling observer + quantize-dequantize, one fused pass; STE backward."""
+
+    @staticmethod
+    def forward(ctx, x, mod):
+        observe, quantize = mod._flags()
+        if not (observe or quantize):
+            return x
+        if not x.is_cuda:
+            raise RuntimeError(
+                f"FusedAmaxObsFakeQuantize got a tensor on {x.device}: the B200 build runs on CUDA only "
+                "(no CPU fallback)")
+        xc = x.detach().contiguous()
+        amax_slot = None
+        outer, channels, inner = 1, 1, xc.numel()
+        if observe:
+            if xc.numel() == 0:
+                raise RuntimeError("amax(): cannot observe an empty tensor")
+            if mod.is_per_channel:
+                outer, channels, inner, stat_shape = _channel_view(tuple(xc.shape), mod.ch_axis)
+            else:
+                stat_shape = ()
+            if mod.amax_history.numel() == 0:  # first observed call: shapes become known
+                mod.amax_history.resize_((mod.amax_history_len,) + stat_shape).fill_(0.0)
+                mod.scale.resize_(stat_shape).fill_(1.0)
+            _C.scale_update(mod.amax_history, mod.amax_history_len, channels, mod.scale, mod.quant_max,
+                            mod.force_scale_power_of_two)
+            amax_slot = mod.amax_history
+        if not quantize:
+            _C.amax(xc, outer, channels, inner, amax_slot)
+            return x
+        scale = mod.scale
+        if scale.numel() == 1:
+            # per tensor, or a bare spec whose scale buffer is the constant 1.0 (the kernel then
+            # takes its exact unit-scale path: the branch is made on the device, no read-back)
+            outer, channels, inner = 1, 1, xc.numel()
+        elif not observe:
+            # frozen per-channel scale: recover the layout from the scale's keepdim shape
+            axes = [i for i, d in enumerate(scale.shape) if d != 1]
+            if len(axes) != 1 or scale.dim() != xc.dim() or scale.shape[axes[0]] != xc.shape[axes[0]]:
+                raise RuntimeError(f"scale of shape {tuple(scale.shape)} does not broadcast over a single "
+                                   f"axis of input {tuple(xc.shape)}")
+            outer, channels, inner, _ = _channel_view(tuple(xc.shape), axes[0])
+        y = torch.empty_like(xc)
+        _C.fq_forward(xc, y, outer, channels, inner, mod._fmt, scale, amax_slot)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None
+
+
+class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
+    r"""Simulated quantization with amax-history ("delayed") scaling.
+
+    ``dtype`` is a format string (``int8``, ``e4m3``, ``fp6_e3m2``, ``posit8_1`` ...).  With
+    ``qscheme=None`` values are rounded to the format as they are (scale 1).  With
+    ``per_tensor_symmetric`` / ``per_channel_symmetric`` the scale used by call *k* is
+    ``max(amax of the previous amax_history_len calls) / quant_max``.
+    """
+
+    amax_history: torch.Tensor
+    scale: torch.Tensor
+    zero_point: torch.Tensor
+
+    def __init__(
+        self,
+        dtype: str,
+        qscheme: Optional[QScheme] = None,
+        quant_min: Optional[float] = None,
+        quant_max: Optional[float] = None,
+        amax_history_len: int = None,
+        ch_axis: Optional[int] = None,
+        block_size: Optional[int] = None,
+        record_histogram: bool = False,
+        scale_dtype: Optional[str] = None,
+        force_scale_power_of_two: bool = False,
+        outlier_threshold: Optional[float] = None,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        if isinstance(qscheme, str):
+            qscheme = QScheme(qscheme)
+        if qscheme in (QScheme.MICROSCALING, QScheme.GROUP_WISE_AFFINE):
+            raise NotImplementedError(
+                f"qscheme={qscheme.value} is outside the B200 hot path built so far (SURVEY.md §8f, rank 1)")
+        if outlier_threshold is not None:
+            raise NotImplementedError("outlier_threshold belongs to the PT2E flow, outside the B200 hot path")
+        if qscheme is not None and (quant_max is None or amax_history_len is None):
+            raise ValueError("quant_max and amax_history_len are required when a qscheme is given")
+        self.dtype = dtype
+        self.qscheme = qscheme
+        self.quant_min = quant_min
+        self.quant_max = quant_max
+        self.amax_history_len = amax_history_len
+        self.ch_axis = ch_axis
+        self.block_size = block_size
+        self.scale_dtype = scale_dtype
+        self.force_scale_power_of_two = force_scale_power_of_two
+        self.outlier_threshold = outlier_threshold
+        self.record_histogram = record_histogram
+        self._fmt = _C.format_from_string(dtype)  # ValueError("Unsupported dtype: ...")
+        self._qmap = None
+        device = kwargs.get("device", None)
+        f32 = dict(device=device, dtype=torch.float)
+        self.register_buffer("amax_history", torch.tensor([], **f32))
+        self.register_buffer("scale", torch.tensor([1.0], **f32))
+        self.register_buffer("zero_point", torch.tensor([1.0], **f32))
+        self.register_buffer("histogram", torch.zeros(254, **f32), persistent=False)
+        self.is_per_channel = qscheme == QScheme.PER_CHANNEL_SYMMETRIC
+        self._flag_versions = None
+        self.enable_observer(qscheme is not None)
+        if device is not None:
+            self.to(device)
+
+    # -- enable flags: uint8 buffers (state-dict / DDP compatible) mirrored on the host so that the
+    #    hot path never reads device memory back.  The mirror is refreshed whenever a buffer's
+    #    version counter moved (in-place writes, load_state_dict), i.e. never in steady state.
+    def _flags(self):
+        versions = (self.observer_enabled._version, self.fake_quant_enabled._version,
+                    id(self.observer_enabled), id(self.fake_quant_enabled))
+        if versions != self._flag_versions:
+            self._observe = bool(self.observer_enabled[0].item() == 1)
+            self._quantize = bool(self.fake_quant_enabled[0].item() == 1)
+            self._flag_versions = versions
+        return self._observe, self._quantize
+
+    @property
+    def qmap(self):
+        if self._qmap is None or self._qmap.device != self.scale.device:
+            self._qmap = get_quantization_map(self.dtype, self.scale.device)
+        return self._qmap
+
+    @property
+    def scale_qmap(self):
+        return None
+
+    @torch.jit.export
+    def calculate_qparams(self):
+        return self.scale
+
+    @torch.jit.export
+    def extra_repr(self):
+        return (f"fake_quant_enabled={self.fake_quant_enabled}, observer_enabled={self.observer_enabled}, "
+                f"dtype={self.dtype}, amax_history_len={self.amax_history_len}, quant_max={self.quant_max}, "
+                f"qscheme={self.qscheme}, ch_axis={self.ch_axis}, block_size={self.block_size}, "
+                f"force_scale_power_of_two={self.force_scale_power_of_two}, scale={self.scale}")
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        if self.scale.device != X.device:
+            self.to(X.device)
+        if self.record_histogram:
+            mag = X.detach().float().abs()
+            self.histogram += torch.histc(torch.log2(mag).floor(), bins=254, min=-126, max=127)
+        return FusedAmaxObsFakeQuantFunction.apply(X, self)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict,
+                              missing_keys, unexpected_keys, error_msgs):
+        # `scale` / `amax_history` are shaped lazily by the first observed call; adopt checkpoint shapes
+        for name in ("scale", "amax_history"):
+            key = prefix + name
+            if key in state_dict:
+                getattr(self, name).resize_(state_dict[key].shape)
+            elif strict:
+                missing_keys.append(key)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict,
+                                      missing_keys, unexpected_keys, error_msgs)
+        self._flag_versions = None
