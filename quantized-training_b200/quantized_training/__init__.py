@@ -8,7 +8,9 @@ CUDA only: there is no CPU or eager fallback.
 from . import _C
 from .fake_quantize import FusedAmaxObsFakeQuantize, get_quantization_map
 from .qconfig import QConfig, get_qconfig
+from .quantize import convert, get_quantized_model, prepare, propagate_config, quantize, replace_softmax
 from .quantizer import QScheme, QuantizationSpec
+from .training_args import add_qspec_args
 
 # qscheme constants, as the reference exposes them at package level
 per_tensor_symmetric = QScheme.PER_TENSOR_SYMMETRIC
@@ -21,6 +23,13 @@ __all__ = [
     "QConfig",
     "QScheme",
     "QuantizationSpec",
+    "add_qspec_args",
+    "convert",
     "get_qconfig",
     "get_quantization_map",
+    "get_quantized_model",
+    "prepare",
+    "propagate_config",
+    "quantize",
+    "replace_softmax",
 ]

@@ -1,0 +1,51 @@
+"""QAT Linear: the weight is fake-quantized on every forward (reference: modules/qat/linear.py:15-80)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.utils.parametrize import (
+    is_parametrized,
+    transfer_parametrizations_and_params,
+    type_before_parametrizations,
+)
+
+__all__ = ["Linear"]
+
+
+class Linear(nn.Linear):
+    """``nn.Linear`` whose weight passes through ``qconfig.weight()`` before the GEMM.
+    Input quantization is not done here: `prepare` installs it as a forward pre-hook."""
+
+    _FLOAT_MODULE = nn.Linear
+
+    def __init__(self, in_features, out_features, bias=True, qconfig=None, device=None, dtype=None) -> None:
+        super().__init__(in_features, out_features, bias, device=device, dtype=dtype)
+        assert qconfig, "qconfig must be provided for QAT module"
+        self.qconfig = qconfig
+        self.weight_fake_quant = qconfig.weight(factory_kwargs={"device": device, "dtype": dtype})
+
+    def forward(self, input):
+        return F.linear(input, self.weight_fake_quant(self.weight), self.bias)
+
+    @classmethod
+    def from_float(cls, mod):
+        """Wrap a float ``nn.Linear``; Parameters are shared, not copied."""
+        assert type_before_parametrizations(mod) == cls._FLOAT_MODULE, (
+            f"qat.{cls.__name__}.from_float only works for {cls._FLOAT_MODULE.__name__}")
+        assert getattr(mod, "qconfig", None), "Input float module must have a valid qconfig"
+        # build on the meta device: the Parameters are replaced by the float module's right below
+        qat = cls(mod.in_features, mod.out_features, bias=mod.bias is not None, qconfig=mod.qconfig, device="meta")
+        qat.weight_fake_quant = mod.qconfig.weight()
+        for name in ("weight", "bias"):
+            if is_parametrized(mod, name):
+                transfer_parametrizations_and_params(mod, qat, name)
+            else:
+                setattr(qat, name, getattr(mod, name))
+        return qat
+
+    def to_float(self):
+        linear = nn.Linear(self.in_features, self.out_features, self.bias is not None)
+        linear.weight = nn.Parameter(self.weight.detach())
+        if self.bias is not None:
+            linear.bias = nn.Parameter(self.bias.detach())
+        linear.train(self.training)
+        return linear

@@ -77,7 +77,8 @@ def test_exhaustive_fp32_round_to_odd(golden):
             continue
         mod = qt.FusedAmaxObsFakeQuantize(d, device=DEV)
         yb = bits_of(mod(x))
-        assert np.all((yb & 0xFFFF) == 0), d
+        not_nan = (yb & 0x7FFFFFFF) <= 0x7F800000
+        assert np.all((yb[not_nan] & 0xFFFF) == 0), d  # outputs are bf16-exact (NaN payloads are free)
         assert nan_eq16((yb >> 16).astype(np.uint16), golden.vmap32[d]).all(), d
         yb = bits_of(mod(x[1:-2]))  # misaligned + tail
         assert nan_eq16((yb >> 16).astype(np.uint16), golden.vmap32[d][1:-2]).all(), d
