@@ -146,12 +146,12 @@ def run_gpu(args):
         x[i:i + chunk] = (torch.randn(min(chunk, n - i), device=dev, generator=gen) * 4.0).to(torch.bfloat16)
     mods = [qt.FusedAmaxObsFakeQuantize(s, device=dev) for s in SWEEP]
     y = torch.empty_like(x)
-    fmts = [m._fmt for m in mods]
+    fmts = [(m._fmt, m.lut) for m in mods]
     unit = torch.ones(1, device=dev)
 
     def step():
-        for f in fmts:  # straight through the C ABI: y = fq(x), output buffer reused
-            qt._C.fq_forward(x, y, 1, 1, n, f, unit, None)
+        for f, lut in fmts:  # straight through the C ABI: y = fq(x), output buffer reused
+            qt._C.fq_forward(x, y, 1, 1, n, f, unit, None, lut)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -166,9 +166,9 @@ def run_gpu(args):
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     for k in range(args.steps):
-        for i, f in enumerate(fmts):
+        for i, (f, lut) in enumerate(fmts):
             ev[k][i][0].record()
-            qt._C.fq_forward(x, y, 1, 1, n, f, unit, None)
+            qt._C.fq_forward(x, y, 1, 1, n, f, unit, None, lut)
             ev[k][i][1].record()
     t1.record()
     barrier()
@@ -186,6 +186,50 @@ def run_gpu(args):
     kernel_ms = sum(per_spec_ms) / len(SWEEP)
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+
+    # ---- side measurements (not part of `value`): other call shapes of the same kernels, same tensor
+    def timed(fn, reps=5):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    extra = {}
+    if rank == 0 and not args.no_extras:
+        nn_ = min(n, 1 << 28)
+        xs, ys = x[:nn_], y[:nn_]
+        sc = torch.full((1,), 0.0123, device=dev)
+        hist = torch.zeros(1, device=dev)
+        for name in ("fp8_e4m3", "posit8_1", "int8"):
+            m = qt.FusedAmaxObsFakeQuantize(name, device=dev)
+            ms = timed(lambda: qt._C.fq_forward(xs, ys, 1, 1, nn_, m._fmt, sc, hist, m.lut))
+            extra[f"{name} bf16 per-tensor scale + amax"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
+            ms = timed(lambda: qt._C.fq_forward(xs, ys, 1, 1, nn_, m._fmt, unit, None, None))
+            extra[f"{name} bf16 bare, direct bitwise path"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
+        rows = nn_ // 4096
+        scr = torch.rand(rows, device=dev) * 0.05 + 0.01
+        scc = torch.rand(4096, device=dev) * 0.05 + 0.01
+        m = qt.FusedAmaxObsFakeQuantize("posit8_1", device=dev)
+        ms = timed(lambda: qt._C.fq_forward(xs, ys, 1, rows, 4096, m._fmt, scr, torch.zeros(rows, device=dev), m.lut))
+        extra["posit8_1 bf16 per-channel ax=0 [N/4096,4096] + amax"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
+        ms = timed(lambda: qt._C.fq_forward(xs, ys, rows, 4096, 1, m._fmt, scc, torch.zeros(4096, device=dev), m.lut))
+        extra["posit8_1 bf16 per-channel ax=-1 [N/4096,4096] + amax"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
+        ms = timed(lambda: qt._C.amax(xs, 1, 1, nn_, hist))
+        extra["amax only bf16 (read bytes)"] = 2.0 * nn_ / (ms * 1e-3) / 1e9
+        x32 = xs[: nn_ // 2].float()
+        y32 = torch.empty_like(x32)
+        for name in ("posit8_1", "int8"):
+            m = qt.FusedAmaxObsFakeQuantize(name, device=dev)
+            ms = timed(lambda: qt._C.fq_forward(x32, y32, 1, 1, x32.numel(), m._fmt, unit, None, m.lut))
+            extra[f"{name} fp32 bare"] = 8.0 * x32.numel() / (ms * 1e-3) / 1e9
+            ms = timed(lambda: qt._C.fq_forward(x32, y32, 1, 1, x32.numel(), m._fmt, sc, hist, m.lut))
+            extra[f"{name} fp32 per-tensor scale + amax"] = 8.0 * x32.numel() / (ms * 1e-3) / 1e9
+        del x32, y32
 
     # ---- end to end through the public module API, host buffers, copies inside the timed region
     ne = 1 << min(args.log2_numel, args.e2e_log2_numel)
@@ -238,7 +282,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * ne * len(SWEEP),
                     "d2h_bytes_per_step": 2 * ne * len(SWEEP), "log2_numel": ne.bit_length() - 1,
                     "api": "FusedAmaxObsFakeQuantize.forward on pinned-host -> device -> pinned-host"},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "other_shapes_GBps": extra,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -254,6 +298,7 @@ def main():
     ap.add_argument("--log2-numel", type=int, default=30)
     ap.add_argument("--e2e-log2-numel", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -30,6 +30,10 @@ extern "C" {
 #define QT_ERR_INVALID_ARGUMENT 2
 #define QT_ERR_CUDA 3
 #define QT_ERR_UNALIGNED 4
+#define QT_NO_LUT 5 /* not an error: the format has no binade-constant table and runs on the direct path */
+
+/* size of the per-format constant table used by the fast path of qt_fq_forward (see qt_lut_build_host) */
+#define QT_LUT_BYTES 8192
 
 /* element type of x / y */
 #define QT_BF16 0
@@ -75,6 +79,14 @@ int qt_format_min_max(const char *dtype, double *qmin, double *qmax);
  * the kernels never read such a table -- this is for API parity and for tests. */
 int qt_table_host(const qt_format_t *fmt, uint16_t *table_host);
 
+/* Fast-path constants for a format: 512 x {p1, p2, d, l} floats, one entry per (sign, exponent) of a bf16
+ * input, such that  round_fmt(x) = fma(saturate(fma(|x|, p1, p2)), d, l)  on every bf16 x (derived from the
+ * bitwise rounding logic and verified on all 65 536 inputs before returning).  This plays the part of the
+ * reference's 128 KB `qmap` buffer (fake_quantize.py:304) at 8 KB and without a per-element gather from HBM:
+ * the caller copies lut_host to the device once and passes it to qt_fq_forward.
+ * Returns QT_OK, or QT_NO_LUT for formats that run on the direct path (intN, uintN, float32, bfloat16). */
+int qt_lut_build_host(const qt_format_t *fmt, void *lut_host);
+
 /* The observer half of FusedAmaxObsFakeQuantFunction.forward, minus the amax of the
  * current tensor (fake_quantize.py:225-242).  Per channel c of `channels`:
  *   amax = max_i history[i][c]  (read BEFORE the insert -> delayed scaling, NaN propagates)
@@ -92,9 +104,11 @@ int qt_scale_update(float *history, int amax_history_len, size_t channels, float
  * x, y: contiguous, viewed as [outer, channels, inner]; per-tensor / unobserved: channels = 1.
  * scale:    `channels` floats on the device, or NULL for an exact scale of 1 (bare specs).
  * amax_out: `channels` floats on the device (non-negative; NaN sticks), or NULL.
- * y may alias x. */
+ * lut:      QT_LUT_BYTES on the device from qt_lut_build_host(fmt), or NULL to round on the direct
+ *           bitwise path (same results, more integer instructions per element).
+ * x and y must not overlap. */
 int qt_fq_forward(const void *x, void *y, size_t outer, size_t channels, size_t inner, int elem_type,
-                  const qt_format_t *fmt, const float *scale, float *amax_out, void *stream);
+                  const qt_format_t *fmt, const float *scale, float *amax_out, const void *lut, void *stream);
 
 /* Observer only (fake quant disabled, e.g. calibration): amax_out[c] = max(amax_out[c], max|x|). */
 int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type,

@@ -1,27 +1,83 @@
 // qt_fq.cu -- fused quantize-dequantize + amax kernels for sm_100a, and their C-ABI launchers.
 //
-// One pass over HBM per call: 128-bit coalesced streaming loads -> (x / s) -> bitwise round to
-// the format (qt_round.h, no table) -> (* s) -> 128-bit streaming stores, while max|x| of the
-// UNSCALED input is reduced warp-wide (redux.sync) and block-wide and merged with one atomicMax
-// per CTA.  The reference's scaling is delayed (the scale applied now comes from earlier calls,
-// fake_quantize.py:230-242), so no grid-wide dependency exists and one pass suffices.
+// One pass over HBM per call: 128-bit coalesced streaming loads -> (x / s) -> round to the format
+// -> (* s) -> 128-bit streaming stores, while max|x| of the UNSCALED input is reduced warp-wide
+// (redux.sync) and block-wide and merged with one atomicMax per CTA.  The reference's scaling is
+// delayed (the scale applied now comes from earlier calls, fake_quantize.py:230-242), so no grid-wide
+// dependency exists and one pass suffices.
 //
 // Replaces (reference, src/quantized_training/): fake_quantize.py:217-223 (amax),
 // :244-246 (divide, vmap, multiply), decomposed.py:146-163 (vmap's Python chunk loop).
+//
+// Rounding engines (same results, checked against each other and the reference's tables):
+//   Direct   qt_round.h -- bitwise logic, integer ALU.  int/uint use it always (a handful of ops).
+//   Table    qt_lut.h   -- per-binade constants in shared memory, 2 FFMA + 1 LDS.128 per element.
+//            Used for fp and posit formats when the caller supplies the 8 KB table: the direct posit
+//            path needs ~30 ALU-pipe ops per element and caps the kernel at ~40 % of HBM bandwidth.
 //
 // Layouts:  x, y contiguous [outer, channels, inner].
 //   flat  kernel: channels == 1 (per-tensor or bare spec); persistent grid-stride over 16-byte vectors.
 //   rows  kernel: inner > 1 per-channel (e.g. weights [out, in], ax=0): one scale per row segment.
 //   cols  kernel: inner == 1 per-channel (ax = last dim): one scale per column, register-resident.
+//   scalar kernel: tails, misaligned views, odd per-channel shapes.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <string.h>
 
 #include "qt_internal.h"
+#include "qt_lut.h"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;  // 16-byte vectors in flight per thread
+
+// ----------------------------------------------------------------------------- rounding engines
+
+template <int KIND>
+struct DirectParams {
+    QtRound P;
+};
+template <int KIND>
+struct DirectRounder {
+    static constexpr bool kTable = false;
+    using Params = DirectParams<KIND>;
+    const QtRound &P;
+    __device__ __forceinline__ DirectRounder(const Params &p, const QtLutEntry *) : P(p.P) {}
+    __device__ __forceinline__ uint32_t operator()(uint32_t u) const { return qt_round<KIND>(P, u); }
+};
+
+struct TableParams {
+    const QtLutEntry *table;  // global memory, QT_LUT_BYTES
+    QtLutCfg cfg;
+};
+template <bool CLAMP, bool MXBAND>
+struct TableRounder {
+    static constexpr bool kTable = true;
+    using Params = TableParams;
+    const QtLutEntry *tab;  // shared memory copy
+    const QtLutCfg cfg;
+    __device__ __forceinline__ TableRounder(const Params &p, const QtLutEntry *smem) : tab(smem), cfg(p.cfg) {}
+    __device__ __forceinline__ uint32_t operator()(uint32_t u) const
+    {
+        return qt_lut_round<CLAMP, MXBAND>(tab, cfg, u);
+    }
+};
+
+// every CTA stages the 8 KB table once (L2-resident after the first CTA)
+template <class R>
+__device__ __forceinline__ const QtLutEntry *stage_table(const typename R::Params &p, QtLutEntry *smem)
+{
+    if constexpr (R::kTable) {
+        const float4 *src = reinterpret_cast<const float4 *>(p.table);
+        float4 *dst = reinterpret_cast<float4 *>(smem);
+        for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < QT_LUT_ENTRIES; i += blockDim.x * blockDim.y)
+            dst[i] = src[i];
+        __syncthreads();
+    }
+    return smem;
+}
+#define QT_TABLE_SMEM(R) __shared__ __align__(16) QtLutEntry s_table[R::kTable ? QT_LUT_ENTRIES : 1]
 
 // ----------------------------------------------------------------------------- small helpers
 
@@ -33,6 +89,12 @@ __device__ __forceinline__ uint32_t bf16_rne_hi(float f)
 {
     return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)) << 16;
 }
+// two floats -> packed bf16x2 (one F2FP instruction)
+__device__ __forceinline__ uint32_t bf16x2_rne(float lo, float hi)
+{
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&p);
+}
 
 // round-to-odd truncation of an fp32 to the bf16 grid: what vmap's index derivation does
 // (decomposed.py:151-153); returns fp32 bits with the low half zero
@@ -41,63 +103,107 @@ __device__ __forceinline__ uint32_t f32_to_bf16_rto_hi(uint32_t b)
     return (b & 0xFFFF0000u) | (((b & 0xFFFFu) != 0u) ? 0x10000u : 0u);
 }
 
-// one bf16 element held as fp32 bits (low half zero): returns result in the same form
-template <int KIND, bool UNIT>
-__device__ __forceinline__ uint32_t fq_bf16(const QtRound &P, uint32_t xh, float s)
+// How x / s is evaluated for bf16 tensors.
+//   UNIT   s == 1: identity.
+//   RECIP  x * (1/s) in fp32, then RNE to bf16.  For bf16 x and s (8-bit significands) the exact quotient
+//          is never a bf16 rounding tie and lies at least 2^-17 (relative) away from every tie point, while
+//          x * rcp(s) is within 2^-23 of it, so both round to the same bf16 as the reference's
+//          bf16(fp32(x / s)).  The argument needs a normal-range quotient: elements whose product is below
+//          2^-120 (other than exact zeros) take the true division.
+//   EXACT  __fdiv_rn (scale outside [2^-100, 2^100], or not finite).
+enum { DIV_UNIT = 0, DIV_RECIP = 1, DIV_EXACT = 2 };
+
+struct ScaleBf16 {
+    float s, rs;
+};
+__device__ __forceinline__ int classify_scale(float s)
 {
-    if (UNIT) return qt_round<KIND>(P, xh);
-    const uint32_t uh = bf16_rne_hi(__fdiv_rn(__uint_as_float(xh), s));  // x / s, rounded to bf16
-    const uint32_t q = qt_round<KIND>(P, uh);
-    return bf16_rne_hi(__fmul_rn(__uint_as_float(q), s));  // q * s, rounded to bf16
+    const float a = fabsf(s);
+    if (s == 1.0f) return DIV_UNIT;
+    return (a >= 0x1p-100f && a <= 0x1p100f) ? DIV_RECIP : DIV_EXACT;
 }
 
-template <int KIND, bool UNIT>
-__device__ __forceinline__ uint32_t fq_f32(const QtRound &P, uint32_t xb, float s)
+template <int DIV>
+__device__ __forceinline__ float bf16_quotient(uint32_t xh, const ScaleBf16 &sc)
 {
-    if (UNIT) return qt_round<KIND>(P, f32_to_bf16_rto_hi(xb));
+    const float x = __uint_as_float(xh);
+    if (DIV == DIV_EXACT) return __fdiv_rn(x, sc.s);
+    float p = __fmul_rn(x, sc.rs);
+    if (fabsf(p) < 0x1p-120f && (xh & 0x7FFFFFFFu) != 0u) p = __fdiv_rn(x, sc.s);
+    return p;
+}
+
+// one bf16 element held as fp32 bits (low half zero): returns the result in the same form
+template <class R, int DIV>
+__device__ __forceinline__ uint32_t fq_bf16(const R &round, uint32_t xh, const ScaleBf16 &sc)
+{
+    if (DIV == DIV_UNIT) return round(xh);
+    const uint32_t q = round(bf16_rne_hi(bf16_quotient<DIV>(xh, sc)));
+    return bf16_rne_hi(__fmul_rn(__uint_as_float(q), sc.s));  // q * s, rounded to bf16
+}
+
+template <class R, bool UNIT>
+__device__ __forceinline__ uint32_t fq_f32(const R &round, uint32_t xb, float s)
+{
+    if (UNIT) return round(f32_to_bf16_rto_hi(xb));
     const float u = __fdiv_rn(__uint_as_float(xb), s);
-    const uint32_t q = qt_round<KIND>(P, f32_to_bf16_rto_hi(__float_as_uint(u)));
+    const uint32_t q = round(f32_to_bf16_rto_hi(__float_as_uint(u)));
     return __float_as_uint(__fmul_rn(__uint_as_float(q), s));
 }
 
 // a 32-bit word holding two bf16 values
-template <int KIND, bool UNIT, bool AMAX>
-__device__ __forceinline__ uint32_t fq_word_bf16(const QtRound &P, uint32_t w, float s, uint32_t &amax)
+template <class R, int DIV, bool AMAX>
+__device__ __forceinline__ uint32_t fq_word_bf16(const R &round, uint32_t w, const ScaleBf16 &sc, uint32_t &amax)
 {
     const uint32_t lo = w << 16, hi = w & 0xFFFF0000u;
     if (AMAX) amax = max(amax, max(lo & 0x7FFFFFFFu, hi & 0x7FFFFFFFu));
-    const uint32_t qlo = fq_bf16<KIND, UNIT>(P, lo, s);
-    const uint32_t qhi = fq_bf16<KIND, UNIT>(P, hi, s);
-    return __byte_perm(qlo, qhi, 0x7632);  // {qhi[31:16], qlo[31:16]}
+    if (DIV == DIV_UNIT) return __byte_perm(round(lo), round(hi), 0x7632);  // {hi[31:16], lo[31:16]}
+    // scaled: both conversions are packed (one F2FP per pair each way)
+    const uint32_t uq = bf16x2_rne(bf16_quotient<DIV>(lo, sc), bf16_quotient<DIV>(hi, sc));
+    const uint32_t qlo = round(uq << 16), qhi = round(uq & 0xFFFF0000u);
+    return bf16x2_rne(__fmul_rn(__uint_as_float(qlo), sc.s), __fmul_rn(__uint_as_float(qhi), sc.s));
 }
 
-template <int KIND, bool F32, bool UNIT, bool AMAX>
-__device__ __forceinline__ uint4 fq_vec(const QtRound &P, uint4 v, float s, uint32_t &amax)
+__device__ __forceinline__ uint32_t amax_of_vec_f32(uint32_t amax, const uint4 &v)
+{
+    return max(max(amax, v.x & 0x7FFFFFFFu), max(max(v.y & 0x7FFFFFFFu, v.z & 0x7FFFFFFFu), v.w & 0x7FFFFFFFu));
+}
+__device__ __forceinline__ uint32_t amax_of_vec_bf16(uint32_t amax, const uint4 &v)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) amax = max(amax, max((w[k] << 16) & 0x7FFFFFFFu, w[k] & 0x7FFF0000u));
+    return amax;
+}
+
+template <class R, bool F32, int DIV, bool AMAX>
+__device__ __forceinline__ uint4 fq_vec(const R &round, uint4 v, const ScaleBf16 &sc, uint32_t &amax)
 {
     uint4 r;
     if (F32) {
-        if (AMAX)
-            amax = max(max(amax, v.x & 0x7FFFFFFFu),
-                       max(max(v.y & 0x7FFFFFFFu, v.z & 0x7FFFFFFFu), v.w & 0x7FFFFFFFu));
-        r.x = fq_f32<KIND, UNIT>(P, v.x, s);
-        r.y = fq_f32<KIND, UNIT>(P, v.y, s);
-        r.z = fq_f32<KIND, UNIT>(P, v.z, s);
-        r.w = fq_f32<KIND, UNIT>(P, v.w, s);
+        if (AMAX) amax = amax_of_vec_f32(amax, v);
+        r.x = fq_f32<R, DIV == DIV_UNIT>(round, v.x, sc.s);
+        r.y = fq_f32<R, DIV == DIV_UNIT>(round, v.y, sc.s);
+        r.z = fq_f32<R, DIV == DIV_UNIT>(round, v.z, sc.s);
+        r.w = fq_f32<R, DIV == DIV_UNIT>(round, v.w, sc.s);
     } else {
-        r.x = fq_word_bf16<KIND, UNIT, AMAX>(P, v.x, s, amax);
-        r.y = fq_word_bf16<KIND, UNIT, AMAX>(P, v.y, s, amax);
-        r.z = fq_word_bf16<KIND, UNIT, AMAX>(P, v.z, s, amax);
-        r.w = fq_word_bf16<KIND, UNIT, AMAX>(P, v.w, s, amax);
+        r.x = fq_word_bf16<R, DIV, AMAX>(round, v.x, sc, amax);
+        r.y = fq_word_bf16<R, DIV, AMAX>(round, v.y, sc, amax);
+        r.z = fq_word_bf16<R, DIV, AMAX>(round, v.z, sc, amax);
+        r.w = fq_word_bf16<R, DIV, AMAX>(round, v.w, sc, amax);
     }
     return r;
 }
 
 // scale.to(x.dtype): bf16 inputs see the scale rounded to bf16 (fake_quantize.py:245)
 template <bool F32>
-__device__ __forceinline__ float load_scale(const float *scale, size_t c)
+__device__ __forceinline__ ScaleBf16 load_scale(const float *scale, size_t c)
 {
+    ScaleBf16 sc;
     const float s = scale[c];
-    return F32 ? s : __uint_as_float(bf16_rne_hi(s));
+    sc.s = F32 ? s : __uint_as_float(bf16_rne_hi(s));
+    sc.rs = __frcp_rn(sc.s);
+    return sc;
 }
 
 // block-wide max of |x| bit patterns, then ONE atomicMax.  Non-negative floats order like
@@ -118,9 +224,59 @@ __device__ __forceinline__ void block_amax_commit(uint32_t amax, float *amax_out
 
 // ----------------------------------------------------------------------------- flat kernel
 // channels == 1.  nvec 16-byte vectors; tile = kThreads * kUnroll vectors; persistent grid.
-template <int KIND, bool F32, bool UNIT, bool AMAX, bool WRITE>
-__device__ __forceinline__ void fq_flat_body(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
-                                             const QtRound &P, float s, float *__restrict__ amax_out)
+template <class R, bool F32, int DIV, bool AMAX>
+__device__ __forceinline__ void fq_span(const R &round, const uint4 *__restrict__ x, uint4 *__restrict__ y,
+                                        size_t nvec, size_t first_tile, size_t tile_stride, const ScaleBf16 &sc,
+                                        uint32_t &amax)
+{
+    const size_t tile = (size_t)kThreads * kUnroll;
+    const size_t ntiles = (nvec + tile - 1) / tile;
+    for (size_t t = first_tile; t < ntiles; t += tile_stride) {
+        const size_t base = t * tile + threadIdx.x;
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * kThreads;
+            v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * kThreads;
+            const uint4 r = fq_vec<R, F32, DIV, AMAX>(round, v[j], sc, amax);
+            if (i < nvec) st_stream(y + i, r);
+        }
+    }
+}
+
+// The scale is one number for the whole launch.  When it is exactly 1 (bare specs such as "e4m3" or
+// "posit8_1", whose `scale` buffer is never written) x / 1 and q * 1 are identities and the CTA takes a
+// path without divide / multiply / re-rounding.  The branch is grid-uniform and made on the device, so
+// the host never reads the scale back.
+template <class R, bool F32, bool AMAX>
+__global__ void __launch_bounds__(kThreads)
+fq_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
+               const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
+               float *__restrict__ amax_out)
+{
+    QT_TABLE_SMEM(R);
+    const R round(params, stage_table<R>(params, s_table));
+    ScaleBf16 sc = {1.0f, 1.0f};
+    if (scale) sc = load_scale<F32>(scale, 0);
+    uint32_t amax = 0u;
+    const int mode = classify_scale(sc.s);
+    if (mode == DIV_UNIT)
+        fq_span<R, F32, DIV_UNIT, AMAX>(round, x, y, nvec, blockIdx.x, gridDim.x, sc, amax);
+    else if (F32 || mode == DIV_EXACT)
+        fq_span<R, F32, DIV_EXACT, AMAX>(round, x, y, nvec, blockIdx.x, gridDim.x, sc, amax);
+    else
+        fq_span<R, F32, DIV_RECIP, AMAX>(round, x, y, nvec, blockIdx.x, gridDim.x, sc, amax);
+    if (AMAX) block_amax_commit(amax, amax_out);
+}
+
+// observer only (fake quant disabled): read, reduce, no store
+template <bool F32>
+__global__ void __launch_bounds__(kThreads)
+amax_flat_kernel(const uint4 *__restrict__ x, size_t nvec, float *__restrict__ amax_out)
 {
     uint32_t amax = 0u;
     const size_t tile = (size_t)kThreads * kUnroll;
@@ -134,67 +290,38 @@ __device__ __forceinline__ void fq_flat_body(const uint4 *__restrict__ x, uint4 
             v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * kThreads;
-            if (WRITE) {
-                const uint4 r = fq_vec<KIND, F32, UNIT, AMAX>(P, v[j], s, amax);
-                if (i < nvec) st_stream(y + i, r);
-            } else {
-                // observer only
-                if (F32)
-                    amax = max(max(amax, v[j].x & 0x7FFFFFFFu),
-                               max(max(v[j].y & 0x7FFFFFFFu, v[j].z & 0x7FFFFFFFu), v[j].w & 0x7FFFFFFFu));
-                else {
-                    const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        amax = max(amax, max((w[k] << 16) & 0x7FFFFFFFu, w[k] & 0x7FFF0000u));
-                }
-            }
-        }
+        for (int j = 0; j < kUnroll; ++j) amax = F32 ? amax_of_vec_f32(amax, v[j]) : amax_of_vec_bf16(amax, v[j]);
     }
-    if (AMAX) block_amax_commit(amax, amax_out);
-}
-
-// The scale is one number for the whole launch.  When it is exactly 1 (bare specs such as "e4m3" or
-// "posit8_1", whose `scale` buffer is never written) x / 1 and q * 1 are identities, so the CTA takes
-// a path without the divide / multiply / bf16 re-rounding.  The branch is grid-uniform.
-template <int KIND, bool F32, bool AMAX, bool WRITE>
-__global__ void __launch_bounds__(kThreads)
-fq_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec, const __grid_constant__ QtRound P,
-               const float *__restrict__ scale, float *__restrict__ amax_out)
-{
-    const float s = scale ? load_scale<F32>(scale, 0) : 1.0f;
-    if (!WRITE || s == 1.0f)
-        fq_flat_body<KIND, F32, true, AMAX, WRITE>(x, y, nvec, P, 1.0f, amax_out);
-    else
-        fq_flat_body<KIND, F32, false, AMAX, WRITE>(x, y, nvec, P, s, amax_out);
+    block_amax_commit(amax, amax_out);
 }
 
 // ----------------------------------------------------------------------------- scalar kernel
 // Any layout, any alignment: element i belongs to channel (i / inner) % channels.  Used for tails,
-// misaligned views and odd per-channel shapes.  Elements [first, first + count).
-template <int KIND, bool F32, bool AMAX, bool WRITE>
+// misaligned views and odd per-channel shapes.  Elements [first, first + count).  WRITE = false: observe only.
+template <class R, bool F32, bool AMAX, bool WRITE>
 __global__ void __launch_bounds__(kThreads)
 fq_scalar_kernel(const void *__restrict__ xv, void *__restrict__ yv, size_t first, size_t count, size_t channels,
-                 size_t inner, const __grid_constant__ QtRound P, const float *__restrict__ scale,
+                 size_t inner, const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
                  float *__restrict__ amax_out)
 {
+    QT_TABLE_SMEM(R);
+    const R round(params, stage_table<R>(params, s_table));
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     uint32_t amax1 = 0u;  // channels == 1: reduce in registers, one atomic per CTA
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
         const size_t i = first + j;
         const size_t c = channels == 1 ? 0 : (i / inner) % channels;
-        const float s = scale ? load_scale<F32>(scale, c) : 1.0f;
-        uint32_t bits, ab;
+        ScaleBf16 sc = {1.0f, 1.0f};
+        if (WRITE && scale) sc = load_scale<F32>(scale, c);
+        uint32_t ab;
         if (F32) {
-            bits = static_cast<const uint32_t *>(xv)[i];
+            const uint32_t bits = static_cast<const uint32_t *>(xv)[i];
             ab = bits & 0x7FFFFFFFu;
-            if (WRITE) static_cast<uint32_t *>(yv)[i] = fq_f32<KIND, false>(P, bits, s);
+            if (WRITE) static_cast<uint32_t *>(yv)[i] = fq_f32<R, false>(round, bits, sc.s);
         } else {
-            bits = (uint32_t) static_cast<const uint16_t *>(xv)[i] << 16;
+            const uint32_t bits = (uint32_t) static_cast<const uint16_t *>(xv)[i] << 16;
             ab = bits & 0x7FFFFFFFu;
-            if (WRITE) static_cast<uint16_t *>(yv)[i] = (uint16_t)(fq_bf16<KIND, false>(P, bits, s) >> 16);
+            if (WRITE) static_cast<uint16_t *>(yv)[i] = (uint16_t)(fq_bf16<R, DIV_EXACT>(round, bits, sc) >> 16);
         }
         if (AMAX) {
             if (channels == 1)
@@ -209,36 +336,45 @@ fq_scalar_kernel(const void *__restrict__ xv, void *__restrict__ yv, size_t firs
 // ----------------------------------------------------------------------------- rows kernel
 // inner > 1 per-channel, inner % VEC == 0, 16-byte aligned.  blockIdx.x enumerates (row, segment):
 // row = o * channels + c, a segment is kThreads * kUnroll vectors of that row.
-template <int KIND, bool F32, bool AMAX, bool WRITE>
+template <class R, bool F32, bool AMAX, bool WRITE>
 __global__ void __launch_bounds__(kThreads)
 fq_rows_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, size_t channels, size_t vec_per_row,
-               size_t segs_per_row, const __grid_constant__ QtRound P, const float *__restrict__ scale,
-               float *__restrict__ amax_out)
+               size_t segs_per_row, const __grid_constant__ typename R::Params params,
+               const float *__restrict__ scale, float *__restrict__ amax_out)
 {
-    const size_t tile = (size_t)kThreads * kUnroll;
+    QT_TABLE_SMEM(R);
+    const R round(params, stage_table<R>(params, s_table));
     const size_t work = rows * segs_per_row;
+    const size_t tile = (size_t)kThreads * kUnroll;
+    const size_t once = ~(size_t)0 >> 1;  // tile stride that ends fq_span after one tile
     for (size_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
         const size_t row = wi / segs_per_row, seg = wi - row * segs_per_row;
         const size_t c = row % channels;
-        const float s = load_scale<F32>(scale, c);
         const uint4 *xr = x + row * vec_per_row;
-        uint4 *yr = y + row * vec_per_row;
         uint32_t amax = 0u;
-        const size_t base = seg * tile + threadIdx.x;
-        uint4 v[kUnroll];
+        if (WRITE) {
+            const ScaleBf16 sc = load_scale<F32>(scale, c);
+            const int mode = classify_scale(sc.s);
+            uint4 *yr = y + row * vec_per_row;
+            if (mode == DIV_UNIT)
+                fq_span<R, F32, DIV_UNIT, AMAX>(round, xr, yr, vec_per_row, seg, once, sc, amax);
+            else if (F32 || mode == DIV_EXACT)
+                fq_span<R, F32, DIV_EXACT, AMAX>(round, xr, yr, vec_per_row, seg, once, sc, amax);
+            else
+                fq_span<R, F32, DIV_RECIP, AMAX>(round, xr, yr, vec_per_row, seg, once, sc, amax);
+        } else {
+            const size_t base = seg * tile + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * kThreads;
-            v[j] = i < vec_per_row ? ld_stream(xr + i) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * kThreads;
-            uint4 r = fq_vec<KIND, F32, false, AMAX>(P, v[j], s, amax);
-            if (WRITE && i < vec_per_row) st_stream(yr + i, r);
+            for (int j = 0; j < kUnroll; ++j) {
+                const size_t i = base + (size_t)j * kThreads;
+                if (i < vec_per_row) {
+                    const uint4 v = ld_stream(xr + i);
+                    amax = F32 ? amax_of_vec_f32(amax, v) : amax_of_vec_bf16(amax, v);
+                }
+            }
         }
         if (AMAX) {
-            __syncthreads();  // warp_max reuse across loop iterations
+            __syncthreads();  // warp_max is reused across loop iterations
             block_amax_commit(amax, amax_out + c);
         }
     }
@@ -248,19 +384,23 @@ fq_rows_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
 // inner == 1 per-channel (channel = last dim), channels % VEC == 0, 16-byte aligned rows.
 // blockDim = (32, 8): threadIdx.x -> a 16-byte column group, threadIdx.y -> row phase.
 // Scales and running maxima for the thread's VEC columns stay in registers over all rows.
-template <int KIND, bool F32, bool AMAX, bool WRITE>
+template <class R, bool F32, bool AMAX, bool WRITE>
 __global__ void __launch_bounds__(kThreads)
 fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, size_t vec_per_row,
-               const __grid_constant__ QtRound P, const float *__restrict__ scale, float *__restrict__ amax_out)
+               const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
+               float *__restrict__ amax_out)
 {
     constexpr int VEC = F32 ? 4 : 8;
+    QT_TABLE_SMEM(R);
+    const R round(params, stage_table<R>(params, s_table));
     const size_t cg = (size_t)blockIdx.x * 32 + threadIdx.x;  // column group
     const bool active = cg < vec_per_row;
-    float s[VEC];
+    ScaleBf16 sc[VEC];
     uint32_t am[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-        s[k] = active ? load_scale<F32>(scale, cg * VEC + k) : 1.0f;
+        sc[k].s = sc[k].rs = 1.0f;
+        if (WRITE && active) sc[k] = load_scale<F32>(scale, cg * VEC + k);
         am[k] = 0u;
     }
     if (active) {
@@ -272,15 +412,16 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
             for (int k = 0; k < 4; ++k) {
                 if (F32) {
                     if (AMAX) am[k] = max(am[k], w[k] & 0x7FFFFFFFu);
-                    o[k] = fq_f32<KIND, false>(P, w[k], s[k]);
+                    if (WRITE) o[k] = fq_f32<R, false>(round, w[k], sc[k].s);
                 } else {
                     const uint32_t lo = w[k] << 16, hi = w[k] & 0xFFFF0000u;
                     if (AMAX) {
                         am[2 * k] = max(am[2 * k], lo & 0x7FFFFFFFu);
                         am[2 * k + 1] = max(am[2 * k + 1], hi & 0x7FFFFFFFu);
                     }
-                    o[k] = __byte_perm(fq_bf16<KIND, false>(P, lo, s[2 * k]), fq_bf16<KIND, false>(P, hi, s[2 * k + 1]),
-                                       0x7632);
+                    if (WRITE)
+                        o[k] = __byte_perm(fq_bf16<R, DIV_EXACT>(round, lo, sc[2 * k]),
+                                           fq_bf16<R, DIV_EXACT>(round, hi, sc[2 * k + 1]), 0x7632);
                 }
             }
             if (WRITE) st_stream(y + r * vec_per_row + cg, make_uint4(o[0], o[1], o[2], o[3]));
@@ -351,11 +492,9 @@ struct Job {
     void *y;
     size_t outer, channels, inner;
     bool f32;
-    QtRound P;
     const float *scale;
     float *amax;
     cudaStream_t stream;
-    bool write;
 };
 
 inline unsigned grid_for(size_t work_items, int ctas_per_sm)
@@ -365,35 +504,38 @@ inline unsigned grid_for(size_t work_items, int ctas_per_sm)
     return (unsigned)(work_items < cap ? (work_items ? work_items : 1) : cap);
 }
 
-template <int KIND, bool F32, bool AMAX, bool WRITE>
-void launch_scalar(const Job &j, size_t first, size_t count)
+template <class R, bool F32, bool AMAX, bool WRITE>
+void launch_scalar(const Job &j, const typename R::Params &p, size_t first, size_t count)
 {
     if (count == 0) return;
     const unsigned grid = grid_for((count + kThreads - 1) / kThreads, 16);
-    fq_scalar_kernel<KIND, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(j.x, j.y, first, count, j.channels,
-                                                                              j.inner, j.P, j.scale, j.amax);
+    fq_scalar_kernel<R, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(j.x, j.y, first, count, j.channels, j.inner,
+                                                                           p, j.scale, j.amax);
 }
 
-template <int KIND, bool F32, bool AMAX, bool WRITE>
-void launch_kind(const Job &j)
+template <class R, bool F32, bool AMAX, bool WRITE>
+void launch_layout(const Job &j, const typename R::Params &p)
 {
     constexpr size_t VEC = F32 ? 4 : 8;
     const size_t n = j.outer * j.channels * j.inner;
     const bool aligned = ((reinterpret_cast<uintptr_t>(j.x) | reinterpret_cast<uintptr_t>(j.y)) & 15u) == 0;
     const uint4 *xv = static_cast<const uint4 *>(j.x);
     uint4 *yv = static_cast<uint4 *>(j.y);
+    const size_t tile = (size_t)kThreads * kUnroll;
 
     if (j.channels == 1) {
         const size_t nvec = aligned ? n / VEC : 0;
         if (nvec) {
-            const size_t tile = (size_t)kThreads * kUnroll;
             const unsigned grid = grid_for((nvec + tile - 1) / tile, 8);
-            fq_flat_kernel<KIND, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(xv, yv, nvec, j.P, j.scale, j.amax);
+            if constexpr (WRITE)
+                fq_flat_kernel<R, F32, AMAX><<<grid, kThreads, 0, j.stream>>>(xv, yv, nvec, p, j.scale, j.amax);
+            else
+                amax_flat_kernel<F32><<<grid, kThreads, 0, j.stream>>>(xv, nvec, j.amax);
         }
-        launch_scalar<KIND, F32, AMAX, WRITE>(j, nvec * VEC, n - nvec * VEC);
+        launch_scalar<R, F32, AMAX, WRITE>(j, p, nvec * VEC, n - nvec * VEC);
         return;
     }
-    // per channel (scale is never NULL here)
+    // per channel (scale is never NULL here when WRITE)
     if (aligned && j.inner == 1 && j.channels % VEC == 0) {
         const size_t rows = j.outer, vec_per_row = j.channels / VEC;
         const unsigned gx = (unsigned)((vec_per_row + 31) / 32);
@@ -402,55 +544,44 @@ void launch_kind(const Job &j)
         if (want_y > max_y) want_y = max_y;
         if (want_y < 1) want_y = 1;
         if (want_y > 65535) want_y = 65535;
-        fq_cols_kernel<KIND, F32, AMAX, WRITE><<<dim3(gx, (unsigned)want_y), dim3(32, 8), 0, j.stream>>>(
-            xv, yv, rows, vec_per_row, j.P, j.scale, j.amax);
+        fq_cols_kernel<R, F32, AMAX, WRITE><<<dim3(gx, (unsigned)want_y), dim3(32, 8), 0, j.stream>>>(
+            xv, yv, rows, vec_per_row, p, j.scale, j.amax);
         return;
     }
     if (aligned && j.inner % VEC == 0 && j.inner >= 32 * VEC) {
         const size_t rows = j.outer * j.channels, vec_per_row = j.inner / VEC;
-        const size_t tile = (size_t)kThreads * kUnroll;
         const size_t segs = (vec_per_row + tile - 1) / tile;
         const unsigned grid = grid_for(rows * segs, 8);
-        fq_rows_kernel<KIND, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(xv, yv, rows, j.channels, vec_per_row,
-                                                                                segs, j.P, j.scale, j.amax);
+        fq_rows_kernel<R, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(xv, yv, rows, j.channels, vec_per_row, segs,
+                                                                             p, j.scale, j.amax);
         return;
     }
-    launch_scalar<KIND, F32, AMAX, WRITE>(j, 0, n);
+    launch_scalar<R, F32, AMAX, WRITE>(j, p, 0, n);
+}
+
+template <class R>
+void launch_flags(const Job &j, const typename R::Params &p)
+{
+    const bool amax = j.amax != nullptr;
+    if (j.f32)
+        amax ? launch_layout<R, true, true, true>(j, p) : launch_layout<R, true, false, true>(j, p);
+    else
+        amax ? launch_layout<R, false, true, true>(j, p) : launch_layout<R, false, false, true>(j, p);
 }
 
 template <int KIND>
-void launch_flags(const Job &j)
+void launch_direct(const Job &j, const QtRound &P)
 {
-    const bool amax = j.amax != nullptr;
-    if (!j.write) {  // observer only: the format is irrelevant, instantiate once
-        if constexpr (KIND == QTR_IDENTITY) {
-            j.f32 ? launch_kind<KIND, true, true, false>(j) : launch_kind<KIND, false, true, false>(j);
-        }
-        return;
-    }
-    if (j.f32)
-        amax ? launch_kind<KIND, true, true, true>(j) : launch_kind<KIND, true, false, true>(j);
-    else
-        amax ? launch_kind<KIND, false, true, true>(j) : launch_kind<KIND, false, false, true>(j);
+    DirectParams<KIND> p;
+    p.P = P;
+    launch_flags<DirectRounder<KIND>>(j, p);
 }
 
-int run_job(const Job &j)
+int no_device()
 {
-    if (num_sms() == 0) {
-        cudaError_t e = cudaGetLastError();
-        return cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e, "qt_b200: no usable CUDA device (there is no CPU fallback)");
-    }
-    switch (j.P.kind) {
-    case QTR_IDENTITY: launch_flags<QTR_IDENTITY>(j); break;
-    case QTR_INT: launch_flags<QTR_INT>(j); break;
-    case QTR_FP_CUSTOM: launch_flags<QTR_FP_CUSTOM>(j); break;
-    case QTR_FP_MX: launch_flags<QTR_FP_MX>(j); break;
-    case QTR_POSIT: launch_flags<QTR_POSIT>(j); break;
-    default: qt_set_error("bad format kind %d", j.P.kind); return QT_ERR_INVALID_ARGUMENT;
-    }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "fake-quant kernel launch");
-    return QT_OK;
+    return cuda_fail(e == cudaSuccess ? cudaErrorNoDevice : e,
+                     "qt_b200: no usable CUDA device (there is no CPU fallback)");
 }
 
 int check_layout(const char *fn, const void *x, size_t outer, size_t channels, size_t inner, int elem_type)
@@ -474,7 +605,8 @@ int check_layout(const char *fn, const void *x, size_t outer, size_t channels, s
 }  // namespace
 
 extern "C" int qt_fq_forward(const void *x, void *y, size_t outer, size_t channels, size_t inner, int elem_type,
-                             const qt_format_t *fmt, const float *scale, float *amax_out, void *stream)
+                             const qt_format_t *fmt, const float *scale, float *amax_out, const void *lut,
+                             void *stream)
 {
     int rc = check_layout("qt_fq_forward", x, outer, channels, inner, elem_type);
     if (rc != QT_OK) return rc;
@@ -486,15 +618,16 @@ extern "C" int qt_fq_forward(const void *x, void *y, size_t outer, size_t channe
         qt_set_error("qt_fq_forward: per-channel call (channels=%zu) needs a scale array", channels);
         return QT_ERR_INVALID_ARGUMENT;
     }
-    Job j;
-    rc = qt_make_round(fmt, &j.P);
+    QtRound P;
+    rc = qt_make_round(fmt, &P);
     if (rc != QT_OK) return rc;
-    const size_t n = outer * channels * inner;
-    if (n == 0) return QT_OK;
+    if (outer * channels * inner == 0) return QT_OK;
     if (!y) {
         qt_set_error("qt_fq_forward: y is NULL");
         return QT_ERR_INVALID_ARGUMENT;
     }
+    if (num_sms() == 0) return no_device();
+    Job j;
     j.x = x;
     j.y = y;
     j.outer = outer;
@@ -504,8 +637,33 @@ extern "C" int qt_fq_forward(const void *x, void *y, size_t outer, size_t channe
     j.scale = scale;
     j.amax = amax_out;
     j.stream = static_cast<cudaStream_t>(stream);
-    j.write = true;
-    return run_job(j);
+
+    TableParams tp;
+    if (lut && qt_lut_config(P, &tp.cfg) == QT_OK) {
+        if (reinterpret_cast<uintptr_t>(lut) & 15u) {
+            qt_set_error("qt_fq_forward: lut must be 16-byte aligned");
+            return QT_ERR_UNALIGNED;
+        }
+        tp.table = static_cast<const QtLutEntry *>(lut);
+        if (tp.cfg.mx_band)
+            launch_flags<TableRounder<true, true>>(j, tp);
+        else if (tp.cfg.clamp_bits != 0x7FFFFFFFu)
+            launch_flags<TableRounder<true, false>>(j, tp);
+        else
+            launch_flags<TableRounder<false, false>>(j, tp);
+    } else {
+        switch (P.kind) {
+        case QTR_IDENTITY: launch_direct<QTR_IDENTITY>(j, P); break;
+        case QTR_INT: launch_direct<QTR_INT>(j, P); break;
+        case QTR_FP_CUSTOM: launch_direct<QTR_FP_CUSTOM>(j, P); break;
+        case QTR_FP_MX: launch_direct<QTR_FP_MX>(j, P); break;
+        case QTR_POSIT: launch_direct<QTR_POSIT>(j, P); break;
+        default: qt_set_error("bad format kind %d", P.kind); return QT_ERR_INVALID_ARGUMENT;
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fake-quant kernel launch");
+    return QT_OK;
 }
 
 extern "C" int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type, float *amax_out,
@@ -518,21 +676,24 @@ extern "C" int qt_amax(const void *x, size_t outer, size_t channels, size_t inne
         return QT_ERR_INVALID_ARGUMENT;
     }
     if (outer * channels * inner == 0) return QT_OK;
+    if (num_sms() == 0) return no_device();
     Job j;
-    memset(&j.P, 0, sizeof(j.P));
-    j.P.kind = QTR_IDENTITY;
     j.x = x;
     j.y = nullptr;
     j.outer = outer;
     j.channels = channels;
     j.inner = inner;
     j.f32 = elem_type == QT_F32;
-    // the rows/cols kernels read scales even when they only observe: give them any valid pointer
-    j.scale = channels > 1 ? amax_out : nullptr;
+    j.scale = nullptr;
     j.amax = amax_out;
     j.stream = static_cast<cudaStream_t>(stream);
-    j.write = false;
-    return run_job(j);
+    DirectParams<QTR_IDENTITY> p;
+    memset(&p, 0, sizeof(p));
+    using R = DirectRounder<QTR_IDENTITY>;
+    j.f32 ? launch_layout<R, true, true, false>(j, p) : launch_layout<R, false, true, false>(j, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "amax kernel launch");
+    return QT_OK;
 }
 
 extern "C" int qt_scale_update(float *history, int amax_history_len, size_t channels, float *scale, float quant_max,
@@ -543,7 +704,7 @@ extern "C" int qt_scale_update(float *history, int amax_history_len, size_t chan
                      (void *)scale, amax_history_len, channels);
         return QT_ERR_INVALID_ARGUMENT;
     }
-    if (num_sms() == 0) return cuda_fail(cudaErrorNoDevice, "qt_b200: no usable CUDA device (there is no CPU fallback)");
+    if (num_sms() == 0) return no_device();
     const unsigned grid = (unsigned)((channels + 127) / 128);
     scale_update_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(history, amax_history_len, channels, scale,
                                                                              quant_max, force_scale_power_of_two);

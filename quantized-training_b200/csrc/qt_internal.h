@@ -10,3 +10,7 @@
 void qt_set_error(const char *fmt, ...);
 // qt_format_t -> kernel parameters; QT_ERR_INVALID_ARGUMENT if the struct is inconsistent
 int qt_make_round(const qt_format_t *fmt, QtRound *P);
+
+struct QtLutCfg;
+// which switches the binade-constant path needs for this format; QT_NO_LUT if it has no such path
+int qt_lut_config(const QtRound &P, QtLutCfg *cfg);

@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libqt_b200.so")
 
 QT_BF16, QT_F32 = 0, 1
+QT_NO_LUT = 5
+QT_LUT_BYTES = 8192
 _ERR = {1: ValueError, 2: ValueError, 3: RuntimeError, 4: ValueError}
 
 
@@ -32,11 +34,12 @@ EXPORTS = {
     "qt_format_min_max": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(ctypes.c_double)]),
     "qt_table_host": (ctypes.c_int, [ctypes.POINTER(QtFormat), ctypes.c_void_p]),
+    "qt_lut_build_host": (ctypes.c_int, [ctypes.POINTER(QtFormat), ctypes.c_void_p]),
     "qt_scale_update": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
                                        ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
     "qt_fq_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                      ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
-                                     ctypes.c_void_p, ctypes.c_void_p]),
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qt_amax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -92,6 +95,17 @@ def table_host(fmt):
     return out.view(torch.bfloat16)
 
 
+def lut_host(fmt):
+    """float32[2048] CPU tensor with the fast-path constants of `fmt` (512 x {p1, p2, d, l}), or None for
+    formats that run on the direct path (int / uint / native dtypes)."""
+    out = torch.empty(QT_LUT_BYTES // 4, dtype=torch.float32)
+    rc = lib().qt_lut_build_host(ctypes.byref(fmt), out.data_ptr())
+    if rc == QT_NO_LUT:
+        return None
+    _check(rc)
+    return out
+
+
 def _elem_type(t):
     if t.dtype == torch.bfloat16:
         return QT_BF16
@@ -110,8 +124,9 @@ def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def fq_forward(x, y, outer, channels, inner, fmt, scale=None, amax_out=None):
-    """y = round_fmt(x / s) * s on the current stream; amax_out[c] max-accumulates max|x|."""
+def fq_forward(x, y, outer, channels, inner, fmt, scale=None, amax_out=None, lut=None):
+    """y = round_fmt(x / s) * s on the current stream; amax_out[c] max-accumulates max|x|.
+    lut: device tensor from lut_host(fmt) (fast path) or None (direct bitwise path)."""
     _require_cuda(x, "input")
     assert x.is_contiguous() and y.is_contiguous() and y.dtype == x.dtype and y.device == x.device
     assert outer * channels * inner == x.numel() == y.numel()
@@ -120,10 +135,14 @@ def fq_forward(x, y, outer, channels, inner, fmt, scale=None, amax_out=None):
             and scale.is_contiguous()
     if amax_out is not None:
         assert amax_out.dtype == torch.float32 and amax_out.device == x.device and amax_out.numel() >= channels
+    if lut is not None:
+        assert lut.dtype == torch.float32 and lut.device == x.device and lut.numel() * 4 == QT_LUT_BYTES \
+            and lut.is_contiguous()
     with torch.cuda.device(x.device):
         _check(lib().qt_fq_forward(x.data_ptr(), y.data_ptr(), outer, channels, inner, _elem_type(x),
                                    ctypes.byref(fmt), scale.data_ptr() if scale is not None else None,
-                                   amax_out.data_ptr() if amax_out is not None else None, _stream(x)))
+                                   amax_out.data_ptr() if amax_out is not None else None,
+                                   lut.data_ptr() if lut is not None else None, _stream(x)))
 
 
 def amax(x, outer, channels, inner, amax_out):

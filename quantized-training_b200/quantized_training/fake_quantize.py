@@ -92,7 +92,7 @@ class FusedAmaxObsFakeQuantFunction(torch.autograd.Function):
                                    f"axis of input {tuple(xc.shape)}")
             outer, channels, inner, _ = _channel_view(tuple(xc.shape), axes[0])
         y = torch.empty_like(xc)
-        _C.fq_forward(xc, y, outer, channels, inner, mod._fmt, scale, amax_slot)
+        _C.fq_forward(xc, y, outer, channels, inner, mod._fmt, scale, amax_slot, mod.lut)
         return y
 
     @staticmethod
@@ -157,6 +157,9 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         self.register_buffer("scale", torch.tensor([1.0], **f32))
         self.register_buffer("zero_point", torch.tensor([1.0], **f32))
         self.register_buffer("histogram", torch.zeros(254, **f32), persistent=False)
+        # 8 KB of per-binade rounding constants for the kernels' fast path (None: int / native dtypes).
+        # The counterpart of the reference's 128 KB `qmap` buffer; non-persistent like it.
+        self.register_buffer("lut", _C.lut_host(self._fmt), persistent=False)
         self.is_per_channel = qscheme == QScheme.PER_CHANNEL_SYMMETRIC
         self._flag_versions = None
         self.enable_observer(qscheme is not None)
