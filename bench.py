@@ -205,7 +205,7 @@ def run_gpu(args):
         xs, ys = x[:nn_], y[:nn_]
         sc = torch.full((1,), 0.0123, device=dev)
         hist = torch.zeros(1, device=dev)
-        for name in ("fp8_e4m3", "posit8_1", "int8"):
+        for name in ("e4m3", "fp8_e4m3", "posit8_1", "int8"):
             m = qt.FusedAmaxObsFakeQuantize(name, device=dev)
             ms = timed(lambda: qt._C.fq_forward(xs, ys, 1, 1, nn_, m._fmt, sc, hist, m.lut))
             extra[f"{name} bf16 per-tensor scale + amax"] = 4.0 * nn_ / (ms * 1e-3) / 1e9

@@ -29,10 +29,13 @@
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kUnroll = 4;  // 16-byte vectors in flight per thread
 
 // ----------------------------------------------------------------------------- rounding engines
+// A rounder maps one bf16 value to its rounded value, both as fp32 bits with the low half zero.  Three entry
+// points so that the packed bf16 path never pays for an unpack it does not need:
+//   operator()(u)   u = fp32 bits (low half zero)
+//   lo(w) / hi(w)   the low / high bf16 of a packed 32-bit word
 
 template <int KIND>
 struct DirectParams {
@@ -41,10 +44,14 @@ struct DirectParams {
 template <int KIND>
 struct DirectRounder {
     static constexpr bool kTable = false;
+    static constexpr int kThreads = 256, kCtasPerSm = 8, kMinCtas = 1;
+    static constexpr size_t kSmemBytes = 0;
     using Params = DirectParams<KIND>;
     const QtRound &P;
-    __device__ __forceinline__ DirectRounder(const Params &p, const QtLutEntry *) : P(p.P) {}
+    __device__ __forceinline__ DirectRounder(const Params &p, const unsigned char *) : P(p.P) {}
     __device__ __forceinline__ uint32_t operator()(uint32_t u) const { return qt_round<KIND>(P, u); }
+    __device__ __forceinline__ uint32_t lo(uint32_t w) const { return qt_round<KIND>(P, w << 16); }
+    __device__ __forceinline__ uint32_t hi(uint32_t w) const { return qt_round<KIND>(P, w & 0xFFFF0000u); }
 };
 
 struct TableParams {
@@ -54,30 +61,41 @@ struct TableParams {
 template <bool CLAMP, bool MXBAND>
 struct TableRounder {
     static constexpr bool kTable = true;
+    static constexpr int kThreads = 512, kCtasPerSm = 2, kMinCtas = 2;  // 2 x 64 KB of replicated table per SM
+    static constexpr size_t kSmemBytes = QT_LUT_SMEM_BYTES;
     using Params = TableParams;
-    const QtLutEntry *tab;  // shared memory copy
-    const QtLutCfg cfg;
-    __device__ __forceinline__ TableRounder(const Params &p, const QtLutEntry *smem) : tab(smem), cfg(p.cfg) {}
-    __device__ __forceinline__ uint32_t operator()(uint32_t u) const
+    const unsigned char *tab;  // shared memory, 8 interleaved replicas (qt_lut.h)
+    const uint32_t clamp_bits;
+    const uint32_t slot16;
+    __device__ __forceinline__ TableRounder(const Params &p, const unsigned char *smem)
+        : tab(smem), clamp_bits(p.cfg.clamp_bits), slot16((threadIdx.x & 7u) << 4)
     {
-        return qt_lut_round<CLAMP, MXBAND>(tab, cfg, u);
     }
+    __device__ __forceinline__ uint32_t go(uint32_t pattern16, uint32_t a) const
+    {
+        const uint32_t ac = CLAMP ? min(a, clamp_bits) : a;
+        return qt_lut_round_smem<MXBAND>(tab, slot16, pattern16, a, ac);
+    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t u) const { return go(u >> 16, u & 0x7FFFFFFFu); }
+    __device__ __forceinline__ uint32_t lo(uint32_t w) const { return go(w, (w << 16) & 0x7FFFFFFFu); }
+    __device__ __forceinline__ uint32_t hi(uint32_t w) const { return go(w >> 16, w & 0x7FFF0000u); }
 };
 
-// every CTA stages the 8 KB table once (L2-resident after the first CTA)
+extern __shared__ __align__(16) unsigned char qt_dyn_smem[];
+
+// every CTA stages the table once: 8 KB from global (L2-resident after the first CTA) -> 8 replicas
 template <class R>
-__device__ __forceinline__ const QtLutEntry *stage_table(const typename R::Params &p, QtLutEntry *smem)
+__device__ __forceinline__ const unsigned char *stage_table(const typename R::Params &p)
 {
     if constexpr (R::kTable) {
         const float4 *src = reinterpret_cast<const float4 *>(p.table);
-        float4 *dst = reinterpret_cast<float4 *>(smem);
-        for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < QT_LUT_ENTRIES; i += blockDim.x * blockDim.y)
-            dst[i] = src[i];
+        float4 *dst = reinterpret_cast<float4 *>(qt_dyn_smem);
+        const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.x + threadIdx.y * blockDim.x;
+        for (int i = tid; i < QT_LUT_ENTRIES * QT_LUT_REPLICAS; i += nthreads) dst[i] = src[i / QT_LUT_REPLICAS];
         __syncthreads();
     }
-    return smem;
+    return qt_dyn_smem;
 }
-#define QT_TABLE_SMEM(R) __shared__ __align__(16) QtLutEntry s_table[R::kTable ? QT_LUT_ENTRIES : 1]
 
 // ----------------------------------------------------------------------------- small helpers
 
@@ -157,10 +175,10 @@ __device__ __forceinline__ uint32_t fq_word_bf16(const R &round, uint32_t w, con
 {
     const uint32_t lo = w << 16, hi = w & 0xFFFF0000u;
     if (AMAX) amax = max(amax, max(lo & 0x7FFFFFFFu, hi & 0x7FFFFFFFu));
-    if (DIV == DIV_UNIT) return __byte_perm(round(lo), round(hi), 0x7632);  // {hi[31:16], lo[31:16]}
+    if (DIV == DIV_UNIT) return __byte_perm(round.lo(w), round.hi(w), 0x7632);  // {hi[31:16], lo[31:16]}
     // scaled: both conversions are packed (one F2FP per pair each way)
     const uint32_t uq = bf16x2_rne(bf16_quotient<DIV>(lo, sc), bf16_quotient<DIV>(hi, sc));
-    const uint32_t qlo = round(uq << 16), qhi = round(uq & 0xFFFF0000u);
+    const uint32_t qlo = round.lo(uq), qhi = round.hi(uq);
     return bf16x2_rne(__fmul_rn(__uint_as_float(qlo), sc.s), __fmul_rn(__uint_as_float(qhi), sc.s));
 }
 
@@ -210,7 +228,7 @@ __device__ __forceinline__ ScaleBf16 load_scale(const float *scale, size_t c)
 // unsigned ints and NaN patterns sit above Inf, so NaN propagates exactly like torch.amax.
 __device__ __forceinline__ void block_amax_commit(uint32_t amax, float *amax_out)
 {
-    __shared__ uint32_t warp_max[kThreads / 32];
+    __shared__ uint32_t warp_max[32];
     amax = __reduce_max_sync(0xFFFFFFFFu, amax);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) warp_max[warp] = amax;
@@ -229,19 +247,20 @@ __device__ __forceinline__ void fq_span(const R &round, const uint4 *__restrict_
                                         size_t nvec, size_t first_tile, size_t tile_stride, const ScaleBf16 &sc,
                                         uint32_t &amax)
 {
-    const size_t tile = (size_t)kThreads * kUnroll;
+    const size_t nthr = blockDim.x;
+    const size_t tile = nthr * kUnroll;
     const size_t ntiles = (nvec + tile - 1) / tile;
     for (size_t t = first_tile; t < ntiles; t += tile_stride) {
         const size_t base = t * tile + threadIdx.x;
         uint4 v[kUnroll];
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * kThreads;
+            const size_t i = base + (size_t)j * nthr;
             v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * kThreads;
+            const size_t i = base + (size_t)j * nthr;
             const uint4 r = fq_vec<R, F32, DIV, AMAX>(round, v[j], sc, amax);
             if (i < nvec) st_stream(y + i, r);
         }
@@ -253,13 +272,12 @@ __device__ __forceinline__ void fq_span(const R &round, const uint4 *__restrict_
 // path without divide / multiply / re-rounding.  The branch is grid-uniform and made on the device, so
 // the host never reads the scale back.
 template <class R, bool F32, bool AMAX>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
 fq_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
                const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
                float *__restrict__ amax_out)
 {
-    QT_TABLE_SMEM(R);
-    const R round(params, stage_table<R>(params, s_table));
+    const R round(params, stage_table<R>(params));
     ScaleBf16 sc = {1.0f, 1.0f};
     if (scale) sc = load_scale<F32>(scale, 0);
     uint32_t amax = 0u;
@@ -275,18 +293,19 @@ fq_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
 
 // observer only (fake quant disabled): read, reduce, no store
 template <bool F32>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 amax_flat_kernel(const uint4 *__restrict__ x, size_t nvec, float *__restrict__ amax_out)
 {
     uint32_t amax = 0u;
-    const size_t tile = (size_t)kThreads * kUnroll;
+    const size_t nthr = blockDim.x;
+    const size_t tile = nthr * kUnroll;
     const size_t ntiles = (nvec + tile - 1) / tile;
     for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const size_t base = t * tile + threadIdx.x;
         uint4 v[kUnroll];
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * kThreads;
+            const size_t i = base + (size_t)j * nthr;
             v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
@@ -299,13 +318,12 @@ amax_flat_kernel(const uint4 *__restrict__ x, size_t nvec, float *__restrict__ a
 // Any layout, any alignment: element i belongs to channel (i / inner) % channels.  Used for tails,
 // misaligned views and odd per-channel shapes.  Elements [first, first + count).  WRITE = false: observe only.
 template <class R, bool F32, bool AMAX, bool WRITE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(R::kThreads)
 fq_scalar_kernel(const void *__restrict__ xv, void *__restrict__ yv, size_t first, size_t count, size_t channels,
                  size_t inner, const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
                  float *__restrict__ amax_out)
 {
-    QT_TABLE_SMEM(R);
-    const R round(params, stage_table<R>(params, s_table));
+    const R round(params, stage_table<R>(params));
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     uint32_t amax1 = 0u;  // channels == 1: reduce in registers, one atomic per CTA
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
@@ -334,48 +352,67 @@ fq_scalar_kernel(const void *__restrict__ xv, void *__restrict__ yv, size_t firs
 }
 
 // ----------------------------------------------------------------------------- rows kernel
-// inner > 1 per-channel, inner % VEC == 0, 16-byte aligned.  blockIdx.x enumerates (row, segment):
-// row = o * channels + c, a segment is kThreads * kUnroll vectors of that row.
+// inner > 1 per-channel, inner % VEC == 0, 16-byte aligned (weights [out, in] with ax = 0, or [B, C, HW]).
+// One WARP per row segment: row = o * channels + c, a segment is 32 * kUnroll * kRowIters vectors of that row.
+// Scale load, mode choice and the amax merge (redux + one atomicMax) are warp-local: no block barrier, and
+// short rows (a 4096-wide bf16 row is 512 vectors) keep every lane busy.
+constexpr int kRowIters = 4;
+template <class R, bool F32, int DIV, bool AMAX>
+__device__ __forceinline__ void fq_row_segment(const R &round, const uint4 *__restrict__ xr, uint4 *__restrict__ yr,
+                                               size_t v0, size_t v1, const ScaleBf16 &sc, uint32_t &amax)
+{
+    const int lane = threadIdx.x & 31;
+    for (size_t base = v0 + lane; base < v1; base += 32 * kUnroll) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * 32;
+            v[j] = i < v1 ? ld_stream(xr + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * 32;
+            const uint4 r = fq_vec<R, F32, DIV, AMAX>(round, v[j], sc, amax);
+            if (i < v1) st_stream(yr + i, r);
+        }
+    }
+}
+
 template <class R, bool F32, bool AMAX, bool WRITE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
 fq_rows_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, size_t channels, size_t vec_per_row,
                size_t segs_per_row, const __grid_constant__ typename R::Params params,
                const float *__restrict__ scale, float *__restrict__ amax_out)
 {
-    QT_TABLE_SMEM(R);
-    const R round(params, stage_table<R>(params, s_table));
+    const R round(params, stage_table<R>(params));
+    const size_t seg_vecs = (size_t)32 * kUnroll * kRowIters;
     const size_t work = rows * segs_per_row;
-    const size_t tile = (size_t)kThreads * kUnroll;
-    const size_t once = ~(size_t)0 >> 1;  // tile stride that ends fq_span after one tile
-    for (size_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
+    const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t wi = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < work; wi += nwarps) {
         const size_t row = wi / segs_per_row, seg = wi - row * segs_per_row;
         const size_t c = row % channels;
         const uint4 *xr = x + row * vec_per_row;
+        const size_t v0 = seg * seg_vecs, v1 = min(vec_per_row, v0 + seg_vecs);
         uint32_t amax = 0u;
         if (WRITE) {
             const ScaleBf16 sc = load_scale<F32>(scale, c);
             const int mode = classify_scale(sc.s);
             uint4 *yr = y + row * vec_per_row;
             if (mode == DIV_UNIT)
-                fq_span<R, F32, DIV_UNIT, AMAX>(round, xr, yr, vec_per_row, seg, once, sc, amax);
+                fq_row_segment<R, F32, DIV_UNIT, AMAX>(round, xr, yr, v0, v1, sc, amax);
             else if (F32 || mode == DIV_EXACT)
-                fq_span<R, F32, DIV_EXACT, AMAX>(round, xr, yr, vec_per_row, seg, once, sc, amax);
+                fq_row_segment<R, F32, DIV_EXACT, AMAX>(round, xr, yr, v0, v1, sc, amax);
             else
-                fq_span<R, F32, DIV_RECIP, AMAX>(round, xr, yr, vec_per_row, seg, once, sc, amax);
+                fq_row_segment<R, F32, DIV_RECIP, AMAX>(round, xr, yr, v0, v1, sc, amax);
         } else {
-            const size_t base = seg * tile + threadIdx.x;
-#pragma unroll
-            for (int j = 0; j < kUnroll; ++j) {
-                const size_t i = base + (size_t)j * kThreads;
-                if (i < vec_per_row) {
-                    const uint4 v = ld_stream(xr + i);
-                    amax = F32 ? amax_of_vec_f32(amax, v) : amax_of_vec_bf16(amax, v);
-                }
+            for (size_t i = v0 + (threadIdx.x & 31); i < v1; i += 32) {
+                const uint4 v = ld_stream(xr + i);
+                amax = F32 ? amax_of_vec_f32(amax, v) : amax_of_vec_bf16(amax, v);
             }
         }
         if (AMAX) {
-            __syncthreads();  // warp_max is reused across loop iterations
-            block_amax_commit(amax, amax_out + c);
+            amax = __reduce_max_sync(0xFFFFFFFFu, amax);
+            if ((threadIdx.x & 31) == 0 && amax != 0u) atomicMax(reinterpret_cast<unsigned int *>(amax_out) + c, amax);
         }
     }
 }
@@ -385,22 +422,23 @@ fq_rows_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
 // blockDim = (32, 8): threadIdx.x -> a 16-byte column group, threadIdx.y -> row phase.
 // Scales and running maxima for the thread's VEC columns stay in registers over all rows.
 template <class R, bool F32, bool AMAX, bool WRITE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, size_t vec_per_row,
                const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
                float *__restrict__ amax_out)
 {
     constexpr int VEC = F32 ? 4 : 8;
-    QT_TABLE_SMEM(R);
-    const R round(params, stage_table<R>(params, s_table));
+    const R round(params, stage_table<R>(params));
     const size_t cg = (size_t)blockIdx.x * 32 + threadIdx.x;  // column group
     const bool active = cg < vec_per_row;
     ScaleBf16 sc[VEC];
+    bool recip_ok[VEC];
     uint32_t am[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
         sc[k].s = sc[k].rs = 1.0f;
         if (WRITE && active) sc[k] = load_scale<F32>(scale, cg * VEC + k);
+        recip_ok[k] = classify_scale(sc[k].s) != DIV_EXACT;  // x * rcp(1) is exact too
         am[k] = 0u;
     }
     if (active) {
@@ -419,9 +457,16 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
                         am[2 * k] = max(am[2 * k], lo & 0x7FFFFFFFu);
                         am[2 * k + 1] = max(am[2 * k + 1], hi & 0x7FFFFFFFu);
                     }
-                    if (WRITE)
-                        o[k] = __byte_perm(fq_bf16<R, DIV_EXACT>(round, lo, sc[2 * k]),
-                                           fq_bf16<R, DIV_EXACT>(round, hi, sc[2 * k + 1]), 0x7632);
+                    if (WRITE) {
+                        // per column: reciprocal multiply when its scale allows it, true division otherwise
+                        const float qlo = recip_ok[2 * k] ? bf16_quotient<DIV_RECIP>(lo, sc[2 * k])
+                                                          : bf16_quotient<DIV_EXACT>(lo, sc[2 * k]);
+                        const float qhi = recip_ok[2 * k + 1] ? bf16_quotient<DIV_RECIP>(hi, sc[2 * k + 1])
+                                                              : bf16_quotient<DIV_EXACT>(hi, sc[2 * k + 1]);
+                        const uint32_t uq = bf16x2_rne(qlo, qhi);
+                        o[k] = bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), sc[2 * k].s),
+                                          __fmul_rn(__uint_as_float(round.hi(uq)), sc[2 * k + 1].s));
+                    }
                 }
             }
             if (WRITE) st_stream(y + r * vec_per_row + cg, make_uint4(o[0], o[1], o[2], o[3]));
@@ -504,13 +549,28 @@ inline unsigned grid_for(size_t work_items, int ctas_per_sm)
     return (unsigned)(work_items < cap ? (work_items ? work_items : 1) : cap);
 }
 
+// kernels that stage the replicated table need 64 KB of dynamic shared memory: opt in once per device
+template <auto kernel>  // one flag table per kernel instantiation
+void allow_smem(size_t bytes)
+{
+    if (bytes <= 48 * 1024) return;
+    static bool done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (dev >= 0 && dev < 64) done[dev] = true;
+}
+
 template <class R, bool F32, bool AMAX, bool WRITE>
 void launch_scalar(const Job &j, const typename R::Params &p, size_t first, size_t count)
 {
     if (count == 0) return;
-    const unsigned grid = grid_for((count + kThreads - 1) / kThreads, 16);
-    fq_scalar_kernel<R, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(j.x, j.y, first, count, j.channels, j.inner,
-                                                                           p, j.scale, j.amax);
+    auto kernel = fq_scalar_kernel<R, F32, AMAX, WRITE>;
+    allow_smem<fq_scalar_kernel<R, F32, AMAX, WRITE>>(R::kSmemBytes);
+    const unsigned grid = grid_for((count + R::kThreads - 1) / R::kThreads, R::kCtasPerSm * 2);
+    kernel<<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(j.x, j.y, first, count, j.channels, j.inner, p, j.scale,
+                                                           j.amax);
 }
 
 template <class R, bool F32, bool AMAX, bool WRITE>
@@ -521,16 +581,20 @@ void launch_layout(const Job &j, const typename R::Params &p)
     const bool aligned = ((reinterpret_cast<uintptr_t>(j.x) | reinterpret_cast<uintptr_t>(j.y)) & 15u) == 0;
     const uint4 *xv = static_cast<const uint4 *>(j.x);
     uint4 *yv = static_cast<uint4 *>(j.y);
-    const size_t tile = (size_t)kThreads * kUnroll;
 
     if (j.channels == 1) {
         const size_t nvec = aligned ? n / VEC : 0;
         if (nvec) {
-            const unsigned grid = grid_for((nvec + tile - 1) / tile, 8);
-            if constexpr (WRITE)
-                fq_flat_kernel<R, F32, AMAX><<<grid, kThreads, 0, j.stream>>>(xv, yv, nvec, p, j.scale, j.amax);
-            else
-                amax_flat_kernel<F32><<<grid, kThreads, 0, j.stream>>>(xv, nvec, j.amax);
+            if constexpr (WRITE) {
+                auto kernel = fq_flat_kernel<R, F32, AMAX>;
+                allow_smem<fq_flat_kernel<R, F32, AMAX>>(R::kSmemBytes);
+                const size_t tile = (size_t)R::kThreads * kUnroll;
+                const unsigned grid = grid_for((nvec + tile - 1) / tile, R::kCtasPerSm);
+                kernel<<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(xv, yv, nvec, p, j.scale, j.amax);
+            } else {
+                const size_t tile = (size_t)256 * kUnroll;
+                amax_flat_kernel<F32><<<grid_for((nvec + tile - 1) / tile, 8), 256, 0, j.stream>>>(xv, nvec, j.amax);
+            }
         }
         launch_scalar<R, F32, AMAX, WRITE>(j, p, nvec * VEC, n - nvec * VEC);
         return;
@@ -539,21 +603,27 @@ void launch_layout(const Job &j, const typename R::Params &p)
     if (aligned && j.inner == 1 && j.channels % VEC == 0) {
         const size_t rows = j.outer, vec_per_row = j.channels / VEC;
         const unsigned gx = (unsigned)((vec_per_row + 31) / 32);
-        size_t want_y = ((size_t)num_sms() * 8 + gx - 1) / gx;
+        size_t want_y = ((size_t)num_sms() * (R::kTable ? 3 : 8) + gx - 1) / gx;
         const size_t max_y = (rows + 7) / 8;
         if (want_y > max_y) want_y = max_y;
         if (want_y < 1) want_y = 1;
         if (want_y > 65535) want_y = 65535;
-        fq_cols_kernel<R, F32, AMAX, WRITE><<<dim3(gx, (unsigned)want_y), dim3(32, 8), 0, j.stream>>>(
-            xv, yv, rows, vec_per_row, p, j.scale, j.amax);
+        auto kernel = fq_cols_kernel<R, F32, AMAX, WRITE>;
+        allow_smem<fq_cols_kernel<R, F32, AMAX, WRITE>>(R::kSmemBytes);
+        kernel<<<dim3(gx, (unsigned)want_y), dim3(32, 8), R::kSmemBytes, j.stream>>>(xv, yv, rows, vec_per_row, p,
+                                                                                  j.scale, j.amax);
         return;
     }
     if (aligned && j.inner % VEC == 0 && j.inner >= 32 * VEC) {
         const size_t rows = j.outer * j.channels, vec_per_row = j.inner / VEC;
-        const size_t segs = (vec_per_row + tile - 1) / tile;
-        const unsigned grid = grid_for(rows * segs, 8);
-        fq_rows_kernel<R, F32, AMAX, WRITE><<<grid, kThreads, 0, j.stream>>>(xv, yv, rows, j.channels, vec_per_row, segs,
-                                                                             p, j.scale, j.amax);
+        const size_t seg_vecs = (size_t)32 * kUnroll * kRowIters;
+        const size_t segs = (vec_per_row + seg_vecs - 1) / seg_vecs;
+        const size_t warps_per_cta = R::kThreads / 32;
+        auto kernel = fq_rows_kernel<R, F32, AMAX, WRITE>;
+        allow_smem<fq_rows_kernel<R, F32, AMAX, WRITE>>(R::kSmemBytes);
+        const unsigned grid = grid_for((rows * segs + warps_per_cta - 1) / warps_per_cta, R::kCtasPerSm);
+        kernel<<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(xv, yv, rows, j.channels, vec_per_row, segs, p, j.scale,
+                                                               j.amax);
         return;
     }
     launch_scalar<R, F32, AMAX, WRITE>(j, p, 0, n);

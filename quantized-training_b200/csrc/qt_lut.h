@@ -63,20 +63,41 @@ QT_HD uint32_t qt_lut_round(const QtLutEntry *tab, const QtLutCfg &cfg, uint32_t
 {
     const uint32_t a = u & 0x7FFFFFFFu;
     const uint32_t ac = CLAMP ? qt_umin(a, cfg.clamp_bits) : a;
-#if defined(__CUDA_ARCH__)
-    const float4 e = *reinterpret_cast<const float4 *>(tab + (u >> 23));
-    const float t = __saturatef(__fmaf_rn(__uint_as_float(ac), e.x, e.y));
-    uint32_t q = __float_as_uint(__fmaf_rn(t, e.z, e.w));
-#else
     const QtLutEntry e = tab[u >> 23];
     const float t = qt_saturate(qt_fma(qt_bits2f(ac), e.p1, e.p2));
     uint32_t q = qt_f2bits(qt_fma(t, e.d, e.l));
-#endif
     if (MXBAND) {
         if (a >= 0x7F580000u && a != 0x7F800000u) q = QT_NAN_BITS;  // finite band and NaN; Inf comes from the table
     }
     return q;
 }
+
+#if defined(__CUDACC__)
+// Shared-memory form used by the kernels.  A warp-wide LDS.128 is served in four 128-byte wavefronts, one per
+// quarter warp, and two lanes of a quarter warp that need DIFFERENT entries from the same 16-byte bank group
+// serialise (measured: 7.8 wavefronts per load with a plain 8 KB table, LSU data pipe 96 % busy).  So the table
+// is replicated eight times, interleaved: replica r of entry i lives at byte (i * 8 + r) * 16, and lane l always
+// reads replica l & 7 -- every lane of a quarter warp owns its bank group, conflict-free for any data.
+// `slot16` = (lane & 7) * 16 is folded into the masking instruction, so the index costs one LOP3 for the low
+// bf16 of a packed word and SHF + LOP3 for the high one.
+#define QT_LUT_REPLICAS 8
+#define QT_LUT_SMEM_BYTES (QT_LUT_BYTES * QT_LUT_REPLICAS)
+
+// hi16: the bf16 bit pattern in bits [15:0] (anything above is ignored); ac: clamped |x| as fp32 bits
+template <bool MXBAND>
+__device__ __forceinline__ uint32_t qt_lut_round_smem(const unsigned char *smem_table, uint32_t slot16,
+                                                      uint32_t pattern16, uint32_t a, uint32_t ac)
+{
+    const uint32_t off = (pattern16 & 0xFF80u) | slot16;  // (sign:exponent) * 128 + replica * 16
+    const float4 e = *reinterpret_cast<const float4 *>(smem_table + off);
+    const float t = __saturatef(__fmaf_rn(__uint_as_float(ac), e.x, e.y));
+    uint32_t q = __float_as_uint(__fmaf_rn(t, e.z, e.w));
+    if (MXBAND) {
+        if (a >= 0x7F580000u && a != 0x7F800000u) q = QT_NAN_BITS;
+    }
+    return q;
+}
+#endif
 
 QT_HD uint32_t qt_lut_round_dyn(const QtLutEntry *tab, const QtLutCfg &cfg, uint32_t u)
 {
