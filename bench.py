@@ -153,12 +153,18 @@ def run_gpu(args):
         for f, lut in fmts:  # straight through the C ABI: y = fq(x), output buffer reused
             qt._C.fq_forward(x, y, 1, 1, n, f, unit, None, lut)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    # the clock sampler starts BEFORE warm-up: nvidia-smi's start-up (NVML init) stalls the GPU for a few ms and
+    # must not land inside the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:
+            step()
+            torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in SWEEP]
           for _ in range(args.steps)]
     barrier()
@@ -182,8 +188,9 @@ def run_gpu(args):
     launches = args.steps * len(SWEEP)
     value = bytes_per_launch * launches * world / (elapsed_ms * 1e-3) / 1e9
     per_spec_ms = [sum(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps)) / args.steps
-                   for i in range(len(SWEEP))]
+                   for i in range(len(SWEEP))]  # mean launch duration per spec over the timed region
     kernel_ms = sum(per_spec_ms) / len(SWEEP)
+    slowest = max(ev[k][i][0].elapsed_time(ev[k][i][1]) for k in range(args.steps) for i in range(len(SWEEP)))
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
 
@@ -277,6 +284,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "fq_flat_kernel",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": kernel_ms,
+                         "max_launch_ms": slowest,
                          "per_spec_GBps": {s: bytes_per_launch / (ms * 1e-3) / 1e9 for s, ms in zip(SWEEP, per_spec_ms)}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * ne * len(SWEEP),
@@ -292,7 +300,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-numel", type=int, default=30)

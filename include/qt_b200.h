@@ -114,6 +114,29 @@ int qt_fq_forward(const void *x, void *y, size_t outer, size_t channels, size_t 
 int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type,
             float *amax_out, void *stream);
 
+/* ---- quantized GEMM / batched GEMM (tcgen05 + TMEM + TMA) -------------------------------------------
+ * C[b, m, n] = epilogue(alpha * sum_k A[b, m, k] * B[b, n, k]),  fp32 accumulation, C in bf16.
+ * Replaces F.linear(x_q, W_q, bias) of the QAT Linear (modules/qat/linear.py:40-41; A = activations [M, K],
+ * B = weight [N, K]) and torch.matmul(q, k^T) of MatmulFunctional (modules/quantizable/functional_modules.py:
+ * 22-27; A = q [B*H, S, D], B = k [B*H, S, D]).  Operands hold values of the quantized format exactly:
+ * as bf16 (any format of this library with <= 8 bits), or as one-byte e4m3 / e5m2 codes (FP8 tensor cores).
+ * Fused epilogue, in this order: * alpha, + bias[n] (bf16), activation, + residual[b, m, n] (bf16), round to bf16.
+ * Leading dimensions and batch strides are in elements; bases, lda/ldb (in bytes), ldc, ldr must be 16-byte
+ * aligned and N % 8 == 0.  batch == 1: strides are ignored. */
+#define QT_GEMM_BF16 0
+#define QT_GEMM_E4M3 1      /* A and B are e4m3 codes */
+#define QT_GEMM_E5M2 2      /* A and B are e5m2 codes */
+#define QT_GEMM_E4M3_E5M2 3 /* A e4m3, B e5m2 */
+#define QT_GEMM_E5M2_E4M3 4 /* A e5m2, B e4m3 (gradient x weight in the backward pass) */
+#define QT_ACT_NONE 0
+#define QT_ACT_RELU 1
+#define QT_ACT_GELU 2 /* exact erf GELU (BERT / RoBERTa) */
+#define QT_ACT_SILU 3
+int qt_gemm_nt(const void *A, const void *B, void *C, int operand_type, int64_t batch, int64_t M, int64_t N,
+               int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC,
+               float alpha, const void *bias, int activation, const void *residual, int64_t ldr, int64_t strideR,
+               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

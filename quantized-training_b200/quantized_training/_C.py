@@ -40,6 +40,9 @@ EXPORTS = {
     "qt_fq_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                      ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_gemm_nt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] +
+                   [ctypes.c_int64] * 10 + [ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     "qt_amax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -159,3 +162,60 @@ def scale_update(history, ahl, channels, scale, quant_max, force_pow2):
     with torch.cuda.device(history.device):
         _check(lib().qt_scale_update(history.data_ptr(), ahl, channels, scale.data_ptr(), float(quant_max),
                                      int(bool(force_pow2)), _stream(history)))
+
+
+GEMM_BF16, GEMM_E4M3, GEMM_E5M2, GEMM_E4M3_E5M2, GEMM_E5M2_E4M3 = range(5)
+ACTIVATIONS = {None: 0, "none": 0, "relu": 1, "gelu": 2, "silu": 3}
+
+
+def _as_batched(t, name):
+    """[..., rows, K] tensor -> (batch, rows, K, ld, batch_stride) with a unit-stride K axis, no copy if possible."""
+    if t.dim() < 2:
+        raise ValueError(f"{name} must have at least 2 dimensions")
+    if t.dim() == 2:
+        t3 = t.unsqueeze(0)
+    else:
+        t3 = t.reshape(-1, t.shape[-2], t.shape[-1])  # a view whenever the leading dims are collapsible
+    if t3.stride(-1) != 1 or (t3.shape[1] > 1 and t3.stride(1) < t3.shape[2]):
+        t3 = t3.contiguous()
+    return t3
+
+
+def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None):
+    """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
+    a, b: bf16 (GEMM_BF16) or uint8 fp8 codes; bias bf16 [n]; residual bf16 broadcastable to out's shape."""
+    _require_cuda(a, "a")
+    a3, b3 = _as_batched(a, "a"), _as_batched(b, "b")
+    if b3.shape[0] != a3.shape[0]:
+        if b3.shape[0] == 1:
+            b3 = b3.expand(a3.shape[0], -1, -1)
+        else:
+            raise ValueError(f"batch mismatch: {tuple(a.shape)} x {tuple(b.shape)}")
+    batch, M, K = a3.shape
+    N = b3.shape[1]
+    if b3.shape[2] != K:
+        raise ValueError(f"inner dimensions differ: {tuple(a.shape)} x {tuple(b.shape)}^T")
+    want = torch.uint8 if operand_type != GEMM_BF16 else torch.bfloat16
+    if a3.dtype != want or b3.dtype != want:
+        raise TypeError(f"operand_type {operand_type} takes {want} operands, got {a3.dtype} and {b3.dtype}")
+    out_shape = (*a.shape[:-1], N) if a.dim() > 2 or b.dim() <= 2 else (*b.shape[:-2], M, N)
+    if out is None:
+        out = torch.empty((batch, M, N), dtype=torch.bfloat16, device=a.device)
+    o3 = out.view(batch, M, N)
+    r3 = None
+    if residual is not None:
+        r3 = residual.expand(out_shape).reshape(batch, M, N)
+        if r3.stride(-1) != 1:
+            r3 = r3.contiguous()
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
+    sa = a3.stride(0) if batch > 1 else 0
+    sb = b3.stride(0) if batch > 1 else 0
+    with torch.cuda.device(a.device):
+        _check(lib().qt_gemm_nt(
+            a3.data_ptr(), b3.data_ptr(), o3.data_ptr(), operand_type, batch, M, N, K,
+            a3.stride(1), b3.stride(1), o3.stride(1), sa, sb, o3.stride(0) if batch > 1 else 0,
+            float(alpha), bias.data_ptr() if bias is not None else None, ACTIVATIONS[activation],
+            r3.data_ptr() if r3 is not None else None, r3.stride(1) if r3 is not None else 0,
+            (r3.stride(0) if batch > 1 else 0) if r3 is not None else 0, _stream(a)))
+    return out.view(out_shape)
