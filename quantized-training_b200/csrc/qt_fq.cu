@@ -442,34 +442,44 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
         am[k] = 0u;
     }
     if (active) {
-        for (size_t r = (size_t)blockIdx.y * blockDim.y + threadIdx.y; r < rows; r += (size_t)gridDim.y * blockDim.y) {
-            const uint4 v = ld_stream(x + r * vec_per_row + cg);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t o[4];
+        const size_t rstep = (size_t)gridDim.y * blockDim.y;
+        for (size_t r0 = (size_t)blockIdx.y * blockDim.y + threadIdx.y; r0 < rows; r0 += rstep * kUnroll) {
+            uint4 vin[kUnroll];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (F32) {
-                    if (AMAX) am[k] = max(am[k], w[k] & 0x7FFFFFFFu);
-                    if (WRITE) o[k] = fq_f32<R, false>(round, w[k], sc[k].s);
-                } else {
-                    const uint32_t lo = w[k] << 16, hi = w[k] & 0xFFFF0000u;
-                    if (AMAX) {
-                        am[2 * k] = max(am[2 * k], lo & 0x7FFFFFFFu);
-                        am[2 * k + 1] = max(am[2 * k + 1], hi & 0x7FFFFFFFu);
-                    }
-                    if (WRITE) {
-                        // per column: reciprocal multiply when its scale allows it, true division otherwise
-                        const float qlo = recip_ok[2 * k] ? bf16_quotient<DIV_RECIP>(lo, sc[2 * k])
-                                                          : bf16_quotient<DIV_EXACT>(lo, sc[2 * k]);
-                        const float qhi = recip_ok[2 * k + 1] ? bf16_quotient<DIV_RECIP>(hi, sc[2 * k + 1])
-                                                              : bf16_quotient<DIV_EXACT>(hi, sc[2 * k + 1]);
-                        const uint32_t uq = bf16x2_rne(qlo, qhi);
-                        o[k] = bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), sc[2 * k].s),
-                                          __fmul_rn(__uint_as_float(round.hi(uq)), sc[2 * k + 1].s));
+            for (int u = 0; u < kUnroll; ++u) {  // kUnroll rows in flight per thread
+                const size_t r = r0 + (size_t)u * rstep;
+                vin[u] = r < rows ? ld_stream(x + r * vec_per_row + cg) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const size_t r = r0 + (size_t)u * rstep;
+                const uint32_t w[4] = {vin[u].x, vin[u].y, vin[u].z, vin[u].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (F32) {
+                        if (AMAX) am[k] = max(am[k], w[k] & 0x7FFFFFFFu);
+                        if (WRITE) o[k] = fq_f32<R, false>(round, w[k], sc[k].s);
+                    } else {
+                        const uint32_t lo = w[k] << 16, hi = w[k] & 0xFFFF0000u;
+                        if (AMAX) {
+                            am[2 * k] = max(am[2 * k], lo & 0x7FFFFFFFu);
+                            am[2 * k + 1] = max(am[2 * k + 1], hi & 0x7FFFFFFFu);
+                        }
+                        if (WRITE) {
+                            // per column: reciprocal multiply when its scale allows it, true division otherwise
+                            const float qlo = recip_ok[2 * k] ? bf16_quotient<DIV_RECIP>(lo, sc[2 * k])
+                                                              : bf16_quotient<DIV_EXACT>(lo, sc[2 * k]);
+                            const float qhi = recip_ok[2 * k + 1] ? bf16_quotient<DIV_RECIP>(hi, sc[2 * k + 1])
+                                                                  : bf16_quotient<DIV_EXACT>(hi, sc[2 * k + 1]);
+                            const uint32_t uq = bf16x2_rne(qlo, qhi);
+                            o[k] = bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), sc[2 * k].s),
+                                              __fmul_rn(__uint_as_float(round.hi(uq)), sc[2 * k + 1].s));
+                        }
                     }
                 }
+                if (WRITE && r < rows) st_stream(y + r * vec_per_row + cg, make_uint4(o[0], o[1], o[2], o[3]));
             }
-            if (WRITE) st_stream(y + r * vec_per_row + cg, make_uint4(o[0], o[1], o[2], o[3]));
         }
     }
     if (AMAX) {

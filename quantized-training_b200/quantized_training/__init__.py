@@ -7,6 +7,7 @@ CUDA only: there is no CPU or eager fallback.
 """
 from . import _C
 from .fake_quantize import FusedAmaxObsFakeQuantize, get_quantization_map
+from .host_io import HostPipeline, fake_quantize_host
 from .qconfig import QConfig, get_qconfig
 from .quantize import convert, get_quantized_model, prepare, propagate_config, quantize, replace_softmax
 from .quantizer import QScheme, QuantizationSpec
@@ -20,10 +21,12 @@ group_wise_affine = QScheme.GROUP_WISE_AFFINE
 
 __all__ = [
     "FusedAmaxObsFakeQuantize",
+    "HostPipeline",
     "QConfig",
     "QScheme",
     "QuantizationSpec",
     "add_qspec_args",
+    "fake_quantize_host",
     "convert",
     "get_qconfig",
     "get_quantization_map",

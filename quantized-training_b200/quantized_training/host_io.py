@@ -1,0 +1,69 @@
+"""Fake-quantize tensors that live in HOST memory.
+
+`fake_quantize_host(mod, x_host)` streams a (pinned) host tensor through the GPU in chunks on several CUDA
+streams, so the upload of chunk c+1, the kernel of chunk c and the download of chunk c-1 overlap (PCIe is
+full duplex; the kernel itself is ~100x faster than the link).  Results are identical to `mod(x_host.cuda())`:
+the delayed scale is updated once per call, and every chunk max-accumulates |x| into the same history slot.
+"""
+import torch
+
+from . import _C
+from .fake_quantize import FusedAmaxObsFakeQuantize, _channel_view
+
+__all__ = ["fake_quantize_host", "HostPipeline"]
+
+
+class HostPipeline:
+    """Reusable staging buffers + streams for one device / dtype / chunk size."""
+
+    def __init__(self, device, dtype=torch.bfloat16, chunk_elems=1 << 23, depth=3):
+        self.device = torch.device(device)
+        self.chunk = int(chunk_elems)
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self.xin = [torch.empty(self.chunk, dtype=dtype, device=self.device) for _ in range(depth)]
+        self.yout = [torch.empty(self.chunk, dtype=dtype, device=self.device) for _ in range(depth)]
+
+    def run(self, mod: FusedAmaxObsFakeQuantize, x_host: torch.Tensor, out: torch.Tensor = None):
+        assert not x_host.is_cuda and x_host.is_contiguous() and x_host.dtype == self.xin[0].dtype
+        if mod.scale.device != self.device:
+            mod.to(self.device)
+        observe, quantize = mod._flags()
+        if mod.is_per_channel:
+            raise NotImplementedError("host streaming handles per-tensor and bare specs (chunks cut across channels)")
+        if out is None:
+            out = torch.empty_like(x_host).pin_memory() if quantize else x_host
+        n = x_host.numel()
+        xf, of = x_host.view(-1), out.view(-1)
+        main = torch.cuda.current_stream(self.device)
+        amax_slot = None
+        if observe:
+            if n == 0:
+                raise RuntimeError("amax(): cannot observe an empty tensor")
+            if mod.amax_history.numel() == 0:
+                mod.amax_history.resize_((mod.amax_history_len,)).fill_(0.0)
+                mod.scale.resize_(()).fill_(1.0)
+            _C.scale_update(mod.amax_history, mod.amax_history_len, 1, mod.scale, mod.quant_max,
+                            mod.force_scale_power_of_two)
+            amax_slot = mod.amax_history
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for c, start in enumerate(range(0, n, self.chunk)):
+            i = c % len(self.streams)
+            m = min(self.chunk, n - start)
+            with torch.cuda.stream(self.streams[i]):
+                self.streams[i].wait_event(ready)
+                xin, yout = self.xin[i][:m], self.yout[i][:m]
+                xin.copy_(xf[start:start + m], non_blocking=True)
+                if quantize:
+                    _C.fq_forward(xin, yout, 1, 1, m, mod._fmt, mod.scale.reshape(1), amax_slot, mod.lut)
+                    of[start:start + m].copy_(yout, non_blocking=True)
+                elif observe:
+                    _C.amax(xin, 1, 1, m, amax_slot)
+        for s in self.streams:
+            main.wait_stream(s)
+        return out
+
+
+def fake_quantize_host(mod, x_host, out=None, device="cuda:0", chunk_elems=1 << 23, depth=3):
+    """One-shot convenience wrapper (allocates the staging buffers each call; keep a HostPipeline to reuse them)."""
+    return HostPipeline(device, x_host.dtype, chunk_elems, depth).run(mod, x_host, out)

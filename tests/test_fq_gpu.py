@@ -188,3 +188,22 @@ def test_full_size_properties(spec):
     for start in (0, 12345 * 8, n - 4096):
         blk = mod(x[start:start + 4096].clone())
         assert torch.equal(blk.view(torch.int16), y[start:start + 4096].view(torch.int16))
+
+
+def test_host_streaming_matches_device_call():
+    """Chunked host pipeline == one device call: values, scale and amax history (delayed scaling across chunks)."""
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(3_000_001, generator=g) * 5).to(torch.bfloat16).pin_memory()
+    for spec in ("posit8_1", "fp8_e4m3,qs=per_tensor_symmetric,ahl=3"):
+        a, _ = module_for(spec)
+        b, _ = module_for(spec)
+        pipe = qt.HostPipeline(DEV, torch.bfloat16, chunk_elems=1 << 18, depth=3)
+        for call in range(3):
+            xi = (x.float() * (call + 1)).to(torch.bfloat16).pin_memory()
+            want = a(xi.to(DEV))
+            got = pipe.run(b, xi)
+            torch.cuda.synchronize()
+            assert nan_eq16(bits_of(got), bits_of(want)).all(), (spec, call)
+            assert nan_eq32(bits_of(a.scale), bits_of(b.scale)).all()
+            if a.qscheme is not None:
+                assert nan_eq32(bits_of(a.amax_history), bits_of(b.amax_history)).all()
