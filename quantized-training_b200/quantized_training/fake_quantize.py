@@ -60,7 +60,17 @@ class FusedAmaxObsFakeQuantFunction(torch.autograd.Function):
             raise RuntimeError(
                 f"FusedAmaxObsFakeQuantize got a tensor on {x.device}: the B200 build runs on CUDA only "
                 "(no CPU fallback)")
-        xc = x.detach().contiguous()
+        xd = x.detach()
+        perm = None
+        if mod.preserve_strides and not xd.is_contiguous() and not mod.is_per_channel and xd.dim() > 1:
+            # A dense permutation (e.g. key.transpose(-1, -2)): the op is elementwise, so quantize the storage
+            # order and hand back the same view -- no transpose copy, and the GEMM keeps a unit-stride K axis.
+            order = sorted(range(xd.dim()), key=lambda i: -xd.stride(i))
+            xp = xd.permute(order)
+            if xp.is_contiguous():
+                perm = [order.index(i) for i in range(xd.dim())]
+                xd = xp
+        xc = xd.contiguous()
         amax_slot = None
         outer, channels, inner = 1, 1, xc.numel()
         if observe:
@@ -93,7 +103,7 @@ class FusedAmaxObsFakeQuantFunction(torch.autograd.Function):
             outer, channels, inner, _ = _channel_view(tuple(xc.shape), axes[0])
         y = torch.empty_like(xc)
         _C.fq_forward(xc, y, outer, channels, inner, mod._fmt, scale, amax_slot, mod.lut)
-        return y
+        return y if perm is None else y.permute(perm)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -149,6 +159,9 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         self.force_scale_power_of_two = force_scale_power_of_two
         self.outlier_threshold = outlier_threshold
         self.record_histogram = record_histogram
+        # False (default): outputs are contiguous, as in the reference.  True: a dense permuted input (k^T) comes
+        # back as the same view; set by `prepare` on the fake-quantizers that feed our own matmul.
+        self.preserve_strides = False
         self._fmt = _C.format_from_string(dtype)  # ValueError("Unsupported dtype: ...")
         self._qmap = None
         device = kwargs.get("device", None)

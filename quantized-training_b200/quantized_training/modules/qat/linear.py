@@ -2,6 +2,8 @@
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from ... import ops
 from torch.nn.utils.parametrize import (
     is_parametrized,
     transfer_parametrizations_and_params,
@@ -24,7 +26,7 @@ class Linear(nn.Linear):
         self.weight_fake_quant = qconfig.weight(factory_kwargs={"device": device, "dtype": dtype})
 
     def forward(self, input):
-        return F.linear(input, self.weight_fake_quant(self.weight), self.bias)
+        return ops.linear(input, self.weight_fake_quant(self.weight), self.bias)
 
     @classmethod
     def from_float(cls, mod):

@@ -5,6 +5,7 @@ called (their ``.weight`` is read directly), so hooks on them do not fire."""
 import torch
 import torch.nn.functional as F
 
+from ... import ops
 from ..lora import LoraLinear as _FloatLora
 
 try:  # the real peft layer, when the package is present
@@ -34,7 +35,7 @@ class Linear(_FloatLora):
                 b = self.weight_fake_quant(self.lora_B[name].weight)
                 merged = merged + _t(b @ a, self.fan_in_fan_out) * self.scaling[name]
         merged = self.weight_fake_quant(merged)
-        return F.linear(x, _t(merged, self.fan_in_fan_out), self.bias).to(in_dtype)
+        return ops.linear(x, _t(merged, self.fan_in_fan_out), self.bias).to(in_dtype)
 
     @classmethod
     def from_float(cls, mod):

@@ -9,6 +9,8 @@ from typing import Union
 import torch
 from torch import Tensor, nn
 
+from ... import ops
+
 __all__ = ["AddFunctional", "MulFunctional", "MatmulFunctional"]
 
 
@@ -24,4 +26,4 @@ class MulFunctional(nn.Module):
 
 class MatmulFunctional(nn.Module):
     def forward(self, x: Tensor, y: Tensor) -> Tensor:
-        return torch.matmul(x, y)
+        return ops.matmul(x, y)

