@@ -110,6 +110,15 @@ int qt_scale_update(float *history, int amax_history_len, size_t channels, float
 int qt_fq_forward(const void *x, void *y, size_t outer, size_t channels, size_t inner, int elem_type,
                   const qt_format_t *fmt, const float *scale, float *amax_out, const void *lut, void *stream);
 
+/* Quantize to one-byte codes for the FP8 tensor-core GEMM: codes[i] = OCP fp8 encoding (e4m3fn / e5m2) of
+ * q = round_fmt(x[i] / s), the value qt_fq_forward multiplies by s; decode(code) == q exactly.  Formats: e4m3, e5m2,
+ * fp8_e4m3, fp8_e5m2 (others: QT_ERR_UNSUPPORTED_DTYPE).  Per tensor only (one scale or NULL), n elements,
+ * `lut` is required.  amax_out as in qt_fq_forward.  This is the fused form of the reference's
+ * fake-quant (fake_quantize.py:244-246) followed by the cast a true-FP8 GEMM needs: 3 bytes of traffic per
+ * bf16 element instead of 4 + 3. */
+int qt_quantize_codes(const void *x, void *codes, size_t n, int elem_type, const qt_format_t *fmt,
+                      const float *scale, float *amax_out, const void *lut, void *stream);
+
 /* Observer only (fake quant disabled, e.g. calibration): amax_out[c] = max(amax_out[c], max|x|). */
 int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type,
             float *amax_out, void *stream);

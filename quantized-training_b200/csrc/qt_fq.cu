@@ -21,6 +21,7 @@
 //   cols  kernel: inner == 1 per-channel (ax = last dim): one scale per column, register-resident.
 //   scalar kernel: tails, misaligned views, odd per-channel shapes.
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <string.h>
 
@@ -498,6 +499,120 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
     }
 }
 
+// ----------------------------------------------------------------------------- quantize to fp8 codes
+// Same rounding as the fake-quant pass, but the pass ends at q = round_fmt(x / s) and stores its one-byte OCP
+// encoding (e4m3fn / e5m2) instead of q * s: 2 + 1 bytes per bf16 element instead of 2 + 2, and the result
+// feeds the FP8 tensor-core GEMM directly (decode(code) == q exactly; NaN -> NaN code; no saturation is needed
+// because q is already clamped to the format's range).
+template <bool E5M2>
+__device__ __forceinline__ uint32_t fp8x2_of(uint32_t qlo, uint32_t qhi)
+{
+    return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(__uint_as_float(qlo), __uint_as_float(qhi)), __NV_NOSAT,
+                                              E5M2 ? __NV_E5M2 : __NV_E4M3);
+}
+
+template <class R, bool F32, int DIV, bool AMAX, bool E5M2>
+__device__ __forceinline__ void codes_span(const R &round, const uint4 *__restrict__ x, uint32_t *__restrict__ y,
+                                           size_t nvec, const ScaleBf16 &sc, uint32_t &amax)
+{
+    // y is indexed in 32-bit words: a bf16 vector (8 elements) yields 2 words, an fp32 vector (4 elements) 1 word
+    const size_t nthr = blockDim.x;
+    const size_t tile = nthr * kUnroll;
+    const size_t ntiles = (nvec + tile - 1) / tile;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t base = t * tile + threadIdx.x;
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * nthr;
+            v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * nthr;
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            uint32_t q[8];
+            if (F32) {
+                if (AMAX) amax = amax_of_vec_f32(amax, v[j]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t u = DIV == DIV_UNIT ? w[k] : __float_as_uint(__fdiv_rn(__uint_as_float(w[k]), sc.s));
+                    q[k] = round(f32_to_bf16_rto_hi(u));
+                }
+                const uint32_t word = fp8x2_of<E5M2>(q[0], q[1]) | (fp8x2_of<E5M2>(q[2], q[3]) << 16);
+                if (i < nvec) y[i] = word;
+            } else {
+                if (AMAX) amax = amax_of_vec_bf16(amax, v[j]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (DIV == DIV_UNIT) {
+                        q[2 * k] = round.lo(w[k]);
+                        q[2 * k + 1] = round.hi(w[k]);
+                    } else {
+                        const uint32_t uq = bf16x2_rne(bf16_quotient<DIV>(w[k] << 16, sc),
+                                                       bf16_quotient<DIV>(w[k] & 0xFFFF0000u, sc));
+                        q[2 * k] = round.lo(uq);
+                        q[2 * k + 1] = round.hi(uq);
+                    }
+                }
+                uint2 o;
+                o.x = fp8x2_of<E5M2>(q[0], q[1]) | (fp8x2_of<E5M2>(q[2], q[3]) << 16);
+                o.y = fp8x2_of<E5M2>(q[4], q[5]) | (fp8x2_of<E5M2>(q[6], q[7]) << 16);
+                if (i < nvec) reinterpret_cast<uint2 *>(y)[i] = o;
+            }
+        }
+    }
+}
+
+template <class R, bool F32, bool AMAX, bool E5M2>
+__global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
+codes_flat_kernel(const uint4 *__restrict__ x, uint32_t *__restrict__ y, size_t nvec,
+                  const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
+                  float *__restrict__ amax_out)
+{
+    const R round(params, stage_table<R>(params));
+    ScaleBf16 sc = {1.0f, 1.0f};
+    if (scale) sc = load_scale<F32>(scale, 0);
+    uint32_t amax = 0u;
+    const int mode = classify_scale(sc.s);
+    if (mode == DIV_UNIT)
+        codes_span<R, F32, DIV_UNIT, AMAX, E5M2>(round, x, y, nvec, sc, amax);
+    else if (F32 || mode == DIV_EXACT)
+        codes_span<R, F32, DIV_EXACT, AMAX, E5M2>(round, x, y, nvec, sc, amax);
+    else
+        codes_span<R, F32, DIV_RECIP, AMAX, E5M2>(round, x, y, nvec, sc, amax);
+    if (AMAX) block_amax_commit(amax, amax_out);
+}
+
+// tails and misaligned views
+template <class R, bool F32, bool AMAX, bool E5M2>
+__global__ void __launch_bounds__(R::kThreads)
+codes_scalar_kernel(const void *__restrict__ xv, uint8_t *__restrict__ y, size_t first, size_t count,
+                    const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
+                    float *__restrict__ amax_out)
+{
+    const R round(params, stage_table<R>(params));
+    ScaleBf16 sc = {1.0f, 1.0f};
+    if (scale) sc = load_scale<F32>(scale, 0);
+    uint32_t amax = 0u;
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = first + j;
+        uint32_t q, ab;
+        if (F32) {
+            const uint32_t bits = static_cast<const uint32_t *>(xv)[i];
+            ab = bits & 0x7FFFFFFFu;
+            q = round(f32_to_bf16_rto_hi(__float_as_uint(__fdiv_rn(__uint_as_float(bits), sc.s))));
+        } else {
+            const uint32_t bits = (uint32_t) static_cast<const uint16_t *>(xv)[i] << 16;
+            ab = bits & 0x7FFFFFFFu;
+            q = round(bf16_rne_hi(bf16_quotient<DIV_EXACT>(bits, sc)));
+        }
+        y[i] = (uint8_t)(fp8x2_of<E5M2>(q, 0u) & 0xFFu);
+        if (AMAX) amax = max(amax, ab);
+    }
+    if (AMAX) block_amax_commit(amax, amax_out);
+}
+
 // ----------------------------------------------------------------------------- scale update
 __global__ void scale_update_kernel(float *__restrict__ history, int ahl, size_t channels, float *__restrict__ scale,
                                     float quant_max, int pow2)
@@ -790,5 +905,80 @@ extern "C" int qt_scale_update(float *history, int amax_history_len, size_t chan
                                                                              quant_max, force_scale_power_of_two);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "scale_update kernel launch");
+    return QT_OK;
+}
+
+namespace {
+template <class R, bool F32, bool AMAX, bool E5M2>
+void launch_codes(const void *x, void *y, size_t n, const typename R::Params &p, const float *scale, float *amax,
+                  cudaStream_t stream)
+{
+    constexpr size_t VEC = F32 ? 4 : 8;
+    const bool aligned = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0;
+    const size_t nvec = aligned ? n / VEC : 0;
+    if (nvec) {
+        allow_smem<codes_flat_kernel<R, F32, AMAX, E5M2>>(R::kSmemBytes);
+        const size_t tile = (size_t)R::kThreads * kUnroll;
+        const unsigned grid = grid_for((nvec + tile - 1) / tile, R::kCtasPerSm);
+        codes_flat_kernel<R, F32, AMAX, E5M2><<<grid, R::kThreads, R::kSmemBytes, stream>>>(
+            static_cast<const uint4 *>(x), static_cast<uint32_t *>(y), nvec, p, scale, amax);
+    }
+    const size_t rest = n - nvec * VEC;
+    if (rest) {
+        allow_smem<codes_scalar_kernel<R, F32, AMAX, E5M2>>(R::kSmemBytes);
+        const unsigned grid = grid_for((rest + R::kThreads - 1) / R::kThreads, R::kCtasPerSm * 2);
+        codes_scalar_kernel<R, F32, AMAX, E5M2><<<grid, R::kThreads, R::kSmemBytes, stream>>>(
+            x, static_cast<uint8_t *>(y), nvec * VEC, rest, p, scale, amax);
+    }
+}
+template <class R, bool E5M2>
+void launch_codes_flags(const void *x, void *y, size_t n, bool f32, const typename R::Params &p, const float *scale,
+                        float *amax, cudaStream_t stream)
+{
+    if (f32)
+        amax ? launch_codes<R, true, true, E5M2>(x, y, n, p, scale, amax, stream)
+             : launch_codes<R, true, false, E5M2>(x, y, n, p, scale, amax, stream);
+    else
+        amax ? launch_codes<R, false, true, E5M2>(x, y, n, p, scale, amax, stream)
+             : launch_codes<R, false, false, E5M2>(x, y, n, p, scale, amax, stream);
+}
+}  // namespace
+
+extern "C" int qt_quantize_codes(const void *x, void *codes, size_t n, int elem_type, const qt_format_t *fmt,
+                                 const float *scale, float *amax_out, const void *lut, void *stream)
+{
+    int rc = check_layout("qt_quantize_codes", x, 1, 1, n, elem_type);
+    if (rc != QT_OK) return rc;
+    if (!fmt || (n && !codes)) {
+        qt_set_error("qt_quantize_codes: NULL argument");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    const bool e4m3 = fmt->kind == QT_KIND_FP && fmt->ebits == 4 && fmt->mbits == 3 && !fmt->is_unsigned;
+    const bool e5m2 = fmt->kind == QT_KIND_FP && fmt->ebits == 5 && fmt->mbits == 2 && !fmt->is_unsigned;
+    if (!e4m3 && !e5m2) {
+        qt_set_error("qt_quantize_codes: one-byte codes exist for e4m3 / e5m2 / fp8_e4m3 / fp8_e5m2 only");
+        return QT_ERR_UNSUPPORTED_DTYPE;
+    }
+    QtRound P;
+    rc = qt_make_round(fmt, &P);
+    if (rc != QT_OK) return rc;
+    if (n == 0) return QT_OK;
+    if (num_sms() == 0) return no_device();
+    TableParams tp;
+    if (!lut || qt_lut_config(P, &tp.cfg) != QT_OK || (reinterpret_cast<uintptr_t>(lut) & 15u)) {
+        qt_set_error("qt_quantize_codes: needs the 16-byte aligned device table from qt_lut_build_host(fmt)");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    tp.table = static_cast<const QtLutEntry *>(lut);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool f32 = elem_type == QT_F32;
+    if (tp.cfg.mx_band)
+        e5m2 ? launch_codes_flags<TableRounder<true, true>, true>(x, codes, n, f32, tp, scale, amax_out, st)
+             : launch_codes_flags<TableRounder<true, true>, false>(x, codes, n, f32, tp, scale, amax_out, st);
+    else
+        e5m2 ? launch_codes_flags<TableRounder<true, false>, true>(x, codes, n, f32, tp, scale, amax_out, st)
+             : launch_codes_flags<TableRounder<true, false>, false>(x, codes, n, f32, tp, scale, amax_out, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "quantize-to-codes kernel launch");
     return QT_OK;
 }

@@ -40,6 +40,9 @@ EXPORTS = {
     "qt_fq_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                      ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_quantize_codes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
     "qt_gemm_nt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] +
                    [ctypes.c_int64] * 10 + [ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
@@ -146,6 +149,18 @@ def fq_forward(x, y, outer, channels, inner, fmt, scale=None, amax_out=None, lut
                                    ctypes.byref(fmt), scale.data_ptr() if scale is not None else None,
                                    amax_out.data_ptr() if amax_out is not None else None,
                                    lut.data_ptr() if lut is not None else None, _stream(x)))
+
+
+def quantize_codes(x, codes, fmt, scale=None, amax_out=None, lut=None):
+    """codes (uint8, same numel) = fp8 encoding of round_fmt(x / s); per tensor."""
+    _require_cuda(x, "input")
+    assert x.is_contiguous() and codes.is_contiguous() and codes.dtype == torch.uint8 and codes.numel() == x.numel()
+    assert lut is not None and lut.device == x.device
+    with torch.cuda.device(x.device):
+        _check(lib().qt_quantize_codes(x.data_ptr(), codes.data_ptr(), x.numel(), _elem_type(x), ctypes.byref(fmt),
+                                       scale.data_ptr() if scale is not None else None,
+                                       amax_out.data_ptr() if amax_out is not None else None, lut.data_ptr(),
+                                       _stream(x)))
 
 
 def amax(x, outer, channels, inner, amax_out):

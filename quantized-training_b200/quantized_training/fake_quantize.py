@@ -48,62 +48,76 @@ def _channel_view(shape, ch_axis):
     return outer, shape[ax], inner, keep
 
 
+def _run(mod, x, emit_codes=False):
+    """Observer step + one fused pass.  emit_codes=False: fake-quantized tensor (x's dtype).
+    emit_codes=True: uint8 fp8 codes of round_fmt(x / s) (per tensor, e4m3 / e5m2 formats)."""
+    observe, quantize = mod._flags()
+    if emit_codes:
+        quantize = True
+    if not (observe or quantize):
+        return x
+    if not x.is_cuda:
+        raise RuntimeError(
+            f"FusedAmaxObsFakeQuantize got a tensor on {x.device}: the B200 build runs on CUDA only "
+            "(no CPU fallback)")
+    xd = x.detach()
+    perm = None
+    if mod.preserve_strides and not xd.is_contiguous() and not mod.is_per_channel and xd.dim() > 1:
+        # A dense permutation (e.g. key.transpose(-1, -2)): the op is elementwise, so quantize the storage
+        # order and hand back the same view -- no transpose copy, and the GEMM keeps a unit-stride K axis.
+        order = sorted(range(xd.dim()), key=lambda i: -xd.stride(i))
+        xp = xd.permute(order)
+        if xp.is_contiguous():
+            perm = [order.index(i) for i in range(xd.dim())]
+            xd = xp
+    xc = xd.contiguous()
+    amax_slot = None
+    outer, channels, inner = 1, 1, xc.numel()
+    if observe:
+        if xc.numel() == 0:
+            raise RuntimeError("amax(): cannot observe an empty tensor")
+        if mod.is_per_channel:
+            outer, channels, inner, stat_shape = _channel_view(tuple(xc.shape), mod.ch_axis)
+        else:
+            stat_shape = ()
+        if mod.amax_history.numel() == 0:  # first observed call: shapes become known
+            mod.amax_history.resize_((mod.amax_history_len,) + stat_shape).fill_(0.0)
+            mod.scale.resize_(stat_shape).fill_(1.0)
+        _C.scale_update(mod.amax_history, mod.amax_history_len, channels, mod.scale, mod.quant_max,
+                        mod.force_scale_power_of_two)
+        amax_slot = mod.amax_history
+    if not quantize:
+        _C.amax(xc, outer, channels, inner, amax_slot)
+        return x
+    scale = mod.scale
+    if scale.numel() == 1:
+        # per tensor, or a bare spec whose scale buffer is the constant 1.0 (the kernel then
+        # takes its exact unit-scale path: the branch is made on the device, no read-back)
+        outer, channels, inner = 1, 1, xc.numel()
+    elif not observe:
+        # frozen per-channel scale: recover the layout from the scale's keepdim shape
+        axes = [i for i, d in enumerate(scale.shape) if d != 1]
+        if len(axes) != 1 or scale.dim() != xc.dim() or scale.shape[axes[0]] != xc.shape[axes[0]]:
+            raise RuntimeError(f"scale of shape {tuple(scale.shape)} does not broadcast over a single "
+                               f"axis of input {tuple(xc.shape)}")
+        outer, channels, inner, _ = _channel_view(tuple(xc.shape), axes[0])
+    if emit_codes:
+        if channels != 1:
+            raise NotImplementedError("fp8 codes are produced per tensor (bare or per_tensor_symmetric specs)")
+        y = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device)
+        _C.quantize_codes(xc, y, mod._fmt, scale.reshape(1), amax_slot, mod.lut)
+    else:
+        y = torch.empty_like(xc)
+        _C.fq_forward(xc, y, outer, channels, inner, mod._fmt, scale, amax_slot, mod.lut)
+    return y if perm is None else y.permute(perm)
+
+
 class FusedAmaxObsFakeQuantFunction(torch.autograd.Function):
     """Delayed-scaling observer + quantize-dequantize, one fused pass; STE backward."""
 
     @staticmethod
     def forward(ctx, x, mod):
-        observe, quantize = mod._flags()
-        if not (observe or quantize):
-            return x
-        if not x.is_cuda:
-            raise RuntimeError(
-                f"FusedAmaxObsFakeQuantize got a tensor on {x.device}: the B200 build runs on CUDA only "
-                "(no CPU fallback)")
-        xd = x.detach()
-        perm = None
-        if mod.preserve_strides and not xd.is_contiguous() and not mod.is_per_channel and xd.dim() > 1:
-            # A dense permutation (e.g. key.transpose(-1, -2)): the op is elementwise, so quantize the storage
-            # order and hand back the same view -- no transpose copy, and the GEMM keeps a unit-stride K axis.
-            order = sorted(range(xd.dim()), key=lambda i: -xd.stride(i))
-            xp = xd.permute(order)
-            if xp.is_contiguous():
-                perm = [order.index(i) for i in range(xd.dim())]
-                xd = xp
-        xc = xd.contiguous()
-        amax_slot = None
-        outer, channels, inner = 1, 1, xc.numel()
-        if observe:
-            if xc.numel() == 0:
-                raise RuntimeError("amax(): cannot observe an empty tensor")
-            if mod.is_per_channel:
-                outer, channels, inner, stat_shape = _channel_view(tuple(xc.shape), mod.ch_axis)
-            else:
-                stat_shape = ()
-            if mod.amax_history.numel() == 0:  # first observed call: shapes become known
-                mod.amax_history.resize_((mod.amax_history_len,) + stat_shape).fill_(0.0)
-                mod.scale.resize_(stat_shape).fill_(1.0)
-            _C.scale_update(mod.amax_history, mod.amax_history_len, channels, mod.scale, mod.quant_max,
-                            mod.force_scale_power_of_two)
-            amax_slot = mod.amax_history
-        if not quantize:
-            _C.amax(xc, outer, channels, inner, amax_slot)
-            return x
-        scale = mod.scale
-        if scale.numel() == 1:
-            # per tensor, or a bare spec whose scale buffer is the constant 1.0 (the kernel then
-            # takes its exact unit-scale path: the branch is made on the device, no read-back)
-            outer, channels, inner = 1, 1, xc.numel()
-        elif not observe:
-            # frozen per-channel scale: recover the layout from the scale's keepdim shape
-            axes = [i for i, d in enumerate(scale.shape) if d != 1]
-            if len(axes) != 1 or scale.dim() != xc.dim() or scale.shape[axes[0]] != xc.shape[axes[0]]:
-                raise RuntimeError(f"scale of shape {tuple(scale.shape)} does not broadcast over a single "
-                                   f"axis of input {tuple(xc.shape)}")
-            outer, channels, inner, _ = _channel_view(tuple(xc.shape), axes[0])
-        y = torch.empty_like(xc)
-        _C.fq_forward(xc, y, outer, channels, inner, mod._fmt, scale, amax_slot, mod.lut)
-        return y if perm is None else y.permute(perm)
+        return _run(mod, x)
 
     @staticmethod
     def backward(ctx, grad_output):
@@ -204,6 +218,23 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
     @torch.jit.export
     def calculate_qparams(self):
         return self.scale
+
+    @property
+    def fp8_kind(self):
+        """"e4m3" / "e5m2" when the format has a one-byte OCP encoding the FP8 tensor cores read, else None."""
+        f = self._fmt
+        if f.kind == 2 and not f.is_unsigned and (f.ebits, f.mbits) in ((4, 3), (5, 2)):
+            return "e4m3" if f.ebits == 4 else "e5m2"
+        return None
+
+    def quantize_to_codes(self, X: torch.Tensor) -> torch.Tensor:
+        """uint8 tensor of fp8 codes of round(X / scale): same observer side effects as forward(), 3 bytes of
+        traffic per bf16 element, and the operand format of ops.linear_fp8.  No gradient flows through it."""
+        if self.fp8_kind is None:
+            raise ValueError(f"dtype {self.dtype} has no fp8 code form")
+        if self.scale.device != X.device:
+            self.to(X.device)
+        return _run(self, X, emit_codes=True)
 
     @torch.jit.export
     def extra_repr(self):

@@ -26,6 +26,9 @@ class Linear(nn.Linear):
         self.weight_fake_quant = qconfig.weight(factory_kwargs={"device": device, "dtype": dtype})
 
     def forward(self, input):
+        kind = ops.fp8_route(self, input, self.weight_fake_quant)
+        if kind is not None:  # bare e4m3/e5m2 on both sides: operands go to the FP8 tensor cores as codes
+            return ops.linear_fp8(input, self.weight, self.bias, self.weight_fake_quant, kind)
         return ops.linear(input, self.weight_fake_quant(self.weight), self.bias)
 
     @classmethod

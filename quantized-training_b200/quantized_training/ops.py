@@ -65,6 +65,64 @@ def linear(x, weight, bias=None):
     return F.linear(x, weight, bias)
 
 
+_FP8_DTYPE = {"e4m3": torch.float8_e4m3fn, "e5m2": torch.float8_e5m2}
+_FP8_OP = {("e4m3", "e4m3"): _C.GEMM_E4M3, ("e5m2", "e5m2"): _C.GEMM_E5M2,
+           ("e4m3", "e5m2"): _C.GEMM_E4M3_E5M2, ("e5m2", "e4m3"): _C.GEMM_E5M2_E4M3}
+
+
+class _LinearFp8Fn(torch.autograd.Function):
+    """x holds values of an fp8 format exactly (it left a bare e4m3/e5m2 fake-quantizer), the weight is quantized
+    straight to codes: both operands go to the FP8 tensor cores.  Products and fp32 accumulation are those of
+    the bf16 path (every fp8 value is a bf16 value), at twice the MMA rate and 3/4 of the weight traffic."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, wq, x_kind):
+        x2 = x.reshape(-1, x.shape[-1])
+        xc = x2.contiguous().to(_FP8_DTYPE[x_kind]).view(torch.uint8)   # exact: x is representable
+        wc = wq.quantize_to_codes(weight)
+        y = _C.gemm_nt(xc, wc, bias=bias.contiguous() if bias is not None else None,
+                       operand_type=_FP8_OP[(x_kind, wq.fp8_kind)])
+        if any(ctx.needs_input_grad[:3]):
+            ctx.save_for_backward(x, wc)
+            ctx.w_kind = wq.fp8_kind
+            ctx.w_scale = wq.scale
+        ctx.has_bias = bias is not None
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wc = ctx.saved_tensors
+        w = (wc.view(_FP8_DTYPE[ctx.w_kind]).to(g.dtype) * ctx.w_scale.to(g.dtype))   # the fake-quantized weight
+        g2 = g.reshape(-1, g.shape[-1])
+        gx = (g2 @ w).view_as(x) if ctx.needs_input_grad[0] else None
+        gw = g2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None   # STE through the quantizer
+        gb = g2.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None, None
+
+
+def linear_fp8(x, weight, bias, weight_fq, x_kind):
+    """F.linear(x, weight_fq(weight), bias) with both operands as fp8 codes.  Caller guarantees that x already holds
+    `x_kind` values exactly and that weight_fq is a bare (scale 1) e4m3/e5m2 quantizer."""
+    return _LinearFp8Fn.apply(x, weight, bias, weight_fq, x_kind)
+
+
+def fp8_route(module, x, weight_fq):
+    """Which fp8 format the input of `module` is already quantized to by its forward pre-hook, if the whole
+    product can run on the FP8 tensor cores; else None."""
+    if not (_ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[-1] % 16 == 0):
+        return None
+    hooks = getattr(module, "activation_pre_process", None)
+    act = hooks["0"] if hooks is not None and "0" in hooks else None
+    for fq in (act, weight_fq):
+        if fq is None or getattr(fq, "fp8_kind", None) is None or fq.qscheme is not None or fq.is_per_channel:
+            return None
+        if fq._flags() != (False, True):
+            return None
+    if module.weight.shape[0] % 8:
+        return None
+    return act.fp8_kind
+
+
 class _MatmulFn(torch.autograd.Function):
     """x [..., M, K] @ y [..., K, N]; the kernel wants y as [..., N, K] with a unit-stride K axis, which is free
     when y is itself a transposed view (k^T in attention) and one transpose copy of the small operand otherwise."""

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--seq", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--torch-gemm", action="store_true")
     ap.add_argument("--ops", default="gemm")
@@ -40,13 +41,17 @@ def main():
     args = qt.add_qspec_args().parse_args(["--activation", a.spec, "--weight", a.spec, "--quantize_forward", a.ops, "--bf16"])
     qt.quantize(model, args)
     build_s = time.time() - t0
-    ids = torch.randint(0, 32000, (1, a.seq), device=dev)
+    ids = torch.randint(0, 32000, (a.batch, a.seq), device=dev)
+    # prebuilt additive causal mask [1, 1, S, S]: HF then skips its own mask construction (which copies a CPU
+    # scalar to the device and cannot be captured in a CUDA graph)
+    mask = torch.full((a.seq, a.seq), torch.finfo(torch.bfloat16).min, device=dev, dtype=torch.bfloat16).triu(1)[None, None]
+    pos = torch.arange(a.seq, device=dev)[None].expand(a.batch, -1)
     if a.torch_gemm:
         ops.set_enabled(False)
 
     def fwd():
         with torch.no_grad():
-            out = model(input_ids=ids, labels=ids, use_cache=False)
+            out = model(input_ids=ids, labels=ids, use_cache=False, attention_mask=mask, position_ids=pos)
         return out.loss
 
     for _ in range(2):
@@ -78,7 +83,7 @@ def main():
     nfq = sum(1 for m in model.modules() if isinstance(m, qt.FusedAmaxObsFakeQuantize))
     print(json.dumps({"workload": f"Llama-2-7B-shape quantized forward, {a.layers} layers, window [1,{a.seq}]",
                       "spec": a.spec, "quantize_forward": a.ops, "graph": a.graph, "gemm": "torch/cuBLAS" if a.torch_gemm else "qt_gemm_nt",
-                      "ms_per_window": ms, "tokens_per_s": a.seq / ms * 1e3, "wall_ms_per_window": wall / a.steps * 1e3,
+                      "ms_per_window": ms, "batch": a.batch, "tokens_per_s": a.batch * a.seq / ms * 1e3, "wall_ms_per_window": wall / a.steps * 1e3,
                       "loss": float(loss), "fake_quant_modules": nfq, "build_s": build_s,
                       "flops_per_window_T": (2 * a.seq * (a.layers * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 32000 * 4096) + a.layers * 4 * 32 * a.seq * a.seq * 128) / 1e12}), flush=True)
 

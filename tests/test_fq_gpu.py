@@ -207,3 +207,30 @@ def test_host_streaming_matches_device_call():
             assert nan_eq32(bits_of(a.scale), bits_of(b.scale)).all()
             if a.qscheme is not None:
                 assert nan_eq32(bits_of(a.amax_history), bits_of(b.amax_history)).all()
+
+
+@pytest.mark.parametrize("spec", ["e4m3", "e5m2", "fp8_e4m3", "fp8_e5m2", "fp8_e4m3,qs=per_tensor_symmetric,ahl=2"])
+@pytest.mark.parametrize("elem", ["bf16", "fp32"])
+def test_codes_decode_to_the_fake_quant_values(spec, elem):
+    """decode(quantize_to_codes(x)) * scale == forward(x), bit for bit, incl. every bf16 pattern."""
+    all_bits = np.arange(65536, dtype=np.uint16)
+    g = torch.Generator().manual_seed(17)
+    xs = [bf16_from_bits(all_bits), (torch.randn(100003, generator=g) * 30).to(torch.bfloat16).to(DEV)]
+    if elem == "fp32":
+        xs = [x.float() * 1.0001 for x in xs]
+    for x in xs:
+        a, qs = module_for(spec)
+        b, _ = module_for(spec)
+        for call in range(2):
+            y = a(x)
+            codes = b.quantize_to_codes(x)
+            assert codes.dtype == torch.uint8 and codes.shape == x.shape
+            f8 = torch.float8_e4m3fn if b.fp8_kind == "e4m3" else torch.float8_e5m2
+            q = codes.view(f8).to(torch.float32)
+            s = b.scale.to(x.dtype).float()
+            dec = (q * s).to(x.dtype) if elem == "bf16" else q * b.scale
+            got, want = bits_of(dec), bits_of(y)
+            finite_codes = ~torch.isinf(y.float().cpu()).numpy().reshape(-1) if b.fp8_kind == "e4m3" else np.ones_like(got, bool)
+            # e4m3 has no Inf: fpN_eXmY's Inf pass-through becomes the NaN code (documented), everything else is exact
+            assert nan_eq(got[finite_codes], want[finite_codes]).all(), (spec, elem, call)
+            assert nan_eq32(bits_of(a.scale), bits_of(b.scale)).all()

@@ -90,3 +90,20 @@ def test_llama_tiny_forward_and_graph_capture():
         want = model(input_ids=ids, use_cache=False).logits
         ops.set_enabled(True)
     assert got.shape == (1, 128, 512) and rel_err(got, want) < 2e-2
+
+
+def test_fp8_linear_route_matches_bf16_route():
+    torch.manual_seed(4)
+    model = nn.Sequential(nn.Linear(512, 768)).to(DEV)
+    qt.quantize(model, parse("--activation", "e4m3", "--weight", "e4m3", "--bf16"))
+    x = (torch.randn(3, 200, 512, device=DEV) * 2).bfloat16().requires_grad_()
+    lin = model[0]
+    y8 = model(x)                                   # bare e4m3 on both sides -> FP8 tensor cores
+    assert ops.fp8_route(lin, lin.activation_pre_process["0"](x), lin.weight_fake_quant) == "e4m3"
+    y8.sum().backward()
+    g8 = x.grad.clone(); x.grad = None
+    xq = lin.activation_pre_process["0"](x.detach())
+    y16 = ops.linear(xq, lin.weight_fake_quant(lin.weight), lin.bias)
+    assert rel_err(y8, y16) < 1e-3                  # same products, fp32 accumulation in both
+    ref_gx = torch.ones_like(y16).reshape(-1, 768) @ lin.weight_fake_quant(lin.weight)
+    assert rel_err(g8.reshape(-1, 512), ref_gx) < 1e-2
