@@ -218,6 +218,11 @@ def run_gpu(args):
             extra[f"{name} bf16 per-tensor scale + amax"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
             ms = timed(lambda: qt._C.fq_forward(xs, ys, 1, 1, nn_, m._fmt, unit, None, None))
             extra[f"{name} bf16 bare, direct bitwise path"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
+        m = qt.FusedAmaxObsFakeQuantize("e4m3", device=dev)
+        codes = torch.empty(nn_, dtype=torch.uint8, device=dev)
+        ms = timed(lambda: qt._C.quantize_codes(xs, codes, m._fmt, unit, None, m.lut))
+        extra["e4m3 bf16 -> fp8 codes (3 B/element)"] = 3.0 * nn_ / (ms * 1e-3) / 1e9
+        del codes
         rows = nn_ // 4096
         scr = torch.rand(rows, device=dev) * 0.05 + 0.01
         scc = torch.rand(4096, device=dev) * 0.05 + 0.01

@@ -46,6 +46,7 @@ template <int KIND>
 struct DirectRounder {
     static constexpr bool kTable = false;
     static constexpr int kThreads = 256, kCtasPerSm = 8, kMinCtas = 1;
+    static constexpr bool kMxBand = KIND == QTR_FP_MX;
     static constexpr size_t kSmemBytes = 0;
     using Params = DirectParams<KIND>;
     const QtRound &P;
@@ -63,6 +64,7 @@ template <bool CLAMP, bool MXBAND>
 struct TableRounder {
     static constexpr bool kTable = true;
     static constexpr int kThreads = 512, kCtasPerSm = 2, kMinCtas = 2;  // 2 x 64 KB of replicated table per SM
+    static constexpr bool kMxBand = MXBAND;
     static constexpr size_t kSmemBytes = QT_LUT_SMEM_BYTES;
     using Params = TableParams;
     const unsigned char *tab;  // shared memory, 8 interleaved replicas (qt_lut.h)
@@ -504,11 +506,21 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
 // encoding (e4m3fn / e5m2) instead of q * s: 2 + 1 bytes per bf16 element instead of 2 + 2, and the result
 // feeds the FP8 tensor-core GEMM directly (decode(code) == q exactly; NaN -> NaN code; no saturation is needed
 // because q is already clamped to the format's range).
-template <bool E5M2>
+// Hardware conversion (cvt.rn.satfinite.{e4m3,e5m2}x2.f32, one instruction per pair; the non-saturating
+// flavour of the intrinsic is a ~50-instruction software routine).  q is already on the format's grid, so
+// the only inputs "satfinite" changes are +-Inf, which only the fpN_eXmY flavour can produce (Inf passes
+// through it): patched to the Inf code for e5m2; e4m3 has no Inf and gets the NaN code.
+template <bool E5M2, bool INF_POSSIBLE>
 __device__ __forceinline__ uint32_t fp8x2_of(uint32_t qlo, uint32_t qhi)
 {
-    return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(__uint_as_float(qlo), __uint_as_float(qhi)), __NV_NOSAT,
-                                              E5M2 ? __NV_E5M2 : __NV_E4M3);
+    uint32_t c = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(__uint_as_float(qlo), __uint_as_float(qhi)),
+                                                    __NV_SATFINITE, E5M2 ? __NV_E5M2 : __NV_E4M3);
+    if (INF_POSSIBLE) {
+        const uint32_t inf_code = E5M2 ? 0x7Cu : 0x7Fu;
+        if ((qlo & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0xFF00u) | ((qlo >> 24) & 0x80u) | inf_code;
+        if ((qhi & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0x00FFu) | ((((qhi >> 24) & 0x80u) | inf_code) << 8);
+    }
+    return c;
 }
 
 template <class R, bool F32, int DIV, bool AMAX, bool E5M2>
@@ -539,7 +551,7 @@ __device__ __forceinline__ void codes_span(const R &round, const uint4 *__restri
                     const uint32_t u = DIV == DIV_UNIT ? w[k] : __float_as_uint(__fdiv_rn(__uint_as_float(w[k]), sc.s));
                     q[k] = round(f32_to_bf16_rto_hi(u));
                 }
-                const uint32_t word = fp8x2_of<E5M2>(q[0], q[1]) | (fp8x2_of<E5M2>(q[2], q[3]) << 16);
+                const uint32_t word = fp8x2_of<E5M2, R::kMxBand>(q[0], q[1]) | (fp8x2_of<E5M2, R::kMxBand>(q[2], q[3]) << 16);
                 if (i < nvec) y[i] = word;
             } else {
                 if (AMAX) amax = amax_of_vec_bf16(amax, v[j]);
@@ -556,8 +568,8 @@ __device__ __forceinline__ void codes_span(const R &round, const uint4 *__restri
                     }
                 }
                 uint2 o;
-                o.x = fp8x2_of<E5M2>(q[0], q[1]) | (fp8x2_of<E5M2>(q[2], q[3]) << 16);
-                o.y = fp8x2_of<E5M2>(q[4], q[5]) | (fp8x2_of<E5M2>(q[6], q[7]) << 16);
+                o.x = fp8x2_of<E5M2, R::kMxBand>(q[0], q[1]) | (fp8x2_of<E5M2, R::kMxBand>(q[2], q[3]) << 16);
+                o.y = fp8x2_of<E5M2, R::kMxBand>(q[4], q[5]) | (fp8x2_of<E5M2, R::kMxBand>(q[6], q[7]) << 16);
                 if (i < nvec) reinterpret_cast<uint2 *>(y)[i] = o;
             }
         }
@@ -607,7 +619,7 @@ codes_scalar_kernel(const void *__restrict__ xv, uint8_t *__restrict__ y, size_t
             ab = bits & 0x7FFFFFFFu;
             q = round(bf16_rne_hi(bf16_quotient<DIV_EXACT>(bits, sc)));
         }
-        y[i] = (uint8_t)(fp8x2_of<E5M2>(q, 0u) & 0xFFu);
+        y[i] = (uint8_t)(fp8x2_of<E5M2, R::kMxBand>(q, 0u) & 0xFFu);
         if (AMAX) amax = max(amax, ab);
     }
     if (AMAX) block_amax_commit(amax, amax_out);
