@@ -1,0 +1,660 @@
+// qt_fused.cu -- the ops BETWEEN the GEMMs of a quantized transformer block, each fused with the fake-quant step
+// that follows it (and, for the hooks that precede it, the one before), one memory pass per op:
+//
+//   qt_softmax_fq    scores -> [fq] -> * alpha -> + mask -> [fq] -> softmax -> [fq]      (attention probabilities)
+//   qt_norm_fq       x -> [fq] -> RMSNorm / LayerNorm -> [fq]                             (block inputs)
+//   qt_act_mul_fq    fq(act(gate) * up), fq(act(x)), strided fq                           (MLP)
+//   qt_rope_fq       fq(x * cos + rotate_half(x) * sin) for q and k in one launch         (Llama)
+//   qt_fq_transpose  v [B, S, H, D] -> fq -> [B, H, D, S]   (the K-major operand of probs x V)
+//
+// In the reference each of these is a chain of bf16 ATen ops (HF modeling code) followed by the fake-quant hook of
+// the consuming module (quantize.py:116-150): 5-15 launches and as many round trips through HBM.  Here the bf16
+// roundings of that chain are reproduced in registers -- every intermediate the reference materialises in bf16 is
+// rounded to bf16 at the same point -- so the only differences are the order of the row reductions and the last-ulp
+// behaviour of exp / rsqrt.  The fake-quant step is the same rounding engine as qt_fq_forward (bit-exact formats);
+// per-tensor scales are read from device memory (NULL = bare spec, scale 1).  Observers (amax) are not fused: a
+// module with a live observer keeps its own qt_fq_forward pass.
+#include <math.h>
+
+#include "qt_fq_common.cuh"
+
+namespace {
+
+constexpr int FQ_PRE = 1;   // fake-quantize the op's input  (hook of the op's own group: scaling / layernorm)
+constexpr int FQ_MID = 2;   // softmax only: fake-quantize scores * alpha + mask (the "activation" hook of nn.Softmax)
+constexpr int FQ_POST = 4;  // fake-quantize the op's output (input hook of the consuming GEMM)
+
+struct FqPoint {
+    ScaleBf16 sc;
+    int mode;
+};
+__device__ __forceinline__ FqPoint load_point(const float *scale)
+{
+    FqPoint p;
+    p.sc.s = p.sc.rs = 1.0f;
+    if (scale) p.sc = load_scale<false>(scale, 0);
+    p.mode = classify_scale(p.sc.s);
+    return p;
+}
+// one bf16 value (fp32 bits, low half zero) through quantize-dequantize
+template <class R>
+__device__ __forceinline__ uint32_t fq_elem(const R &round, uint32_t xh, const FqPoint &p)
+{
+    if (p.mode == DIV_UNIT) return round(xh);
+    if (p.mode == DIV_RECIP) return fq_bf16<R, DIV_RECIP>(round, xh, p.sc);
+    return fq_bf16<R, DIV_EXACT>(round, xh, p.sc);
+}
+__device__ __forceinline__ float bf16_round(float f) { return __uint_as_float(bf16_rne_hi(f)); }
+__device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8])
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        f[2 * k] = __uint_as_float(w[k] << 16);
+        f[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+}
+// values already on the bf16 grid -> packed
+__device__ __forceinline__ uint4 pack8(const float (&f)[8])
+{
+    uint4 o;
+    o.x = __byte_perm(__float_as_uint(f[0]), __float_as_uint(f[1]), 0x7632);
+    o.y = __byte_perm(__float_as_uint(f[2]), __float_as_uint(f[3]), 0x7632);
+    o.z = __byte_perm(__float_as_uint(f[4]), __float_as_uint(f[5]), 0x7632);
+    o.w = __byte_perm(__float_as_uint(f[6]), __float_as_uint(f[7]), 0x7632);
+    return o;
+}
+// Launch shapes.  Row kernels: 128-thread CTAs; a row is owned by TPR = 32 threads (short rows, four rows per CTA)
+// or by all 128 (long rows), VPL 16-byte vectors per thread.  Elementwise kernels: 256-thread CTAs.  The rounding
+// table (64 KB of shared memory per CTA when the format uses it) allows 3 resp. 2 CTAs per SM.
+constexpr int ROW_THREADS = 128, ROW_MIN_CTAS = 3;
+constexpr int EW_THREADS = 256, EW_MIN_CTAS = 2;
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    return v;
+}
+
+// reductions over the TPR threads that own a row (TPR == 32: one warp; TPR == 128: the whole CTA through smem)
+template <int TPR, bool MAX>
+__device__ __forceinline__ float row_reduce(float v)
+{
+    v = MAX ? warp_max(v) : warp_sum(v);
+    if (TPR == 32) return v;
+    static_assert(ROW_THREADS == 128, "row_reduce assumes four warps");
+    __shared__ float part[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) part[warp] = v;
+    __syncthreads();
+    const float a = part[0], b = part[1], c = part[2], d = part[3];
+    __syncthreads();  // the next reduction may overwrite part[]
+    return MAX ? fmaxf(fmaxf(a, b), fmaxf(c, d)) : (a + b) + (c + d);
+}
+
+// ----------------------------------------------------------------------------- softmax
+// TPR threads per row of `cols` (<= TPR * VPL * 8) scores; the row lives in registers between the passes.
+// Reference chain (modules/quantizable/modeling_bert.py:118-158, modeling_llama.py:228-246), all bf16 tensors:
+//   s = qk_matmul(q, k^T); [s = fq(s)]; s = s * scaling; s = s + mask; [s = fq(s)]; p = softmax(s, -1); [p = fq(p)]
+template <class R, int TPR, int VPL>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
+softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, size_t rows, int cols, float alpha,
+                  int has_alpha, const uint4 *__restrict__ mask, size_t rows_per_batch, size_t mask_rows,
+                  size_t mask_batch_stride_vec, int flags, const __grid_constant__ typename R::Params params,
+                  const float *__restrict__ scale_pre, const float *__restrict__ scale_mid,
+                  const float *__restrict__ scale_post)
+{
+    const R round(params, stage_table<R>(params));
+    const FqPoint pre = load_point(scale_pre), mid = load_point(scale_mid), post = load_point(scale_post);
+    constexpr int RPC = ROW_THREADS / TPR;  // rows per CTA pass
+    const int lane = threadIdx.x % TPR;
+    const int nvec = cols >> 3;
+    const size_t row_stride = (size_t)gridDim.x * RPC;
+    // every thread of a CTA runs the same number of passes (the long-row reductions contain block barriers)
+    for (size_t row0 = (size_t)blockIdx.x * RPC; row0 < rows; row0 += row_stride) {
+        const size_t row = row0 + threadIdx.x / TPR;
+        const bool live = row < rows;
+        const uint4 *srow = scores + (live ? row : 0) * nvec;
+        const uint4 *mrow = nullptr;
+        if (mask && live) mrow = mask + (row / rows_per_batch) * mask_batch_stride_vec + (row % mask_rows) * (size_t)nvec;
+        float f[VPL][8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int i = lane + TPR * j;
+            if (i < nvec && live) {
+                unpack8(__ldcs(srow + i), f[j]);
+                float m8[8];
+                if (mrow) unpack8(__ldg(mrow + i), m8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float s = f[j][k];
+                    if (flags & FQ_PRE) s = __uint_as_float(fq_elem(round, __float_as_uint(s), pre));
+                    if (has_alpha) s = bf16_round(s * alpha);
+                    if (mrow) s = bf16_round(s + m8[k]);
+                    if (flags & FQ_MID) s = __uint_as_float(fq_elem(round, __float_as_uint(s), mid));
+                    f[j][k] = s;
+                    mx = fmaxf(mx, s);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[j][k] = -INFINITY;
+            }
+        }
+        mx = row_reduce<TPR, true>(mx);
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                f[j][k] = expf(f[j][k] - mx);
+                sum += f[j][k];
+            }
+        sum = row_reduce<TPR, false>(sum);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int i = lane + TPR * j;
+            if (i < nvec && live) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float p = bf16_round(__fdiv_rn(f[j][k], sum));
+                    if (flags & FQ_POST) p = __uint_as_float(fq_elem(round, __float_as_uint(p), post));
+                    f[j][k] = p;
+                }
+                __stcs(probs + row * nvec + i, pack8(f[j]));
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- RMSNorm / LayerNorm
+// TPR threads per row of `cols` (<= TPR * VPL * 8).  kind 0: LlamaRMSNorm (HF modeling_llama.py): n = bf16(x * rsqrt(mean(x^2)
+// + eps)) computed in fp32, y = bf16(weight * n).  kind 1: nn.LayerNorm: y = bf16((x - mean) * rstd * w + b), fp32 inside.
+template <class R, int TPR, int VPL>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
+norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, int cols, int kind,
+               const uint4 *__restrict__ weight, const uint4 *__restrict__ bias, float eps, int flags,
+               const __grid_constant__ typename R::Params params, const float *__restrict__ scale_pre,
+               const float *__restrict__ scale_post)
+{
+    const R round(params, stage_table<R>(params));
+    const FqPoint pre = load_point(scale_pre), post = load_point(scale_post);
+    constexpr int RPC = ROW_THREADS / TPR;
+    const int lane = threadIdx.x % TPR;
+    const int nvec = cols >> 3;
+    const float inv_n = 1.0f / (float)cols;
+    const size_t row_stride = (size_t)gridDim.x * RPC;
+    for (size_t row0 = (size_t)blockIdx.x * RPC; row0 < rows; row0 += row_stride) {
+        const size_t row = row0 + threadIdx.x / TPR;
+        const bool live = row < rows;
+        uint4 v[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int i = lane + TPR * j;
+            v[j] = (i < nvec && live) ? __ldcs(x + row * nvec + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (flags & FQ_PRE) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                float f[8];
+                unpack8(v[j], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(fq_elem(round, __float_as_uint(f[k]), pre));
+                v[j] = pack8(f);
+            }
+        }
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            float f[8];
+            unpack8(v[j], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s1 += f[k];
+                s2 += f[k] * f[k];
+            }
+        }
+        float mean = 0.0f, rstd;
+        if (kind == 0) {
+            rstd = rsqrtf(row_reduce<TPR, false>(s2) * inv_n + eps);
+        } else {
+            mean = row_reduce<TPR, false>(s1) * inv_n;
+            float ss = 0.0f;  // second pass over the registers: sum (x - mean)^2 over the row's real elements
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                if (lane + TPR * j < nvec) {
+                    float f[8];
+                    unpack8(v[j], f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) ss += (f[k] - mean) * (f[k] - mean);
+                }
+            }
+            rstd = rsqrtf(row_reduce<TPR, false>(ss) * inv_n + eps);
+        }
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int i = lane + TPR * j;
+            if (i < nvec && live) {
+                float f[8], w[8], b[8];
+                unpack8(v[j], f);
+                unpack8(__ldg(weight + i), w);
+                if (kind != 0 && bias) unpack8(__ldg(bias + i), b);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float o;
+                    if (kind == 0)
+                        o = bf16_round(w[k] * bf16_round(f[k] * rstd));
+                    else
+                        o = bf16_round((f[k] - mean) * rstd * w[k] + (bias ? b[k] : 0.0f));
+                    if (flags & FQ_POST) o = __uint_as_float(fq_elem(round, __float_as_uint(o), post));
+                    f[k] = o;
+                }
+                __stcs(y + row * nvec + i, pack8(f));
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- activation (x up) + fq, strided rows
+// out[r, c] = fq( bf16( bf16(act(gate[r, c])) * up[r, c] ) )   (up == NULL: no product).  act: QT_ACT_*.
+// HF LlamaMLP: down_proj(act_fn(gate_proj(x)) * up_proj(x)); each op rounds to bf16.
+enum { FACT_NONE = 0, FACT_RELU = 1, FACT_GELU = 2, FACT_SILU = 3 };
+template <class R>
+__global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
+act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, uint4 *__restrict__ out, size_t rows,
+                  int vec_per_row, size_t ld_gate_vec, size_t ld_up_vec, size_t ld_out_vec, int act, int flags,
+                  const __grid_constant__ typename R::Params params, const float *__restrict__ scale_post)
+{
+    const R round(params, stage_table<R>(params));
+    const FqPoint post = load_point(scale_post);
+    const size_t total = rows * (size_t)vec_per_row;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const size_t r = t / vec_per_row, c = t - r * vec_per_row;
+        float g[8], u[8];
+        unpack8(__ldcs(gate + r * ld_gate_vec + c), g);
+        if (up) unpack8(__ldcs(up + r * ld_up_vec + c), u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float a = g[k];
+            if (act == FACT_SILU)
+                a = bf16_round(__fdiv_rn(a, 1.0f + expf(-a)));
+            else if (act == FACT_GELU)
+                a = bf16_round(0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)));
+            else if (act == FACT_RELU)
+                a = fmaxf(a, 0.0f);
+            if (up) a = bf16_round(a * u[k]);
+            if (flags & FQ_POST) a = __uint_as_float(fq_elem(round, __float_as_uint(a), post));
+            g[k] = a;
+        }
+        __stcs(out + r * ld_out_vec + c, pack8(g));
+    }
+}
+
+// ----------------------------------------------------------------------------- rotary embedding + fq
+// HF apply_rotary_pos_emb: x_embed = (x * cos) + (rotate_half(x) * sin), three bf16 ops.  x: [tokens, heads, D] with a
+// token stride (projection output [B*S, heads*D], possibly a slice of a fused QKV buffer); cos/sin: [cos_rows, D],
+// token t uses row t % cos_rows.  Up to two tensors (q and k) per launch.  A thread owns columns [8c, 8c+8) and their
+// partners [8c + D/2, ...).
+struct RopeTensor {
+    const uint4 *x;
+    uint4 *y;
+    size_t ld_x_vec, ld_y_vec;  // token strides, 16-byte vectors
+    int heads;
+};
+template <class R>
+__global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
+rope_fq_kernel(RopeTensor t0, RopeTensor t1, size_t tokens, int head_dim, const uint4 *__restrict__ cos_t,
+               const uint4 *__restrict__ sin_t, size_t cos_rows, int flags,
+               const __grid_constant__ typename R::Params params, const float *__restrict__ scale0,
+               const float *__restrict__ scale1)
+{
+    const R round(params, stage_table<R>(params));
+    const FqPoint p0 = load_point(scale0), p1 = load_point(scale1);
+    const int hv = head_dim >> 4;  // vector pairs per head
+    const int dv = head_dim >> 3;  // vectors per head
+    const size_t work0 = tokens * (size_t)t0.heads * hv, work1 = tokens * (size_t)t1.heads * hv;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < work0 + work1; w += stride) {
+        const bool second = w >= work0;
+        const RopeTensor &t = second ? t1 : t0;
+        const FqPoint &pt = second ? p1 : p0;
+        const size_t i = second ? w - work0 : w;
+        const int c = (int)(i % hv);
+        const size_t th = i / hv;
+        const int h = (int)(th % t.heads);
+        const size_t tok = th / t.heads;
+        const uint4 *xp = t.x + tok * t.ld_x_vec + (size_t)h * dv;
+        const size_t crow = (tok % cos_rows) * dv;
+        float a[8], b[8], ca[8], cb[8], sa[8], sb[8];
+        unpack8(__ldcs(xp + c), a);
+        unpack8(__ldcs(xp + c + hv), b);
+        unpack8(__ldg(cos_t + crow + c), ca);
+        unpack8(__ldg(cos_t + crow + c + hv), cb);
+        unpack8(__ldg(sin_t + crow + c), sa);
+        unpack8(__ldg(sin_t + crow + c + hv), sb);
+        float ra[8], rb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // first half: x1 * cos - x2 * sin (rotate_half gives -x2); second half: x2 * cos + x1 * sin
+            float lo = bf16_round(bf16_round(a[k] * ca[k]) + bf16_round(-b[k] * sa[k]));
+            float hi = bf16_round(bf16_round(b[k] * cb[k]) + bf16_round(a[k] * sb[k]));
+            if (flags & FQ_POST) {
+                lo = __uint_as_float(fq_elem(round, __float_as_uint(lo), pt));
+                hi = __uint_as_float(fq_elem(round, __float_as_uint(hi), pt));
+            }
+            ra[k] = lo;
+            rb[k] = hi;
+        }
+        uint4 *yp = t.y + tok * t.ld_y_vec + (size_t)h * dv;
+        __stcs(yp + c, pack8(ra));
+        __stcs(yp + c + hv, pack8(rb));
+    }
+}
+
+// ----------------------------------------------------------------------------- fq + transpose
+// v: [B, S, H, D] (token stride ld_tok, heads contiguous) -> out [B, H, D, S] contiguous, fake-quantized: the K-major
+// operand of probabilities x values.  One CTA per (b, h, 64 tokens): coalesced loads, fq, padded smem tile, then
+// 128-byte rows of the transposed output.
+constexpr int TR_TOK = 64;
+template <class R>
+__global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
+fq_transpose_kernel(const uint16_t *__restrict__ v, uint16_t *__restrict__ out, int B, int S, int H, int D,
+                    size_t ld_tok, size_t batch_stride, int flags, const __grid_constant__ typename R::Params params,
+                    const float *__restrict__ scale_post)
+{
+    const unsigned char *tab = stage_table<R>(params);
+    const R round(params, tab);
+    const FqPoint post = load_point(scale_post);
+    // tile after the (optional) rounding table in dynamic shared memory: [TR_TOK][D + 2] bf16
+    uint16_t *tile = reinterpret_cast<uint16_t *>(qt_dyn_smem + R::kSmemBytes);
+    const int pitch = D + 2;
+    const int s_tiles = (S + TR_TOK - 1) / TR_TOK;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int job = blockIdx.x; job < B * H * s_tiles; job += gridDim.x) {
+        const int st = job % s_tiles, bh = job / s_tiles, h = bh % H, b = bh / H;
+        const int s0 = st * TR_TOK;
+        const int dvec = D >> 3;
+        __syncthreads();  // previous tile fully written out
+        for (int i = tid; i < TR_TOK * dvec; i += nthr) {
+            const int r = i / dvec, c = i - r * dvec;
+            float f[8];
+            if (s0 + r < S) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(v + (size_t)b * batch_stride + (size_t)(s0 + r) * ld_tok +
+                                                                   (size_t)h * D) + c;
+                unpack8(__ldcs(src), f);
+                if (flags & FQ_POST) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(fq_elem(round, __float_as_uint(f[k]), post));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = 0.0f;
+            }
+            uint32_t *dst = reinterpret_cast<uint32_t *>(tile + r * pitch + c * 8);  // (r * pitch + c * 8) is even
+            const uint4 pk = pack8(f);
+            dst[0] = pk.x;
+            dst[1] = pk.y;
+            dst[2] = pk.z;
+            dst[3] = pk.w;
+        }
+        __syncthreads();
+        // out[b, h, d, s0 + 8 g .. + 8): lane -> (d_sub = lane / 8, g = lane % 8)
+        const bool full = (s0 + TR_TOK <= S) && (S % 8 == 0);
+        for (int i = tid; i < D * (TR_TOK / 8); i += nthr) {
+            const int d = i >> 3, g = i & 7;
+            uint16_t e[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = tile[(g * 8 + k) * pitch + d];
+            uint16_t *dst = out + ((size_t)bh * D + d) * S + s0 + g * 8;
+            if (full) {
+                uint4 o;
+                o.x = e[0] | ((uint32_t)e[1] << 16);
+                o.y = e[2] | ((uint32_t)e[3] << 16);
+                o.z = e[4] | ((uint32_t)e[5] << 16);
+                o.w = e[6] | ((uint32_t)e[7] << 16);
+                *reinterpret_cast<uint4 *>(dst) = o;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (s0 + g * 8 + k < S) dst[k] = e[k];
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- launch helpers
+// Rounding engines of the fused kernels: the binade-constant table for fp / posit formats (the caller always has it:
+// qt_lut_build_host), the direct logic for intN / uintN and the identity ("bfloat16": the op without fake quant).
+template <class Fn>
+int dispatch_fused(const QtRound &P, const void *lut, Fn &&fn)
+{
+    if (P.kind == QTR_INT || P.kind == QTR_IDENTITY) return dispatch_direct_small(P, fn);
+    QtLutCfg cfg;
+    if (!lut || qt_lut_config(P, &cfg) != QT_OK) {
+        qt_set_error("qt_b200 fused ops: fp / posit formats need the device table from qt_lut_build_host(fmt)");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    TableParams tp;
+    tp.cfg = cfg;
+    if (reinterpret_cast<uintptr_t>(lut) & 15u) {
+        qt_set_error("qt_b200: lut must be 16-byte aligned");
+        return QT_ERR_UNALIGNED;
+    }
+    tp.table = static_cast<const QtLutEntry *>(lut);
+    if (cfg.mx_band)
+        fn(RounderTag<TableRounder<true, true>>{}, tp);
+    else if (cfg.clamp_bits != 0x7FFFFFFFu)
+        fn(RounderTag<TableRounder<true, false>>{}, tp);
+    else
+        fn(RounderTag<TableRounder<false, false>>{}, tp);
+    return QT_OK;
+}
+int check_common(const char *fn, const qt_format_t *fmt, QtRound *P)
+{
+    if (!fmt) {
+        qt_set_error("%s: fmt is NULL", fn);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    int rc = qt_make_round(fmt, P);
+    if (rc != QT_OK) return rc;
+    if (num_sms() == 0) return no_device();
+    return QT_OK;
+}
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int finish(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return QT_OK;
+}
+
+}  // namespace
+
+extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_t cols, float alpha, const void *mask,
+                             size_t rows_per_batch, size_t mask_rows, size_t mask_batches, int fq_points,
+                             const qt_format_t *fmt, const float *scale_pre, const float *scale_mid,
+                             const float *scale_post, const void *lut, void *stream)
+{
+    QtRound P;
+    int rc = check_common("qt_softmax_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    if (rows == 0 || cols == 0) return QT_OK;
+    if (!scores || !probs || cols % 8 || cols > 4096 || !aligned16(scores) || !aligned16(probs) ||
+        (mask && (!aligned16(mask) || mask_rows == 0 || rows_per_batch == 0 || mask_batches == 0))) {
+        qt_set_error("qt_softmax_fq: needs 16-byte aligned contiguous bf16 rows, cols %% 8 == 0, cols <= 4096 (got %zu)",
+                     cols);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    const size_t mask_batch_stride_vec = mask_batches > 1 ? mask_rows * (cols / 8) : 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int has_alpha = alpha != 1.0f;
+    rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
+        using R = typename decltype(tag)::type;
+#define QT_SOFTMAX_LAUNCH(TPR, VPL)                                                                                  \
+    do {                                                                                                             \
+        const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                                  \
+        allow_smem<softmax_fq_kernel<R, TPR, VPL>>(R::kSmemBytes);                                                   \
+        softmax_fq_kernel<R, TPR, VPL><<<grid_for(ctas, ROW_MIN_CTAS), ROW_THREADS, R::kSmemBytes, st>>>(            \
+            static_cast<const uint4 *>(scores), static_cast<uint4 *>(probs), rows, (int)cols, alpha, has_alpha,      \
+            static_cast<const uint4 *>(mask), rows_per_batch, mask_rows, mask_batch_stride_vec, fq_points, params,   \
+            scale_pre, scale_mid, scale_post);                                                                       \
+    } while (0)
+        if (cols <= 256)
+            QT_SOFTMAX_LAUNCH(32, 1);
+        else if (cols <= 512)
+            QT_SOFTMAX_LAUNCH(32, 2);
+        else if (cols <= 1024)
+            QT_SOFTMAX_LAUNCH(128, 1);
+        else if (cols <= 2048)
+            QT_SOFTMAX_LAUNCH(128, 2);
+        else
+            QT_SOFTMAX_LAUNCH(128, 4);
+#undef QT_SOFTMAX_LAUNCH
+    });
+    if (rc != QT_OK) return rc;
+    return finish("softmax_fq kernel launch");
+}
+
+extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int kind, const void *weight,
+                          const void *bias, float eps, int fq_points, const qt_format_t *fmt, const float *scale_pre,
+                          const float *scale_post, const void *lut, void *stream)
+{
+    QtRound P;
+    int rc = check_common("qt_norm_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    if (rows == 0 || cols == 0) return QT_OK;
+    if (!x || !y || !weight || cols % 8 || cols > 8192 || (kind != 0 && kind != 1) || !aligned16(x) || !aligned16(y) ||
+        !aligned16(weight) || (bias && !aligned16(bias))) {
+        qt_set_error("qt_norm_fq: needs 16-byte aligned contiguous bf16 rows, cols %% 8 == 0, cols <= 8192 (got %zu), "
+                     "kind 0 (RMSNorm) or 1 (LayerNorm)", cols);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
+        using R = typename decltype(tag)::type;
+#define QT_NORM_LAUNCH(TPR, VPL)                                                                                 \
+    do {                                                                                                         \
+        const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                              \
+        allow_smem<norm_fq_kernel<R, TPR, VPL>>(R::kSmemBytes);                                                  \
+        norm_fq_kernel<R, TPR, VPL><<<grid_for(ctas, ROW_MIN_CTAS), ROW_THREADS, R::kSmemBytes, st>>>(           \
+            static_cast<const uint4 *>(x), static_cast<uint4 *>(y), rows, (int)cols, kind,                       \
+            static_cast<const uint4 *>(weight), static_cast<const uint4 *>(bias), eps, fq_points, params,        \
+            scale_pre, scale_post);                                                                              \
+    } while (0)
+        if (cols <= 256)
+            QT_NORM_LAUNCH(32, 1);
+        else if (cols <= 512)
+            QT_NORM_LAUNCH(32, 2);
+        else if (cols <= 1024)
+            QT_NORM_LAUNCH(128, 1);
+        else if (cols <= 2048)
+            QT_NORM_LAUNCH(128, 2);
+        else if (cols <= 4096)
+            QT_NORM_LAUNCH(128, 4);
+        else
+            QT_NORM_LAUNCH(128, 8);
+#undef QT_NORM_LAUNCH
+    });
+    if (rc != QT_OK) return rc;
+    return finish("norm_fq kernel launch");
+}
+
+extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t rows, size_t cols, size_t ld_gate,
+                             size_t ld_up, size_t ld_out, int activation, int fq_points, const qt_format_t *fmt,
+                             const float *scale_post, const void *lut, void *stream)
+{
+    QtRound P;
+    int rc = check_common("qt_act_mul_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    if (rows == 0 || cols == 0) return QT_OK;
+    if (!gate || !out || cols % 8 || ld_gate % 8 || ld_out % 8 || (up && ld_up % 8) || !aligned16(gate) ||
+        !aligned16(out) || (up && !aligned16(up)) || activation < FACT_NONE || activation > FACT_SILU) {
+        qt_set_error("qt_act_mul_fq: needs 16-byte aligned bf16 rows (cols, row strides multiples of 8) and a QT_ACT_* "
+                     "activation");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
+        using R = typename decltype(tag)::type;
+        const size_t total = rows * (cols / 8);
+        const unsigned grid = grid_for((total + EW_THREADS - 1) / EW_THREADS, EW_MIN_CTAS * 2);
+        allow_smem<act_mul_fq_kernel<R>>(R::kSmemBytes);
+        act_mul_fq_kernel<R><<<grid, EW_THREADS, R::kSmemBytes, st>>>(
+            static_cast<const uint4 *>(gate), static_cast<const uint4 *>(up), static_cast<uint4 *>(out), rows,
+            (int)(cols / 8), ld_gate / 8, ld_up / 8, ld_out / 8, activation, fq_points, params, scale_post);
+    });
+    if (rc != QT_OK) return rc;
+    return finish("act_mul_fq kernel launch");
+}
+
+extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_out, int q_heads, const void *k,
+                          void *k_out, size_t ld_k, size_t ld_k_out, int k_heads, size_t tokens, int head_dim,
+                          const void *cos_table, const void *sin_table, size_t cos_rows, int fq_points,
+                          const qt_format_t *fmt, const float *scale_q, const float *scale_k, const void *lut,
+                          void *stream)
+{
+    QtRound P;
+    int rc = check_common("qt_rope_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    if (tokens == 0) return QT_OK;
+    if (!q || !q_out || !cos_table || !sin_table || cos_rows == 0 || head_dim % 16 || head_dim <= 0 || ld_q % 8 ||
+        ld_q_out % 8 || q_heads < 1 || !aligned16(q) || !aligned16(q_out) || !aligned16(cos_table) ||
+        !aligned16(sin_table) ||
+        (k && (!k_out || ld_k % 8 || ld_k_out % 8 || k_heads < 1 || !aligned16(k) || !aligned16(k_out)))) {
+        qt_set_error("qt_rope_fq: needs 16-byte aligned bf16 tensors, head_dim %% 16 == 0, token strides %% 8 == 0");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    RopeTensor t0 = {static_cast<const uint4 *>(q), static_cast<uint4 *>(q_out), ld_q / 8, ld_q_out / 8, q_heads};
+    RopeTensor t1 = {static_cast<const uint4 *>(k), static_cast<uint4 *>(k_out), ld_k / 8, ld_k_out / 8,
+                     k ? k_heads : 0};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
+        using R = typename decltype(tag)::type;
+        const size_t total = tokens * (size_t)(t0.heads + t1.heads) * (head_dim / 16);
+        const unsigned grid = grid_for((total + EW_THREADS - 1) / EW_THREADS, EW_MIN_CTAS * 2);
+        allow_smem<rope_fq_kernel<R>>(R::kSmemBytes);
+        rope_fq_kernel<R><<<grid, EW_THREADS, R::kSmemBytes, st>>>(
+            t0, t1, tokens, head_dim, static_cast<const uint4 *>(cos_table), static_cast<const uint4 *>(sin_table),
+            cos_rows, fq_points, params, scale_q, scale_k);
+    });
+    if (rc != QT_OK) return rc;
+    return finish("rope_fq kernel launch");
+}
+
+extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int heads, int head_dim, size_t ld_tok,
+                               size_t batch_stride, int fq_points, const qt_format_t *fmt, const float *scale_post,
+                               const void *lut, void *stream)
+{
+    QtRound P;
+    int rc = check_common("qt_fq_transpose", fmt, &P);
+    if (rc != QT_OK) return rc;
+    if (batch <= 0 || seq <= 0 || heads <= 0) return QT_OK;
+    if (!v || !out || head_dim % 8 || head_dim <= 0 || head_dim > 256 || ld_tok % 8 || batch_stride % 8 ||
+        !aligned16(v) || !aligned16(out)) {
+        qt_set_error("qt_fq_transpose: needs 16-byte aligned bf16 tensors, head_dim %% 8 == 0 (<= 256), strides %% 8 == 0");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
+        using R = typename decltype(tag)::type;
+        const size_t jobs = (size_t)batch * heads * ((seq + TR_TOK - 1) / TR_TOK);
+        const size_t smem = R::kSmemBytes + (size_t)TR_TOK * (head_dim + 2) * 2;
+        const unsigned grid = grid_for(jobs, EW_MIN_CTAS * 2);
+        allow_smem<fq_transpose_kernel<R>>(R::kSmemBytes + (size_t)TR_TOK * (256 + 2) * 2);  // the largest tile
+        fq_transpose_kernel<R><<<grid, EW_THREADS, smem, st>>>(static_cast<const uint16_t *>(v),
+                                                                static_cast<uint16_t *>(out), batch, seq, heads,
+                                                                head_dim, ld_tok, batch_stride, fq_points, params,
+                                                                scale_post);
+    });
+    if (rc != QT_OK) return rc;
+    return finish("fq_transpose kernel launch");
+}

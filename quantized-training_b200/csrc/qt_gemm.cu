@@ -11,17 +11,21 @@
 // Epilogue (the paper's fusion levels, README table / SURVEY App. B): * alpha (attention scaling), + bias,
 // activation (ReLU / GELU-erf / SiLU), + residual, then one rounding to bf16.
 //
-// Kernel shape (one CTA per SM, persistent over output tiles, 192 threads):
-//   warp 0      TMA producer: 128 x 128-byte A tile + 256 x 128-byte B tile per k-block, 128-byte swizzle
+// Kernel shape (one CTA per SM, persistent over output tiles, 320 threads):
+//   warp 0      TMA producer: 128 x 128-byte A tile + block_n x 128-byte B tile per k-block, 128-byte swizzle
 //   warp 1      allocates TMEM (512 columns = two 128 x 256 fp32 accumulators); one lane issues tcgen05.mma
-//               (M = 128, N = 256, K = 32 bytes per instruction, 4 per k-block) and commits to mbarriers
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> registers -> math -> 64-byte stores,
-//               overlapped with the MMAs of the next tile through the second accumulator
-// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+//               (M = 128, N = block_n, K = 32 bytes per instruction, 4 per k-block) and commits to mbarriers
+//   warps 2-9   epilogue: tcgen05.ld (32 lanes x 64 columns) -> registers -> fp32 math -> bf16 -> swizzled smem
+//               -> TMA store of 32 x 64 boxes (full 128-byte rows), overlapped with the MMAs of the next tile
+//               through the second accumulator
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), bulk-store groups.
+// block_n (64 / 128 / 256) is chosen per problem on the host so that short-K batched products (attention
+// scores) and small-N layers fill the 148 SMs.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "qt_internal.h"
@@ -29,29 +33,33 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_N = 256;
+constexpr int MAX_BLOCK_N = 256;  // the tile width is a launch parameter: 64, 128 or 256 columns (see pick_block_n)
 constexpr int ROW_BYTES = 128;  // one k-block of a row: 64 bf16 or 128 fp8, = the swizzle span
 constexpr int MMA_K_BYTES = 32;  // K extent of one tcgen05.mma in bytes (16 bf16 / 32 fp8)
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * ROW_BYTES;  // 32 KB
+constexpr int B_STAGE_BYTES = MAX_BLOCK_N * ROW_BYTES;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter, splitting the tile's 64-column chunks between them
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_CHUNK_COLS = 64;                      // one TMA store box: 32 rows x 64 bf16 (128-byte rows)
+constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK_COLS * 2;  // 4 KB per epilogue warp
+constexpr size_t SMEM_BYTES =
+    (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_BUF_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3 };
 
 struct GemmParams {
-    int64_t batch, M, N, K;  // K in elements
+    int64_t M, N, K;         // K in elements
+    uint32_t batch_inner;    // batch index b = outer * batch_inner + inner (e.g. outer = sequence, inner = head)
     int k_blocks;            // ceil(K * elem_bytes / 128)
-    int64_t m_tiles, n_tiles, num_tiles;
-    __nv_bfloat16 *C;
-    int64_t ldc, strideC;
+    uint32_t m_tiles, n_tiles, num_tiles;  // < 2^31 (checked by the launcher)
+    int block_n;             // 64, 128 or 256
+    int debug;               // QT_GEMM_DEBUG bit mask (timing experiments only; results are wrong when set)
     const __nv_bfloat16 *bias;      // [N] or null
     const __nv_bfloat16 *residual;  // same layout as C, or null
-    int64_t ldr, strideR;
+    int64_t ldr, strideR_inner, strideR_outer;
     float alpha;
     int act;
     uint32_t idesc;
@@ -90,12 +98,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         if (spins > (1u << 24)) __trap();  // try_wait itself blocks for a while; this is many seconds
     }
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
             "r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -122,7 +131,8 @@ __device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t desc_a, ui
             : "memory");
 }
 // 32 TMEM lanes (one per thread of the warp) x 32 consecutive 32-bit columns
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
+// (asynchronous: the registers are valid after tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t *v)
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -134,7 +144,6 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // K-major operand tile in shared memory, 128-byte rows, 128-byte swizzle (what TMA wrote):
@@ -152,25 +161,42 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
     return d;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act)
+// Compile-time activation: a run-time switch inside the 64-way unrolled epilogue made ~77 KB of SASS whose
+// skipped blocks still thrashed the instruction cache (measured: 2400 cycles per 64-column chunk for a plain store).
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v)
 {
-    switch (act) {
-    case ACT_RELU: return fmaxf(v, 0.0f);
-    case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-    case ACT_SILU: return v / (1.0f + __expf(-v));
-    default: return v;
-    }
+    if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    if (ACT == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+    return v;
 }
 
+// Timeline of CTA 0 (QT_GEMM_DEBUG & 32): [role][event] -> clock64.  Roles: 0 producer (after the empty wait of
+// each k-block), 1 MMA (after the tmem_empty wait, after each full wait), 2 epilogue warp 2 (after the tmem_full wait,
+// after the chunk's store was issued).
+// Compiled only with -DQT_GEMM_TRACE (scripts/bmm_trace.py); the product build has no trace code.
+#ifdef QT_GEMM_TRACE
+__device__ long long qt_gemm_trace[3][256];
+__device__ __forceinline__ void trace(const GemmParams &p, int role, int &slot)
+{
+    if ((p.debug & 32) && blockIdx.x == 0 && slot < 256) qt_gemm_trace[role][slot++] = clock64();
+}
+#else
+__device__ __forceinline__ void trace(const GemmParams &, int, int &) {}
+#endif
+
 // ----------------------------------------------------------------------------- kernel
-template <bool FP8>
+// ACT: activation; AUX: the problem has a bias and / or a residual (pointers checked at run time)
+template <bool FP8, int ACT, bool AUX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ GemmParams p)
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p)
 {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;         // EPI_WARPS x 4 KB store staging
+    const uint32_t bars = epi_base + EPI_WARPS * EPI_BUF_BYTES;
     // barrier slots (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -179,6 +205,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int block_n = p.block_n;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -187,9 +214,12 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), EPI_THREADS);
+            mbar_init(tmem_empty_bar(a), EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
@@ -206,18 +236,21 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0;
+            int stage = 0, tslot = 0;
             uint32_t phase = 0;
-            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int64_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
-                const int64_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
+            const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES);
+            for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const uint32_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
+                const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
+                const int bi = (int)(b % p.batch_inner), bo = (int)(b / p.batch_inner);
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+                    trace(p, 0, tslot);
+                    mbar_arrive_expect_tx(full_bar(stage), stage_tx);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     const int kcoord = kb * (FP8 ? ROW_BYTES : ROW_BYTES / 2);
-                    tma_load_3d(sa, &map_a, full_bar(stage), kcoord, (int)(mt * BLOCK_M), (int)b);
-                    tma_load_3d(sb, &map_b, full_bar(stage), kcoord, (int)(nt * BLOCK_N), (int)b);
+                    tma_load_4d(sa, &map_a, full_bar(stage), kcoord, (int)(mt * BLOCK_M), bi, bo);
+                    tma_load_4d(sb, &map_b, full_bar(stage), kcoord, (int)(nt * block_n), bi, bo);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -230,14 +263,16 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int acc = 0;
+            int acc = 0, tslot = 0;
             uint32_t acc_phase = 0;
-            for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+                trace(p, 1, tslot);
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)acc * BLOCK_N;
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+                    trace(p, 1, tslot);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
@@ -261,72 +296,117 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-        const int quarter = warp & 3;
-        int acc = 0;
+        // ===== epilogue warps 2..9 =====
+        // A warp may touch only the TMEM lanes of its quarter (warp id % 4); the two warps of a quarter take
+        // alternate 64-column chunks.  Per chunk: 2 x tcgen05.ld (thread = row, registers = columns) -> fp32 math
+        // -> bf16 -> the warp's 4 KB staging buffer in the 128-byte-swizzle layout -> one TMA store of the
+        // 32 x 64 box (full 128-byte rows in HBM; rows / columns outside C are clipped by the TMA unit).
+        const int e = warp - 2;
+        const int quarter = warp & 3, half = e >> 2;
+        const uint32_t buf = epi_base + (uint32_t)e * EPI_BUF_BYTES;
+        const int chunks = block_n / EPI_CHUNK_COLS;
+        int acc = 0, tslot = 0;
         uint32_t acc_phase = 0;
-        for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int64_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
-            const int64_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
-            const int64_t row = mt * BLOCK_M + quarter * 32 + lane;
+        for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const uint32_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
+            const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
+            const int bi = (int)(b % p.batch_inner), bo = (int)(b / p.batch_inner);
+            const int64_t row0 = (int64_t)mt * BLOCK_M + quarter * 32;
+            const int64_t row = row0 + lane;
             mbar_wait(tmem_full_bar(acc), acc_phase);
+            if (warp == 2 && lane == 0) trace(p, 2, tslot);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * BLOCK_N;
-            __nv_bfloat16 *crow = p.C + b * p.strideC + row * p.ldc;
-            const __nv_bfloat16 *rrow = p.residual ? p.residual + b * p.strideR + row * p.ldr : nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c * 32, v);  // warp-collective: every lane participates
-                const int64_t n0 = nt * BLOCK_N + c * 32;
-                if (row < p.M && n0 < p.N) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
+            const __nv_bfloat16 *rrow =
+                (AUX && p.residual && row < p.M)
+                    ? p.residual + (int64_t)bo * p.strideR_outer + (int64_t)bi * p.strideR_inner + row * p.ldr
+                    : nullptr;
+            if (half >= chunks) {  // 64-column tiles: the second warp of the quarter has no chunk, only the hand-back
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            }
+            for (int c = half; c < chunks; c += 2) {
+                uint32_t v[64];
+                tmem_ld_32x32_nowait(taddr + c * EPI_CHUNK_COLS, v);
+                tmem_ld_32x32_nowait(taddr + c * EPI_CHUNK_COLS + 32, v + 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T1: accumulator chunk in registers
+                if (c + 2 >= chunks) {  // last TMEM read of this warp for this tile: hand the accumulator back
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                }
+                const int64_t n0 = (int64_t)nt * block_n + c * EPI_CHUNK_COLS;
+                uint32_t packed[32];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {  // four 16-byte groups of 8 columns
-                        const int64_t n = n0 + g * 8;
-                        if (n >= p.N) break;  // N % 8 == 0: groups are entirely in or out
-                        float f[8];
+                for (int g = 0; g < 8; ++g) {  // eight 16-byte groups of 8 columns
+                    const int64_t n = n0 + g * 8;
+                    const bool in_n = n < p.N;  // N % 8 == 0: groups are entirely in or out
+                    float f[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) * p.alpha;
-                        if (p.bias) {
-                            const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(p.bias + n));
-                            const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                f[2 * j] += __uint_as_float(w[j] << 16);
-                                f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-                            }
-                        }
-                        if (p.act != ACT_NONE) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
-                        }
-                        if (rrow) {
-                            const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + n));
-                            const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                f[2 * j] += __uint_as_float(w[j] << 16);
-                                f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-                            }
-                        }
-                        uint4 o;
-                        uint32_t *ow = reinterpret_cast<uint32_t *>(&o);
+                    for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) * p.alpha;
+                    if (AUX && p.bias && in_n) {
+                        const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(p.bias + n));
+                        const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                            ow[j] = *reinterpret_cast<const uint32_t *>(&pk);
+                            f[2 * j] += __uint_as_float(w[j] << 16);
+                            f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
                         }
-                        *reinterpret_cast<uint4 *>(crow + n) = o;
+                    }
+                    if (ACT != ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(f[j]);
+                    }
+                    if (AUX && rrow && in_n) {
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + n));
+                        const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            f[2 * j] += __uint_as_float(w[j] << 16);
+                            f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        packed[g * 4 + j] = *reinterpret_cast<const uint32_t *>(&pk);
                     }
                 }
+                if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T2: math done
+                // the previous store from this buffer must have finished READING it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+                if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T3: staging buffer free
+                const uint32_t rowbuf = buf + (uint32_t)lane * 128u;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const uint32_t dst = rowbuf + (uint32_t)((g ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[g * 4]),
+                                 "r"(packed[g * 4 + 1]), "r"(packed[g * 4 + 2]), "r"(packed[g * 4 + 3])
+                                 : "memory");
+                }
+                if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T4: staged
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
+                __syncwarp();
+                if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T5: fenced
+                if (lane == 0 && n0 < p.N && row0 < p.M) {
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                            reinterpret_cast<uint64_t>(&map_c)),
+                        "r"(buf), "r"((int)n0), "r"((int)row0), "r"(bi), "r"(bo)
+                        : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (warp == 2 && lane == 0) trace(p, 2, tslot);
             }
-            tcgen05_fence_before();
-            mbar_arrive(tmem_empty_bar(acc));
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
     }
 
     tcgen05_fence_before();
@@ -356,27 +436,32 @@ EncodeTiledFn encode_tiled()
     return fn;
 }
 
-// [batch, rows, K] K-major operand: dims {K, rows, batch}, box {128 bytes of K, box_rows, 1}, 128-byte swizzle.
-// Out-of-bounds elements (K tail, row tail) are filled with zeros by TMA.
-int make_operand_map(CUtensorMap *map, const void *ptr, bool fp8, int64_t K, int64_t rows, int64_t batch, int64_t ld,
-                     int64_t stride, int box_rows)
+// [outer, inner, rows, cols] tensor with a unit-stride last axis and arbitrary (16-byte aligned) strides on the other
+// three: dims {cols, rows, inner, outer}, box {box_cols, box_rows, 1, 1}, 128-byte swizzle (box_cols * esz == 128).
+// Loads: out-of-bounds elements (K tail, row tail) are filled with zeros.  Stores: they are not written.
+int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int64_t rows, int64_t inner, int64_t outer,
+             int64_t ld, int64_t stride_inner, int64_t stride_outer, int box_rows)
 {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) {
         qt_set_error("cuTensorMapEncodeTiled is not available from this driver");
         return QT_ERR_CUDA;
     }
-    const int esz = fp8 ? 1 : 2;
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)(batch > 1 ? stride : rows * ld) * esz};
-    cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)box_rows, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+    const int esz = one_byte ? 1 : 2;
+    // size-1 axes never move: give them a harmless, valid stride
+    if (inner <= 1) stride_inner = rows * ld;
+    if (outer <= 1) stride_outer = (inner <= 1 ? rows * ld : inner * stride_inner);
+    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)stride_inner * esz, (cuuint64_t)stride_outer * esz};
+    cuuint32_t box[4] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, one_byte ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        qt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (K=%lld rows=%lld batch=%lld ld=%lld)", (int)r,
-                     (long long)K, (long long)rows, (long long)batch, (long long)ld);
+        qt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld batch=%lldx%lld ld=%lld "
+                     "strides=%lld,%lld)", (int)r, (long long)cols, (long long)rows, (long long)outer, (long long)inner,
+                     (long long)ld, (long long)stride_inner, (long long)stride_outer);
         return QT_ERR_INVALID_ARGUMENT;
     }
     return QT_OK;
@@ -385,40 +470,92 @@ int make_operand_map(CUtensorMap *map, const void *ptr, bool fp8, int64_t K, int
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D = F32 [4,6) = 1;
 // A/B format [7,10) / [10,13): kind::f16 BF16 = 1, kind::f8f6f4 E4M3 = 0 / E5M2 = 1; both K-major;
 // N >> 3 at [17,23); M >> 4 at [24,29).
-uint32_t make_idesc(int a_fmt, int b_fmt)
+uint32_t make_idesc(int a_fmt, int b_fmt, int block_n)
 {
-    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(block_n >> 3) << 17) |
            ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// Tile width.  The persistent grid runs ceil(tiles / SMs) rounds; a round costs the larger of the tile's MMA time
+// and its epilogue time, plus a per-tile hand-over.  Constants measured on B200 (scripts/bmm_probe.py):
+// an MMA instruction takes N/2 cycles at N = 256 but never less than ~96 (narrow tiles are bound by the
+// shared-memory reads of the A operand), the epilogue ~11.3 cycles per output column of a 128-row tile.
+int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms)
+{
+    const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    int best = MAX_BLOCK_N;
+    double best_cost = 0.0;
+    for (int bn = MAX_BLOCK_N; bn >= 64; bn >>= 1) {
+        const int64_t tiles = m_tiles * ((N + bn - 1) / bn) * batch;
+        const double rounds = (double)((tiles + sms - 1) / sms);
+        const double mma = (double)k_blocks * 4.0 * (bn / 2.0 > 96.0 ? bn / 2.0 : 96.0);
+        const double epi = 11.3 * bn;
+        const double cost = rounds * ((mma > epi ? mma : epi) + 500.0) + epi;
+        if (bn == MAX_BLOCK_N || cost < best_cost * 0.97) {
+            best = bn;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
+template <bool FP8, int ACT, bool AUX>
+void launch_variant(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
+                    const CUtensorMap &map_c, const GemmParams &p)
+{
+    static bool done[64] = {};
+    if (dev >= 64 || !done[dev]) {
+        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES);
+        if (dev < 64) done[dev] = true;
+    }
+    qt_gemm_kernel<FP8, ACT, AUX><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
 }
 
 }  // namespace
 
-extern "C" int qt_gemm_nt(const void *A, const void *B, void *C, int operand_type, int64_t batch, int64_t M, int64_t N,
-                          int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
-                          int64_t strideC, float alpha, const void *bias, int activation, const void *residual,
-                          int64_t ldr, int64_t strideR, void *stream)
+#ifdef QT_GEMM_TRACE
+extern "C" int qt_gemm_debug_trace(long long *host_out)
 {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host_out, qt_gemm_trace, sizeof(long long) * 3 * 256) == cudaSuccess ? QT_OK : QT_ERR_CUDA;
+}
+#endif
+
+extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
+{
+    if (!d) {
+        qt_set_error("qt_gemm_nt_ex: NULL descriptor");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    const int operand_type = d->operand_type;
     const bool fp8 = operand_type != QT_GEMM_BF16;
     if (operand_type < QT_GEMM_BF16 || operand_type > QT_GEMM_E5M2_E4M3) {
         qt_set_error("qt_gemm_nt: unknown operand_type %d", operand_type);
         return QT_ERR_INVALID_ARGUMENT;
     }
-    if (batch < 1 || M < 1 || N < 1 || K < 1 || !A || !B || !C) {
-        qt_set_error("qt_gemm_nt: empty problem or NULL pointer (batch=%lld M=%lld N=%lld K=%lld)", (long long)batch,
-                     (long long)M, (long long)N, (long long)K);
+    const int64_t M = d->M, N = d->N, K = d->K, inner = d->batch_inner, outer = d->batch_outer;
+    if (inner < 1 || outer < 1 || M < 1 || N < 1 || K < 1 || !d->A || !d->B || !d->C) {
+        qt_set_error("qt_gemm_nt: empty problem or NULL pointer (batch=%lldx%lld M=%lld N=%lld K=%lld)",
+                     (long long)outer, (long long)inner, (long long)M, (long long)N, (long long)K);
         return QT_ERR_INVALID_ARGUMENT;
     }
     const int esz = fp8 ? 1 : 2;
     const int64_t k_align = 16 / esz;
     auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0; };
-    if (lda % k_align || ldb % k_align || strideA % k_align || strideB % k_align || N % 8 || ldc % 8 || strideC % 8 ||
-        misaligned(A) || misaligned(B) || misaligned(C) || (bias && misaligned(bias)) ||
-        (residual && (misaligned(residual) || ldr % 8 || strideR % 8))) {
-        qt_set_error("qt_gemm_nt: operands need 16-byte aligned bases and leading dimensions, N %% 8 == 0");
+    const bool bad_ab = d->lda % k_align || d->ldb % k_align || (inner > 1 && (d->strideA_inner % k_align ||
+                        d->strideB_inner % k_align)) || (outer > 1 && (d->strideA_outer % k_align ||
+                        d->strideB_outer % k_align));
+    const bool bad_c = N % 8 || d->ldc % 8 || (inner > 1 && d->strideC_inner % 8) || (outer > 1 && d->strideC_outer % 8);
+    const bool bad_r = d->residual && (misaligned(d->residual) || d->ldr % 8 || (inner > 1 && d->strideR_inner % 8) ||
+                                       (outer > 1 && d->strideR_outer % 8));
+    if (bad_ab || bad_c || bad_r || misaligned(d->A) || misaligned(d->B) || misaligned(d->C) ||
+        (d->bias && misaligned(d->bias))) {
+        qt_set_error("qt_gemm_nt: operands need 16-byte aligned bases, leading dimensions and batch strides, N %% 8 == 0");
         return QT_ERR_UNALIGNED;
     }
-    if (activation < ACT_NONE || activation > ACT_SILU) {
-        qt_set_error("qt_gemm_nt: unknown activation %d", activation);
+    if (d->activation < ACT_NONE || d->activation > ACT_SILU) {
+        qt_set_error("qt_gemm_nt: unknown activation %d", d->activation);
         return QT_ERR_INVALID_ARGUMENT;
     }
     int dev = 0, sms = 0;
@@ -427,60 +564,107 @@ extern "C" int qt_gemm_nt(const void *A, const void *B, void *C, int operand_typ
         qt_set_error("qt_b200: no usable CUDA device (there is no CPU fallback)");
         return QT_ERR_CUDA;
     }
-    CUtensorMap map_a, map_b;
-    int rc = make_operand_map(&map_a, A, fp8, K, M, batch, lda, strideA, BLOCK_M);
-    if (rc != QT_OK) return rc;
-    rc = make_operand_map(&map_b, B, fp8, K, N, batch, ldb, strideB, BLOCK_N);
-    if (rc != QT_OK) return rc;
-
+    const int64_t batch = inner * outer;
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.batch = batch;
     p.M = M;
     p.N = N;
     p.K = K;
+    p.batch_inner = (uint32_t)inner;
     p.k_blocks = (int)((K * esz + ROW_BYTES - 1) / ROW_BYTES);
-    p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    p.n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-    p.num_tiles = p.m_tiles * p.n_tiles * batch;
-    p.C = static_cast<__nv_bfloat16 *>(C);
-    p.ldc = ldc;
-    p.strideC = strideC;
-    p.bias = static_cast<const __nv_bfloat16 *>(bias);
-    p.residual = static_cast<const __nv_bfloat16 *>(residual);
-    p.ldr = ldr;
-    p.strideR = strideR;
-    p.alpha = alpha;
-    p.act = activation;
+    p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms);
+    if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
+        p.debug = atoi(dbg);
+        if (p.debug & 4) p.block_n = 128;
+        if (p.debug & 8) p.block_n = 64;
+        if (p.debug & 16) p.block_n = 256;
+    }
+    const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + p.block_n - 1) / p.block_n;
+    if (m_tiles * n_tiles * batch >= (int64_t)1 << 31 || M >= (int64_t)1 << 31 || N >= (int64_t)1 << 31 ||
+        inner >= (int64_t)1 << 31 || outer >= (int64_t)1 << 31) {
+        qt_set_error("qt_gemm_nt: problem too large (%lld tiles)", (long long)(m_tiles * n_tiles * batch));
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    p.m_tiles = (uint32_t)m_tiles;
+    p.n_tiles = (uint32_t)n_tiles;
+    p.num_tiles = (uint32_t)(m_tiles * n_tiles * batch);
+
+    CUtensorMap map_a, map_b, map_c;
+    int rc = make_map(&map_a, d->A, fp8, K, M, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, BLOCK_M);
+    if (rc != QT_OK) return rc;
+    rc = make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n);
+    if (rc != QT_OK) return rc;
+    rc = make_map(&map_c, d->C, false, N, M, inner, outer, d->ldc, d->strideC_inner, d->strideC_outer, 32);
+    if (rc != QT_OK) return rc;
+
+    p.bias = static_cast<const __nv_bfloat16 *>(d->bias);
+    p.residual = static_cast<const __nv_bfloat16 *>(d->residual);
+    p.ldr = d->ldr;
+    p.strideR_inner = d->strideR_inner;
+    p.strideR_outer = d->strideR_outer;
+    p.alpha = d->alpha;
+    p.act = d->activation;
     switch (operand_type) {
-    case QT_GEMM_BF16: p.idesc = make_idesc(1, 1); break;
-    case QT_GEMM_E4M3: p.idesc = make_idesc(0, 0); break;
-    case QT_GEMM_E5M2: p.idesc = make_idesc(1, 1); break;
-    case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1); break;
-    default: p.idesc = make_idesc(1, 0); break;  // QT_GEMM_E5M2_E4M3
+    case QT_GEMM_BF16: p.idesc = make_idesc(1, 1, p.block_n); break;
+    case QT_GEMM_E4M3: p.idesc = make_idesc(0, 0, p.block_n); break;
+    case QT_GEMM_E5M2: p.idesc = make_idesc(1, 1, p.block_n); break;
+    case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1, p.block_n); break;
+    default: p.idesc = make_idesc(1, 0, p.block_n); break;  // QT_GEMM_E5M2_E4M3
     }
-    const unsigned grid = (unsigned)(p.num_tiles < sms ? p.num_tiles : sms);
+    const unsigned grid = p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e;
-    if (fp8) {
-        static bool done[64] = {};
-        if (dev >= 64 || !done[dev]) {
-            cudaFuncSetAttribute(qt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-            if (dev < 64) done[dev] = true;
-        }
-        qt_gemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
-    } else {
-        static bool done[64] = {};
-        if (dev >= 64 || !done[dev]) {
-            cudaFuncSetAttribute(qt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-            if (dev < 64) done[dev] = true;
-        }
-        qt_gemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, p);
+    const bool aux = d->bias != nullptr || d->residual != nullptr;
+    const int variant = (fp8 ? 8 : 0) + d->activation * 2 + (aux ? 1 : 0);
+    switch (variant) {
+#define QT_GEMM_CASE(F, A, X)                                           \
+    case (F ? 8 : 0) + A * 2 + (X ? 1 : 0):                             \
+        launch_variant<F, A, X>(dev, grid, st, map_a, map_b, map_c, p); \
+        break;
+        QT_GEMM_CASE(false, ACT_NONE, false) QT_GEMM_CASE(false, ACT_NONE, true)
+        QT_GEMM_CASE(false, ACT_RELU, false) QT_GEMM_CASE(false, ACT_RELU, true)
+        QT_GEMM_CASE(false, ACT_GELU, false) QT_GEMM_CASE(false, ACT_GELU, true)
+        QT_GEMM_CASE(false, ACT_SILU, false) QT_GEMM_CASE(false, ACT_SILU, true)
+        QT_GEMM_CASE(true, ACT_NONE, false) QT_GEMM_CASE(true, ACT_NONE, true)
+        QT_GEMM_CASE(true, ACT_RELU, false) QT_GEMM_CASE(true, ACT_RELU, true)
+        QT_GEMM_CASE(true, ACT_GELU, false) QT_GEMM_CASE(true, ACT_GELU, true)
+        QT_GEMM_CASE(true, ACT_SILU, false) QT_GEMM_CASE(true, ACT_SILU, true)
+#undef QT_GEMM_CASE
     }
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         qt_set_error("qt_gemm_nt launch: %s", cudaGetErrorString(e));
         return QT_ERR_CUDA;
     }
     return QT_OK;
+}
+
+extern "C" int qt_gemm_nt(const void *A, const void *B, void *C, int operand_type, int64_t batch, int64_t M, int64_t N,
+                          int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+                          int64_t strideC, float alpha, const void *bias, int activation, const void *residual,
+                          int64_t ldr, int64_t strideR, void *stream)
+{
+    qt_gemm_desc_t d;
+    memset(&d, 0, sizeof(d));
+    d.A = A;
+    d.B = B;
+    d.C = C;
+    d.operand_type = operand_type;
+    d.M = M;
+    d.N = N;
+    d.K = K;
+    d.batch_inner = batch;
+    d.batch_outer = 1;
+    d.lda = lda;
+    d.ldb = ldb;
+    d.ldc = ldc;
+    d.strideA_inner = strideA;
+    d.strideB_inner = strideB;
+    d.strideC_inner = strideC;
+    d.alpha = alpha;
+    d.bias = bias;
+    d.activation = activation;
+    d.residual = residual;
+    d.ldr = ldr;
+    d.strideR_inner = strideR;
+    return qt_gemm_nt_ex(&d, stream);
 }

@@ -46,6 +46,26 @@ EXPORTS = {
     "qt_gemm_nt": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int] +
                    [ctypes.c_int64] * 10 + [ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "qt_gemm_nt_ex": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_softmax_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float,
+                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                     ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_norm_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
+                                  ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_void_p]),
+    "qt_act_mul_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_size_t] * 5 +
+                      [ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p,
+                       ctypes.c_void_p]),
+    "qt_rope_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                  ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                  ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_fq_transpose": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
+                        [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
+                         ctypes.c_void_p, ctypes.c_void_p]),
     "qt_amax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -183,54 +203,159 @@ GEMM_BF16, GEMM_E4M3, GEMM_E5M2, GEMM_E4M3_E5M2, GEMM_E5M2_E4M3 = range(5)
 ACTIVATIONS = {None: 0, "none": 0, "relu": 1, "gelu": 2, "silu": 3}
 
 
-def _as_batched(t, name):
-    """[..., rows, K] tensor -> (batch, rows, K, ld, batch_stride) with a unit-stride K axis, no copy if possible."""
+class QtGemmDesc(ctypes.Structure):
+    """qt_gemm_desc_t"""
+    _fields_ = [
+        ("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("C", ctypes.c_void_p),
+        ("operand_type", ctypes.c_int32), ("activation", ctypes.c_int32),
+        ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
+        ("batch_inner", ctypes.c_int64), ("batch_outer", ctypes.c_int64),
+        ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64), ("ldc", ctypes.c_int64),
+        ("strideA_inner", ctypes.c_int64), ("strideA_outer", ctypes.c_int64),
+        ("strideB_inner", ctypes.c_int64), ("strideB_outer", ctypes.c_int64),
+        ("strideC_inner", ctypes.c_int64), ("strideC_outer", ctypes.c_int64),
+        ("alpha", ctypes.c_float), ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+        ("ldr", ctypes.c_int64), ("strideR_inner", ctypes.c_int64), ("strideR_outer", ctypes.c_int64),
+    ]
+
+
+def _as4d(t, name, align):
+    """[..., rows, cols] tensor -> a [outer, inner, rows, cols] view the kernel's 4-D tensor maps can address:
+    unit-stride last axis, every other stride a multiple of `align` elements (16 bytes), 16-byte aligned base.
+    No copy when the tensor already qualifies (projections viewed as [B, H, S, D], k^T, strided outputs)."""
     if t.dim() < 2:
         raise ValueError(f"{name} must have at least 2 dimensions")
-    if t.dim() == 2:
-        t3 = t.unsqueeze(0)
-    else:
-        t3 = t.reshape(-1, t.shape[-2], t.shape[-1])  # a view whenever the leading dims are collapsible
-    if t3.stride(-1) != 1 or (t3.shape[1] > 1 and t3.stride(1) < t3.shape[2]):
-        t3 = t3.contiguous()
-    return t3
+    if t.dim() > 4:
+        t = t.reshape(-1, *t.shape[-3:])
+    while t.dim() < 4:
+        t = t.unsqueeze(0)
+    ok = t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and all(
+        t.shape[i] == 1 or (t.stride(i) % align == 0 and t.stride(i) > 0) for i in range(3))
+    return t if ok else t.contiguous()
 
 
 def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None):
     """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
-    a, b: bf16 (GEMM_BF16) or uint8 fp8 codes; bias bf16 [n]; residual bf16 broadcastable to out's shape."""
+    a, b: bf16 (GEMM_BF16) or uint8 fp8 codes, up to two leading batch dimensions with arbitrary strides;
+    bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional bf16 destination (any 16-byte
+    aligned strides, e.g. a [B, H, S, D] view of a [B, S, H*D] buffer)."""
     _require_cuda(a, "a")
-    a3, b3 = _as_batched(a, "a"), _as_batched(b, "b")
-    if b3.shape[0] != a3.shape[0]:
-        if b3.shape[0] == 1:
-            b3 = b3.expand(a3.shape[0], -1, -1)
-        else:
-            raise ValueError(f"batch mismatch: {tuple(a.shape)} x {tuple(b.shape)}")
-    batch, M, K = a3.shape
-    N = b3.shape[1]
-    if b3.shape[2] != K:
-        raise ValueError(f"inner dimensions differ: {tuple(a.shape)} x {tuple(b.shape)}^T")
     want = torch.uint8 if operand_type != GEMM_BF16 else torch.bfloat16
-    if a3.dtype != want or b3.dtype != want:
-        raise TypeError(f"operand_type {operand_type} takes {want} operands, got {a3.dtype} and {b3.dtype}")
-    out_shape = (*a.shape[:-1], N) if a.dim() > 2 or b.dim() <= 2 else (*b.shape[:-2], M, N)
+    if a.dtype != want or b.dtype != want:
+        raise TypeError(f"operand_type {operand_type} takes {want} operands, got {a.dtype} and {b.dtype}")
+    if b.dim() == 2 and a.dim() > 2:   # one weight for every batch entry: the batch is just more rows
+        a = a.reshape(-1, a.shape[-1])
+    align = 16 if operand_type != GEMM_BF16 else 8
+    a4, b4 = _as4d(a, "a", align), _as4d(b, "b", align)
+    if a4.shape[:2] != b4.shape[:2]:
+        raise ValueError(f"batch mismatch: {tuple(a.shape)} x {tuple(b.shape)}")
+    outer, inner, M, K = a4.shape
+    N = b4.shape[2]
+    if b4.shape[3] != K:
+        raise ValueError(f"inner dimensions differ: {tuple(a.shape)} x {tuple(b.shape)}^T")
+    lead = a.shape[:-2] if a.dim() >= b.dim() else b.shape[:-2]
+    out_shape = (*lead, M, N)
     if out is None:
-        out = torch.empty((batch, M, N), dtype=torch.bfloat16, device=a.device)
-    o3 = out.view(batch, M, N)
-    r3 = None
-    if residual is not None:
-        r3 = residual.expand(out_shape).reshape(batch, M, N)
-        if r3.stride(-1) != 1:
-            r3 = r3.contiguous()
+        out = torch.empty(out_shape, dtype=torch.bfloat16, device=a.device)
+    elif tuple(out.shape) != tuple(out_shape) or out.dtype != torch.bfloat16:
+        raise ValueError(f"out must be bf16 of shape {tuple(out_shape)}, got {out.dtype} {tuple(out.shape)}")
+    o4 = _as4d(out, "out", 8)
+    if o4.data_ptr() != out.data_ptr() or o4.numel() != out.numel():
+        raise ValueError("out needs a unit-stride last axis and 16-byte aligned strides")
+    d = QtGemmDesc()
+    d.A, d.B, d.C = a4.data_ptr(), b4.data_ptr(), o4.data_ptr()
+    d.operand_type, d.activation = operand_type, ACTIVATIONS[activation]
+    d.M, d.N, d.K, d.batch_inner, d.batch_outer = M, N, K, inner, outer
+    d.lda, d.ldb, d.ldc = a4.stride(2), b4.stride(2), o4.stride(2)
+    d.strideA_outer, d.strideA_inner = a4.stride(0), a4.stride(1)
+    d.strideB_outer, d.strideB_inner = b4.stride(0), b4.stride(1)
+    d.strideC_outer, d.strideC_inner = o4.stride(0), o4.stride(1)
+    d.alpha = float(alpha)
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
-    sa = a3.stride(0) if batch > 1 else 0
-    sb = b3.stride(0) if batch > 1 else 0
+        d.bias = bias.data_ptr()
+    r4 = None
+    if residual is not None:
+        r4 = _as4d(residual.expand(out_shape), "residual", 8)
+        if r4.dtype != torch.bfloat16:
+            raise TypeError("residual must be bf16")
+        d.residual, d.ldr, d.strideR_outer, d.strideR_inner = r4.data_ptr(), r4.stride(2), r4.stride(0), r4.stride(1)
     with torch.cuda.device(a.device):
-        _check(lib().qt_gemm_nt(
-            a3.data_ptr(), b3.data_ptr(), o3.data_ptr(), operand_type, batch, M, N, K,
-            a3.stride(1), b3.stride(1), o3.stride(1), sa, sb, o3.stride(0) if batch > 1 else 0,
-            float(alpha), bias.data_ptr() if bias is not None else None, ACTIVATIONS[activation],
-            r3.data_ptr() if r3 is not None else None, r3.stride(1) if r3 is not None else 0,
-            (r3.stride(0) if batch > 1 else 0) if r3 is not None else 0, _stream(a)))
-    return out.view(out_shape)
+        _check(lib().qt_gemm_nt_ex(ctypes.addressof(d), _stream(a)))
+    return out
+
+
+# ---- fused ops (qt_fused.cu): thin wrappers; argument checking beyond dtype/device lives in the C library --------
+FQ_PRE, FQ_MID, FQ_POST = 1, 2, 4
+NORM_RMS, NORM_LAYER = 0, 1
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _bf16_cuda(t, what):
+    _require_cuda(t, what)
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"{what} must be bfloat16, got {t.dtype}")
+
+
+def softmax_fq(scores, probs, alpha, mask, rows_per_batch, mask_rows, mask_batches, fq_points, fmt,
+               scale_pre=None, scale_mid=None, scale_post=None, lut=None):
+    _bf16_cuda(scores, "scores")
+    assert scores.is_contiguous() and probs.is_contiguous() and probs.dtype == torch.bfloat16
+    cols = scores.shape[-1]
+    with torch.cuda.device(scores.device):
+        _check(lib().qt_softmax_fq(scores.data_ptr(), probs.data_ptr(), scores.numel() // cols, cols, float(alpha),
+                                   _ptr(mask), rows_per_batch, mask_rows, mask_batches, fq_points, ctypes.byref(fmt),
+                                   _ptr(scale_pre), _ptr(scale_mid), _ptr(scale_post), _ptr(lut), _stream(scores)))
+
+
+def norm_fq(x, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale_post=None, lut=None):
+    _bf16_cuda(x, "x")
+    assert x.is_contiguous() and y.is_contiguous() and weight.is_contiguous() and weight.dtype == torch.bfloat16
+    cols = x.shape[-1]
+    with torch.cuda.device(x.device):
+        _check(lib().qt_norm_fq(x.data_ptr(), y.data_ptr(), x.numel() // cols, cols, kind, weight.data_ptr(),
+                                _ptr(bias), float(eps), fq_points, ctypes.byref(fmt), _ptr(scale_pre),
+                                _ptr(scale_post), _ptr(lut), _stream(x)))
+
+
+def act_mul_fq(gate, up, out, activation, fq_points, fmt, scale_post=None, lut=None):
+    """gate, up, out: 2-D bf16 views [rows, cols] with a unit-stride last axis (row strides may differ)."""
+    _bf16_cuda(gate, "gate")
+    assert gate.dim() == 2 and out.shape == gate.shape and gate.stride(1) == 1 and out.stride(1) == 1
+    assert up is None or (up.shape == gate.shape and up.stride(1) == 1)
+    with torch.cuda.device(gate.device):
+        _check(lib().qt_act_mul_fq(gate.data_ptr(), _ptr(up), out.data_ptr(), gate.shape[0], gate.shape[1],
+                                   gate.stride(0), up.stride(0) if up is not None else 0, out.stride(0),
+                                   ACTIVATIONS[activation], fq_points, ctypes.byref(fmt), _ptr(scale_post), _ptr(lut),
+                                   _stream(gate)))
+
+
+def rope_fq(q, q_out, k, k_out, cos, sin, fq_points, fmt, scale_q=None, scale_k=None, lut=None):
+    """q, k: [tokens, heads, head_dim] bf16 views (contiguous heads, any token stride); cos, sin: [rows, head_dim]."""
+    _bf16_cuda(q, "q")
+    tokens, qh, d = q.shape
+    assert q.stride(2) == 1 and q.stride(1) == d and q_out.stride(2) == 1 and q_out.stride(1) == d
+    assert cos.is_contiguous() and sin.is_contiguous() and cos.shape == sin.shape and cos.shape[-1] == d
+    kh = 0
+    if k is not None:
+        kh = k.shape[1]
+        assert k.shape[0] == tokens and k.stride(2) == 1 and k.stride(1) == d and k_out.stride(1) == d
+    with torch.cuda.device(q.device):
+        _check(lib().qt_rope_fq(q.data_ptr(), q_out.data_ptr(), q.stride(0), q_out.stride(0), qh,
+                                _ptr(k), _ptr(k_out), k.stride(0) if k is not None else 0,
+                                k_out.stride(0) if k is not None else 0, kh, tokens, d, cos.data_ptr(), sin.data_ptr(),
+                                cos.numel() // d, fq_points, ctypes.byref(fmt), _ptr(scale_q), _ptr(scale_k), _ptr(lut),
+                                _stream(q)))
+
+
+def fq_transpose(v, out, fq_points, fmt, scale_post=None, lut=None):
+    """v: [B, S, H, D] bf16 view (contiguous heads; token / batch strides free) -> out [B, H, D, S] contiguous."""
+    _bf16_cuda(v, "v")
+    b, s_, h, d = v.shape
+    assert v.stride(3) == 1 and v.stride(2) == d and out.is_contiguous() and tuple(out.shape) == (b, h, d, s_)
+    with torch.cuda.device(v.device):
+        _check(lib().qt_fq_transpose(v.data_ptr(), out.data_ptr(), b, s_, h, d, v.stride(1), v.stride(0), fq_points,
+                                     ctypes.byref(fmt), _ptr(scale_post), _ptr(lut), _stream(v)))

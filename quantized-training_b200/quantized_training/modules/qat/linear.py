@@ -28,8 +28,29 @@ class Linear(nn.Linear):
     def forward(self, input):
         kind = ops.fp8_route(self, input, self.weight_fake_quant)
         if kind is not None:  # bare e4m3/e5m2 on both sides: operands go to the FP8 tensor cores as codes
-            return ops.linear_fp8(input, self.weight, self.bias, self.weight_fake_quant, kind)
-        return ops.linear(input, self.weight_fake_quant(self.weight), self.bias)
+            return ops.linear_fp8(input, self.weight, self.bias, self.weight_fake_quant, kind,
+                                  codes=self._quantized_weight(codes=True))
+        return ops.linear(input, self._quantized_weight(), self.bias)
+
+    def _quantized_weight(self, codes=False):
+        """weight_fake_quant(weight), or its fp8 codes.  The reference re-quantizes the weight on every forward
+        (linear.py:41); that is kept whenever it is observable -- live observer (amax history advances per call)
+        or autograd recording through the quantizer.  Otherwise (evaluation with a frozen or bare quantizer) the
+        result is a pure function of (weight, scale) and is reused until either is written to: for Llama-2-7B
+        this removes 6.6 G elements of re-quantization traffic per forward."""
+        fq, w = self.weight_fake_quant, self.weight
+        run = (lambda: fq.quantize_to_codes(w)) if codes else (lambda: fq(w))
+        flags = getattr(fq, "_flags", None)
+        if flags is None or (torch.is_grad_enabled() and w.requires_grad):
+            return None if codes else run()
+        observe, quantize = flags()
+        if observe:
+            return None if codes else run()
+        key = (codes, w.data_ptr(), w._version, fq.scale.data_ptr(), fq.scale._version, quantize, w.dtype, w.device)
+        if self.__dict__.get("_wq_key") != key:
+            self.__dict__["_wq"] = run().detach()
+            self.__dict__["_wq_key"] = key
+        return self.__dict__["_wq"]
 
     @classmethod
     def from_float(cls, mod):

@@ -76,10 +76,10 @@ class _LinearFp8Fn(torch.autograd.Function):
     the bf16 path (every fp8 value is a bf16 value), at twice the MMA rate and 3/4 of the weight traffic."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, wq, x_kind):
+    def forward(ctx, x, weight, bias, wq, x_kind, codes):
         x2 = x.reshape(-1, x.shape[-1])
         xc = x2.contiguous().to(_FP8_DTYPE[x_kind]).view(torch.uint8)   # exact: x is representable
-        wc = wq.quantize_to_codes(weight)
+        wc = codes if codes is not None else wq.quantize_to_codes(weight)
         y = _C.gemm_nt(xc, wc, bias=bias.contiguous() if bias is not None else None,
                        operand_type=_FP8_OP[(x_kind, wq.fp8_kind)])
         if any(ctx.needs_input_grad[:3]):
@@ -97,13 +97,13 @@ class _LinearFp8Fn(torch.autograd.Function):
         gx = (g2 @ w).view_as(x) if ctx.needs_input_grad[0] else None
         gw = g2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None   # STE through the quantizer
         gb = g2.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
-def linear_fp8(x, weight, bias, weight_fq, x_kind):
+def linear_fp8(x, weight, bias, weight_fq, x_kind, codes=None):
     """F.linear(x, weight_fq(weight), bias) with both operands as fp8 codes.  Caller guarantees that x already holds
     `x_kind` values exactly and that weight_fq is a bare (scale 1) e4m3/e5m2 quantizer."""
-    return _LinearFp8Fn.apply(x, weight, bias, weight_fq, x_kind)
+    return _LinearFp8Fn.apply(x, weight, bias, weight_fq, x_kind, codes)
 
 
 def fp8_route(module, x, weight_fq):

@@ -39,6 +39,50 @@ def test_linear_shapes(M, N, K):
     check(out, a.double() @ w.double().t())
 
 
+@pytest.mark.parametrize("B,M,N,K", [(32, 1024, 1024, 128), (192, 384, 384, 64), (192, 384, 64, 384), (3, 130, 72, 40),
+                                     (5, 128, 64, 64), (2, 257, 136, 264)])
+def test_batched_tile_widths(B, M, N, K):
+    """Short-K batched products: the launcher narrows the tile (64 / 128 / 256 columns) to fill the SMs; every
+    width, with ragged M and N (rows / columns clipped by the TMA store), must give the same numbers."""
+    g = torch.Generator().manual_seed(B * 11 + M + N + K)
+    a = quantized_operand((B, M, K), "e4m3", g)
+    w = quantized_operand((B, N, K), "e4m3", g, 0.25)
+    out = _C.gemm_nt(a, w)
+    assert out.shape == (B, M, N)
+    check(out, a.double() @ w.double().transpose(-1, -2))
+
+
+def test_two_level_batch_strided_attention_layouts():
+    """[B, S, H*D] projections viewed as [B, H, S, D] (two batch strides, no copies) and a context written
+    straight into the [B, S, H*D] layout the output projection reads."""
+    g = torch.Generator().manual_seed(21)
+    B, H, S, D = 3, 4, 200, 64
+    q = quantized_operand((B, S, H * D), "posit8_1", g).view(B, S, H, D).transpose(1, 2)
+    k = quantized_operand((B, S, H * D), "posit8_1", g).view(B, S, H, D).transpose(1, 2)
+    assert not q.is_contiguous()
+    scores = _C.gemm_nt(q, k, alpha=0.125)
+    check(scores, (q.double() @ k.double().transpose(-1, -2)) * 0.125)
+    p = quantized_operand((B, H, S, S), "posit8_1", g, 0.1)
+    vt = quantized_operand((B, H, D, S), "posit8_1", g)
+    ctx = torch.zeros(B, S, H * D, dtype=torch.bfloat16, device=DEV)
+    out_view = ctx.view(B, S, H, D).transpose(1, 2)              # [B, H, S, D] strided destination
+    _C.gemm_nt(p, vt, out=out_view)
+    check(out_view, p.double() @ vt.double().transpose(-1, -2))
+
+
+def test_output_is_fully_written_and_nothing_else():
+    """The epilogue stores 32 x 64 boxes through TMA: a strided C (ldc > N) must keep its padding untouched."""
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 200, 72, 128
+    a = quantized_operand((M, K), "posit8_1", g)
+    w = quantized_operand((N, K), "posit8_1", g, 0.1)
+    big = torch.full((M + 5, 128), 7.0, dtype=torch.bfloat16, device=DEV)
+    view = big[:M, :N]
+    _C.gemm_nt(a, w, out=view)
+    check(view, a.double() @ w.double().t())
+    assert bool((big[M:] == 7.0).all()) and bool((big[:, N:] == 7.0).all())
+
+
 def test_epilogue_bias_act_residual_alpha():
     g = torch.Generator().manual_seed(5)
     M, N, K = 384, 768, 512
