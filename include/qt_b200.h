@@ -129,7 +129,8 @@ int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem
  * B = weight [N, K]) and torch.matmul(q, k^T) of MatmulFunctional (modules/quantizable/functional_modules.py:
  * 22-27; A = q [B*H, S, D], B = k [B*H, S, D]).  Operands hold values of the quantized format exactly:
  * as bf16 (any format of this library with <= 8 bits), or as one-byte e4m3 / e5m2 codes (FP8 tensor cores).
- * Fused epilogue, in this order: * alpha, + bias[n] (bf16), activation, + residual[b, m, n] (bf16), round to bf16.
+ * Fused epilogue, in this order: * alpha, + bias[n] (bf16), [round] activation, [round] + residual[b, m, n] (bf16),
+ * round to bf16 -- the intermediate roundings are those of the reference's separate bf16 ops, applied in registers.
  * Leading dimensions and batch strides are in elements; bases, lda/ldb (in bytes), ldc, ldr must be 16-byte
  * aligned and N % 8 == 0.  batch == 1: strides are ignored. */
 #define QT_GEMM_BF16 0

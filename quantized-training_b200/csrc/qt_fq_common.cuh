@@ -41,12 +41,13 @@ struct TableParams {
     const QtLutEntry *table;  // global memory, QT_LUT_BYTES
     QtLutCfg cfg;
 };
-template <bool CLAMP, bool MXBAND>
+template <bool CLAMP, bool MXBAND, int REPL = QT_LUT_REPLICAS>
 struct TableRounder {
     static constexpr bool kTable = true;
     static constexpr int kThreads = 512, kCtasPerSm = 2, kMinCtas = 2;  // 2 x 64 KB of replicated table per SM
     static constexpr bool kMxBand = MXBAND;
-    static constexpr size_t kSmemBytes = QT_LUT_SMEM_BYTES;
+    static constexpr int kReplicas = REPL;
+    static constexpr size_t kSmemBytes = (size_t)QT_LUT_BYTES * REPL;
     using Params = TableParams;
     const unsigned char *tab;  // shared memory, 8 interleaved replicas (qt_lut.h)
     const uint32_t clamp_bits;
@@ -58,7 +59,7 @@ struct TableRounder {
     __device__ __forceinline__ uint32_t go(uint32_t pattern16, uint32_t a) const
     {
         const uint32_t ac = CLAMP ? min(a, clamp_bits) : a;
-        return qt_lut_round_smem<MXBAND>(tab, slot16, pattern16, a, ac);
+        return qt_lut_round_smem<MXBAND, REPL>(tab, slot16, pattern16, a, ac);
     }
     __device__ __forceinline__ uint32_t operator()(uint32_t u) const { return go(u >> 16, u & 0x7FFFFFFFu); }
     __device__ __forceinline__ uint32_t lo(uint32_t w) const { return go(w, (w << 16) & 0x7FFFFFFFu); }
@@ -75,7 +76,7 @@ __device__ __forceinline__ const unsigned char *stage_table(const typename R::Pa
         const float4 *src = reinterpret_cast<const float4 *>(p.table);
         float4 *dst = reinterpret_cast<float4 *>(qt_dyn_smem);
         const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.x + threadIdx.y * blockDim.x;
-        for (int i = tid; i < QT_LUT_ENTRIES * QT_LUT_REPLICAS; i += nthreads) dst[i] = src[i / QT_LUT_REPLICAS];
+        for (int i = tid; i < QT_LUT_ENTRIES * R::kReplicas; i += nthreads) dst[i] = src[i / R::kReplicas];
         __syncthreads();
     }
     return qt_dyn_smem;

@@ -24,6 +24,31 @@ constexpr int FQ_PRE = 1;   // fake-quantize the op's input  (hook of the op's o
 constexpr int FQ_MID = 2;   // softmax only: fake-quantize scores * alpha + mask (the "activation" hook of nn.Softmax)
 constexpr int FQ_POST = 4;  // fake-quantize the op's output (input hook of the consuming GEMM)
 
+// Table rounder of the fused kernels: single-replica 8 KB table (staging 64 KB per CTA would dominate these small
+// launches), clamp / NaN-band switches read at run time so that ONE instantiation serves every fp / posit format.
+struct TableRounderDyn {
+    static constexpr bool kTable = true;
+    static constexpr int kReplicas = 1;
+    static constexpr bool kMxBand = true;
+    static constexpr size_t kSmemBytes = QT_LUT_BYTES;
+    using Params = TableParams;
+    const unsigned char *tab;
+    const uint32_t clamp_bits, mx_band;
+    __device__ __forceinline__ TableRounderDyn(const Params &p, const unsigned char *smem)
+        : tab(smem), clamp_bits(p.cfg.clamp_bits), mx_band(p.cfg.mx_band)
+    {
+    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t u) const
+    {
+        const uint32_t a = u & 0x7FFFFFFFu;
+        uint32_t q = qt_lut_round_smem<false, 1>(tab, 0u, u >> 16, a, min(a, clamp_bits));
+        if (mx_band && a >= 0x7F580000u && a != 0x7F800000u) q = QT_NAN_BITS;
+        return q;
+    }
+    __device__ __forceinline__ uint32_t lo(uint32_t w) const { return (*this)(w << 16); }
+    __device__ __forceinline__ uint32_t hi(uint32_t w) const { return (*this)(w & 0xFFFF0000u); }
+};
+
 struct FqPoint {
     ScaleBf16 sc;
     int mode;
@@ -36,15 +61,25 @@ __device__ __forceinline__ FqPoint load_point(const float *scale)
     p.mode = classify_scale(p.sc.s);
     return p;
 }
-// one bf16 value (fp32 bits, low half zero) through quantize-dequantize
-template <class R>
-__device__ __forceinline__ uint32_t fq_elem(const R &round, uint32_t xh, const FqPoint &p)
-{
-    if (p.mode == DIV_UNIT) return round(xh);
-    if (p.mode == DIV_RECIP) return fq_bf16<R, DIV_RECIP>(round, xh, p.sc);
-    return fq_bf16<R, DIV_EXACT>(round, xh, p.sc);
-}
 __device__ __forceinline__ float bf16_round(float f) { return __uint_as_float(bf16_rne_hi(f)); }
+
+// Eight bf16 values (as floats) through quantize-dequantize.  SCALED = false (bare specs: every BASELINE config):
+// the rounding alone.  SCALED = true: the frozen per-tensor scale, divide / round / multiply as qt_fq_forward does;
+// the mode is uniform over the launch, so the three-way branch is taken per vector, not per element.
+template <class R, bool SCALED>
+__device__ __forceinline__ void fq8(const R &round, float (&f)[8], const FqPoint &p)
+{
+    if (!SCALED || p.mode == DIV_UNIT) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(round(__float_as_uint(f[k])));
+    } else if (p.mode == DIV_RECIP) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(fq_bf16<R, DIV_RECIP>(round, __float_as_uint(f[k]), p.sc));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(fq_bf16<R, DIV_EXACT>(round, __float_as_uint(f[k]), p.sc));
+    }
+}
 __device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8])
 {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -64,11 +99,18 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8])
     o.w = __byte_perm(__float_as_uint(f[6]), __float_as_uint(f[7]), 0x7632);
     return o;
 }
-// Launch shapes.  Row kernels: 128-thread CTAs; a row is owned by TPR = 32 threads (short rows, four rows per CTA)
-// or by all 128 (long rows), VPL 16-byte vectors per thread.  Elementwise kernels: 256-thread CTAs.  The rounding
-// table (64 KB of shared memory per CTA when the format uses it) allows 3 resp. 2 CTAs per SM.
-constexpr int ROW_THREADS = 128, ROW_MIN_CTAS = 3;
-constexpr int EW_THREADS = 256, EW_MIN_CTAS = 2;
+// fp32 values -> RNE to bf16 -> packed (one F2FP per pair)
+__device__ __forceinline__ uint4 round_pack8(const float (&f)[8])
+{
+    return make_uint4(bf16x2_rne(f[0], f[1]), bf16x2_rne(f[2], f[3]), bf16x2_rne(f[4], f[5]), bf16x2_rne(f[6], f[7]));
+}
+
+// Launch shapes.  Row kernels: 256-thread CTAs; a row is owned by TPR = 32 threads (rows up to 1024 elements: eight
+// rows per CTA, warp-shuffle reductions only) or by 128 (longer rows: two rows per CTA), VPL 16-byte vectors per
+// thread, i.e. 64 bytes in flight per thread -- these launches are latency-bound unless every SM keeps ~40 KB of
+// loads in flight.  Elementwise kernels: 256-thread CTAs.
+constexpr int ROW_THREADS = 256, ROW_MIN_CTAS = 3;
+constexpr int EW_THREADS = 256, EW_MIN_CTAS = 3;
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -83,27 +125,33 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
-// reductions over the TPR threads that own a row (TPR == 32: one warp; TPR == 128: the whole CTA through smem)
+// reductions over the TPR threads that own a row (TPR == 32: one warp; TPR == 128: four warps through smem)
 template <int TPR, bool MAX>
 __device__ __forceinline__ float row_reduce(float v)
 {
     v = MAX ? warp_max(v) : warp_sum(v);
-    if (TPR == 32) return v;
-    static_assert(ROW_THREADS == 128, "row_reduce assumes four warps");
-    __shared__ float part[4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) part[warp] = v;
-    __syncthreads();
-    const float a = part[0], b = part[1], c = part[2], d = part[3];
-    __syncthreads();  // the next reduction may overwrite part[]
-    return MAX ? fmaxf(fmaxf(a, b), fmaxf(c, d)) : (a + b) + (c + d);
+    if constexpr (TPR == 32) {
+        return v;
+    } else {
+        static_assert(TPR == 128, "a long row is owned by four warps");
+        __shared__ float part[ROW_THREADS / 32];
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) part[warp] = v;
+        __syncthreads();
+        const int g = (warp >> 2) << 2;  // first warp of this row's group
+        const float a = part[g], b = part[g + 1], c = part[g + 2], d = part[g + 3];
+        __syncthreads();  // the next reduction may overwrite part[]
+        return MAX ? fmaxf(fmaxf(a, b), fmaxf(c, d)) : (a + b) + (c + d);
+    }
 }
 
 // ----------------------------------------------------------------------------- softmax
 // TPR threads per row of `cols` (<= TPR * VPL * 8) scores; the row lives in registers between the passes.
 // Reference chain (modules/quantizable/modeling_bert.py:118-158, modeling_llama.py:228-246), all bf16 tensors:
 //   s = qk_matmul(q, k^T); [s = fq(s)]; s = s * scaling; s = s + mask; [s = fq(s)]; p = softmax(s, -1); [p = fq(p)]
-template <class R, int TPR, int VPL>
+// Which steps exist is a run-time mask tested once per 8-element vector (a per-element test multiplies the
+// unrolled code by the number of combinations and thrashes the instruction cache).
+template <class R, bool SCALED, int TPR, int VPL>
 __global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
 softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, size_t rows, int cols, float alpha,
                   int has_alpha, const uint4 *__restrict__ mask, size_t rows_per_batch, size_t mask_rows,
@@ -124,25 +172,35 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, s
         const uint4 *srow = scores + (live ? row : 0) * nvec;
         const uint4 *mrow = nullptr;
         if (mask && live) mrow = mask + (row / rows_per_batch) * mask_batch_stride_vec + (row % mask_rows) * (size_t)nvec;
+        uint4 raw[VPL], mraw[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {  // all loads first: VPL (x2 with a mask) 16-byte requests in flight per thread
+            const int i = lane + TPR * j;
+            const bool in = i < nvec && live;
+            raw[j] = in ? __ldcs(srow + i) : make_uint4(0u, 0u, 0u, 0u);
+            mraw[j] = (in && mrow) ? __ldg(mrow + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
         float f[VPL][8];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int i = lane + TPR * j;
             if (i < nvec && live) {
-                unpack8(__ldcs(srow + i), f[j]);
-                float m8[8];
-                if (mrow) unpack8(__ldg(mrow + i), m8);
+                unpack8(raw[j], f[j]);
+                if (flags & FQ_PRE) fq8<R, SCALED>(round, f[j], pre);
+                if (has_alpha) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float s = f[j][k];
-                    if (flags & FQ_PRE) s = __uint_as_float(fq_elem(round, __float_as_uint(s), pre));
-                    if (has_alpha) s = bf16_round(s * alpha);
-                    if (mrow) s = bf16_round(s + m8[k]);
-                    if (flags & FQ_MID) s = __uint_as_float(fq_elem(round, __float_as_uint(s), mid));
-                    f[j][k] = s;
-                    mx = fmaxf(mx, s);
+                    for (int k = 0; k < 8; ++k) f[j][k] = bf16_round(f[j][k] * alpha);
                 }
+                if (mrow) {
+                    float m8[8];
+                    unpack8(mraw[j], m8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[j][k] = bf16_round(f[j][k] + m8[k]);
+                }
+                if (flags & FQ_MID) fq8<R, SCALED>(round, f[j], mid);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mx = fmaxf(mx, f[j][k]);
             } else {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[j][k] = -INFINITY;
@@ -154,20 +212,20 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, s
         for (int j = 0; j < VPL; ++j)
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                f[j][k] = expf(f[j][k] - mx);
+                // s and mx are bf16 values: the difference is exact; exp through ex2.approx (relative error ~2^-21
+                // for the arguments that survive the following rounding to bf16)
+                f[j][k] = __expf(f[j][k] - mx);
                 sum += f[j][k];
             }
         sum = row_reduce<TPR, false>(sum);
+        const float inv = __frcp_rn(sum);
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int i = lane + TPR * j;
             if (i < nvec && live) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float p = bf16_round(__fdiv_rn(f[j][k], sum));
-                    if (flags & FQ_POST) p = __uint_as_float(fq_elem(round, __float_as_uint(p), post));
-                    f[j][k] = p;
-                }
+                for (int k = 0; k < 8; ++k) f[j][k] = bf16_round(f[j][k] * inv);
+                if (flags & FQ_POST) fq8<R, SCALED>(round, f[j], post);
                 __stcs(probs + row * nvec + i, pack8(f[j]));
             }
         }
@@ -175,9 +233,10 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, s
 }
 
 // ----------------------------------------------------------------------------- RMSNorm / LayerNorm
-// TPR threads per row of `cols` (<= TPR * VPL * 8).  kind 0: LlamaRMSNorm (HF modeling_llama.py): n = bf16(x * rsqrt(mean(x^2)
-// + eps)) computed in fp32, y = bf16(weight * n).  kind 1: nn.LayerNorm: y = bf16((x - mean) * rstd * w + b), fp32 inside.
-template <class R, int TPR, int VPL>
+// TPR threads per row of `cols` (<= TPR * VPL * 8).  kind 0: LlamaRMSNorm (HF modeling_llama.py): n = bf16(x *
+// rsqrt(mean(x^2) + eps)) computed in fp32, y = bf16(weight * n).  kind 1: nn.LayerNorm: y = bf16((x - mean) * rstd * w
+// + b), fp32 inside.
+template <class R, bool SCALED, int TPR, int VPL>
 __global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
 norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, int cols, int kind,
                const uint4 *__restrict__ weight, const uint4 *__restrict__ bias, float eps, int flags,
@@ -200,21 +259,15 @@ norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
             const int i = lane + TPR * j;
             v[j] = (i < nvec && live) ? __ldcs(x + row * nvec + i) : make_uint4(0u, 0u, 0u, 0u);
         }
-        if (flags & FQ_PRE) {
-#pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-                float f[8];
-                unpack8(v[j], f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(fq_elem(round, __float_as_uint(f[k]), pre));
-                v[j] = pack8(f);
-            }
-        }
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             float f[8];
             unpack8(v[j], f);
+            if (flags & FQ_PRE) {
+                fq8<R, SCALED>(round, f, pre);  // zeros of the padding stay zeros for every format
+                v[j] = pack8(f);
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 s1 += f[k];
@@ -242,20 +295,19 @@ norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
         for (int j = 0; j < VPL; ++j) {
             const int i = lane + TPR * j;
             if (i < nvec && live) {
-                float f[8], w[8], b[8];
+                float f[8], w[8];
                 unpack8(v[j], f);
                 unpack8(__ldg(weight + i), w);
-                if (kind != 0 && bias) unpack8(__ldg(bias + i), b);
+                if (kind == 0) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    float o;
-                    if (kind == 0)
-                        o = bf16_round(w[k] * bf16_round(f[k] * rstd));
-                    else
-                        o = bf16_round((f[k] - mean) * rstd * w[k] + (bias ? b[k] : 0.0f));
-                    if (flags & FQ_POST) o = __uint_as_float(fq_elem(round, __float_as_uint(o), post));
-                    f[k] = o;
+                    for (int k = 0; k < 8; ++k) f[k] = bf16_round(w[k] * bf16_round(f[k] * rstd));
+                } else {
+                    float b[8];
+                    if (bias) unpack8(__ldg(bias + i), b);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] = bf16_round((f[k] - mean) * rstd * w[k] + (bias ? b[k] : 0.0f));
                 }
+                if (flags & FQ_POST) fq8<R, SCALED>(round, f, post);
                 __stcs(y + row * nvec + i, pack8(f));
             }
         }
@@ -263,38 +315,57 @@ norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
 }
 
 // ----------------------------------------------------------------------------- activation (x up) + fq, strided rows
-// out[r, c] = fq( bf16( bf16(act(gate[r, c])) * up[r, c] ) )   (up == NULL: no product).  act: QT_ACT_*.
+// out[r, c] = fq( bf16( bf16(act(gate[r, c])) * up[r, c] ) )   (up == NULL: no product).  ACT: compile time.
 // HF LlamaMLP: down_proj(act_fn(gate_proj(x)) * up_proj(x)); each op rounds to bf16.
 enum { FACT_NONE = 0, FACT_RELU = 1, FACT_GELU = 2, FACT_SILU = 3 };
-template <class R>
+template <class R, bool SCALED, int ACT>
 __global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
 act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, uint4 *__restrict__ out, size_t rows,
-                  int vec_per_row, size_t ld_gate_vec, size_t ld_up_vec, size_t ld_out_vec, int act, int flags,
+                  int vec_per_row, size_t ld_gate_vec, size_t ld_up_vec, size_t ld_out_vec, int flags,
                   const __grid_constant__ typename R::Params params, const float *__restrict__ scale_post)
 {
     const R round(params, stage_table<R>(params));
     const FqPoint post = load_point(scale_post);
     const size_t total = rows * (size_t)vec_per_row;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const size_t r = t / vec_per_row, c = t - r * vec_per_row;
-        float g[8], u[8];
-        unpack8(__ldcs(gate + r * ld_gate_vec + c), g);
-        if (up) unpack8(__ldcs(up + r * ld_up_vec + c), u);
+    constexpr int U = 2;  // independent vectors in flight per thread
+    for (size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * U) {
+        uint4 gv[U], uv[U];
+        size_t off_out[U];
+        bool live[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float a = g[k];
-            if (act == FACT_SILU)
-                a = bf16_round(__fdiv_rn(a, 1.0f + expf(-a)));
-            else if (act == FACT_GELU)
-                a = bf16_round(0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)));
-            else if (act == FACT_RELU)
-                a = fmaxf(a, 0.0f);
-            if (up) a = bf16_round(a * u[k]);
-            if (flags & FQ_POST) a = __uint_as_float(fq_elem(round, __float_as_uint(a), post));
-            g[k] = a;
+        for (int i = 0; i < U; ++i) {
+            const size_t t = t0 + (size_t)i * stride;
+            live[i] = t < total;
+            const size_t r = live[i] ? t / vec_per_row : 0, c = live[i] ? t - r * vec_per_row : 0;
+            off_out[i] = r * ld_out_vec + c;
+            gv[i] = live[i] ? __ldcs(gate + r * ld_gate_vec + c) : make_uint4(0u, 0u, 0u, 0u);
+            uv[i] = (live[i] && up) ? __ldcs(up + r * ld_up_vec + c) : make_uint4(0u, 0u, 0u, 0u);
         }
-        __stcs(out + r * ld_out_vec + c, pack8(g));
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            float g[8];
+            unpack8(gv[i], g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float a = g[k];
+                if (ACT == FACT_SILU)
+                    a = bf16_round(__fdividef(a, 1.0f + __expf(-a)));
+                else if (ACT == FACT_GELU)
+                    a = bf16_round(0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)));
+                else if (ACT == FACT_RELU)
+                    a = fmaxf(a, 0.0f);
+                g[k] = a;
+            }
+            if (up) {
+                float u[8];
+                unpack8(uv[i], u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = bf16_round(g[k] * u[k]);
+            }
+            if (flags & FQ_POST) fq8<R, SCALED>(round, g, post);
+            if (live[i]) __stcs(out + off_out[i], pack8(g));
+        }
     }
 }
 
@@ -309,7 +380,7 @@ struct RopeTensor {
     size_t ld_x_vec, ld_y_vec;  // token strides, 16-byte vectors
     int heads;
 };
-template <class R>
+template <class R, bool SCALED>
 __global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
 rope_fq_kernel(RopeTensor t0, RopeTensor t1, size_t tokens, int head_dim, const uint4 *__restrict__ cos_t,
                const uint4 *__restrict__ sin_t, size_t cos_rows, int flags,
@@ -333,25 +404,28 @@ rope_fq_kernel(RopeTensor t0, RopeTensor t1, size_t tokens, int head_dim, const 
         const size_t tok = th / t.heads;
         const uint4 *xp = t.x + tok * t.ld_x_vec + (size_t)h * dv;
         const size_t crow = (tok % cos_rows) * dv;
-        float a[8], b[8], ca[8], cb[8], sa[8], sb[8];
-        unpack8(__ldcs(xp + c), a);
-        unpack8(__ldcs(xp + c + hv), b);
-        unpack8(__ldg(cos_t + crow + c), ca);
-        unpack8(__ldg(cos_t + crow + c + hv), cb);
-        unpack8(__ldg(sin_t + crow + c), sa);
-        unpack8(__ldg(sin_t + crow + c + hv), sb);
-        float ra[8], rb[8];
+        const uint4 xa = __ldcs(xp + c), xb = __ldcs(xp + c + hv);
+        const uint4 ca4 = __ldg(cos_t + crow + c), cb4 = __ldg(cos_t + crow + c + hv);
+        const uint4 sa4 = __ldg(sin_t + crow + c), sb4 = __ldg(sin_t + crow + c + hv);
+        float a[8], b[8], ra[8], rb[8];
+        unpack8(xa, a);
+        unpack8(xb, b);
+        {
+            float cw[8], sw[8];
+            unpack8(ca4, cw);
+            unpack8(sa4, sw);
+            // first half: x1 * cos - x2 * sin (rotate_half gives -x2)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            // first half: x1 * cos - x2 * sin (rotate_half gives -x2); second half: x2 * cos + x1 * sin
-            float lo = bf16_round(bf16_round(a[k] * ca[k]) + bf16_round(-b[k] * sa[k]));
-            float hi = bf16_round(bf16_round(b[k] * cb[k]) + bf16_round(a[k] * sb[k]));
-            if (flags & FQ_POST) {
-                lo = __uint_as_float(fq_elem(round, __float_as_uint(lo), pt));
-                hi = __uint_as_float(fq_elem(round, __float_as_uint(hi), pt));
-            }
-            ra[k] = lo;
-            rb[k] = hi;
+            for (int k = 0; k < 8; ++k) ra[k] = bf16_round(bf16_round(a[k] * cw[k]) + bf16_round(-b[k] * sw[k]));
+            unpack8(cb4, cw);
+            unpack8(sb4, sw);
+            // second half: x2 * cos + x1 * sin
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rb[k] = bf16_round(bf16_round(b[k] * cw[k]) + bf16_round(a[k] * sw[k]));
+        }
+        if (flags & FQ_POST) {
+            fq8<R, SCALED>(round, ra, pt);
+            fq8<R, SCALED>(round, rb, pt);
         }
         uint4 *yp = t.y + tok * t.ld_y_vec + (size_t)h * dv;
         __stcs(yp + c, pack8(ra));
@@ -364,7 +438,7 @@ rope_fq_kernel(RopeTensor t0, RopeTensor t1, size_t tokens, int head_dim, const 
 // operand of probabilities x values.  One CTA per (b, h, 64 tokens): coalesced loads, fq, padded smem tile, then
 // 128-byte rows of the transposed output.
 constexpr int TR_TOK = 64;
-template <class R>
+template <class R, bool SCALED>
 __global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
 fq_transpose_kernel(const uint16_t *__restrict__ v, uint16_t *__restrict__ out, int B, int S, int H, int D,
                     size_t ld_tok, size_t batch_stride, int flags, const __grid_constant__ typename R::Params params,
@@ -390,10 +464,7 @@ fq_transpose_kernel(const uint16_t *__restrict__ v, uint16_t *__restrict__ out, 
                 const uint4 *src = reinterpret_cast<const uint4 *>(v + (size_t)b * batch_stride + (size_t)(s0 + r) * ld_tok +
                                                                    (size_t)h * D) + c;
                 unpack8(__ldcs(src), f);
-                if (flags & FQ_POST) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(fq_elem(round, __float_as_uint(f[k]), post));
-                }
+                if (flags & FQ_POST) fq8<R, SCALED>(round, f, post);
             } else {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = 0.0f;
@@ -449,12 +520,7 @@ int dispatch_fused(const QtRound &P, const void *lut, Fn &&fn)
         return QT_ERR_UNALIGNED;
     }
     tp.table = static_cast<const QtLutEntry *>(lut);
-    if (cfg.mx_band)
-        fn(RounderTag<TableRounder<true, true>>{}, tp);
-    else if (cfg.clamp_bits != 0x7FFFFFFFu)
-        fn(RounderTag<TableRounder<true, false>>{}, tp);
-    else
-        fn(RounderTag<TableRounder<false, false>>{}, tp);
+    fn(RounderTag<TableRounderDyn>{}, tp);
     return QT_OK;
 }
 int check_common(const char *fn, const qt_format_t *fmt, QtRound *P)
@@ -497,13 +563,14 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
     const size_t mask_batch_stride_vec = mask_batches > 1 ? mask_rows * (cols / 8) : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int has_alpha = alpha != 1.0f;
+    const bool scaled = scale_pre || scale_mid || scale_post;
     rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
         using R = typename decltype(tag)::type;
 #define QT_SOFTMAX_LAUNCH(TPR, VPL)                                                                                  \
     do {                                                                                                             \
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                                  \
-        allow_smem<softmax_fq_kernel<R, TPR, VPL>>(R::kSmemBytes);                                                   \
-        softmax_fq_kernel<R, TPR, VPL><<<grid_for(ctas, ROW_MIN_CTAS), ROW_THREADS, R::kSmemBytes, st>>>(            \
+        auto kernel = scaled ? softmax_fq_kernel<R, true, TPR, VPL> : softmax_fq_kernel<R, false, TPR, VPL>;         \
+        kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                                \
             static_cast<const uint4 *>(scores), static_cast<uint4 *>(probs), rows, (int)cols, alpha, has_alpha,      \
             static_cast<const uint4 *>(mask), rows_per_batch, mask_rows, mask_batch_stride_vec, fq_points, params,   \
             scale_pre, scale_mid, scale_post);                                                                       \
@@ -513,7 +580,7 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
         else if (cols <= 512)
             QT_SOFTMAX_LAUNCH(32, 2);
         else if (cols <= 1024)
-            QT_SOFTMAX_LAUNCH(128, 1);
+            QT_SOFTMAX_LAUNCH(32, 4);
         else if (cols <= 2048)
             QT_SOFTMAX_LAUNCH(128, 2);
         else
@@ -539,13 +606,14 @@ extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int 
         return QT_ERR_INVALID_ARGUMENT;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool scaled = scale_pre || scale_post;
     rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
         using R = typename decltype(tag)::type;
 #define QT_NORM_LAUNCH(TPR, VPL)                                                                                 \
     do {                                                                                                         \
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                              \
-        allow_smem<norm_fq_kernel<R, TPR, VPL>>(R::kSmemBytes);                                                  \
-        norm_fq_kernel<R, TPR, VPL><<<grid_for(ctas, ROW_MIN_CTAS), ROW_THREADS, R::kSmemBytes, st>>>(           \
+        auto kernel = scaled ? norm_fq_kernel<R, true, TPR, VPL> : norm_fq_kernel<R, false, TPR, VPL>;           \
+        kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                            \
             static_cast<const uint4 *>(x), static_cast<uint4 *>(y), rows, (int)cols, kind,                       \
             static_cast<const uint4 *>(weight), static_cast<const uint4 *>(bias), eps, fq_points, params,        \
             scale_pre, scale_post);                                                                              \
@@ -555,7 +623,7 @@ extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int 
         else if (cols <= 512)
             QT_NORM_LAUNCH(32, 2);
         else if (cols <= 1024)
-            QT_NORM_LAUNCH(128, 1);
+            QT_NORM_LAUNCH(32, 4);
         else if (cols <= 2048)
             QT_NORM_LAUNCH(128, 2);
         else if (cols <= 4096)
@@ -586,11 +654,23 @@ extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t
     rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
         using R = typename decltype(tag)::type;
         const size_t total = rows * (cols / 8);
-        const unsigned grid = grid_for((total + EW_THREADS - 1) / EW_THREADS, EW_MIN_CTAS * 2);
-        allow_smem<act_mul_fq_kernel<R>>(R::kSmemBytes);
-        act_mul_fq_kernel<R><<<grid, EW_THREADS, R::kSmemBytes, st>>>(
+        const unsigned grid = grid_for((total + EW_THREADS * 2 - 1) / (EW_THREADS * 2), EW_MIN_CTAS * 2);
+        void (*kernel)(const uint4 *, const uint4 *, uint4 *, size_t, int, size_t, size_t, size_t, int,
+                       const typename R::Params, const float *) = nullptr;
+        const bool scaled = scale_post != nullptr;
+        switch (activation * 2 + (scaled ? 1 : 0)) {
+        case 0: kernel = act_mul_fq_kernel<R, false, FACT_NONE>; break;
+        case 1: kernel = act_mul_fq_kernel<R, true, FACT_NONE>; break;
+        case 2: kernel = act_mul_fq_kernel<R, false, FACT_RELU>; break;
+        case 3: kernel = act_mul_fq_kernel<R, true, FACT_RELU>; break;
+        case 4: kernel = act_mul_fq_kernel<R, false, FACT_GELU>; break;
+        case 5: kernel = act_mul_fq_kernel<R, true, FACT_GELU>; break;
+        case 6: kernel = act_mul_fq_kernel<R, false, FACT_SILU>; break;
+        default: kernel = act_mul_fq_kernel<R, true, FACT_SILU>; break;
+        }
+        kernel<<<grid, EW_THREADS, R::kSmemBytes, st>>>(
             static_cast<const uint4 *>(gate), static_cast<const uint4 *>(up), static_cast<uint4 *>(out), rows,
-            (int)(cols / 8), ld_gate / 8, ld_up / 8, ld_out / 8, activation, fq_points, params, scale_post);
+            (int)(cols / 8), ld_gate / 8, ld_up / 8, ld_out / 8, fq_points, params, scale_post);
     });
     if (rc != QT_OK) return rc;
     return finish("act_mul_fq kernel launch");
@@ -621,8 +701,8 @@ extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_o
         using R = typename decltype(tag)::type;
         const size_t total = tokens * (size_t)(t0.heads + t1.heads) * (head_dim / 16);
         const unsigned grid = grid_for((total + EW_THREADS - 1) / EW_THREADS, EW_MIN_CTAS * 2);
-        allow_smem<rope_fq_kernel<R>>(R::kSmemBytes);
-        rope_fq_kernel<R><<<grid, EW_THREADS, R::kSmemBytes, st>>>(
+        auto kernel = (scale_q || scale_k) ? rope_fq_kernel<R, true> : rope_fq_kernel<R, false>;
+        kernel<<<grid, EW_THREADS, R::kSmemBytes, st>>>(
             t0, t1, tokens, head_dim, static_cast<const uint4 *>(cos_table), static_cast<const uint4 *>(sin_table),
             cos_rows, fq_points, params, scale_q, scale_k);
     });
@@ -649,10 +729,9 @@ extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int
         const size_t jobs = (size_t)batch * heads * ((seq + TR_TOK - 1) / TR_TOK);
         const size_t smem = R::kSmemBytes + (size_t)TR_TOK * (head_dim + 2) * 2;
         const unsigned grid = grid_for(jobs, EW_MIN_CTAS * 2);
-        allow_smem<fq_transpose_kernel<R>>(R::kSmemBytes + (size_t)TR_TOK * (256 + 2) * 2);  // the largest tile
-        fq_transpose_kernel<R><<<grid, EW_THREADS, smem, st>>>(static_cast<const uint16_t *>(v),
-                                                                static_cast<uint16_t *>(out), batch, seq, heads,
-                                                                head_dim, ld_tok, batch_stride, fq_points, params,
+        auto kernel = scale_post ? fq_transpose_kernel<R, true> : fq_transpose_kernel<R, false>;
+        kernel<<<grid, EW_THREADS, smem, st>>>(static_cast<const uint16_t *>(v), static_cast<uint16_t *>(out), batch,
+                                               seq, heads, head_dim, ld_tok, batch_stride, fq_points, params,
                                                                 scale_post);
     });
     if (rc != QT_OK) return rc;

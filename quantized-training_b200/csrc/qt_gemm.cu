@@ -9,7 +9,8 @@
 //   * bf16 storage (every <= 8-bit format of this library is exactly representable in bf16) -> kind::f16 MMA
 //   * e4m3 / e5m2 one-byte codes -> kind::f8f6f4 MMA at twice the rate
 // Epilogue (the paper's fusion levels, README table / SURVEY App. B): * alpha (attention scaling), + bias,
-// activation (ReLU / GELU-erf / SiLU), + residual, then one rounding to bf16.
+// activation (ReLU / GELU-erf / SiLU), + residual, evaluated in fp32 registers but ROUNDED to bf16 wherever the
+// reference's op chain materialises a bf16 tensor (after the Linear, after the activation, after the add).
 //
 // Kernel shape (one CTA per SM, persistent over output tiles, 320 threads):
 //   warp 0      TMA producer: 128 x 128-byte A tile + block_n x 128-byte B tile per k-block, 128-byte swizzle
@@ -160,6 +161,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;
     return d;
 }
+
+__device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
 // Compile-time activation: a run-time switch inside the 64-way unrolled epilogue made ~77 KB of SASS whose
 // skipped blocks still thrashed the instruction cache (measured: 2400 cycles per 64-column chunk for a plain store).
@@ -355,17 +358,21 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
                         }
                     }
+                    // The reference materialises a bf16 tensor after the Linear, after the activation and after the
+                    // residual add (three ATen ops); rounding at the same points keeps the fused epilogue on the
+                    // reference's values instead of merely near them (a 1-ulp bf16 difference flips ~3 % of the codes
+                    // of an 8-bit format downstream).
                     if (ACT != ACT_NONE) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(f[j]);
+                        for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(bf16_round(f[j]));
                     }
                     if (AUX && rrow && in_n) {
                         const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + n));
                         const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            f[2 * j] += __uint_as_float(w[j] << 16);
-                            f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                            f[2 * j] = bf16_round(f[2 * j]) + __uint_as_float(w[j] << 16);
+                            f[2 * j + 1] = bf16_round(f[2 * j + 1]) + __uint_as_float(w[j] & 0xFFFF0000u);
                         }
                     }
 #pragma unroll

@@ -83,12 +83,17 @@ QT_HD uint32_t qt_lut_round(const QtLutEntry *tab, const QtLutCfg &cfg, uint32_t
 #define QT_LUT_REPLICAS 8
 #define QT_LUT_SMEM_BYTES (QT_LUT_BYTES * QT_LUT_REPLICAS)
 
-// hi16: the bf16 bit pattern in bits [15:0] (anything above is ignored); ac: clamped |x| as fp32 bits
-template <bool MXBAND>
+// hi16: the bf16 bit pattern in bits [15:0] (anything above is ignored); ac: clamped |x| as fp32 bits.
+// REPL = 8: the replicated layout above (streaming kernels).  REPL = 1: a plain 8 KB table, entry i at byte i * 16
+// (fused row / elementwise kernels: small launches where staging 64 KB per CTA would dominate, and whose inputs
+// span few binades, so the residual bank conflicts are rare).
+template <bool MXBAND, int REPL = QT_LUT_REPLICAS>
 __device__ __forceinline__ uint32_t qt_lut_round_smem(const unsigned char *smem_table, uint32_t slot16,
                                                       uint32_t pattern16, uint32_t a, uint32_t ac)
 {
-    const uint32_t off = (pattern16 & 0xFF80u) | slot16;  // (sign:exponent) * 128 + replica * 16
+    static_assert(REPL == 8 || REPL == 1, "table layouts: 8 interleaved replicas or one");
+    // (sign:exponent) * 128 + replica * 16, or (sign:exponent) * 16
+    const uint32_t off = REPL == 8 ? ((pattern16 & 0xFF80u) | slot16) : ((pattern16 >> 3) & 0x1FF0u);
     const float4 e = *reinterpret_cast<const float4 *>(smem_table + off);
     const float t = __saturatef(__fmaf_rn(__uint_as_float(ac), e.x, e.y));
     uint32_t q = __float_as_uint(__fmaf_rn(t, e.z, e.w));

@@ -1,0 +1,274 @@
+"""Fused execution of quantize()-d transformer blocks (inference).
+
+`quantize(model, args)` expresses a quantized block the way the reference does: QAT Linear modules and hookable
+matmul / mul / add / softmax modules, with one fake-quantizer per hooked tensor (quantize.py:116-150).  Executed
+module by module that is ~60 launches per Llama layer, most of them small bf16 ATen ops between the GEMMs.  This file
+executes the SAME computation -- same weights, same fake-quantizers, same rounding points -- as ~13 launches:
+
+    norm+fq -> QKV GEMM -> rope+fq / fq+transpose -> QK^T GEMM -> scale+mask+softmax+fq -> PV GEMM -> fq
+            -> O GEMM (+residual) -> norm+fq -> gate|up GEMM -> silu*up+fq -> down GEMM (+residual)
+
+Which fake-quant steps exist is read from the hooks `prepare` installed (the paper's fusion levels = which op groups
+are hooked); a step that is absent simply is not applied, and the producing kernel's fp32 epilogue carries the value
+(residual adds move into the GEMM epilogue when the `residual` group is not hooked).  A block is executed fused only
+when that is unobservable: no autograd recording, every fake-quantizer involved is a bare or frozen per-tensor one
+(no live observer, whose amax history must advance per call), and nobody else hooked the submodules.  Otherwise the
+block runs module by module on the same kernels (fake_quantize.py, ops.py).
+"""
+import torch
+from torch import nn
+
+from . import _C
+from .fake_quantize import FusedAmaxObsFakeQuantize
+
+__all__ = ["llama_layer_forward", "set_enabled", "enabled"]
+
+_ENABLED = True
+
+
+def set_enabled(flag: bool):
+    """Fused block execution on (default) / off (module-by-module, for A/B comparison and debugging)."""
+    global _ENABLED
+    _ENABLED = bool(flag)
+
+
+def enabled():
+    return _ENABLED
+
+
+class _NotReady(Exception):
+    """A lazily created fake-quantizer does not exist yet (first forward): run module by module."""
+
+
+class _NotFusable(Exception):
+    pass
+
+
+_IDENTITY = {}
+
+
+def _identity_fmt():
+    if "fmt" not in _IDENTITY:
+        _IDENTITY["fmt"] = _C.format_from_string("bfloat16")
+    return _IDENTITY["fmt"]
+
+
+def _only_our_hooks(module, hooked):
+    if len(module._forward_hooks) or len(module._backward_hooks) or len(module._forward_pre_hooks) != (1 if hooked else 0):
+        raise _NotFusable
+
+
+def point(module, arg="0"):
+    """The fake-quant step `prepare` put on positional input `arg` of `module`: a FusedAmaxObsFakeQuantize, or None
+    when that input is not quantized."""
+    hooks = module._modules.get("activation_pre_process")
+    _only_our_hooks(module, hooks is not None)
+    if hooks is None:
+        return None
+    if arg not in hooks:
+        raise _NotReady
+    fq = hooks[arg]
+    if isinstance(fq, nn.Identity):
+        return None
+    if not isinstance(fq, FusedAmaxObsFakeQuantize):
+        raise _NotFusable
+    observe, quantize = fq._flags()
+    if observe or fq.is_per_channel or fq.record_histogram or fq.scale.numel() != 1:
+        raise _NotFusable
+    return fq if quantize else None
+
+
+def same_points(*fqs):
+    """Several consumers of one tensor (q/k/v projections, gate/up) quantize it identically -> one step."""
+    first = fqs[0]
+    for fq in fqs[1:]:
+        if (fq is None) != (first is None):
+            raise _NotFusable
+        if fq is not None and (fq.dtype != first.dtype or fq.qscheme is not None or first.qscheme is not None):
+            raise _NotFusable  # frozen scales could differ per consumer; bare specs cannot
+    return first
+
+
+def _spec(*fqs):
+    """(fmt, lut, [scale or None per step]) for the steps of one kernel; they must share a format."""
+    present = [f for f in fqs if f is not None]
+    if not present:
+        return _identity_fmt(), None, [None] * len(fqs)
+    d = present[0].dtype
+    if any(f.dtype != d for f in present):
+        raise _NotFusable
+    scales = [None if (f is None or f.qscheme is None) else f.scale.reshape(1) for f in fqs]
+    return present[0]._fmt, present[0].lut, scales
+
+
+def _flags(pre=None, mid=None, post=None):
+    return (_C.FQ_PRE if pre is not None else 0) | (_C.FQ_MID if mid is not None else 0) | \
+        (_C.FQ_POST if post is not None else 0)
+
+
+# ---- op wrappers (allocate the output, resolve the fake-quant steps) ------------------------------------------
+
+def norm(x2, weight, bias, eps, kind, pre, post):
+    fmt, lut, (s_pre, s_post) = _spec(pre, post)
+    y = torch.empty_like(x2)
+    _C.norm_fq(x2, y, kind, weight, bias, eps, _flags(pre=pre, post=post), fmt, s_pre, s_post, lut)
+    return y
+
+
+def softmax(scores, alpha, mask, pre, mid, post):
+    """scores [B, H, Sq, Sk] contiguous; mask None or additive [Bm, 1, Sq, >=Sk] (Bm in {1, B})."""
+    B, H, Sq, Sk = scores.shape
+    m3, mb = None, 1
+    if mask is not None:
+        if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] != Sq or mask.shape[0] not in (1, B):
+            raise _NotFusable
+        m3 = mask[:, 0, :, :Sk]
+        if m3.dtype != torch.bfloat16:
+            m3 = m3.to(torch.bfloat16)
+        m3 = m3.contiguous()
+        mb = m3.shape[0]
+    fmt, lut, (s_pre, s_mid, s_post) = _spec(pre, mid, post)
+    probs = torch.empty_like(scores)
+    _C.softmax_fq(scores, probs, alpha, m3, H * Sq, Sq, mb, _flags(pre, mid, post), fmt, s_pre, s_mid, s_post, lut)
+    return probs
+
+
+def act_mul(gate, up, activation, post):
+    fmt, lut, (s_post,) = _spec(post)
+    out = torch.empty(gate.shape, dtype=torch.bfloat16, device=gate.device)
+    _C.act_mul_fq(gate, up, out, activation, _flags(post=post), fmt, s_post, lut)
+    return out
+
+
+def fake_quant(x2, post):
+    """Plain fake quant of a 2-D activation through the module's own kernel path (observer-free by construction)."""
+    return x2 if post is None else post(x2)
+
+
+# ---- quantized weights of a block, concatenated once -----------------------------------------------------------
+
+def _quantized_cat(owner, tag, linears):
+    """cat([fq(W) for each Linear]) along the output axis, cached on `owner` until a weight or a scale is written.
+    The weight fake-quantizers must be observer-free (checked) so that skipping their per-forward re-run is
+    unobservable."""
+    key = []
+    for lin in linears:
+        fq, w = lin.weight_fake_quant, lin.weight
+        if isinstance(fq, FusedAmaxObsFakeQuantize):
+            observe, quantize = fq._flags()
+            if observe:
+                raise _NotFusable
+            key += [w.data_ptr(), w._version, fq.scale.data_ptr(), fq.scale._version, quantize]
+        elif isinstance(fq, nn.Identity):
+            key += [w.data_ptr(), w._version]
+        else:
+            raise _NotFusable
+        _only_our_hooks(lin, lin._modules.get("activation_pre_process") is not None)
+    key = tuple(key)
+    cache = owner.__dict__.setdefault("_qt_wcache", {})
+    hit = cache.get(tag)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            ws = [lin.weight_fake_quant(lin.weight).detach() for lin in linears]
+            w = ws[0] if len(ws) == 1 else torch.cat(ws, 0)
+            bs = [lin.bias for lin in linears]
+            b = None
+            if any(x is not None for x in bs):
+                b = torch.cat([x.detach() if x is not None else torch.zeros(lin.weight.shape[0], dtype=w.dtype,
+                                                                             device=w.device)
+                               for x, lin in zip(bs, linears)], 0).contiguous()
+        hit = (key, w.contiguous(), b)
+        cache[tag] = hit
+    return hit[1], hit[2]
+
+
+def _usable(x):
+    return _ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+
+
+# ---- Llama decoder layer ------------------------------------------------------------------------------------
+
+def llama_layer_forward(layer, hidden_states, attention_mask, position_embeddings, past_key_values=None):
+    """Fused forward of a quantizable LlamaDecoderLayer, or None when the layer must run module by module."""
+    if not _usable(hidden_states) or past_key_values is not None or position_embeddings is None:
+        return None
+    attn, mlp = layer.self_attn, layer.mlp
+    try:
+        if attn.num_key_value_groups != 1 or (attn.training and attn.attention_dropout > 0.0):
+            return None
+        if hidden_states.dim() != 3 or getattr(mlp.config, "pretraining_tp", 1) > 1:
+            return None
+        act_name = getattr(mlp.config, "hidden_act", "silu")
+        if act_name not in ("silu", "gelu", "relu"):
+            return None
+        for m in (attn, mlp, attn.attn_scaling, attn.softmax, attn.qk_matmul, attn.av_matmul):
+            if len(m._forward_hooks) or len(m._backward_hooks):
+                return None
+        # fake-quant steps, from the hooks
+        ln1_in, ln2_in = point(layer.input_layernorm), point(layer.post_attention_layernorm)
+        x_in = same_points(point(attn.q_proj), point(attn.k_proj), point(attn.v_proj))
+        q_in, k_in = point(attn.qk_matmul, "0"), point(attn.qk_matmul, "1")
+        p_in, v_in = point(attn.av_matmul, "0"), point(attn.av_matmul, "1")
+        sc_in, sm_in = point(attn.attn_scaling), point(attn.softmax)
+        o_in = point(attn.o_proj)
+        gu_in = same_points(point(mlp.gate_proj), point(mlp.up_proj))
+        d_in = point(mlp.down_proj)
+        res1 = (point(layer.self_attn_residual, "0"), point(layer.self_attn_residual, "1"))
+        res2 = (point(layer.mlp_residual, "0"), point(layer.mlp_residual, "1"))
+        w_qkv, b_qkv = _quantized_cat(layer, "qkv", (attn.q_proj, attn.k_proj, attn.v_proj))
+        w_o, b_o = _quantized_cat(layer, "o", (attn.o_proj,))
+        w_gu, b_gu = _quantized_cat(layer, "gu", (mlp.gate_proj, mlp.up_proj))
+        w_d, b_d = _quantized_cat(layer, "d", (mlp.down_proj,))
+
+        B, S, hidden = hidden_states.shape
+        H, D = attn.config.num_attention_heads, attn.head_dim
+        T = B * S
+        x = hidden_states.reshape(T, hidden)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        cos, sin = position_embeddings
+        cos2, sin2 = cos.reshape(-1, D), sin.reshape(-1, D)
+        if cos2.dtype != torch.bfloat16 or cos2.shape[0] not in (S, T) or not cos2.is_contiguous():
+            return None
+
+        # attention
+        n1 = layer.input_layernorm
+        xq = norm(x, n1.weight, None, n1.variance_epsilon, _C.NORM_RMS, ln1_in, x_in)
+        qkv = _C.gemm_nt(xq, w_qkv, bias=b_qkv)                                  # [T, 3 * H * D]
+        q = qkv[:, :H * D].view(T, H, D)
+        k = qkv[:, H * D:2 * H * D].view(T, H, D)
+        v = qkv[:, 2 * H * D:].view(B, S, H, D)
+        fmt, lut, (s_q, s_k) = _spec(q_in, k_in)
+        qk = torch.empty(2, T, H, D, dtype=torch.bfloat16, device=x.device)
+        _C.rope_fq(q, qk[0], k, qk[1], cos2, sin2, _C.FQ_POST if (q_in is not None or k_in is not None) else 0, fmt,
+                   s_q, s_k, lut)
+        if (q_in is None) != (k_in is None):
+            raise _NotFusable
+        fmt, lut, (s_v,) = _spec(v_in)
+        vt = torch.empty(B, H, D, S, dtype=torch.bfloat16, device=x.device)
+        _C.fq_transpose(v, vt, _flags(post=v_in), fmt, s_v, lut)
+        q4 = qk[0].view(B, S, H, D).transpose(1, 2)
+        k4 = qk[1].view(B, S, H, D).transpose(1, 2)
+        scores = _C.gemm_nt(q4, k4)                                              # [B, H, S, S]
+        probs = softmax(scores, attn.scaling, attention_mask, sc_in, sm_in, p_in)
+        ctx = torch.empty(B, S, H * D, dtype=torch.bfloat16, device=x.device)
+        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2))
+        ctx2 = fake_quant(ctx.view(T, H * D), o_in)
+        if res1 == (None, None):
+            h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x)                     # residual add in the fp32 epilogue
+        else:
+            h1 = layer.self_attn_residual(x, _C.gemm_nt(ctx2, w_o, bias=b_o))
+
+        # MLP
+        n2 = layer.post_attention_layernorm
+        x2 = norm(h1, n2.weight, None, n2.variance_epsilon, _C.NORM_RMS, ln2_in, gu_in)
+        gu = _C.gemm_nt(x2, w_gu, bias=b_gu)                                     # [T, 2 * I]
+        inter = w_gu.shape[0] // 2
+        a = act_mul(gu[:, :inter], gu[:, inter:], act_name, d_in)
+        if res2 == (None, None):
+            h2 = _C.gemm_nt(a, w_d, bias=b_d, residual=h1)
+        else:
+            h2 = layer.mlp_residual(h1, _C.gemm_nt(a, w_d, bias=b_d))
+        return h2.view(B, S, hidden)
+    except (_NotReady, _NotFusable, AttributeError):
+        return None

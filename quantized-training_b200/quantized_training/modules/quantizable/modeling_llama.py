@@ -4,6 +4,7 @@ five fusion levels of the README Llama table have their hook points).  The softm
 tensor dtype, as in the reference's block (no fp32 upcast, modeling_llama.py:244)."""
 from transformers.models.llama import modeling_llama as hf
 
+from ... import fused
 from ._common import attention_ops, hooked_attention, rebrand
 from .functional_modules import AddFunctional
 
@@ -44,6 +45,10 @@ class LlamaDecoderLayer(hf.LlamaDecoderLayer):
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_values=None,
                 use_cache=False, position_embeddings=None, **kwargs):
+        # inference with observer-free fake-quantizers: the whole layer as ~13 fused launches (fused.py)
+        out = fused.llama_layer_forward(self, hidden_states, attention_mask, position_embeddings, past_key_values)
+        if out is not None:
+            return out
         attn_out, _ = self.self_attn(
             hidden_states=self.input_layernorm(hidden_states), attention_mask=attention_mask,
             position_ids=position_ids, past_key_values=past_key_values, use_cache=use_cache,

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--torch-gemm", action="store_true")
+    ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--ops", default="gemm")
     a = ap.parse_args()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -48,6 +49,9 @@ def main():
     pos = torch.arange(a.seq, device=dev)[None].expand(a.batch, -1)
     if a.torch_gemm:
         ops.set_enabled(False)
+    if a.no_fused:
+        from quantized_training import fused
+        fused.set_enabled(False)
 
     def fwd():
         with torch.no_grad():
@@ -82,7 +86,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.steps
     nfq = sum(1 for m in model.modules() if isinstance(m, qt.FusedAmaxObsFakeQuantize))
     print(json.dumps({"workload": f"Llama-2-7B-shape quantized forward, {a.layers} layers, window [1,{a.seq}]",
-                      "spec": a.spec, "quantize_forward": a.ops, "graph": a.graph, "gemm": "torch/cuBLAS" if a.torch_gemm else "qt_gemm_nt",
+                      "spec": a.spec, "quantize_forward": a.ops, "graph": a.graph, "fused_blocks": not a.no_fused, "gemm": "torch/cuBLAS" if a.torch_gemm else "qt_gemm_nt",
                       "ms_per_window": ms, "batch": a.batch, "tokens_per_s": a.batch * a.seq / ms * 1e3, "wall_ms_per_window": wall / a.steps * 1e3,
                       "loss": float(loss), "fake_quant_modules": nfq, "build_s": build_s,
                       "flops_per_window_T": (2 * a.seq * (a.layers * (4 * 4096 * 4096 + 3 * 4096 * 11008) + 32000 * 4096) + a.layers * 4 * 32 * a.seq * a.seq * 128) / 1e12}), flush=True)

@@ -12,7 +12,7 @@ from torch import nn
 from transformers import BertConfig, BertForQuestionAnswering, LlamaConfig, LlamaForCausalLM
 
 import quantized_training as qt
-from quantized_training import ops
+from quantized_training import _C, fused, ops
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -107,3 +107,37 @@ def test_fp8_linear_route_matches_bf16_route():
     assert rel_err(y8, y16) < 1e-3                  # same products, fp32 accumulation in both
     ref_gx = torch.ones_like(y16).reshape(-1, 768) @ lin.weight_fake_quant(lin.weight)
     assert rel_err(g8.reshape(-1, 512), ref_gx) < 1e-2
+
+
+@pytest.mark.parametrize("spec", ["posit8_1", "e4m3"])
+@pytest.mark.parametrize("ops_str", ["gemm", "gemm,residual,layernorm,activation,scaling", "gemm,scaling,activation"])
+def test_llama_fused_layer_matches_module_by_module(spec, ops_str, monkeypatch):
+    """The fused block (fused.py, ~13 launches per layer) against the same model executed module by module through
+    the hooks (the reference's structure) -- same kernels for every fake-quant step, same rounding points.
+    Tolerance: relative Frobenius error of the logits <= 2 % (fp32 epilogue vs bf16 intermediate for the un-hooked
+    residual adds, different reduction orders); the fused path must actually have run."""
+    torch.manual_seed(5)
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=704, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=512, attn_implementation="eager")
+    model = LlamaForCausalLM(cfg).to(DEV).eval()
+    qt.quantize(model, parse("--activation", spec, "--weight", spec, "--quantize_forward", ops_str, "--bf16"))
+    ids = torch.randint(0, 512, (2, 96), device=DEV)
+    calls = {"n": 0}
+    real = _C.norm_fq
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+
+    monkeypatch.setattr(_C, "norm_fq", counting)
+    with torch.no_grad():
+        model(input_ids=ids, use_cache=False)           # first call creates the lazy fake-quantizers (module path)
+        assert calls["n"] == 0
+        got = model(input_ids=ids, use_cache=False).logits
+        assert calls["n"] == 4                          # 2 layers x 2 norms went through the fused kernels
+        fused.set_enabled(False)
+        want = model(input_ids=ids, use_cache=False).logits
+        fused.set_enabled(True)
+    assert rel_err(got, want) < 2e-2
+    x = torch.randn(2, 96, 256, device=DEV).bfloat16().requires_grad_()
+    assert fused.llama_layer_forward(model.model.layers[0], x, None, None) is None     # autograd on: module path
