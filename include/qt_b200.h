@@ -178,6 +178,12 @@ int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
 #define QT_FQ_PRE 1
 #define QT_FQ_MID 2
 #define QT_FQ_POST 4
+/* out_type: what the op stores.  QT_OUT_BF16: the fake-quantized values.  QT_OUT_E4M3 / QT_OUT_E5M2: their one-byte
+ * fp8 codes (operands of the QT_GEMM_E4M3.. products); allowed only when the output step (QT_FQ_POST) is an unscaled
+ * e4m3 / e5m2 fake quant, so that decode(code) is exactly the value the bf16 form would hold. */
+#define QT_OUT_BF16 0
+#define QT_OUT_E4M3 1
+#define QT_OUT_E5M2 2
 
 /* probs = fq_post(softmax(fq_mid(fq_pre(scores) * alpha + mask)))  over the last axis.
  * Replaces attn_scaling -> (+ mask) -> nn.Softmax -> av_matmul input hook (modules/quantizable/modeling_bert.py:
@@ -185,37 +191,37 @@ int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
  * [mask_batches, mask_rows, cols] added to row r as mask[(r / rows_per_batch) % .., r % mask_rows]
  * (rows_per_batch = heads * mask_rows; mask_batches == 1 broadcasts over the batch). */
 int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_t cols, float alpha, const void *mask,
-                  size_t rows_per_batch, size_t mask_rows, size_t mask_batches, int fq_points, const qt_format_t *fmt,
-                  const float *scale_pre, const float *scale_mid, const float *scale_post, const void *lut,
-                  void *stream);
+                  size_t rows_per_batch, size_t mask_rows, size_t mask_batches, int fq_points, int out_type,
+                  const qt_format_t *fmt, const float *scale_pre, const float *scale_mid, const float *scale_post,
+                  const void *lut, void *stream);
 
 /* y = fq_post(norm(fq_pre(x))), rows of `cols` <= 8192.  kind 0: LlamaRMSNorm (x * rsqrt(mean x^2 + eps) rounded to
  * bf16, then * weight); kind 1: nn.LayerNorm (weight, bias may be NULL for no bias).  Replaces the norm module plus the
  * input hooks of the Linear layers that read it (same tensor quantized once instead of once per consumer). */
 int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int kind, const void *weight, const void *bias,
-               float eps, int fq_points, const qt_format_t *fmt, const float *scale_pre, const float *scale_post,
-               const void *lut, void *stream);
+               float eps, int fq_points, int out_type, const qt_format_t *fmt, const float *scale_pre,
+               const float *scale_post, const void *lut, void *stream);
 
 /* out = fq_post(act(gate) * up)  (up == NULL: fq_post(act(gate))); rows with independent strides ld_* (elements), so
  * gate and up can be the two halves of one fused projection.  activation: QT_ACT_*.  Replaces act_fn, the product
  * and down_proj's input hook of the HF MLP blocks. */
 int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t rows, size_t cols, size_t ld_gate, size_t ld_up,
-                  size_t ld_out, int activation, int fq_points, const qt_format_t *fmt, const float *scale_post,
-                  const void *lut, void *stream);
+                  size_t ld_out, int activation, int fq_points, int out_type, const qt_format_t *fmt,
+                  const float *scale_post, const void *lut, void *stream);
 
 /* Rotary position embedding + the qk_matmul input hooks, q and k (k may be NULL) in one launch:
  * out = fq(x * cos + rotate_half(x) * sin).  x: [tokens, heads, head_dim] with token stride ld (elements);
  * cos/sin: [cos_rows, head_dim], token t reads row t % cos_rows.  Replaces HF apply_rotary_pos_emb + two hooks. */
 int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_out, int q_heads, const void *k, void *k_out,
                size_t ld_k, size_t ld_k_out, int k_heads, size_t tokens, int head_dim, const void *cos_table,
-               const void *sin_table, size_t cos_rows, int fq_points, const qt_format_t *fmt, const float *scale_q,
-               const float *scale_k, const void *lut, void *stream);
+               const void *sin_table, size_t cos_rows, int fq_points, int out_type, const qt_format_t *fmt,
+               const float *scale_q, const float *scale_k, const void *lut, void *stream);
 
 /* out[b, h, d, s] = fq(v[b, s, h, d]): the values as the K-major operand of probabilities x values.
  * v: token stride ld_tok, batch stride batch_stride (elements); out contiguous [batch, heads, head_dim, seq]. */
 int qt_fq_transpose(const void *v, void *out, int batch, int seq, int heads, int head_dim, size_t ld_tok,
-                    size_t batch_stride, int fq_points, const qt_format_t *fmt, const float *scale_post,
-                    const void *lut, void *stream);
+                    size_t batch_stride, int fq_points, int out_type, const qt_format_t *fmt,
+                    const float *scale_post, const void *lut, void *stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@
 // behaviour of exp / rsqrt.  The fake-quant step is the same rounding engine as qt_fq_forward (bit-exact formats);
 // per-tensor scales are read from device memory (NULL = bare spec, scale 1).  Observers (amax) are not fused: a
 // module with a live observer keeps its own qt_fq_forward pass.
+#include <cuda_fp8.h>
 #include <math.h>
 
 #include "qt_fq_common.cuh"
@@ -105,6 +106,35 @@ __device__ __forceinline__ uint4 round_pack8(const float (&f)[8])
     return make_uint4(bf16x2_rne(f[0], f[1]), bf16x2_rne(f[2], f[3]), bf16x2_rne(f[4], f[5]), bf16x2_rne(f[6], f[7]));
 }
 
+// Output forms.  OUT_BF16: the fake-quantized values.  OUT_E4M3 / OUT_E5M2: their one-byte OCP fp8 encodings (8 bytes
+// per vector) for the FP8 tensor-core GEMM -- only after an UNSCALED fake-quant step of that very format, so that
+// decode(code) == value exactly (the launchers enforce it).  +-Inf (which only the fpN_eXmY flavour lets through)
+// gets the format's Inf / NaN code instead of the saturated maximum.
+enum { OUT_BF16 = 0, OUT_E4M3 = 1, OUT_E5M2 = 2 };
+__device__ __forceinline__ uint32_t fp8x2_dyn(float lo, float hi, int out_type)
+{
+    uint32_t c = out_type == OUT_E5M2
+                     ? (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E5M2)
+                     : (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t inf_code = out_type == OUT_E5M2 ? 0x7Cu : 0x7Fu;
+    const uint32_t bl = __float_as_uint(lo), bh = __float_as_uint(hi);
+    if ((bl & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0xFF00u) | ((bl >> 24) & 0x80u) | inf_code;
+    if ((bh & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0x00FFu) | ((((bh >> 24) & 0x80u) | inf_code) << 8);
+    return c;
+}
+// vector `idx` (8 elements) of an output whose base is `base`: 16 bytes of bf16 or 8 bytes of codes
+__device__ __forceinline__ void store8(void *base, size_t idx, const float (&f)[8], int out_type)
+{
+    if (out_type == OUT_BF16) {
+        __stcs(static_cast<uint4 *>(base) + idx, pack8(f));
+    } else {
+        uint2 o;
+        o.x = fp8x2_dyn(f[0], f[1], out_type) | (fp8x2_dyn(f[2], f[3], out_type) << 16);
+        o.y = fp8x2_dyn(f[4], f[5], out_type) | (fp8x2_dyn(f[6], f[7], out_type) << 16);
+        __stcs(static_cast<uint2 *>(base) + idx, o);
+    }
+}
+
 // Launch shapes.  Row kernels: 256-thread CTAs; a row is owned by TPR = 32 threads (rows up to 1024 elements: eight
 // rows per CTA, warp-shuffle reductions only) or by 128 (longer rows: two rows per CTA), VPL 16-byte vectors per
 // thread, i.e. 64 bytes in flight per thread -- these launches are latency-bound unless every SM keeps ~40 KB of
@@ -153,7 +183,7 @@ __device__ __forceinline__ float row_reduce(float v)
 // unrolled code by the number of combinations and thrashes the instruction cache).
 template <class R, bool SCALED, int TPR, int VPL>
 __global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
-softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, size_t rows, int cols, float alpha,
+softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, int out_type, size_t rows, int cols, float alpha,
                   int has_alpha, const uint4 *__restrict__ mask, size_t rows_per_batch, size_t mask_rows,
                   size_t mask_batch_stride_vec, int flags, const __grid_constant__ typename R::Params params,
                   const float *__restrict__ scale_pre, const float *__restrict__ scale_mid,
@@ -226,7 +256,7 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, s
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[j][k] = bf16_round(f[j][k] * inv);
                 if (flags & FQ_POST) fq8<R, SCALED>(round, f[j], post);
-                __stcs(probs + row * nvec + i, pack8(f[j]));
+                store8(probs, row * nvec + i, f[j], out_type);
             }
         }
     }
@@ -238,7 +268,7 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, uint4 *__restrict__ probs, s
 // + b), fp32 inside.
 template <class R, bool SCALED, int TPR, int VPL>
 __global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
-norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, int cols, int kind,
+norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, int out_type, size_t rows, int cols, int kind,
                const uint4 *__restrict__ weight, const uint4 *__restrict__ bias, float eps, int flags,
                const __grid_constant__ typename R::Params params, const float *__restrict__ scale_pre,
                const float *__restrict__ scale_post)
@@ -308,7 +338,7 @@ norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
                     for (int k = 0; k < 8; ++k) f[k] = bf16_round((f[k] - mean) * rstd * w[k] + (bias ? b[k] : 0.0f));
                 }
                 if (flags & FQ_POST) fq8<R, SCALED>(round, f, post);
-                __stcs(y + row * nvec + i, pack8(f));
+                store8(y, row * nvec + i, f, out_type);
             }
         }
     }
@@ -320,7 +350,8 @@ norm_fq_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
 enum { FACT_NONE = 0, FACT_RELU = 1, FACT_GELU = 2, FACT_SILU = 3 };
 template <class R, bool SCALED, int ACT>
 __global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
-act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, uint4 *__restrict__ out, size_t rows,
+act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, void *__restrict__ out, int out_type,
+                  size_t rows,
                   int vec_per_row, size_t ld_gate_vec, size_t ld_up_vec, size_t ld_out_vec, int flags,
                   const __grid_constant__ typename R::Params params, const float *__restrict__ scale_post)
 {
@@ -364,7 +395,7 @@ act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, 
                 for (int k = 0; k < 8; ++k) g[k] = bf16_round(g[k] * u[k]);
             }
             if (flags & FQ_POST) fq8<R, SCALED>(round, g, post);
-            if (live[i]) __stcs(out + off_out[i], pack8(g));
+            if (live[i]) store8(out, off_out[i], g, out_type);
         }
     }
 }
@@ -376,13 +407,13 @@ act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, 
 // partners [8c + D/2, ...).
 struct RopeTensor {
     const uint4 *x;
-    uint4 *y;
+    void *y;
     size_t ld_x_vec, ld_y_vec;  // token strides, 16-byte vectors
     int heads;
 };
 template <class R, bool SCALED>
 __global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
-rope_fq_kernel(RopeTensor t0, RopeTensor t1, size_t tokens, int head_dim, const uint4 *__restrict__ cos_t,
+rope_fq_kernel(RopeTensor t0, RopeTensor t1, int out_type, size_t tokens, int head_dim, const uint4 *__restrict__ cos_t,
                const uint4 *__restrict__ sin_t, size_t cos_rows, int flags,
                const __grid_constant__ typename R::Params params, const float *__restrict__ scale0,
                const float *__restrict__ scale1)
@@ -427,9 +458,9 @@ rope_fq_kernel(RopeTensor t0, RopeTensor t1, size_t tokens, int head_dim, const 
             fq8<R, SCALED>(round, ra, pt);
             fq8<R, SCALED>(round, rb, pt);
         }
-        uint4 *yp = t.y + tok * t.ld_y_vec + (size_t)h * dv;
-        __stcs(yp + c, pack8(ra));
-        __stcs(yp + c + hv, pack8(rb));
+        const size_t yv = tok * t.ld_y_vec + (size_t)h * dv + c;
+        store8(t.y, yv, ra, out_type);
+        store8(t.y, yv + hv, rb, out_type);
     }
 }
 
@@ -440,7 +471,7 @@ rope_fq_kernel(RopeTensor t0, RopeTensor t1, size_t tokens, int head_dim, const 
 constexpr int TR_TOK = 64;
 template <class R, bool SCALED>
 __global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
-fq_transpose_kernel(const uint16_t *__restrict__ v, uint16_t *__restrict__ out, int B, int S, int H, int D,
+fq_transpose_kernel(const uint16_t *__restrict__ v, void *__restrict__ out_v, int out_type, int B, int S, int H, int D,
                     size_t ld_tok, size_t batch_stride, int flags, const __grid_constant__ typename R::Params params,
                     const float *__restrict__ scale_post)
 {
@@ -484,18 +515,38 @@ fq_transpose_kernel(const uint16_t *__restrict__ v, uint16_t *__restrict__ out, 
             uint16_t e[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) e[k] = tile[(g * 8 + k) * pitch + d];
-            uint16_t *dst = out + ((size_t)bh * D + d) * S + s0 + g * 8;
-            if (full) {
-                uint4 o;
-                o.x = e[0] | ((uint32_t)e[1] << 16);
-                o.y = e[2] | ((uint32_t)e[3] << 16);
-                o.z = e[4] | ((uint32_t)e[5] << 16);
-                o.w = e[6] | ((uint32_t)e[7] << 16);
-                *reinterpret_cast<uint4 *>(dst) = o;
-            } else {
+            const size_t o0 = ((size_t)bh * D + d) * S + s0 + g * 8;
+            if (out_type == OUT_BF16) {
+                uint16_t *dst = static_cast<uint16_t *>(out_v) + o0;
+                if (full) {
+                    uint4 o;
+                    o.x = e[0] | ((uint32_t)e[1] << 16);
+                    o.y = e[2] | ((uint32_t)e[3] << 16);
+                    o.z = e[4] | ((uint32_t)e[5] << 16);
+                    o.w = e[6] | ((uint32_t)e[7] << 16);
+                    *reinterpret_cast<uint4 *>(dst) = o;
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (s0 + g * 8 + k < S) dst[k] = e[k];
+                    for (int k = 0; k < 8; ++k)
+                        if (s0 + g * 8 + k < S) dst[k] = e[k];
+                }
+            } else {
+                uint8_t *dst = static_cast<uint8_t *>(out_v) + o0;
+                uint32_t c2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    c2[k] = fp8x2_dyn(__uint_as_float((uint32_t)e[2 * k] << 16), __uint_as_float((uint32_t)e[2 * k + 1] << 16),
+                                      out_type);
+                if (full) {
+                    uint2 o;
+                    o.x = c2[0] | (c2[1] << 16);
+                    o.y = c2[2] | (c2[3] << 16);
+                    *reinterpret_cast<uint2 *>(dst) = o;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (s0 + g * 8 + k < S) dst[k] = (uint8_t)((c2[k >> 1] >> ((k & 1) * 8)) & 0xFFu);
+                }
             }
         }
     }
@@ -536,6 +587,20 @@ int check_common(const char *fn, const qt_format_t *fmt, QtRound *P)
 }
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// fp8 codes may only follow an unscaled fake-quant step of the same fp8 format (decode(code) == value)
+int check_out_type(const char *fn, int out_type, int fq_points, const qt_format_t *fmt, const float *scale_post)
+{
+    if (out_type == OUT_BF16) return QT_OK;
+    const bool e4m3 = fmt->kind == QT_KIND_FP && fmt->ebits == 4 && fmt->mbits == 3 && !fmt->is_unsigned;
+    const bool e5m2 = fmt->kind == QT_KIND_FP && fmt->ebits == 5 && fmt->mbits == 2 && !fmt->is_unsigned;
+    if ((out_type != OUT_E4M3 && out_type != OUT_E5M2) || !(fq_points & FQ_POST) || scale_post ||
+        (out_type == OUT_E4M3 && !e4m3) || (out_type == OUT_E5M2 && !e5m2)) {
+        qt_set_error("%s: fp8 code output needs an unscaled output fake-quant step of the same fp8 format", fn);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    return QT_OK;
+}
+
 int finish(const char *what)
 {
     cudaError_t e = cudaGetLastError();
@@ -547,11 +612,13 @@ int finish(const char *what)
 
 extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_t cols, float alpha, const void *mask,
                              size_t rows_per_batch, size_t mask_rows, size_t mask_batches, int fq_points,
-                             const qt_format_t *fmt, const float *scale_pre, const float *scale_mid,
+                             int out_type, const qt_format_t *fmt, const float *scale_pre, const float *scale_mid,
                              const float *scale_post, const void *lut, void *stream)
 {
     QtRound P;
     int rc = check_common("qt_softmax_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    rc = check_out_type("qt_softmax_fq", out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
     if (!scores || !probs || cols % 8 || cols > 4096 || !aligned16(scores) || !aligned16(probs) ||
@@ -571,7 +638,7 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                                  \
         auto kernel = scaled ? softmax_fq_kernel<R, true, TPR, VPL> : softmax_fq_kernel<R, false, TPR, VPL>;         \
         kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                                \
-            static_cast<const uint4 *>(scores), static_cast<uint4 *>(probs), rows, (int)cols, alpha, has_alpha,      \
+            static_cast<const uint4 *>(scores), probs, out_type, rows, (int)cols, alpha, has_alpha,                  \
             static_cast<const uint4 *>(mask), rows_per_batch, mask_rows, mask_batch_stride_vec, fq_points, params,   \
             scale_pre, scale_mid, scale_post);                                                                       \
     } while (0)
@@ -592,11 +659,13 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
 }
 
 extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int kind, const void *weight,
-                          const void *bias, float eps, int fq_points, const qt_format_t *fmt, const float *scale_pre,
-                          const float *scale_post, const void *lut, void *stream)
+                          const void *bias, float eps, int fq_points, int out_type, const qt_format_t *fmt,
+                          const float *scale_pre, const float *scale_post, const void *lut, void *stream)
 {
     QtRound P;
     int rc = check_common("qt_norm_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    rc = check_out_type("qt_norm_fq", out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
     if (!x || !y || !weight || cols % 8 || cols > 8192 || (kind != 0 && kind != 1) || !aligned16(x) || !aligned16(y) ||
@@ -614,7 +683,7 @@ extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int 
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                              \
         auto kernel = scaled ? norm_fq_kernel<R, true, TPR, VPL> : norm_fq_kernel<R, false, TPR, VPL>;           \
         kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                            \
-            static_cast<const uint4 *>(x), static_cast<uint4 *>(y), rows, (int)cols, kind,                       \
+            static_cast<const uint4 *>(x), y, out_type, rows, (int)cols, kind,                                   \
             static_cast<const uint4 *>(weight), static_cast<const uint4 *>(bias), eps, fq_points, params,        \
             scale_pre, scale_post);                                                                              \
     } while (0)
@@ -637,11 +706,13 @@ extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int 
 }
 
 extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t rows, size_t cols, size_t ld_gate,
-                             size_t ld_up, size_t ld_out, int activation, int fq_points, const qt_format_t *fmt,
-                             const float *scale_post, const void *lut, void *stream)
+                             size_t ld_up, size_t ld_out, int activation, int fq_points, int out_type,
+                             const qt_format_t *fmt, const float *scale_post, const void *lut, void *stream)
 {
     QtRound P;
     int rc = check_common("qt_act_mul_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    rc = check_out_type("qt_act_mul_fq", out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
     if (!gate || !out || cols % 8 || ld_gate % 8 || ld_out % 8 || (up && ld_up % 8) || !aligned16(gate) ||
@@ -655,7 +726,7 @@ extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t
         using R = typename decltype(tag)::type;
         const size_t total = rows * (cols / 8);
         const unsigned grid = grid_for((total + EW_THREADS * 2 - 1) / (EW_THREADS * 2), EW_MIN_CTAS * 2);
-        void (*kernel)(const uint4 *, const uint4 *, uint4 *, size_t, int, size_t, size_t, size_t, int,
+        void (*kernel)(const uint4 *, const uint4 *, void *, int, size_t, int, size_t, size_t, size_t, int,
                        const typename R::Params, const float *) = nullptr;
         const bool scaled = scale_post != nullptr;
         switch (activation * 2 + (scaled ? 1 : 0)) {
@@ -669,8 +740,8 @@ extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t
         default: kernel = act_mul_fq_kernel<R, true, FACT_SILU>; break;
         }
         kernel<<<grid, EW_THREADS, R::kSmemBytes, st>>>(
-            static_cast<const uint4 *>(gate), static_cast<const uint4 *>(up), static_cast<uint4 *>(out), rows,
-            (int)(cols / 8), ld_gate / 8, ld_up / 8, ld_out / 8, fq_points, params, scale_post);
+            static_cast<const uint4 *>(gate), static_cast<const uint4 *>(up), out, out_type, rows, (int)(cols / 8),
+            ld_gate / 8, ld_up / 8, ld_out / 8, fq_points, params, scale_post);
     });
     if (rc != QT_OK) return rc;
     return finish("act_mul_fq kernel launch");
@@ -678,12 +749,14 @@ extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t
 
 extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_out, int q_heads, const void *k,
                           void *k_out, size_t ld_k, size_t ld_k_out, int k_heads, size_t tokens, int head_dim,
-                          const void *cos_table, const void *sin_table, size_t cos_rows, int fq_points,
+                          const void *cos_table, const void *sin_table, size_t cos_rows, int fq_points, int out_type,
                           const qt_format_t *fmt, const float *scale_q, const float *scale_k, const void *lut,
                           void *stream)
 {
     QtRound P;
     int rc = check_common("qt_rope_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    rc = check_out_type("qt_rope_fq", out_type, fq_points, fmt, scale_q ? scale_q : scale_k);
     if (rc != QT_OK) return rc;
     if (tokens == 0) return QT_OK;
     if (!q || !q_out || !cos_table || !sin_table || cos_rows == 0 || head_dim % 16 || head_dim <= 0 || ld_q % 8 ||
@@ -693,8 +766,8 @@ extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_o
         qt_set_error("qt_rope_fq: needs 16-byte aligned bf16 tensors, head_dim %% 16 == 0, token strides %% 8 == 0");
         return QT_ERR_INVALID_ARGUMENT;
     }
-    RopeTensor t0 = {static_cast<const uint4 *>(q), static_cast<uint4 *>(q_out), ld_q / 8, ld_q_out / 8, q_heads};
-    RopeTensor t1 = {static_cast<const uint4 *>(k), static_cast<uint4 *>(k_out), ld_k / 8, ld_k_out / 8,
+    RopeTensor t0 = {static_cast<const uint4 *>(q), q_out, ld_q / 8, ld_q_out / 8, q_heads};
+    RopeTensor t1 = {static_cast<const uint4 *>(k), k_out, ld_k / 8, ld_k_out / 8,
                      k ? k_heads : 0};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
@@ -703,19 +776,21 @@ extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_o
         const unsigned grid = grid_for((total + EW_THREADS - 1) / EW_THREADS, EW_MIN_CTAS * 2);
         auto kernel = (scale_q || scale_k) ? rope_fq_kernel<R, true> : rope_fq_kernel<R, false>;
         kernel<<<grid, EW_THREADS, R::kSmemBytes, st>>>(
-            t0, t1, tokens, head_dim, static_cast<const uint4 *>(cos_table), static_cast<const uint4 *>(sin_table),
-            cos_rows, fq_points, params, scale_q, scale_k);
+            t0, t1, out_type, tokens, head_dim, static_cast<const uint4 *>(cos_table),
+            static_cast<const uint4 *>(sin_table), cos_rows, fq_points, params, scale_q, scale_k);
     });
     if (rc != QT_OK) return rc;
     return finish("rope_fq kernel launch");
 }
 
 extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int heads, int head_dim, size_t ld_tok,
-                               size_t batch_stride, int fq_points, const qt_format_t *fmt, const float *scale_post,
-                               const void *lut, void *stream)
+                               size_t batch_stride, int fq_points, int out_type, const qt_format_t *fmt,
+                               const float *scale_post, const void *lut, void *stream)
 {
     QtRound P;
     int rc = check_common("qt_fq_transpose", fmt, &P);
+    if (rc != QT_OK) return rc;
+    rc = check_out_type("qt_fq_transpose", out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (batch <= 0 || seq <= 0 || heads <= 0) return QT_OK;
     if (!v || !out || head_dim % 8 || head_dim <= 0 || head_dim > 256 || ld_tok % 8 || batch_stride % 8 ||
@@ -730,8 +805,8 @@ extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int
         const size_t smem = R::kSmemBytes + (size_t)TR_TOK * (head_dim + 2) * 2;
         const unsigned grid = grid_for(jobs, EW_MIN_CTAS * 2);
         auto kernel = scale_post ? fq_transpose_kernel<R, true> : fq_transpose_kernel<R, false>;
-        kernel<<<grid, EW_THREADS, smem, st>>>(static_cast<const uint16_t *>(v), static_cast<uint16_t *>(out), batch,
-                                               seq, heads, head_dim, ld_tok, batch_stride, fq_points, params,
+        kernel<<<grid, EW_THREADS, smem, st>>>(static_cast<const uint16_t *>(v), out, out_type, batch, seq, heads,
+                                               head_dim, ld_tok, batch_stride, fq_points, params,
                                                                 scale_post);
     });
     if (rc != QT_OK) return rc;

@@ -49,23 +49,23 @@ EXPORTS = {
     "qt_gemm_nt_ex": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qt_softmax_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float,
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
-                                     ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                     ctypes.c_void_p, ctypes.c_void_p]),
+                                     ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qt_norm_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
-                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                   ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_void_p]),
     "qt_act_mul_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_size_t] * 5 +
-                      [ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p,
-                       ctypes.c_void_p]),
+                      [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
+                       ctypes.c_void_p, ctypes.c_void_p]),
     "qt_rope_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                   ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
-                                  ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p,
-                                  ctypes.c_void_p, ctypes.c_void_p]),
+                                  ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qt_fq_transpose": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
-                        [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
-                         ctypes.c_void_p, ctypes.c_void_p]),
+                        [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat),
+                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qt_amax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -288,6 +288,7 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
 # ---- fused ops (qt_fused.cu): thin wrappers; argument checking beyond dtype/device lives in the C library --------
 FQ_PRE, FQ_MID, FQ_POST = 1, 2, 4
 NORM_RMS, NORM_LAYER = 0, 1
+OUT_BF16, OUT_E4M3, OUT_E5M2 = 0, 1, 2
 
 
 def _ptr(t):
@@ -300,37 +301,61 @@ def _bf16_cuda(t, what):
         raise TypeError(f"{what} must be bfloat16, got {t.dtype}")
 
 
+def _out_type(out):
+    """bf16 destination -> values; uint8 destination -> fp8 codes (the format decides e4m3 / e5m2: see callers)."""
+    if out.dtype == torch.bfloat16:
+        return OUT_BF16
+    if out.dtype != torch.uint8:
+        raise TypeError(f"output must be bfloat16 (values) or uint8 (fp8 codes), got {out.dtype}")
+    return None
+
+
+def _codes_type(fmt):
+    if fmt.kind == 2 and not fmt.is_unsigned and (fmt.ebits, fmt.mbits) == (4, 3):
+        return OUT_E4M3
+    if fmt.kind == 2 and not fmt.is_unsigned and (fmt.ebits, fmt.mbits) == (5, 2):
+        return OUT_E5M2
+    raise ValueError("fp8 code output needs an e4m3 / e5m2 format")
+
+
+def _resolve_out(out, fmt):
+    t = _out_type(out)
+    return _codes_type(fmt) if t is None else t
+
+
 def softmax_fq(scores, probs, alpha, mask, rows_per_batch, mask_rows, mask_batches, fq_points, fmt,
                scale_pre=None, scale_mid=None, scale_post=None, lut=None):
     _bf16_cuda(scores, "scores")
-    assert scores.is_contiguous() and probs.is_contiguous() and probs.dtype == torch.bfloat16
+    assert scores.is_contiguous() and probs.is_contiguous() and probs.shape == scores.shape
     cols = scores.shape[-1]
     with torch.cuda.device(scores.device):
         _check(lib().qt_softmax_fq(scores.data_ptr(), probs.data_ptr(), scores.numel() // cols, cols, float(alpha),
-                                   _ptr(mask), rows_per_batch, mask_rows, mask_batches, fq_points, ctypes.byref(fmt),
-                                   _ptr(scale_pre), _ptr(scale_mid), _ptr(scale_post), _ptr(lut), _stream(scores)))
+                                   _ptr(mask), rows_per_batch, mask_rows, mask_batches, fq_points,
+                                   _resolve_out(probs, fmt), ctypes.byref(fmt), _ptr(scale_pre), _ptr(scale_mid),
+                                   _ptr(scale_post), _ptr(lut), _stream(scores)))
 
 
 def norm_fq(x, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale_post=None, lut=None):
     _bf16_cuda(x, "x")
     assert x.is_contiguous() and y.is_contiguous() and weight.is_contiguous() and weight.dtype == torch.bfloat16
+    assert y.shape == x.shape
     cols = x.shape[-1]
     with torch.cuda.device(x.device):
         _check(lib().qt_norm_fq(x.data_ptr(), y.data_ptr(), x.numel() // cols, cols, kind, weight.data_ptr(),
-                                _ptr(bias), float(eps), fq_points, ctypes.byref(fmt), _ptr(scale_pre),
-                                _ptr(scale_post), _ptr(lut), _stream(x)))
+                                _ptr(bias), float(eps), fq_points, _resolve_out(y, fmt), ctypes.byref(fmt),
+                                _ptr(scale_pre), _ptr(scale_post), _ptr(lut), _stream(x)))
 
 
 def act_mul_fq(gate, up, out, activation, fq_points, fmt, scale_post=None, lut=None):
-    """gate, up, out: 2-D bf16 views [rows, cols] with a unit-stride last axis (row strides may differ)."""
+    """gate, up, out: 2-D views [rows, cols] with a unit-stride last axis (row strides may differ)."""
     _bf16_cuda(gate, "gate")
     assert gate.dim() == 2 and out.shape == gate.shape and gate.stride(1) == 1 and out.stride(1) == 1
     assert up is None or (up.shape == gate.shape and up.stride(1) == 1)
     with torch.cuda.device(gate.device):
         _check(lib().qt_act_mul_fq(gate.data_ptr(), _ptr(up), out.data_ptr(), gate.shape[0], gate.shape[1],
                                    gate.stride(0), up.stride(0) if up is not None else 0, out.stride(0),
-                                   ACTIVATIONS[activation], fq_points, ctypes.byref(fmt), _ptr(scale_post), _ptr(lut),
-                                   _stream(gate)))
+                                   ACTIVATIONS[activation], fq_points, _resolve_out(out, fmt), ctypes.byref(fmt),
+                                   _ptr(scale_post), _ptr(lut), _stream(gate)))
 
 
 def rope_fq(q, q_out, k, k_out, cos, sin, fq_points, fmt, scale_q=None, scale_k=None, lut=None):
@@ -343,12 +368,13 @@ def rope_fq(q, q_out, k, k_out, cos, sin, fq_points, fmt, scale_q=None, scale_k=
     if k is not None:
         kh = k.shape[1]
         assert k.shape[0] == tokens and k.stride(2) == 1 and k.stride(1) == d and k_out.stride(1) == d
+        assert k_out.dtype == q_out.dtype
     with torch.cuda.device(q.device):
         _check(lib().qt_rope_fq(q.data_ptr(), q_out.data_ptr(), q.stride(0), q_out.stride(0), qh,
                                 _ptr(k), _ptr(k_out), k.stride(0) if k is not None else 0,
                                 k_out.stride(0) if k is not None else 0, kh, tokens, d, cos.data_ptr(), sin.data_ptr(),
-                                cos.numel() // d, fq_points, ctypes.byref(fmt), _ptr(scale_q), _ptr(scale_k), _ptr(lut),
-                                _stream(q)))
+                                cos.numel() // d, fq_points, _resolve_out(q_out, fmt), ctypes.byref(fmt), _ptr(scale_q),
+                                _ptr(scale_k), _ptr(lut), _stream(q)))
 
 
 def fq_transpose(v, out, fq_points, fmt, scale_post=None, lut=None):
@@ -358,4 +384,5 @@ def fq_transpose(v, out, fq_points, fmt, scale_post=None, lut=None):
     assert v.stride(3) == 1 and v.stride(2) == d and out.is_contiguous() and tuple(out.shape) == (b, h, d, s_)
     with torch.cuda.device(v.device):
         _check(lib().qt_fq_transpose(v.data_ptr(), out.data_ptr(), b, s_, h, d, v.stride(1), v.stride(0), fq_points,
-                                     ctypes.byref(fmt), _ptr(scale_post), _ptr(lut), _stream(v)))
+                                     _resolve_out(out, fmt), ctypes.byref(fmt), _ptr(scale_post), _ptr(lut),
+                                     _stream(v)))

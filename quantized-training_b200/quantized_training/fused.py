@@ -108,14 +108,39 @@ def _flags(pre=None, mid=None, post=None):
 
 # ---- op wrappers (allocate the output, resolve the fake-quant steps) ------------------------------------------
 
-def norm(x2, weight, bias, eps, kind, pre, post):
+_FP8_OP = {("e4m3", "e4m3"): _C.GEMM_E4M3, ("e5m2", "e5m2"): _C.GEMM_E5M2,
+           ("e4m3", "e5m2"): _C.GEMM_E4M3_E5M2, ("e5m2", "e4m3"): _C.GEMM_E5M2_E4M3}
+
+
+def fp8_kind(fq):
+    """"e4m3" / "e5m2" when `fq` is an UNSCALED fake-quantizer of that format: its output can be handed to the FP8
+    tensor cores as one-byte codes without changing a single value."""
+    if fq is None or not isinstance(fq, FusedAmaxObsFakeQuantize) or fq.qscheme is not None:
+        return None
+    return fq.fp8_kind
+
+
+def gemm_operands(a_fq, b_fq, k):
+    """(operand_type, use_codes) for a product whose operands leave fake-quantizers a_fq / b_fq."""
+    ka, kb = fp8_kind(a_fq), fp8_kind(b_fq)
+    if ka is not None and kb is not None and k % 16 == 0:
+        return _FP8_OP[(ka, kb)], True
+    return _C.GEMM_BF16, False
+
+
+def _out_like(x, codes, shape=None):
+    return torch.empty(x.shape if shape is None else shape, dtype=torch.uint8 if codes else torch.bfloat16,
+                       device=x.device)
+
+
+def norm(x2, weight, bias, eps, kind, pre, post, codes=False):
     fmt, lut, (s_pre, s_post) = _spec(pre, post)
-    y = torch.empty_like(x2)
+    y = _out_like(x2, codes)
     _C.norm_fq(x2, y, kind, weight, bias, eps, _flags(pre=pre, post=post), fmt, s_pre, s_post, lut)
     return y
 
 
-def softmax(scores, alpha, mask, pre, mid, post):
+def softmax(scores, alpha, mask, pre, mid, post, codes=False):
     """scores [B, H, Sq, Sk] contiguous; mask None or additive [Bm, 1, Sq, >=Sk] (Bm in {1, B})."""
     B, H, Sq, Sk = scores.shape
     m3, mb = None, 1
@@ -128,26 +153,42 @@ def softmax(scores, alpha, mask, pre, mid, post):
         m3 = m3.contiguous()
         mb = m3.shape[0]
     fmt, lut, (s_pre, s_mid, s_post) = _spec(pre, mid, post)
-    probs = torch.empty_like(scores)
+    probs = _out_like(scores, codes)
     _C.softmax_fq(scores, probs, alpha, m3, H * Sq, Sq, mb, _flags(pre, mid, post), fmt, s_pre, s_mid, s_post, lut)
     return probs
 
 
-def act_mul(gate, up, activation, post):
+def act_mul(gate, up, activation, post, codes=False):
     fmt, lut, (s_post,) = _spec(post)
-    out = torch.empty(gate.shape, dtype=torch.bfloat16, device=gate.device)
+    out = _out_like(gate, codes)
     _C.act_mul_fq(gate, up, out, activation, _flags(post=post), fmt, s_post, lut)
     return out
 
 
-def fake_quant(x2, post):
+def fake_quant(x2, post, codes=False):
     """Plain fake quant of a 2-D activation through the module's own kernel path (observer-free by construction)."""
+    if codes:
+        return post.quantize_to_codes(x2)
     return x2 if post is None else post(x2)
 
 
 # ---- quantized weights of a block, concatenated once -----------------------------------------------------------
 
-def _quantized_cat(owner, tag, linears):
+def _weight_fq(lin):
+    fq = lin.weight_fake_quant
+    if isinstance(fq, FusedAmaxObsFakeQuantize) and fq._flags() == (False, True):
+        return fq
+    return None
+
+
+def _common_weight_fq(*linears):
+    """The weight fake-quantizer shared by several Linears when all are unscaled fp8 of one format, else None."""
+    fqs = [_weight_fq(lin) for lin in linears]
+    kinds = {fp8_kind(f) for f in fqs}
+    return fqs[0] if len(kinds) == 1 and None not in kinds else None
+
+
+def _quantized_cat(owner, tag, linears, codes=False):
     """cat([fq(W) for each Linear]) along the output axis, cached on `owner` until a weight or a scale is written.
     The weight fake-quantizers must be observer-free (checked) so that skipping their per-forward re-run is
     unobservable."""
@@ -164,17 +205,20 @@ def _quantized_cat(owner, tag, linears):
         else:
             raise _NotFusable
         _only_our_hooks(lin, lin._modules.get("activation_pre_process") is not None)
-    key = tuple(key)
+    key = tuple(key + [codes])
     cache = owner.__dict__.setdefault("_qt_wcache", {})
     hit = cache.get(tag)
     if hit is None or hit[0] != key:
         with torch.no_grad():
-            ws = [lin.weight_fake_quant(lin.weight).detach() for lin in linears]
+            if codes:
+                ws = [lin.weight_fake_quant.quantize_to_codes(lin.weight.detach()) for lin in linears]
+            else:
+                ws = [lin.weight_fake_quant(lin.weight).detach() for lin in linears]
             w = ws[0] if len(ws) == 1 else torch.cat(ws, 0)
             bs = [lin.bias for lin in linears]
             b = None
             if any(x is not None for x in bs):
-                b = torch.cat([x.detach() if x is not None else torch.zeros(lin.weight.shape[0], dtype=w.dtype,
+                b = torch.cat([x.detach() if x is not None else torch.zeros(lin.weight.shape[0], dtype=lin.weight.dtype,
                                                                              device=w.device)
                                for x, lin in zip(bs, linears)], 0).contiguous()
         hit = (key, w.contiguous(), b)
@@ -215,14 +259,24 @@ def llama_layer_forward(layer, hidden_states, attention_mask, position_embedding
         d_in = point(mlp.down_proj)
         res1 = (point(layer.self_attn_residual, "0"), point(layer.self_attn_residual, "1"))
         res2 = (point(layer.mlp_residual, "0"), point(layer.mlp_residual, "1"))
-        w_qkv, b_qkv = _quantized_cat(layer, "qkv", (attn.q_proj, attn.k_proj, attn.v_proj))
-        w_o, b_o = _quantized_cat(layer, "o", (attn.o_proj,))
-        w_gu, b_gu = _quantized_cat(layer, "gu", (mlp.gate_proj, mlp.up_proj))
-        w_d, b_d = _quantized_cat(layer, "d", (mlp.down_proj,))
-
         B, S, hidden = hidden_states.shape
         H, D = attn.config.num_attention_heads, attn.head_dim
         T = B * S
+        inter = mlp.gate_proj.weight.shape[0]
+        # which products run on the FP8 tensor cores (both operands leave unscaled e4m3 / e5m2 fake-quantizers)
+        wq = _common_weight_fq(attn.q_proj, attn.k_proj, attn.v_proj)
+        wgu = _common_weight_fq(mlp.gate_proj, mlp.up_proj)
+        t_qkv, c_qkv = gemm_operands(x_in, wq, hidden)
+        t_qk, c_qk = gemm_operands(q_in, k_in, D)
+        t_pv, c_pv = gemm_operands(p_in, v_in, S)
+        t_o, c_o = gemm_operands(o_in, _weight_fq(attn.o_proj), H * D)
+        t_gu, c_gu = gemm_operands(gu_in, wgu, hidden)
+        t_d, c_d = gemm_operands(d_in, _weight_fq(mlp.down_proj), inter)
+        w_qkv, b_qkv = _quantized_cat(layer, "qkv", (attn.q_proj, attn.k_proj, attn.v_proj), c_qkv)
+        w_o, b_o = _quantized_cat(layer, "o", (attn.o_proj,), c_o)
+        w_gu, b_gu = _quantized_cat(layer, "gu", (mlp.gate_proj, mlp.up_proj), c_gu)
+        w_d, b_d = _quantized_cat(layer, "d", (mlp.down_proj,), c_d)
+
         x = hidden_states.reshape(T, hidden)
         if not x.is_contiguous():
             x = x.contiguous()
@@ -230,45 +284,43 @@ def llama_layer_forward(layer, hidden_states, attention_mask, position_embedding
         cos2, sin2 = cos.reshape(-1, D), sin.reshape(-1, D)
         if cos2.dtype != torch.bfloat16 or cos2.shape[0] not in (S, T) or not cos2.is_contiguous():
             return None
+        if (q_in is None) != (k_in is None):
+            raise _NotFusable
 
         # attention
         n1 = layer.input_layernorm
-        xq = norm(x, n1.weight, None, n1.variance_epsilon, _C.NORM_RMS, ln1_in, x_in)
-        qkv = _C.gemm_nt(xq, w_qkv, bias=b_qkv)                                  # [T, 3 * H * D]
+        xq = norm(x, n1.weight, None, n1.variance_epsilon, _C.NORM_RMS, ln1_in, x_in, c_qkv)
+        qkv = _C.gemm_nt(xq, w_qkv, bias=b_qkv, operand_type=t_qkv)              # [T, 3 * H * D]
         q = qkv[:, :H * D].view(T, H, D)
         k = qkv[:, H * D:2 * H * D].view(T, H, D)
         v = qkv[:, 2 * H * D:].view(B, S, H, D)
         fmt, lut, (s_q, s_k) = _spec(q_in, k_in)
-        qk = torch.empty(2, T, H, D, dtype=torch.bfloat16, device=x.device)
-        _C.rope_fq(q, qk[0], k, qk[1], cos2, sin2, _C.FQ_POST if (q_in is not None or k_in is not None) else 0, fmt,
-                   s_q, s_k, lut)
-        if (q_in is None) != (k_in is None):
-            raise _NotFusable
+        qk = _out_like(x, c_qk, (2, T, H, D))
+        _C.rope_fq(q, qk[0], k, qk[1], cos2, sin2, _C.FQ_POST if q_in is not None else 0, fmt, s_q, s_k, lut)
         fmt, lut, (s_v,) = _spec(v_in)
-        vt = torch.empty(B, H, D, S, dtype=torch.bfloat16, device=x.device)
+        vt = _out_like(x, c_pv, (B, H, D, S))
         _C.fq_transpose(v, vt, _flags(post=v_in), fmt, s_v, lut)
         q4 = qk[0].view(B, S, H, D).transpose(1, 2)
         k4 = qk[1].view(B, S, H, D).transpose(1, 2)
-        scores = _C.gemm_nt(q4, k4)                                              # [B, H, S, S]
-        probs = softmax(scores, attn.scaling, attention_mask, sc_in, sm_in, p_in)
+        scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                           # [B, H, S, S]
+        probs = softmax(scores, attn.scaling, attention_mask, sc_in, sm_in, p_in, c_pv)
         ctx = torch.empty(B, S, H * D, dtype=torch.bfloat16, device=x.device)
-        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2))
-        ctx2 = fake_quant(ctx.view(T, H * D), o_in)
+        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv)
+        ctx2 = fake_quant(ctx.view(T, H * D), o_in, c_o)
         if res1 == (None, None):
-            h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x)                     # residual add in the fp32 epilogue
+            h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x, operand_type=t_o)   # residual add in the epilogue
         else:
-            h1 = layer.self_attn_residual(x, _C.gemm_nt(ctx2, w_o, bias=b_o))
+            h1 = layer.self_attn_residual(x, _C.gemm_nt(ctx2, w_o, bias=b_o, operand_type=t_o))
 
         # MLP
         n2 = layer.post_attention_layernorm
-        x2 = norm(h1, n2.weight, None, n2.variance_epsilon, _C.NORM_RMS, ln2_in, gu_in)
-        gu = _C.gemm_nt(x2, w_gu, bias=b_gu)                                     # [T, 2 * I]
-        inter = w_gu.shape[0] // 2
-        a = act_mul(gu[:, :inter], gu[:, inter:], act_name, d_in)
+        x2 = norm(h1, n2.weight, None, n2.variance_epsilon, _C.NORM_RMS, ln2_in, gu_in, c_gu)
+        gu = _C.gemm_nt(x2, w_gu, bias=b_gu, operand_type=t_gu)                  # [T, 2 * I]
+        a = act_mul(gu[:, :inter], gu[:, inter:], act_name, d_in, c_d)
         if res2 == (None, None):
-            h2 = _C.gemm_nt(a, w_d, bias=b_d, residual=h1)
+            h2 = _C.gemm_nt(a, w_d, bias=b_d, residual=h1, operand_type=t_d)
         else:
-            h2 = layer.mlp_residual(h1, _C.gemm_nt(a, w_d, bias=b_d))
+            h2 = layer.mlp_residual(h1, _C.gemm_nt(a, w_d, bias=b_d, operand_type=t_d))
         return h2.view(B, S, hidden)
     except (_NotReady, _NotFusable, AttributeError):
         return None

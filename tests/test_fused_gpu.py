@@ -181,3 +181,47 @@ def test_fused_ops_reject_what_they_cannot_do():
                        torch.ones(64, device=DEV, dtype=torch.bfloat16), None, 1e-5, 4, fmt, lut=None)  # no table
     with pytest.raises(TypeError):
         _C.norm_fq(x.float(), x.float(), 0, x[0], None, 1e-5, 4, fmt, lut=lut)
+
+
+@pytest.mark.parametrize("spec,tdt", [("e4m3", torch.float8_e4m3fn), ("e5m2", torch.float8_e5m2), ("fp8_e4m3", torch.float8_e4m3fn)])
+def test_fp8_code_outputs_decode_to_the_bf16_outputs(spec, tdt):
+    """uint8 destinations receive the fp8 codes of exactly the values the bf16 destinations receive."""
+    torch.manual_seed(8)
+    fmt, lut = fmt_lut(spec)
+    dec = lambda c: c.view(tdt).to(torch.bfloat16)
+    x = (torch.randn(40, 1024, device=DEV) * 3).bfloat16()
+    x[0, :4] = torch.tensor([float("inf"), -float("inf"), 1e30, -0.0], device=DEV)
+    w = (1 + 0.1 * torch.randn(1024, device=DEV)).bfloat16()
+    yb, yc = torch.empty_like(x), torch.empty(x.shape, dtype=torch.uint8, device=DEV)
+    _C.norm_fq(x[1:], yb[1:], _C.NORM_RMS, w, None, 1e-5, _C.FQ_POST, fmt, lut=lut)
+    _C.norm_fq(x[1:], yc[1:], _C.NORM_RMS, w, None, 1e-5, _C.FQ_POST, fmt, lut=lut)
+    assert torch.equal(bits(dec(yc[1:])), bits(yb[1:]))
+    _C.act_mul_fq(x, None, yb, None, _C.FQ_POST, fmt, lut=lut)          # plain fake quant incl. Inf / huge / -0
+    _C.act_mul_fq(x, None, yc, None, _C.FQ_POST, fmt, lut=lut)
+    got, want = dec(yc).float(), yb.float()
+    same = (got == want) | (torch.isnan(got) & torch.isnan(want)) | (torch.isnan(got) & torch.isinf(want))  # e4m3 has no Inf
+    assert bool(same.all())
+    _C.act_mul_fq(x, x, yb, "silu", _C.FQ_POST, fmt, lut=lut)
+    _C.act_mul_fq(x, x, yc, "silu", _C.FQ_POST, fmt, lut=lut)
+    assert torch.equal(bits(dec(yc[1:])), bits(yb[1:]))
+    s = (torch.randn(2, 2, 16, 1024, device=DEV) * 4).bfloat16()
+    pb, pc = torch.empty_like(s), torch.empty(s.shape, dtype=torch.uint8, device=DEV)
+    _C.softmax_fq(s, pb, 0.5, None, 32, 16, 1, _C.FQ_POST, fmt, lut=lut)
+    _C.softmax_fq(s, pc, 0.5, None, 32, 16, 1, _C.FQ_POST, fmt, lut=lut)
+    assert torch.equal(bits(dec(pc)), bits(pb))
+    v = (torch.randn(2, 100, 4, 64, device=DEV) * 2).bfloat16()
+    tb, tc = torch.empty(2, 4, 64, 100, device=DEV, dtype=torch.bfloat16), torch.empty(2, 4, 64, 100, device=DEV, dtype=torch.uint8)
+    _C.fq_transpose(v, tb, _C.FQ_POST, fmt, lut=lut)
+    _C.fq_transpose(v, tc, _C.FQ_POST, fmt, lut=lut)
+    assert torch.equal(bits(dec(tc)), bits(tb))
+    q = (torch.randn(50, 4, 64, device=DEV)).bfloat16()
+    cos = torch.rand(50, 64, device=DEV).bfloat16(); sin = torch.rand(50, 64, device=DEV).bfloat16()
+    rb, rc = torch.empty_like(q), torch.empty(q.shape, dtype=torch.uint8, device=DEV)
+    _C.rope_fq(q, rb, None, None, cos, sin, _C.FQ_POST, fmt, lut=lut)
+    _C.rope_fq(q, rc, None, None, cos, sin, _C.FQ_POST, fmt, lut=lut)
+    assert torch.equal(bits(dec(rc)), bits(rb))
+    with pytest.raises(ValueError):       # codes need the output fake-quant step ...
+        _C.norm_fq(x, yc, _C.NORM_RMS, w, None, 1e-5, 0, fmt, lut=lut)
+    pfmt, plut = fmt_lut("posit8_1")
+    with pytest.raises(ValueError):       # ... of an fp8 format
+        _C.norm_fq(x, yc, _C.NORM_RMS, w, None, 1e-5, _C.FQ_POST, pfmt, lut=plut)

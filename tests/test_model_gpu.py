@@ -139,5 +139,8 @@ def test_llama_fused_layer_matches_module_by_module(spec, ops_str, monkeypatch):
         want = model(input_ids=ids, use_cache=False).logits
         fused.set_enabled(True)
     assert rel_err(got, want) < 2e-2
+    if spec == "e4m3":     # every product of the fused layer took fp8 codes (FP8 tensor cores)
+        cache = model.model.layers[0].__dict__["_qt_wcache"]
+        assert all(v[1].dtype == torch.uint8 for v in cache.values())
     x = torch.randn(2, 96, 256, device=DEV).bfloat16().requires_grad_()
     assert fused.llama_layer_forward(model.model.layers[0], x, None, None) is None     # autograd on: module path
