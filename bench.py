@@ -31,12 +31,75 @@ UNIT = "GB/s"
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
 
 
-def peaks():
+FALLBACK_BF16_TFLOPS = 1590.0  # burst; ~1400 sustained (B200_PROFILING.md)
+
+
+def _measured():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return json.load(f)
+    return None
+
+
+def peaks():
+    m = _measured()
+    if m:
+        return float(m["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    """Dense bf16 TFLOP/s for a kernel timed inside a long step (sustained figure)."""
+    m = _measured()
+    if m and "bf16_tflops_sustained" in m:
+        return float(m["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md, sustained)"
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, scaled to this run's
+    launch size (the capture's own size is recorded beside it)."""
+    p = os.path.join(ROOT, "profiles", "fq_flat_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
+def run_llama(args, dev, rank, world, dist, barrier):
+    """Llama-2-7B-shape quantized forward (BASELINE configs[4]): windows [1, 1024], posit8_1 and e4m3, --quantize_forward
+    gemm, data-parallel over ranks (each rank its own windows, no collective on the data path)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import llama_bench as LB
+
+    out = {"workload": "Llama-2-7B shape (32 layers, hidden 4096, 32 heads, inter 11008, vocab 32000), random-init "
+                       "bf16 weights, synthetic tokens, windows [1,1024], quantize_forward=gemm, whole forward "
+                       "captured in one CUDA graph", "windows_per_rank": args.llama_steps, "n_gpus": world,
+           "flops_per_window_T": LB.flops_per_window(32, 1024) / 1e12, "specs": {}}
+    peak, peak_src = tensor_peak()
+    for spec in ("posit8_1", "e4m3"):
+        model, fwd, ids = LB.setup(spec, dev, seed=rank)
+        ms, e2e_s, loss = LB.measure(fwd, args.llama_steps, graph=True, warmup=max(args.warmup, 3), ids=ids,
+                                     barrier=barrier)
+        if dist is not None:
+            t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, e2e_s = float(t[0]), float(t[1])
+        tf = LB.flops_per_window(32, 1024) / ms / 1e9
+        fp8 = spec == "e4m3"
+        out["specs"][spec] = {
+            "tokens_per_s": world * 1024 / ms * 1e3, "ms_per_window": ms, "loss": loss,
+            "e2e_tokens_per_s": world * 1024 / e2e_s, "tflops_per_gpu": tf,
+            "roofline": {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s",
+                         "peak": peak * (2.0 if fp8 else 1.0), "frac": tf / (peak * (2.0 if fp8 else 1.0)),
+                         "peak_source": peak_src + (" x 2 (fp8 MMA rate)" if fp8 else ""),
+                         "operands": "e4m3 codes, kind::f8f6f4" if fp8 else "posit8 values held in bf16, kind::f16"}}
+        del model, fwd
+        torch.cuda.empty_cache()
+    return out
+
 
 
 class ClockSampler:
@@ -271,6 +334,12 @@ def run_gpu(args):
         e2e_s = float(t.item())
     e2e_val = 4.0 * ne * len(SWEEP) * e2e_steps * world / e2e_s / 1e9
 
+    del pipe, xh, yh, x, y
+    torch.cuda.empty_cache()
+    llama = None
+    if not args.no_llama:
+        llama = run_llama(args, dev, rank, world, dist, barrier)
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -279,6 +348,11 @@ def run_gpu(args):
             gbs, threads, dt = cpu_port_gbs(24, reps)
             cpu = {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{reps} x {len(SWEEP)} specs x 2^24 bf16 elements, {dt:.1f} s"}
+        tr = measured_traffic()
+        traffic_per_launch, traffic_src = None, None
+        if tr:  # measured DRAM bytes / algorithmic bytes of the captured launch, applied to this launch size
+            traffic_per_launch = bytes_per_launch * tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_per_launch"]
+            traffic_src = tr["source"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -289,7 +363,8 @@ def run_gpu(args):
                        "l2": "input+output 4*2^L bytes per launch >> 126 MB L2 (no flush needed)",
                        "parallelism": f"dp{world} (independent shards, no collective)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "fq_flat_kernel",
+                         "traffic": traffic_per_launch, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "fq_flat_kernel",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": kernel_ms,
                          "max_launch_ms": slowest,
                          "per_spec_GBps": {s: bytes_per_launch / (ms * 1e-3) / 1e9 for s, ms in zip(SWEEP, per_spec_ms)}},
@@ -298,7 +373,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": 2 * ne * len(SWEEP), "log2_numel": ne.bit_length() - 1,
                     "api": "quantized_training.host_io.HostPipeline.run(module, pinned host in, pinned host out): "
                            "8 MB chunks, H2D / kernel / D2H overlapped on 4 streams"},
-            "gpu_launches": launches, "clocks": clocks, "other_shapes_GBps": extra,
+            "gpu_launches": launches, "clocks": clocks, "other_shapes_GBps": extra, "llama_forward": llama,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -315,6 +390,8 @@ def main():
     ap.add_argument("--e2e-log2-numel", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-llama", action="store_true")
+    ap.add_argument("--llama-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
