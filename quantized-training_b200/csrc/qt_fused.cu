@@ -35,20 +35,42 @@ struct TableRounderDyn {
     using Params = TableParams;
     const unsigned char *tab;
     const uint32_t clamp_bits, mx_band;
+    const bool plain;  // no clamp, no NaN band (posit formats): the two-FMA core alone
     __device__ __forceinline__ TableRounderDyn(const Params &p, const unsigned char *smem)
-        : tab(smem), clamp_bits(p.cfg.clamp_bits), mx_band(p.cfg.mx_band)
+        : tab(smem), clamp_bits(p.cfg.clamp_bits), mx_band(p.cfg.mx_band),
+          plain(p.cfg.clamp_bits == 0x7FFFFFFFu && p.cfg.mx_band == 0u)
     {
     }
-    __device__ __forceinline__ uint32_t operator()(uint32_t u) const
+    template <bool PLAIN>
+    __device__ __forceinline__ uint32_t apply(uint32_t u) const
     {
         const uint32_t a = u & 0x7FFFFFFFu;
-        uint32_t q = qt_lut_round_smem<false, 1>(tab, 0u, u >> 16, a, min(a, clamp_bits));
-        if (mx_band && a >= 0x7F580000u && a != 0x7F800000u) q = QT_NAN_BITS;
+        uint32_t q = qt_lut_round_smem<false, 1>(tab, 0u, u >> 16, a, PLAIN ? a : min(a, clamp_bits));
+        if (!PLAIN && mx_band && a >= 0x7F580000u && a != 0x7F800000u) q = QT_NAN_BITS;
         return q;
     }
+    __device__ __forceinline__ uint32_t operator()(uint32_t u) const { return apply<false>(u); }
     __device__ __forceinline__ uint32_t lo(uint32_t w) const { return (*this)(w << 16); }
     __device__ __forceinline__ uint32_t hi(uint32_t w) const { return (*this)(w & 0xFFFF0000u); }
+    // eight values; the format switches are uniform over the launch, so they are tested once per vector
+    __device__ __forceinline__ void round8(float (&f)[8]) const
+    {
+        if (plain) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(apply<true>(__float_as_uint(f[k])));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(apply<false>(__float_as_uint(f[k])));
+        }
+    }
 };
+template <class R>
+__device__ __forceinline__ void rounder8(const R &round, float (&f)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(round(__float_as_uint(f[k])));
+}
+__device__ __forceinline__ void rounder8(const TableRounderDyn &round, float (&f)[8]) { round.round8(f); }
 
 struct FqPoint {
     ScaleBf16 sc;
@@ -62,7 +84,27 @@ __device__ __forceinline__ FqPoint load_point(const float *scale)
     p.mode = classify_scale(p.sc.s);
     return p;
 }
-__device__ __forceinline__ float bf16_round(float f) { return __uint_as_float(bf16_rne_hi(f)); }
+// ex2.approx.ftz alone (MUFU.EX2): arguments are <= 0 here, results below 2^-126 flush to zero, which is what the
+// following rounding to bf16 / to the format would make of them anyway (__expf adds a range fix-up of 3 instructions)
+__device__ __forceinline__ float exp2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Rounding to the bf16 grid, eight values at a time through the PACKED conversion (F2FP.BF16.PACK_AB, ALU pipe, one
+// instruction per pair + two to unpack).  The scalar cvt.rn.bf16.f32 is an XU-pipe instruction (16 lanes / clock / SM,
+// shared with MUFU.EX2): with three roundings and one exp per element the softmax kernel was XU-bound (ncu: XU 47 %,
+// issue 54 %, DRAM 14 %).
+__device__ __forceinline__ void round8(float (&f)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t p = bf16x2_rne(f[2 * k], f[2 * k + 1]);
+        f[2 * k] = __uint_as_float(p << 16);
+        f[2 * k + 1] = __uint_as_float(p & 0xFFFF0000u);
+    }
+}
 
 // Eight bf16 values (as floats) through quantize-dequantize.  SCALED = false (bare specs: every BASELINE config):
 // the rounding alone.  SCALED = true: the frozen per-tensor scale, divide / round / multiply as qt_fq_forward does;
@@ -71,8 +113,7 @@ template <class R, bool SCALED>
 __device__ __forceinline__ void fq8(const R &round, float (&f)[8], const FqPoint &p)
 {
     if (!SCALED || p.mode == DIV_UNIT) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(round(__float_as_uint(f[k])));
+        rounder8(round, f);
     } else if (p.mode == DIV_RECIP) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(fq_bf16<R, DIV_RECIP>(round, __float_as_uint(f[k]), p.sc));
@@ -110,17 +151,32 @@ __device__ __forceinline__ uint4 round_pack8(const float (&f)[8])
 // per vector) for the FP8 tensor-core GEMM -- only after an UNSCALED fake-quant step of that very format, so that
 // decode(code) == value exactly (the launchers enforce it).  +-Inf (which only the fpN_eXmY flavour lets through)
 // gets the format's Inf / NaN code instead of the saturated maximum.
-enum { OUT_BF16 = 0, OUT_E4M3 = 1, OUT_E5M2 = 2 };
+enum { OUT_BF16 = 0, OUT_E4M3 = 1, OUT_E5M2 = 2, OUT_INF_POSSIBLE = 4 /* flag, set by the launcher for fpN_eXmY */ };
+template <bool INF>
 __device__ __forceinline__ uint32_t fp8x2_dyn(float lo, float hi, int out_type)
 {
-    uint32_t c = out_type == OUT_E5M2
-                     ? (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E5M2)
-                     : (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E4M3);
-    const uint32_t inf_code = out_type == OUT_E5M2 ? 0x7Cu : 0x7Fu;
-    const uint32_t bl = __float_as_uint(lo), bh = __float_as_uint(hi);
-    if ((bl & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0xFF00u) | ((bl >> 24) & 0x80u) | inf_code;
-    if ((bh & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0x00FFu) | ((((bh >> 24) & 0x80u) | inf_code) << 8);
+    const bool e5m2 = (out_type & 3) == OUT_E5M2;
+    uint32_t c = e5m2 ? (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E5M2)
+                      : (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E4M3);
+    if (INF) {
+        const uint32_t inf_code = e5m2 ? 0x7Cu : 0x7Fu;
+        const uint32_t bl = __float_as_uint(lo), bh = __float_as_uint(hi);
+        if ((bl & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0xFF00u) | ((bl >> 24) & 0x80u) | inf_code;
+        if ((bh & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0x00FFu) | ((((bh >> 24) & 0x80u) | inf_code) << 8);
+    }
     return c;
+}
+__device__ __forceinline__ uint2 codes8(const float (&f)[8], int out_type)
+{
+    uint2 o;
+    if (out_type & OUT_INF_POSSIBLE) {
+        o.x = fp8x2_dyn<true>(f[0], f[1], out_type) | (fp8x2_dyn<true>(f[2], f[3], out_type) << 16);
+        o.y = fp8x2_dyn<true>(f[4], f[5], out_type) | (fp8x2_dyn<true>(f[6], f[7], out_type) << 16);
+    } else {
+        o.x = fp8x2_dyn<false>(f[0], f[1], out_type) | (fp8x2_dyn<false>(f[2], f[3], out_type) << 16);
+        o.y = fp8x2_dyn<false>(f[4], f[5], out_type) | (fp8x2_dyn<false>(f[6], f[7], out_type) << 16);
+    }
+    return o;
 }
 // vector `idx` (8 elements) of an output whose base is `base`: 16 bytes of bf16 or 8 bytes of codes
 __device__ __forceinline__ void store8(void *base, size_t idx, const float (&f)[8], int out_type)
@@ -128,10 +184,7 @@ __device__ __forceinline__ void store8(void *base, size_t idx, const float (&f)[
     if (out_type == OUT_BF16) {
         __stcs(static_cast<uint4 *>(base) + idx, pack8(f));
     } else {
-        uint2 o;
-        o.x = fp8x2_dyn(f[0], f[1], out_type) | (fp8x2_dyn(f[2], f[3], out_type) << 16);
-        o.y = fp8x2_dyn(f[4], f[5], out_type) | (fp8x2_dyn(f[6], f[7], out_type) << 16);
-        __stcs(static_cast<uint2 *>(base) + idx, o);
+        __stcs(static_cast<uint2 *>(base) + idx, codes8(f, out_type));
     }
 }
 
@@ -220,13 +273,15 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
                 if (flags & FQ_PRE) fq8<R, SCALED>(round, f[j], pre);
                 if (has_alpha) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) f[j][k] = bf16_round(f[j][k] * alpha);
+                    for (int k = 0; k < 8; ++k) f[j][k] *= alpha;
+                    round8(f[j]);
                 }
                 if (mrow) {
                     float m8[8];
                     unpack8(mraw[j], m8);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) f[j][k] = bf16_round(f[j][k] + m8[k]);
+                    for (int k = 0; k < 8; ++k) f[j][k] += m8[k];
+                    round8(f[j]);
                 }
                 if (flags & FQ_MID) fq8<R, SCALED>(round, f[j], mid);
 #pragma unroll
@@ -238,25 +293,44 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
         }
         mx = row_reduce<TPR, true>(mx);
         float sum = 0.0f;
+        // A vector whose eight inputs are all below mx - 128 contributes exp() == 0 exactly (the fp32 exp underflows
+        // below -103.97): masked positions (s + finfo.min) take this path -- half of a causal row -- and skip the
+        // exp, the normalisation and the fake quant, whose result for 0 is the same 0 for every format.
+        const float dead = mx - 128.0f;
+        unsigned alive = 0u;
 #pragma unroll
-        for (int j = 0; j < VPL; ++j)
+        for (int j = 0; j < VPL; ++j) {
+            float vmax = f[j][0];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                // s and mx are bf16 values: the difference is exact; exp through ex2.approx (relative error ~2^-21
-                // for the arguments that survive the following rounding to bf16)
-                f[j][k] = __expf(f[j][k] - mx);
-                sum += f[j][k];
+            for (int k = 1; k < 8; ++k) vmax = fmaxf(vmax, f[j][k]);
+            if (vmax > dead || !(mx == mx) || mx == -INFINITY) {  // NaN / all-masked rows: keep torch's NaN semantics
+                alive |= 1u << j;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    // s and mx are bf16 values: the difference is exact; exp through ex2.approx (relative error
+                    // ~2^-21 for the arguments that survive the following rounding to bf16)
+                    f[j][k] = exp2_approx((f[j][k] - mx) * 1.4426950408889634f);
+                    sum += f[j][k];
+                }
             }
+        }
         sum = row_reduce<TPR, false>(sum);
         const float inv = __frcp_rn(sum);
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int i = lane + TPR * j;
             if (i < nvec && live) {
+                if (alive & (1u << j)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) f[j][k] = bf16_round(f[j][k] * inv);
-                if (flags & FQ_POST) fq8<R, SCALED>(round, f[j], post);
-                store8(probs, row * nvec + i, f[j], out_type);
+                    for (int k = 0; k < 8; ++k) f[j][k] *= inv;
+                    round8(f[j]);
+                    if (flags & FQ_POST) fq8<R, SCALED>(round, f[j], post);
+                    store8(probs, row * nvec + i, f[j], out_type);
+                } else if (out_type == OUT_BF16) {
+                    __stcs(static_cast<uint4 *>(probs) + row * nvec + i, make_uint4(0u, 0u, 0u, 0u));
+                } else {
+                    __stcs(static_cast<uint2 *>(probs) + row * nvec + i, make_uint2(0u, 0u));
+                }
             }
         }
     }
@@ -330,12 +404,17 @@ norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, int out_type, 
                 unpack8(__ldg(weight + i), w);
                 if (kind == 0) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) f[k] = bf16_round(w[k] * bf16_round(f[k] * rstd));
+                    for (int k = 0; k < 8; ++k) f[k] *= rstd;
+                    round8(f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] *= w[k];
+                    round8(f);
                 } else {
                     float b[8];
                     if (bias) unpack8(__ldg(bias + i), b);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) f[k] = bf16_round((f[k] - mean) * rstd * w[k] + (bias ? b[k] : 0.0f));
+                    for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean) * rstd * w[k] + (bias ? b[k] : 0.0f);
+                    round8(f);
                 }
                 if (flags & FQ_POST) fq8<R, SCALED>(round, f, post);
                 store8(y, row * nvec + i, f, out_type);
@@ -381,18 +460,20 @@ act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, 
             for (int k = 0; k < 8; ++k) {
                 float a = g[k];
                 if (ACT == FACT_SILU)
-                    a = bf16_round(__fdividef(a, 1.0f + __expf(-a)));
+                    a = __fdividef(a, 1.0f + __expf(-a));
                 else if (ACT == FACT_GELU)
-                    a = bf16_round(0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)));
+                    a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752440f));
                 else if (ACT == FACT_RELU)
                     a = fmaxf(a, 0.0f);
                 g[k] = a;
             }
+            if (ACT == FACT_SILU || ACT == FACT_GELU) round8(g);
             if (up) {
                 float u[8];
                 unpack8(uv[i], u);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) g[k] = bf16_round(g[k] * u[k]);
+                for (int k = 0; k < 8; ++k) g[k] *= u[k];
+                round8(g);
             }
             if (flags & FQ_POST) fq8<R, SCALED>(round, g, post);
             if (live[i]) store8(out, off_out[i], g, out_type);
@@ -442,17 +523,33 @@ rope_fq_kernel(RopeTensor t0, RopeTensor t1, int out_type, size_t tokens, int he
         unpack8(xa, a);
         unpack8(xb, b);
         {
-            float cw[8], sw[8];
+            float cw[8], sw[8], t2[8];
             unpack8(ca4, cw);
             unpack8(sa4, sw);
             // first half: x1 * cos - x2 * sin (rotate_half gives -x2)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) ra[k] = bf16_round(bf16_round(a[k] * cw[k]) + bf16_round(-b[k] * sw[k]));
+            for (int k = 0; k < 8; ++k) {
+                ra[k] = a[k] * cw[k];
+                t2[k] = -b[k] * sw[k];
+            }
+            round8(ra);
+            round8(t2);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ra[k] += t2[k];
+            round8(ra);
             unpack8(cb4, cw);
             unpack8(sb4, sw);
             // second half: x2 * cos + x1 * sin
 #pragma unroll
-            for (int k = 0; k < 8; ++k) rb[k] = bf16_round(bf16_round(b[k] * cw[k]) + bf16_round(a[k] * sw[k]));
+            for (int k = 0; k < 8; ++k) {
+                rb[k] = b[k] * cw[k];
+                t2[k] = a[k] * sw[k];
+            }
+            round8(rb);
+            round8(t2);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rb[k] += t2[k];
+            round8(rb);
         }
         if (flags & FQ_POST) {
             fq8<R, SCALED>(round, ra, pt);
@@ -532,11 +629,11 @@ fq_transpose_kernel(const uint16_t *__restrict__ v, void *__restrict__ out_v, in
                 }
             } else {
                 uint8_t *dst = static_cast<uint8_t *>(out_v) + o0;
-                uint32_t c2[4];
+                float fe[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    c2[k] = fp8x2_dyn(__uint_as_float((uint32_t)e[2 * k] << 16), __uint_as_float((uint32_t)e[2 * k + 1] << 16),
-                                      out_type);
+                for (int k = 0; k < 8; ++k) fe[k] = __uint_as_float((uint32_t)e[k] << 16);
+                const uint2 cc = codes8(fe, out_type);
+                const uint32_t c2[4] = {cc.x & 0xFFFFu, cc.x >> 16, cc.y & 0xFFFFu, cc.y >> 16};
                 if (full) {
                     uint2 o;
                     o.x = c2[0] | (c2[1] << 16);
@@ -588,8 +685,9 @@ int check_common(const char *fn, const qt_format_t *fmt, QtRound *P)
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // fp8 codes may only follow an unscaled fake-quant step of the same fp8 format (decode(code) == value)
-int check_out_type(const char *fn, int out_type, int fq_points, const qt_format_t *fmt, const float *scale_post)
+int check_out_type(const char *fn, int *out_type_io, int fq_points, const qt_format_t *fmt, const float *scale_post)
 {
+    const int out_type = *out_type_io;
     if (out_type == OUT_BF16) return QT_OK;
     const bool e4m3 = fmt->kind == QT_KIND_FP && fmt->ebits == 4 && fmt->mbits == 3 && !fmt->is_unsigned;
     const bool e5m2 = fmt->kind == QT_KIND_FP && fmt->ebits == 5 && fmt->mbits == 2 && !fmt->is_unsigned;
@@ -598,6 +696,7 @@ int check_out_type(const char *fn, int out_type, int fq_points, const qt_format_
         qt_set_error("%s: fp8 code output needs an unscaled output fake-quant step of the same fp8 format", fn);
         return QT_ERR_INVALID_ARGUMENT;
     }
+    if (fmt->flavour == QT_FP_MX) *out_type_io |= OUT_INF_POSSIBLE;  // fpN_eXmY lets +-Inf through
     return QT_OK;
 }
 
@@ -618,7 +717,7 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
     QtRound P;
     int rc = check_common("qt_softmax_fq", fmt, &P);
     if (rc != QT_OK) return rc;
-    rc = check_out_type("qt_softmax_fq", out_type, fq_points, fmt, scale_post);
+    rc = check_out_type("qt_softmax_fq", &out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
     if (!scores || !probs || cols % 8 || cols > 4096 || !aligned16(scores) || !aligned16(probs) ||
@@ -665,7 +764,7 @@ extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int 
     QtRound P;
     int rc = check_common("qt_norm_fq", fmt, &P);
     if (rc != QT_OK) return rc;
-    rc = check_out_type("qt_norm_fq", out_type, fq_points, fmt, scale_post);
+    rc = check_out_type("qt_norm_fq", &out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
     if (!x || !y || !weight || cols % 8 || cols > 8192 || (kind != 0 && kind != 1) || !aligned16(x) || !aligned16(y) ||
@@ -712,7 +811,7 @@ extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t
     QtRound P;
     int rc = check_common("qt_act_mul_fq", fmt, &P);
     if (rc != QT_OK) return rc;
-    rc = check_out_type("qt_act_mul_fq", out_type, fq_points, fmt, scale_post);
+    rc = check_out_type("qt_act_mul_fq", &out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
     if (!gate || !out || cols % 8 || ld_gate % 8 || ld_out % 8 || (up && ld_up % 8) || !aligned16(gate) ||
@@ -756,7 +855,7 @@ extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_o
     QtRound P;
     int rc = check_common("qt_rope_fq", fmt, &P);
     if (rc != QT_OK) return rc;
-    rc = check_out_type("qt_rope_fq", out_type, fq_points, fmt, scale_q ? scale_q : scale_k);
+    rc = check_out_type("qt_rope_fq", &out_type, fq_points, fmt, scale_q ? scale_q : scale_k);
     if (rc != QT_OK) return rc;
     if (tokens == 0) return QT_OK;
     if (!q || !q_out || !cos_table || !sin_table || cos_rows == 0 || head_dim % 16 || head_dim <= 0 || ld_q % 8 ||
@@ -790,7 +889,7 @@ extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int
     QtRound P;
     int rc = check_common("qt_fq_transpose", fmt, &P);
     if (rc != QT_OK) return rc;
-    rc = check_out_type("qt_fq_transpose", out_type, fq_points, fmt, scale_post);
+    rc = check_out_type("qt_fq_transpose", &out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (batch <= 0 || seq <= 0 || heads <= 0) return QT_OK;
     if (!v || !out || head_dim % 8 || head_dim <= 0 || head_dim > 256 || ld_tok % 8 || batch_stride % 8 ||
