@@ -195,10 +195,12 @@ int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_t cols, flo
                   const qt_format_t *fmt, const float *scale_pre, const float *scale_mid, const float *scale_post,
                   const void *lut, void *stream);
 
-/* y = fq_post(norm(fq_pre(x))), rows of `cols` <= 8192.  kind 0: LlamaRMSNorm (x * rsqrt(mean x^2 + eps) rounded to
+/* y = fq_post(norm(fq_pre(x))), rows of `cols` <= 8192; y_raw (optional, bf16): norm(fq_pre(x)) before the output step,
+ * for consumers that read the un-quantized tensor (BERT: the residual input of the next add).  kind 0: LlamaRMSNorm (x * rsqrt(mean x^2 + eps) rounded to
  * bf16, then * weight); kind 1: nn.LayerNorm (weight, bias may be NULL for no bias).  Replaces the norm module plus the
  * input hooks of the Linear layers that read it (same tensor quantized once instead of once per consumer). */
-int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int kind, const void *weight, const void *bias,
+int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size_t cols, int kind, const void *weight,
+               const void *bias,
                float eps, int fq_points, int out_type, const qt_format_t *fmt, const float *scale_pre,
                const float *scale_post, const void *lut, void *stream);
 

@@ -342,7 +342,8 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
 // + b), fp32 inside.
 template <class R, bool SCALED, int TPR, int VPL>
 __global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
-norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, int out_type, size_t rows, int cols, int kind,
+norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, uint4 *__restrict__ y_raw, int out_type, size_t rows,
+               int cols, int kind,
                const uint4 *__restrict__ weight, const uint4 *__restrict__ bias, float eps, int flags,
                const __grid_constant__ typename R::Params params, const float *__restrict__ scale_pre,
                const float *__restrict__ scale_post)
@@ -416,6 +417,7 @@ norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, int out_type, 
                     for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean) * rstd * w[k] + (bias ? b[k] : 0.0f);
                     round8(f);
                 }
+                if (y_raw) __stcs(y_raw + row * nvec + i, pack8(f));  // the normalised values before the output step
                 if (flags & FQ_POST) fq8<R, SCALED>(round, f, post);
                 store8(y, row * nvec + i, f, out_type);
             }
@@ -757,7 +759,7 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
     return finish("softmax_fq kernel launch");
 }
 
-extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int kind, const void *weight,
+extern "C" int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size_t cols, int kind, const void *weight,
                           const void *bias, float eps, int fq_points, int out_type, const qt_format_t *fmt,
                           const float *scale_pre, const float *scale_post, const void *lut, void *stream)
 {
@@ -768,6 +770,7 @@ extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int 
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
     if (!x || !y || !weight || cols % 8 || cols > 8192 || (kind != 0 && kind != 1) || !aligned16(x) || !aligned16(y) ||
+        (y_raw && !aligned16(y_raw)) ||
         !aligned16(weight) || (bias && !aligned16(bias))) {
         qt_set_error("qt_norm_fq: needs 16-byte aligned contiguous bf16 rows, cols %% 8 == 0, cols <= 8192 (got %zu), "
                      "kind 0 (RMSNorm) or 1 (LayerNorm)", cols);
@@ -782,7 +785,7 @@ extern "C" int qt_norm_fq(const void *x, void *y, size_t rows, size_t cols, int 
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                              \
         auto kernel = scaled ? norm_fq_kernel<R, true, TPR, VPL> : norm_fq_kernel<R, false, TPR, VPL>;           \
         kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                            \
-            static_cast<const uint4 *>(x), y, out_type, rows, (int)cols, kind,                                   \
+            static_cast<const uint4 *>(x), y, static_cast<uint4 *>(y_raw), out_type, rows, (int)cols, kind,      \
             static_cast<const uint4 *>(weight), static_cast<const uint4 *>(bias), eps, fq_points, params,        \
             scale_pre, scale_post);                                                                              \
     } while (0)

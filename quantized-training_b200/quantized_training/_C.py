@@ -51,7 +51,8 @@ EXPORTS = {
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                      ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "qt_norm_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+    "qt_norm_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                  ctypes.c_int,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                   ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_void_p]),
@@ -335,13 +336,14 @@ def softmax_fq(scores, probs, alpha, mask, rows_per_batch, mask_rows, mask_batch
                                    _ptr(scale_post), _ptr(lut), _stream(scores)))
 
 
-def norm_fq(x, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale_post=None, lut=None):
+def norm_fq(x, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale_post=None, lut=None, y_raw=None):
     _bf16_cuda(x, "x")
     assert x.is_contiguous() and y.is_contiguous() and weight.is_contiguous() and weight.dtype == torch.bfloat16
     assert y.shape == x.shape
+    assert y_raw is None or (y_raw.is_contiguous() and y_raw.shape == x.shape and y_raw.dtype == torch.bfloat16)
     cols = x.shape[-1]
     with torch.cuda.device(x.device):
-        _check(lib().qt_norm_fq(x.data_ptr(), y.data_ptr(), x.numel() // cols, cols, kind, weight.data_ptr(),
+        _check(lib().qt_norm_fq(x.data_ptr(), y.data_ptr(), _ptr(y_raw), x.numel() // cols, cols, kind, weight.data_ptr(),
                                 _ptr(bias), float(eps), fq_points, _resolve_out(y, fmt), ctypes.byref(fmt),
                                 _ptr(scale_pre), _ptr(scale_post), _ptr(lut), _stream(x)))
 

@@ -15,13 +15,16 @@ when that is unobservable: no autograd recording, every fake-quantizer involved 
 (no live observer, whose amax history must advance per call), and nobody else hooked the submodules.  Otherwise the
 block runs module by module on the same kernels (fake_quantize.py, ops.py).
 """
+import os
+import traceback
+
 import torch
 from torch import nn
 
 from . import _C
 from .fake_quantize import FusedAmaxObsFakeQuantize
 
-__all__ = ["llama_layer_forward", "set_enabled", "enabled"]
+__all__ = ["llama_layer_forward", "bert_layer_forward", "set_enabled", "enabled"]
 
 _ENABLED = True
 
@@ -34,6 +37,12 @@ def set_enabled(flag: bool):
 
 def enabled():
     return _ENABLED
+
+
+def _why(where):
+    """QT_FUSED_DEBUG=1: say why a block fell back to module-by-module execution."""
+    if os.environ.get("QT_FUSED_DEBUG"):
+        print(f"[qt fused] {where}: module-by-module because of", traceback.format_exc(limit=-2).strip().splitlines()[-3:])
 
 
 class _NotReady(Exception):
@@ -133,28 +142,36 @@ def _out_like(x, codes, shape=None):
                        device=x.device)
 
 
-def norm(x2, weight, bias, eps, kind, pre, post, codes=False):
+def norm(x2, weight, bias, eps, kind, pre, post, codes=False, want_raw=False):
+    """fq_post(norm(fq_pre(x2))); with want_raw also the normalised tensor before the output step."""
     fmt, lut, (s_pre, s_post) = _spec(pre, post)
     y = _out_like(x2, codes)
-    _C.norm_fq(x2, y, kind, weight, bias, eps, _flags(pre=pre, post=post), fmt, s_pre, s_post, lut)
+    raw = torch.empty_like(x2) if want_raw and post is not None else None
+    _C.norm_fq(x2, y, kind, weight, bias, eps, _flags(pre=pre, post=post), fmt, s_pre, s_post, lut, raw)
+    if want_raw:
+        return y, (raw if raw is not None else y)
     return y
 
 
 def softmax(scores, alpha, mask, pre, mid, post, codes=False):
-    """scores [B, H, Sq, Sk] contiguous; mask None or additive [Bm, 1, Sq, >=Sk] (Bm in {1, B})."""
+    """scores [B, H, Sq, Sk] contiguous; mask None or additive [Bm, 1, Sq or 1, >=Sk] (Bm in {1, B})."""
     B, H, Sq, Sk = scores.shape
-    m3, mb = None, 1
+    m3, mb, mrows = None, 1, Sq
+    if mask is not None and mask.dtype == torch.bool:
+        from .modules.quantizable._common import additive_mask
+        mask = additive_mask(mask, torch.bfloat16)
     if mask is not None:
-        if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] != Sq or mask.shape[0] not in (1, B):
+        if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] not in (1, Sq) or mask.shape[0] not in (1, B) \
+                or not mask.dtype.is_floating_point or mask.shape[3] < Sk:
             raise _NotFusable
         m3 = mask[:, 0, :, :Sk]
         if m3.dtype != torch.bfloat16:
             m3 = m3.to(torch.bfloat16)
         m3 = m3.contiguous()
-        mb = m3.shape[0]
+        mb, mrows = m3.shape[0], m3.shape[1]
     fmt, lut, (s_pre, s_mid, s_post) = _spec(pre, mid, post)
     probs = _out_like(scores, codes)
-    _C.softmax_fq(scores, probs, alpha, m3, H * Sq, Sq, mb, _flags(pre, mid, post), fmt, s_pre, s_mid, s_post, lut)
+    _C.softmax_fq(scores, probs, alpha, m3, H * Sq, mrows, mb, _flags(pre, mid, post), fmt, s_pre, s_mid, s_post, lut)
     return probs
 
 
@@ -323,4 +340,108 @@ def llama_layer_forward(layer, hidden_states, attention_mask, position_embedding
             h2 = layer.mlp_residual(h1, _C.gemm_nt(a, w_d, bias=b_d, operand_type=t_d))
         return h2.view(B, S, hidden)
     except (_NotReady, _NotFusable, AttributeError):
+        _why("layer")
+        return None
+
+
+# ---- BERT / RoBERTa encoder layer ------------------------------------------------------------------------------
+
+def strided_fq(x2, post, codes=False):
+    """fake quant of a 2-D view with a row stride (a column slice of a fused projection) into a contiguous tensor."""
+    fmt, lut, (s_post,) = _spec(post)
+    out = _out_like(x2, codes)
+    _C.act_mul_fq(x2, None, out, None, _flags(post=post), fmt, s_post, lut)
+    return out
+
+
+def bert_layer_forward(layer, hidden_states, attention_mask):
+    """Fused forward of a quantizable BERT / RoBERTa encoder layer (self-attention only), or None.
+    Reference structure: modules/quantizable/modeling_bert.py:32-222 inside HF BertLayer."""
+    if not _usable(hidden_states) or hidden_states.dim() != 3:
+        return None
+    att, so, inter, out = layer.attention.self, layer.attention.output, layer.intermediate, layer.output
+    try:
+        if layer.training and (att.dropout.p > 0.0 or so.dropout.p > 0.0 or out.dropout.p > 0.0):
+            return None
+        if getattr(att, "position_embedding_type", "absolute") not in (None, "absolute") or layer.chunk_size_feed_forward:
+            return None
+        for m in (layer.attention, att, so, inter, out, att.attn_scaling, att.softmax, att.qk_matmul, att.av_matmul):
+            if len(m._forward_hooks) or len(m._backward_hooks):
+                return None
+        act_mod = inter.intermediate_act_fn
+        act_name = {"GELUActivation": "gelu", "GELU": "gelu", "ReLU": "relu"}.get(type(act_mod).__name__)
+        if act_name is None or (isinstance(act_mod, nn.GELU) and act_mod.approximate != "none"):
+            return None
+        x_in = same_points(point(att.query), point(att.key), point(att.value))
+        q_in, k_in = point(att.qk_matmul, "0"), point(att.qk_matmul, "1")
+        p_in, v_in = point(att.av_matmul, "0"), point(att.av_matmul, "1")
+        sc_in, sm_in = point(att.attn_scaling), point(att.softmax)
+        o_in, i_in, o2_in = point(so.dense), point(inter.dense), point(out.dense)
+        ln1_in, ln2_in = point(so.LayerNorm), point(out.LayerNorm)
+        act_in = point(act_mod) if isinstance(act_mod, nn.Module) else None
+        res1 = (point(so.residual, "0"), point(so.residual, "1"))
+        res2 = (point(out.residual, "0"), point(out.residual, "1"))
+        if (q_in is None) != (k_in is None):
+            raise _NotFusable
+
+        B, S, hidden = hidden_states.shape
+        H, D = att.num_attention_heads, att.attention_head_size
+        T = B * S
+        isz = inter.dense.weight.shape[0]
+        wq = _common_weight_fq(att.query, att.key, att.value)
+        t_qkv, c_qkv = gemm_operands(x_in, wq, hidden)
+        t_qk, c_qk = gemm_operands(q_in, k_in, D)
+        t_pv, c_pv = gemm_operands(p_in, v_in, S)
+        t_o, c_o = gemm_operands(o_in, _weight_fq(so.dense), hidden)
+        t_i, c_i = gemm_operands(i_in, _weight_fq(inter.dense), hidden)
+        t_o2, c_o2 = gemm_operands(o2_in, _weight_fq(out.dense), isz)
+        w_qkv, b_qkv = _quantized_cat(layer, "qkv", (att.query, att.key, att.value), c_qkv)
+        w_o, b_o = _quantized_cat(layer, "o", (so.dense,), c_o)
+        w_i, b_i = _quantized_cat(layer, "i", (inter.dense,), c_i)
+        w_o2, b_o2 = _quantized_cat(layer, "o2", (out.dense,), c_o2)
+
+        x = hidden_states.reshape(T, hidden)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        scaling = getattr(att, "scaling", D ** -0.5)
+
+        # self-attention
+        xq = x if x_in is None else (x_in.quantize_to_codes(x) if c_qkv else x_in(x))
+        qkv = _C.gemm_nt(xq, w_qkv, bias=b_qkv, operand_type=t_qkv)             # [T, 3 * hidden]
+        qk = strided_fq(qkv[:, :2 * hidden], q_in if q_in is not None else None, c_qk)   # [T, 2 * hidden]
+        if q_in is not None and k_in is not None and (q_in.dtype != k_in.dtype or q_in.qscheme is not None
+                                                      or k_in.qscheme is not None):
+            raise _NotFusable  # one launch quantizes q and k: they must share a bare format
+        fmt, lut, (s_v,) = _spec(v_in)
+        vt = _out_like(x, c_pv, (B, H, D, S))
+        _C.fq_transpose(qkv[:, 2 * hidden:].view(B, S, H, D), vt, _flags(post=v_in), fmt, s_v, lut)
+        q4 = qk[:, :hidden].view(B, S, H, D).transpose(1, 2)
+        k4 = qk[:, hidden:].view(B, S, H, D).transpose(1, 2)
+        scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                          # [B, H, S, S]
+        probs = softmax(scores, scaling, attention_mask, sc_in, sm_in, p_in, c_pv)
+        ctx = torch.empty(B, S, hidden, dtype=torch.bfloat16, device=x.device)
+        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv)
+        ctx2 = fake_quant(ctx.view(T, hidden), o_in, c_o)
+        if res1 == (None, None):
+            h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x, operand_type=t_o)
+        else:
+            h1 = so.residual(_C.gemm_nt(ctx2, w_o, bias=b_o, operand_type=t_o), x)
+        n1 = so.LayerNorm
+        a_q, a_raw = norm(h1, n1.weight, n1.bias, n1.eps, _C.NORM_LAYER, ln1_in, i_in, c_i, want_raw=True)
+
+        # feed-forward
+        if act_in is None:
+            mid = _C.gemm_nt(a_q, w_i, bias=b_i, activation=act_name, operand_type=t_i)   # activation in the epilogue
+        else:
+            mid = act_mod(_C.gemm_nt(a_q, w_i, bias=b_i, operand_type=t_i))                # hooked activation module
+        mid_q = fake_quant(mid, o2_in, c_o2)
+        if res2 == (None, None):
+            h2 = _C.gemm_nt(mid_q, w_o2, bias=b_o2, residual=a_raw, operand_type=t_o2)
+        else:
+            h2 = out.residual(_C.gemm_nt(mid_q, w_o2, bias=b_o2, operand_type=t_o2), a_raw)
+        n2 = out.LayerNorm
+        y = norm(h2, n2.weight, n2.bias, n2.eps, _C.NORM_LAYER, ln2_in, None)
+        return y.view(B, S, hidden)
+    except (_NotReady, _NotFusable, AttributeError):
+        _why("layer")
         return None

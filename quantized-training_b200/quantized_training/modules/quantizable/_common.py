@@ -41,11 +41,31 @@ def repeat_kv(x, n_rep):
     return x[:, :, None, :, :].expand(b, h, n_rep, s, d).reshape(b, h * n_rep, s, d)
 
 
+_MASK_CACHE = {}
+
+
+def additive_mask(mask, dtype):
+    """The attention mask as an additive tensor of `dtype`.  HF builds a BOOLEAN mask (True = attend) when the model's
+    attention implementation is sdpa (the default) and an additive float mask for "eager"; the quantizable blocks
+    always compute attention explicitly (their matmul / softmax modules are the hook points), so a boolean mask
+    is converted -- once per mask tensor: every layer of a forward receives the same object."""
+    if mask is None or mask.dtype != torch.bool:
+        return mask
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), dtype, mask.device)
+    hit = _MASK_CACHE.get("last")
+    if hit is None or hit[0] != key:
+        add = torch.zeros(mask.shape, dtype=dtype, device=mask.device).masked_fill_(~mask, torch.finfo(dtype).min)
+        hit = (key, add, mask)   # keep `mask` alive so that its data_ptr cannot be reused by another tensor
+        _MASK_CACHE["last"] = hit
+    return hit[1]
+
+
 def hooked_attention(block, query, key, value, attention_mask, scaling, dropout_p=0.0, kv_groups=1):
     """softmax(q k^T * scaling + mask) v through the block's hookable op modules.
     Shapes [B, H, S, D]; returns ([B, S, H, D] contiguous, probabilities)."""
     key, value = repeat_kv(key, kv_groups), repeat_kv(value, kv_groups)
     scores = block.attn_scaling(block.qk_matmul(query, key.transpose(-1, -2)), scaling)
+    attention_mask = additive_mask(attention_mask, scores.dtype)
     if attention_mask is not None:
         scores = scores + attention_mask[..., : key.shape[-2]]
     probs = block.softmax(scores).to(query.dtype)

@@ -30,6 +30,8 @@ except Exception:  # pragma: no cover
 _B, _R, _M, _L = (bert.modeling_bert, roberta.modeling_roberta, mobilebert.modeling_mobilebert,
                   llama.modeling_llama)
 TRANSFORMER_MODULE_MAPPINGS: Dict[Callable, Any] = {
+    _B.BertLayer: quantizable.BertLayer,
+    _R.RobertaLayer: quantizable.BertLayer,
     _B.BertSelfAttention: quantizable.BertSelfAttention,
     _B.BertSelfOutput: quantizable.BertSelfOutput,
     _B.BertOutput: quantizable.BertOutput,

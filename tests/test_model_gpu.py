@@ -144,3 +144,37 @@ def test_llama_fused_layer_matches_module_by_module(spec, ops_str, monkeypatch):
         assert all(v[1].dtype == torch.uint8 for v in cache.values())
     x = torch.randn(2, 96, 256, device=DEV).bfloat16().requires_grad_()
     assert fused.llama_layer_forward(model.model.layers[0], x, None, None) is None     # autograd on: module path
+
+
+@pytest.mark.parametrize("spec", ["posit8_1", "e4m3"])
+@pytest.mark.parametrize("ops_str", ["gemm", "gemm,residual,layernorm,activation,scaling", "gemm,layernorm"])
+def test_bert_fused_layer_matches_module_by_module(spec, ops_str, monkeypatch):
+    """BERT encoder layer: fused execution (fused.bert_layer_forward) against the hooked module-by-module execution of
+    the same quantize()-d model, with a padding mask.  Same tolerance statement as the Llama test."""
+    torch.manual_seed(7)
+    cfg = BertConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                     vocab_size=500, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = BertForQuestionAnswering(cfg).to(DEV).eval()
+    qt.quantize(model, parse("--activation", spec, "--weight", spec, "--quantize_forward", ops_str,
+                             "--bf16", "--op_fusion", "qa_outputs"))
+    ids = torch.randint(0, 500, (3, 64), device=DEV)
+    am = torch.ones(3, 64, device=DEV, dtype=torch.long)
+    am[1, 40:] = 0
+    calls = {"n": 0}
+    real = _C.norm_fq
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+
+    monkeypatch.setattr(_C, "norm_fq", counting)
+    with torch.no_grad():
+        model(input_ids=ids, attention_mask=am)
+        assert calls["n"] == 0
+        got = model(input_ids=ids, attention_mask=am)
+        assert calls["n"] == 4                          # 2 layers x 2 LayerNorms through the fused kernel
+        fused.set_enabled(False)
+        want = model(input_ids=ids, attention_mask=am)
+        fused.set_enabled(True)
+    assert rel_err(got.start_logits, want.start_logits) < 2e-2
+    assert rel_err(got.end_logits, want.end_logits) < 2e-2
