@@ -156,6 +156,11 @@ def main():
             out[f"{name}/gx"] = bits16(xb.grad)
             gw = model.head.weight.grad
             out[f"{name}/g_head"] = bits16(gw)
+            # gradient fake-quantizer state after the two steps (delayed scaling: scale in use + amax history)
+            for mn, m in model.named_modules():
+                if isinstance(m, ref.fq.FusedAmaxObsFakeQuantize) and "error_" in mn:
+                    out[f"{name}/scale/{mn}"] = m.scale.detach().float().reshape(-1).numpy().copy()
+                    out[f"{name}/hist/{mn}"] = m.amax_history.detach().float().reshape(-1).numpy().copy()
         else:
             model.eval()
             with torch.no_grad():
