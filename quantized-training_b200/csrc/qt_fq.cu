@@ -47,11 +47,33 @@ __device__ __forceinline__ void fq_span(const R &round, const uint4 *__restrict_
             const size_t i = base + (size_t)j * nthr;
             v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
         }
+        if constexpr (!F32 && DIV == DIV_RECIP) {
+            // Reciprocal path: the inputs are consumed as they are processed (no register is held back for a
+            // fallback); the rare tile with a sub-2^-120 quotient is redone from memory with the true division.
+            bool tiny = false;
 #pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * nthr;
-            const uint4 r = fq_vec<R, F32, DIV, AMAX>(round, v[j], sc, amax);
-            if (i < nvec) st_stream(y + i, r);
+            for (int j = 0; j < kUnroll; ++j) {
+                const size_t i = base + (size_t)j * nthr;
+                if (AMAX) amax = amax_of_vec_bf16(amax, v[j]);
+                const uint4 r = fq_vec_bf16_recip_fast<R>(round, v[j], sc, tiny);
+                if (i < nvec) st_stream(y + i, r);
+            }
+            if (tiny) {
+                for (int j = 0; j < kUnroll; ++j) {
+                    const size_t i = base + (size_t)j * nthr;
+                    if (i < nvec) {
+                        uint32_t unused = 0u;
+                        st_stream(y + i, fq_vec<R, false, DIV_EXACT, false>(round, ld_stream(x + i), sc, unused));
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const size_t i = base + (size_t)j * nthr;
+                const uint4 r = fq_vec<R, F32, DIV, AMAX>(round, v[j], sc, amax);
+                if (i < nvec) st_stream(y + i, r);
+            }
         }
     }
 }
