@@ -166,6 +166,17 @@ typedef struct qt_gemm_desc {
     const void *bias;     /* bf16 [N] or NULL */
     const void *residual; /* bf16, indexed like C with its own strides, or NULL */
     int64_t ldr, strideR_inner, strideR_outer;
+    /* Output re-quantization in the epilogue -- the input hook of the CONSUMING module (quantize.py:116-150) applied
+     * by the producer: C = fq(bf16(result)) for a bare (scale 1) spec.  fq_fmt NULL = off.  fq_lut: device table from
+     * qt_lut_build_host(fq_fmt) (fp / posit formats).  out_type QT_OUT_BF16: C holds the fake-quantized bf16 values;
+     * QT_OUT_E4M3 / QT_OUT_E5M2: C is a one-byte tensor of their fp8 codes (ldc and strides in elements = bytes).
+     * glu != 0: B is a gate|up projection interleaved in blocks of 64 rows (64 gate features, then the same 64
+     * features of up, ...; N = 2 * features, N % 128 == 0); the epilogue computes act(bf16(gate)) * bf16(up) with the
+     * bf16 roundings of HF's LlamaMLP op chain and C has N / 2 columns.  activation must be QT_ACT_SILU. */
+    const qt_format_t *fq_fmt;
+    const void *fq_lut;
+    int32_t out_type;
+    int32_t glu;
 } qt_gemm_desc_t;
 int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
 

@@ -24,12 +24,14 @@
 // scores) and small-N layers fill the 148 SMs.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "qt_internal.h"
+#include "qt_lut.h"
 
 namespace {
 
@@ -64,7 +66,15 @@ struct GemmParams {
     float alpha;
     int act;
     uint32_t idesc;
+    // output re-quantization in the epilogue (OUT_FQ / OUT_GLU kernels)
+    int fq_kind;              // 0 none, 1 binade table (fp / posit formats), 2 direct integer rounding
+    int out_codes;            // 0: bf16 values; 1 / 2: e4m3 / e5m2 one-byte codes (C is uint8)
+    const QtLutEntry *lut;    // QT_LUT_BYTES in global memory (read through L1)
+    QtLutCfg lut_cfg;
+    QtRound rp;
 };
+
+enum { OUT_PLAIN = 0, OUT_FQ = 1, OUT_GLU = 2 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,6 +185,35 @@ __device__ __forceinline__ float apply_act(float v)
     return v;
 }
 
+// fake quant of a value already on the bf16 grid (bare spec: scale 1), table read through L1
+__device__ __forceinline__ float epi_fq(const GemmParams &p, float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    if (p.fq_kind == 1) return __uint_as_float(qt_lut_round_dyn(p.lut, p.lut_cfg, u));
+    if (p.fq_kind == 2) return __uint_as_float(qt_round<QTR_INT>(p.rp, u));
+    return f;
+}
+__device__ __forceinline__ uint32_t epi_fp8x2(float lo, float hi, int out_codes)
+{
+    uint32_t c = out_codes == 2 ? (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E5M2)
+                                : (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t inf_code = out_codes == 2 ? 0x7Cu : 0x7Fu;  // +-Inf survives only fpN_eXmY; keep it Inf / NaN
+    const uint32_t bl = __float_as_uint(lo), bh = __float_as_uint(hi);
+    if ((bl & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0xFF00u) | ((bl >> 24) & 0x80u) | inf_code;
+    if ((bh & 0x7FFFFFFFu) == 0x7F800000u) c = (c & 0x00FFu) | ((((bh >> 24) & 0x80u) | inf_code) << 8);
+    return c;
+}
+__device__ __forceinline__ void add_bf16x8(float (&f)[8], const __nv_bfloat16 *src)
+{
+    const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(src));
+    const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f[2 * j] += __uint_as_float(w[j] << 16);
+        f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+}
+
 // Timeline of CTA 0 (QT_GEMM_DEBUG & 32): [role][event] -> clock64.  Roles: 0 producer (after the empty wait of
 // each k-block), 1 MMA (after the tmem_empty wait, after each full wait), 2 epilogue warp 2 (after the tmem_full wait,
 // after the chunk's store was issued).
@@ -190,8 +229,10 @@ __device__ __forceinline__ void trace(const GemmParams &, int, int &) {}
 #endif
 
 // ----------------------------------------------------------------------------- kernel
-// ACT: activation; AUX: the problem has a bias and / or a residual (pointers checked at run time)
-template <bool FP8, int ACT, bool AUX>
+// ACT: activation; AUX: the problem has a bias and / or a residual (pointers checked at run time);
+// OUT: OUT_PLAIN bf16 result | OUT_FQ result fake-quantized (bf16 values or fp8 codes) | OUT_GLU act(gate) * up of a
+// column-interleaved gate|up projection (64 gate columns, then the 64 up columns of the same features), fake-quantized.
+template <bool FP8, int ACT, bool AUX, int OUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p)
@@ -324,61 +365,105 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 (AUX && p.residual && row < p.M)
                     ? p.residual + (int64_t)bo * p.strideR_outer + (int64_t)bi * p.strideR_inner + row * p.ldr
                     : nullptr;
-            if (half >= chunks) {  // 64-column tiles: the second warp of the quarter has no chunk, only the hand-back
+            // output chunks of 64 columns; a GLU output chunk consumes two accumulator chunks (gate, up)
+            const int out_chunks = OUT == OUT_GLU ? chunks >> 1 : chunks;
+            const int out_block_n = OUT == OUT_GLU ? block_n >> 1 : block_n;
+            const int64_t n_out_total = OUT == OUT_GLU ? p.N >> 1 : p.N;
+            if (half >= out_chunks) {  // narrow tiles: the second warp of the quarter has no chunk, only the hand-back
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
             }
-            for (int c = half; c < chunks; c += 2) {
+            for (int oc = half; oc < out_chunks; oc += 2) {
+                const int c = OUT == OUT_GLU ? 2 * oc : oc;  // first accumulator chunk
+                const bool last = oc + 2 >= out_chunks;
                 uint32_t v[64];
                 tmem_ld_32x32_nowait(taddr + c * EPI_CHUNK_COLS, v);
                 tmem_ld_32x32_nowait(taddr + c * EPI_CHUNK_COLS + 32, v + 32);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T1: accumulator chunk in registers
-                if (c + 2 >= chunks) {  // last TMEM read of this warp for this tile: hand the accumulator back
+                if (OUT != OUT_GLU && last) {  // last TMEM read of this warp for this tile: hand the accumulator back
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
                 }
-                const int64_t n0 = (int64_t)nt * block_n + c * EPI_CHUNK_COLS;
-                uint32_t packed[32];
+                const int64_t n_in0 = (int64_t)nt * block_n + c * EPI_CHUNK_COLS;     // accumulator / bias column
+                const int64_t n0 = (int64_t)nt * out_block_n + oc * EPI_CHUNK_COLS;   // output column
+                uint32_t gate[OUT == OUT_GLU ? 32 : 1];
+                if constexpr (OUT == OUT_GLU) {
+                    // gate half: bf16(act(bf16(acc + bias))), kept packed while the up half is fetched
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {  // eight 16-byte groups of 8 columns
+                    for (int g = 0; g < 8; ++g) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) * p.alpha;
+                        if (AUX && p.bias && n_in0 + g * 8 < p.N) add_bf16x8(f, p.bias + n_in0 + g * 8);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const __nv_bfloat162 pk = __floats2bfloat162_rn(apply_act<ACT>(bf16_round(f[2 * j])),
+                                                                            apply_act<ACT>(bf16_round(f[2 * j + 1])));
+                            gate[g * 4 + j] = *reinterpret_cast<const uint32_t *>(&pk);
+                        }
+                    }
+                    tmem_ld_32x32_nowait(taddr + (c + 1) * EPI_CHUNK_COLS, v);
+                    tmem_ld_32x32_nowait(taddr + (c + 1) * EPI_CHUNK_COLS + 32, v + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (last) {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                    }
+                }
+                uint32_t packed[32];  // bf16: 64 values; codes: the first 16 words
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {  // eight groups of 8 columns
                     const int64_t n = n0 + g * 8;
-                    const bool in_n = n < p.N;  // N % 8 == 0: groups are entirely in or out
+                    const bool in_n = n < n_out_total;  // N % 8 == 0: groups are entirely in or out
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]) * p.alpha;
-                    if (AUX && p.bias && in_n) {
-                        const uint4 bb = __ldg(reinterpret_cast<const uint4 *>(p.bias + n));
-                        const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
+                    if constexpr (OUT == OUT_GLU) {
+                        if (AUX && p.bias && n_in0 + EPI_CHUNK_COLS + g * 8 < p.N)
+                            add_bf16x8(f, p.bias + n_in0 + EPI_CHUNK_COLS + g * 8);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            f[2 * j] += __uint_as_float(w[j] << 16);
-                            f[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                        for (int j = 0; j < 4; ++j) {  // bf16(gate) * bf16(up), rounded: the product op of the MLP
+                            f[2 * j] = bf16_round(f[2 * j]) * __uint_as_float(gate[g * 4 + j] << 16);
+                            f[2 * j + 1] = bf16_round(f[2 * j + 1]) * __uint_as_float(gate[g * 4 + j] & 0xFFFF0000u);
+                        }
+                    } else {
+                        if (AUX && p.bias && in_n) add_bf16x8(f, p.bias + n);
+                        // The reference materialises a bf16 tensor after the Linear, after the activation and after
+                        // the residual add (three ATen ops); rounding at the same points keeps the fused epilogue on
+                        // the reference's values instead of merely near them (a 1-ulp bf16 difference flips ~3 % of
+                        // the codes of an 8-bit format downstream).
+                        if (ACT != ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(bf16_round(f[j]));
+                        }
+                        if (AUX && rrow && in_n) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j]);
+                            add_bf16x8(f, rrow + n);
                         }
                     }
-                    // The reference materialises a bf16 tensor after the Linear, after the activation and after the
-                    // residual add (three ATen ops); rounding at the same points keeps the fused epilogue on the
-                    // reference's values instead of merely near them (a 1-ulp bf16 difference flips ~3 % of the codes
-                    // of an 8-bit format downstream).
-                    if (ACT != ACT_NONE) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(bf16_round(f[j]));
-                    }
-                    if (AUX && rrow && in_n) {
-                        const uint4 rr = __ldg(reinterpret_cast<const uint4 *>(rrow + n));
-                        const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+                    if constexpr (OUT == OUT_PLAIN) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            f[2 * j] = bf16_round(f[2 * j]) + __uint_as_float(w[j] << 16);
-                            f[2 * j + 1] = bf16_round(f[2 * j + 1]) + __uint_as_float(w[j] & 0xFFFF0000u);
+                            const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                            packed[g * 4 + j] = *reinterpret_cast<const uint32_t *>(&pk);
                         }
-                    }
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const __nv_bfloat162 pk = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                        packed[g * 4 + j] = *reinterpret_cast<const uint32_t *>(&pk);
+                        for (int j = 0; j < 8; ++j) f[j] = epi_fq(p, bf16_round(f[j]));  // the consumer's input hook
+                        if (p.out_codes) {
+                            packed[g * 2] = epi_fp8x2(f[0], f[1], p.out_codes) | (epi_fp8x2(f[2], f[3], p.out_codes) << 16);
+                            packed[g * 2 + 1] =
+                                epi_fp8x2(f[4], f[5], p.out_codes) | (epi_fp8x2(f[6], f[7], p.out_codes) << 16);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                packed[g * 4 + j] = __byte_perm(__float_as_uint(f[2 * j]), __float_as_uint(f[2 * j + 1]), 0x7632);
+                        }
                     }
                 }
                 if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T2: math done
@@ -386,19 +471,31 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
                 if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T3: staging buffer free
-                const uint32_t rowbuf = buf + (uint32_t)lane * 128u;
+                if (OUT != OUT_PLAIN && p.out_codes) {
+                    // 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk c of row r sits at c ^ ((r >> 1) & 3)
+                    const uint32_t rowbuf = buf + (uint32_t)lane * 64u;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint32_t dst = rowbuf + (uint32_t)((g ^ (lane & 7)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[g * 4]),
-                                 "r"(packed[g * 4 + 1]), "r"(packed[g * 4 + 2]), "r"(packed[g * 4 + 3])
-                                 : "memory");
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t dst = rowbuf + (uint32_t)((g ^ ((lane >> 1) & 3)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[g * 4]),
+                                     "r"(packed[g * 4 + 1]), "r"(packed[g * 4 + 2]), "r"(packed[g * 4 + 3])
+                                     : "memory");
+                    }
+                } else {
+                    const uint32_t rowbuf = buf + (uint32_t)lane * 128u;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const uint32_t dst = rowbuf + (uint32_t)((g ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[g * 4]),
+                                     "r"(packed[g * 4 + 1]), "r"(packed[g * 4 + 2]), "r"(packed[g * 4 + 3])
+                                     : "memory");
+                    }
                 }
                 if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T4: staged
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
                 __syncwarp();
                 if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T5: fenced
-                if (lane == 0 && n0 < p.N && row0 < p.M) {
+                if (lane == 0 && n0 < n_out_total && row0 < p.M) {
                     asm volatile(
                         "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                             reinterpret_cast<uint64_t>(&map_c)),
@@ -447,7 +544,7 @@ EncodeTiledFn encode_tiled()
 // three: dims {cols, rows, inner, outer}, box {box_cols, box_rows, 1, 1}, 128-byte swizzle (box_cols * esz == 128).
 // Loads: out-of-bounds elements (K tail, row tail) are filled with zeros.  Stores: they are not written.
 int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int64_t rows, int64_t inner, int64_t outer,
-             int64_t ld, int64_t stride_inner, int64_t stride_outer, int box_rows)
+             int64_t ld, int64_t stride_inner, int64_t stride_outer, int box_rows, int box_bytes = ROW_BYTES)
 {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) {
@@ -460,11 +557,12 @@ int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int
     if (outer <= 1) stride_outer = (inner <= 1 ? rows * ld : inner * stride_inner);
     cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)stride_inner * esz, (cuuint64_t)stride_outer * esz};
-    cuuint32_t box[4] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(box_bytes / esz), (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, one_byte ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         qt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld batch=%lldx%lld ld=%lld "
                      "strides=%lld,%lld)", (int)r, (long long)cols, (long long)rows, (long long)outer, (long long)inner,
@@ -487,12 +585,12 @@ uint32_t make_idesc(int a_fmt, int b_fmt, int block_n)
 // and its epilogue time, plus a per-tile hand-over.  Constants measured on B200 (scripts/bmm_probe.py):
 // an MMA instruction takes N/2 cycles at N = 256 but never less than ~96 (narrow tiles are bound by the
 // shared-memory reads of the A operand), the epilogue ~11.3 cycles per output column of a 128-row tile.
-int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms)
+int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int min_bn = 64)
 {
     const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int best = MAX_BLOCK_N;
     double best_cost = 0.0;
-    for (int bn = MAX_BLOCK_N; bn >= 64; bn >>= 1) {
+    for (int bn = MAX_BLOCK_N; bn >= min_bn; bn >>= 1) {
         const int64_t tiles = m_tiles * ((N + bn - 1) / bn) * batch;
         const double rounds = (double)((tiles + sms - 1) / sms);
         const double mma = (double)k_blocks * 4.0 * (bn / 2.0 > 96.0 ? bn / 2.0 : 96.0);
@@ -506,17 +604,17 @@ int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms)
     return best;
 }
 
-template <bool FP8, int ACT, bool AUX>
+template <bool FP8, int ACT, bool AUX, int OUT = OUT_PLAIN>
 void launch_variant(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
                     const CUtensorMap &map_c, const GemmParams &p)
 {
     static bool done[64] = {};
     if (dev >= 64 || !done[dev]) {
-        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)SMEM_BYTES);
         if (dev < 64) done[dev] = true;
     }
-    qt_gemm_kernel<FP8, ACT, AUX><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
+    qt_gemm_kernel<FP8, ACT, AUX, OUT><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
 }
 
 }  // namespace
@@ -553,7 +651,9 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     const bool bad_ab = d->lda % k_align || d->ldb % k_align || (inner > 1 && (d->strideA_inner % k_align ||
                         d->strideB_inner % k_align)) || (outer > 1 && (d->strideA_outer % k_align ||
                         d->strideB_outer % k_align));
-    const bool bad_c = N % 8 || d->ldc % 8 || (inner > 1 && d->strideC_inner % 8) || (outer > 1 && d->strideC_outer % 8);
+    const int c_align = d->out_type ? 16 : 8;
+    const bool bad_c = N % 8 || d->ldc % c_align || (inner > 1 && d->strideC_inner % c_align) ||
+                       (outer > 1 && d->strideC_outer % c_align) || (d->out_type && (d->glu ? N / 2 : N) % 16);
     const bool bad_r = d->residual && (misaligned(d->residual) || d->ldr % 8 || (inner > 1 && d->strideR_inner % 8) ||
                                        (outer > 1 && d->strideR_outer % 8));
     if (bad_ab || bad_c || bad_r || misaligned(d->A) || misaligned(d->B) || misaligned(d->C) ||
@@ -574,16 +674,50 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     const int64_t batch = inner * outer;
     GemmParams p;
     memset(&p, 0, sizeof(p));
+    // output re-quantization / gated product
+    const bool glu = d->glu != 0;
+    const bool requant = d->fq_fmt != nullptr;
+    const int64_t n_out = glu ? N / 2 : N;
+    if (d->out_type < 0 || d->out_type > 2 || (d->out_type != 0 && !requant) || (glu && (N % 128 || d->residual)) ||
+        (glu && d->activation == ACT_NONE) || (requant && !glu && d->activation != ACT_NONE)) {
+        qt_set_error("qt_gemm_nt: output options: fp8 codes need fq_fmt; glu needs N %% 128 == 0, an activation and no "
+                     "residual; fq_fmt without glu takes no activation");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (requant) {
+        int rc2 = qt_make_round(d->fq_fmt, &p.rp);
+        if (rc2 != QT_OK) return rc2;
+        const bool e4m3 = d->fq_fmt->kind == QT_KIND_FP && d->fq_fmt->ebits == 4 && d->fq_fmt->mbits == 3 && !d->fq_fmt->is_unsigned;
+        const bool e5m2 = d->fq_fmt->kind == QT_KIND_FP && d->fq_fmt->ebits == 5 && d->fq_fmt->mbits == 2 && !d->fq_fmt->is_unsigned;
+        if ((d->out_type == 1 && !e4m3) || (d->out_type == 2 && !e5m2)) {
+            qt_set_error("qt_gemm_nt: fp8 code output needs an e4m3 / e5m2 fq_fmt of the same kind");
+            return QT_ERR_INVALID_ARGUMENT;
+        }
+        if (p.rp.kind == QTR_INT) {
+            p.fq_kind = 2;
+        } else if (p.rp.kind == QTR_IDENTITY) {
+            p.fq_kind = 0;
+        } else {
+            if (!d->fq_lut || (reinterpret_cast<uintptr_t>(d->fq_lut) & 15u) || qt_lut_config(p.rp, &p.lut_cfg) != QT_OK) {
+                qt_set_error("qt_gemm_nt: fq_fmt of an fp / posit format needs the 16-byte aligned device table (fq_lut)");
+                return QT_ERR_INVALID_ARGUMENT;
+            }
+            p.fq_kind = 1;
+            p.lut = static_cast<const QtLutEntry *>(d->fq_lut);
+        }
+        p.out_codes = d->out_type;
+    }
+    const int c_esz = p.out_codes ? 1 : 2;
     p.M = M;
     p.N = N;
     p.K = K;
     p.batch_inner = (uint32_t)inner;
     p.k_blocks = (int)((K * esz + ROW_BYTES - 1) / ROW_BYTES);
-    p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms);
+    p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, glu ? 128 : 64);
     if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
         p.debug = atoi(dbg);
         if (p.debug & 4) p.block_n = 128;
-        if (p.debug & 8) p.block_n = 64;
+        if ((p.debug & 8) && !glu) p.block_n = 64;
         if (p.debug & 16) p.block_n = 256;
     }
     const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + p.block_n - 1) / p.block_n;
@@ -601,7 +735,8 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     if (rc != QT_OK) return rc;
     rc = make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n);
     if (rc != QT_OK) return rc;
-    rc = make_map(&map_c, d->C, false, N, M, inner, outer, d->ldc, d->strideC_inner, d->strideC_outer, 32);
+    rc = make_map(&map_c, d->C, c_esz == 1, n_out, M, inner, outer, d->ldc, d->strideC_inner, d->strideC_outer, 32,
+                  c_esz == 1 ? 64 : ROW_BYTES);
     if (rc != QT_OK) return rc;
 
     p.bias = static_cast<const __nv_bfloat16 *>(d->bias);
@@ -621,21 +756,41 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     const unsigned grid = p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool aux = d->bias != nullptr || d->residual != nullptr;
-    const int variant = (fp8 ? 8 : 0) + d->activation * 2 + (aux ? 1 : 0);
-    switch (variant) {
+    if (glu) {
+        if (d->activation != ACT_SILU) {
+            qt_set_error("qt_gemm_nt: the gated epilogue is built for SiLU (Llama-style MLP)");
+            return QT_ERR_INVALID_ARGUMENT;
+        }
+        if (fp8)
+            aux ? launch_variant<true, ACT_SILU, true, OUT_GLU>(dev, grid, st, map_a, map_b, map_c, p)
+                : launch_variant<true, ACT_SILU, false, OUT_GLU>(dev, grid, st, map_a, map_b, map_c, p);
+        else
+            aux ? launch_variant<false, ACT_SILU, true, OUT_GLU>(dev, grid, st, map_a, map_b, map_c, p)
+                : launch_variant<false, ACT_SILU, false, OUT_GLU>(dev, grid, st, map_a, map_b, map_c, p);
+    } else if (requant) {
+        if (fp8)
+            aux ? launch_variant<true, ACT_NONE, true, OUT_FQ>(dev, grid, st, map_a, map_b, map_c, p)
+                : launch_variant<true, ACT_NONE, false, OUT_FQ>(dev, grid, st, map_a, map_b, map_c, p);
+        else
+            aux ? launch_variant<false, ACT_NONE, true, OUT_FQ>(dev, grid, st, map_a, map_b, map_c, p)
+                : launch_variant<false, ACT_NONE, false, OUT_FQ>(dev, grid, st, map_a, map_b, map_c, p);
+    } else {
+        const int variant = (fp8 ? 8 : 0) + d->activation * 2 + (aux ? 1 : 0);
+        switch (variant) {
 #define QT_GEMM_CASE(F, A, X)                                           \
     case (F ? 8 : 0) + A * 2 + (X ? 1 : 0):                             \
         launch_variant<F, A, X>(dev, grid, st, map_a, map_b, map_c, p); \
         break;
-        QT_GEMM_CASE(false, ACT_NONE, false) QT_GEMM_CASE(false, ACT_NONE, true)
-        QT_GEMM_CASE(false, ACT_RELU, false) QT_GEMM_CASE(false, ACT_RELU, true)
-        QT_GEMM_CASE(false, ACT_GELU, false) QT_GEMM_CASE(false, ACT_GELU, true)
-        QT_GEMM_CASE(false, ACT_SILU, false) QT_GEMM_CASE(false, ACT_SILU, true)
-        QT_GEMM_CASE(true, ACT_NONE, false) QT_GEMM_CASE(true, ACT_NONE, true)
-        QT_GEMM_CASE(true, ACT_RELU, false) QT_GEMM_CASE(true, ACT_RELU, true)
-        QT_GEMM_CASE(true, ACT_GELU, false) QT_GEMM_CASE(true, ACT_GELU, true)
-        QT_GEMM_CASE(true, ACT_SILU, false) QT_GEMM_CASE(true, ACT_SILU, true)
+            QT_GEMM_CASE(false, ACT_NONE, false) QT_GEMM_CASE(false, ACT_NONE, true)
+            QT_GEMM_CASE(false, ACT_RELU, false) QT_GEMM_CASE(false, ACT_RELU, true)
+            QT_GEMM_CASE(false, ACT_GELU, false) QT_GEMM_CASE(false, ACT_GELU, true)
+            QT_GEMM_CASE(false, ACT_SILU, false) QT_GEMM_CASE(false, ACT_SILU, true)
+            QT_GEMM_CASE(true, ACT_NONE, false) QT_GEMM_CASE(true, ACT_NONE, true)
+            QT_GEMM_CASE(true, ACT_RELU, false) QT_GEMM_CASE(true, ACT_RELU, true)
+            QT_GEMM_CASE(true, ACT_GELU, false) QT_GEMM_CASE(true, ACT_GELU, true)
+            QT_GEMM_CASE(true, ACT_SILU, false) QT_GEMM_CASE(true, ACT_SILU, true)
 #undef QT_GEMM_CASE
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

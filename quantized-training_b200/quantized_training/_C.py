@@ -217,6 +217,8 @@ class QtGemmDesc(ctypes.Structure):
         ("strideC_inner", ctypes.c_int64), ("strideC_outer", ctypes.c_int64),
         ("alpha", ctypes.c_float), ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
         ("ldr", ctypes.c_int64), ("strideR_inner", ctypes.c_int64), ("strideR_outer", ctypes.c_int64),
+        ("fq_fmt", ctypes.POINTER(QtFormat)), ("fq_lut", ctypes.c_void_p),
+        ("out_type", ctypes.c_int32), ("glu", ctypes.c_int32),
     ]
 
 
@@ -235,11 +237,15 @@ def _as4d(t, name, align):
     return t if ok else t.contiguous()
 
 
-def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None):
+def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None,
+            fq=None, out_codes=False, glu=False):
     """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
     a, b: bf16 (GEMM_BF16) or uint8 fp8 codes, up to two leading batch dimensions with arbitrary strides;
-    bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional bf16 destination (any 16-byte
-    aligned strides, e.g. a [B, H, S, D] view of a [B, S, H*D] buffer)."""
+    bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional destination (any 16-byte
+    aligned strides, e.g. a [B, H, S, D] view of a [B, S, H*D] buffer).
+    fq: (fmt, lut) of a BARE fake-quantizer applied to the result in the epilogue (the consumer's input hook);
+    out_codes: with an e4m3 / e5m2 `fq`, store one-byte fp8 codes (out is uint8); glu: b is a gate|up projection
+    interleaved in blocks of 64 rows and the result is activation(gate) * up with n / 2 columns."""
     _require_cuda(a, "a")
     want = torch.uint8 if operand_type != GEMM_BF16 else torch.bfloat16
     if a.dtype != want or b.dtype != want:
@@ -255,12 +261,15 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     if b4.shape[3] != K:
         raise ValueError(f"inner dimensions differ: {tuple(a.shape)} x {tuple(b.shape)}^T")
     lead = a.shape[:-2] if a.dim() >= b.dim() else b.shape[:-2]
-    out_shape = (*lead, M, N)
+    out_shape = (*lead, M, N // 2 if glu else N)
+    out_dtype = torch.uint8 if out_codes else torch.bfloat16
+    if out_codes and fq is None:
+        raise ValueError("fp8 code output needs the fake-quantizer (fq) whose codes they are")
     if out is None:
-        out = torch.empty(out_shape, dtype=torch.bfloat16, device=a.device)
-    elif tuple(out.shape) != tuple(out_shape) or out.dtype != torch.bfloat16:
-        raise ValueError(f"out must be bf16 of shape {tuple(out_shape)}, got {out.dtype} {tuple(out.shape)}")
-    o4 = _as4d(out, "out", 8)
+        out = torch.empty(out_shape, dtype=out_dtype, device=a.device)
+    elif tuple(out.shape) != tuple(out_shape) or out.dtype != out_dtype:
+        raise ValueError(f"out must be {out_dtype} of shape {tuple(out_shape)}, got {out.dtype} {tuple(out.shape)}")
+    o4 = _as4d(out, "out", 16 if out_codes else 8)
     if o4.data_ptr() != out.data_ptr() or o4.numel() != out.numel():
         raise ValueError("out needs a unit-stride last axis and 16-byte aligned strides")
     d = QtGemmDesc()
@@ -272,6 +281,12 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     d.strideB_outer, d.strideB_inner = b4.stride(0), b4.stride(1)
     d.strideC_outer, d.strideC_inner = o4.stride(0), o4.stride(1)
     d.alpha = float(alpha)
+    d.glu = 1 if glu else 0
+    if fq is not None:
+        fq_fmt, fq_lut = fq
+        d.fq_fmt = ctypes.pointer(fq_fmt)
+        d.fq_lut = fq_lut.data_ptr() if fq_lut is not None else None
+        d.out_type = _codes_type(fq_fmt) if out_codes else OUT_BF16
     if bias is not None:
         assert bias.dtype == torch.bfloat16 and bias.numel() == N and bias.is_contiguous()
         d.bias = bias.data_ptr()

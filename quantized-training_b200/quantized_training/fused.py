@@ -205,7 +205,14 @@ def _common_weight_fq(*linears):
     return fqs[0] if len(kinds) == 1 and None not in kinds else None
 
 
-def _quantized_cat(owner, tag, linears, codes=False):
+def _interleave(ts, block):
+    """[t0 rows 0..block), [t1 rows 0..block), [t0 rows block..2 block), ...: the gate|up layout of the gated epilogue."""
+    n = ts[0].shape[0]
+    parts = [t.reshape(n // block, block, *t.shape[1:]) for t in ts]
+    return torch.stack(parts, 1).reshape(len(ts) * n, *ts[0].shape[1:])
+
+
+def _quantized_cat(owner, tag, linears, codes=False, interleave=0):
     """cat([fq(W) for each Linear]) along the output axis, cached on `owner` until a weight or a scale is written.
     The weight fake-quantizers must be observer-free (checked) so that skipping their per-forward re-run is
     unobservable."""
@@ -222,7 +229,7 @@ def _quantized_cat(owner, tag, linears, codes=False):
         else:
             raise _NotFusable
         _only_our_hooks(lin, lin._modules.get("activation_pre_process") is not None)
-    key = tuple(key + [codes])
+    key = tuple(key + [codes, interleave])
     cache = owner.__dict__.setdefault("_qt_wcache", {})
     hit = cache.get(tag)
     if hit is None or hit[0] != key:
@@ -231,20 +238,46 @@ def _quantized_cat(owner, tag, linears, codes=False):
                 ws = [lin.weight_fake_quant.quantize_to_codes(lin.weight.detach()) for lin in linears]
             else:
                 ws = [lin.weight_fake_quant(lin.weight).detach() for lin in linears]
-            w = ws[0] if len(ws) == 1 else torch.cat(ws, 0)
+            join = (lambda ts: _interleave(ts, interleave)) if interleave else (lambda ts: torch.cat(ts, 0))
+            w = ws[0] if len(ws) == 1 else join(ws)
             bs = [lin.bias for lin in linears]
             b = None
             if any(x is not None for x in bs):
-                b = torch.cat([x.detach() if x is not None else torch.zeros(lin.weight.shape[0], dtype=lin.weight.dtype,
-                                                                             device=w.device)
-                               for x, lin in zip(bs, linears)], 0).contiguous()
+                b = join([x.detach() if x is not None else torch.zeros(lin.weight.shape[0], dtype=lin.weight.dtype,
+                                                                         device=w.device)
+                          for x, lin in zip(bs, linears)]).contiguous()
         hit = (key, w.contiguous(), b)
         cache[tag] = hit
     return hit[1], hit[2]
 
 
+def _epilogue_fq(fq):
+    """(fmt, lut) when `fq` can be applied by the producing GEMM's epilogue (bare spec), None when there is nothing to
+    apply; raises _NotFusable for a scaled one (callers then keep the separate pass)."""
+    if fq is None:
+        return None
+    if fq.qscheme is not None:
+        raise _NotFusable
+    return (fq._fmt, fq.lut)
+
+
 def _usable(x):
     return _ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+
+
+def _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D):
+    """probabilities x values written straight into [B*S, H*D].  The output projection's input fake quant is applied
+    by the product's epilogue only for long reductions: at S = 1024 the product is epilogue-bound (128 x 128 tiles,
+    16 k-blocks) and the table lookups of the re-quantization cost more there than the separate 7 us pass
+    (measured: 26.6 vs 14 + 6.7 us per Llama-2-7B layer)."""
+    if o_in is None or (o_in.qscheme is None and S >= 4096):
+        ctx = torch.empty(B, S, H * D, dtype=torch.uint8 if c_o else torch.bfloat16, device=probs.device)
+        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv,
+                   fq=_epilogue_fq(o_in), out_codes=c_o)
+        return ctx.view(B * S, H * D)
+    ctx = torch.empty(B, S, H * D, dtype=torch.bfloat16, device=probs.device)
+    _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv)
+    return fake_quant(ctx.view(B * S, H * D), o_in, c_o)
 
 
 # ---- Llama decoder layer ------------------------------------------------------------------------------------
@@ -291,7 +324,8 @@ def llama_layer_forward(layer, hidden_states, attention_mask, position_embedding
         t_d, c_d = gemm_operands(d_in, _weight_fq(mlp.down_proj), inter)
         w_qkv, b_qkv = _quantized_cat(layer, "qkv", (attn.q_proj, attn.k_proj, attn.v_proj), c_qkv)
         w_o, b_o = _quantized_cat(layer, "o", (attn.o_proj,), c_o)
-        w_gu, b_gu = _quantized_cat(layer, "gu", (mlp.gate_proj, mlp.up_proj), c_gu)
+        glu = act_name == "silu" and inter % 64 == 0 and (d_in is None or d_in.qscheme is None)
+        w_gu, b_gu = _quantized_cat(layer, "gu", (mlp.gate_proj, mlp.up_proj), c_gu, interleave=64 if glu else 0)
         w_d, b_d = _quantized_cat(layer, "d", (mlp.down_proj,), c_d)
 
         x = hidden_states.reshape(T, hidden)
@@ -321,9 +355,7 @@ def llama_layer_forward(layer, hidden_states, attention_mask, position_embedding
         k4 = qk[1].view(B, S, H, D).transpose(1, 2)
         scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                           # [B, H, S, S]
         probs = softmax(scores, attn.scaling, attention_mask, sc_in, sm_in, p_in, c_pv)
-        ctx = torch.empty(B, S, H * D, dtype=torch.bfloat16, device=x.device)
-        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv)
-        ctx2 = fake_quant(ctx.view(T, H * D), o_in, c_o)
+        ctx2 = _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D)
         if res1 == (None, None):
             h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x, operand_type=t_o)   # residual add in the epilogue
         else:
@@ -332,8 +364,12 @@ def llama_layer_forward(layer, hidden_states, attention_mask, position_embedding
         # MLP
         n2 = layer.post_attention_layernorm
         x2 = norm(h1, n2.weight, None, n2.variance_epsilon, _C.NORM_RMS, ln2_in, gu_in, c_gu)
-        gu = _C.gemm_nt(x2, w_gu, bias=b_gu, operand_type=t_gu)                  # [T, 2 * I]
-        a = act_mul(gu[:, :inter], gu[:, inter:], act_name, d_in, c_d)
+        if glu:   # silu(gate) * up and down_proj's input fake quant inside the gate|up GEMM's epilogue
+            a = _C.gemm_nt(x2, w_gu, bias=b_gu, operand_type=t_gu, activation="silu", glu=True,
+                           fq=_epilogue_fq(d_in), out_codes=c_d)
+        else:
+            gu = _C.gemm_nt(x2, w_gu, bias=b_gu, operand_type=t_gu)              # [T, 2 * I]
+            a = act_mul(gu[:, :inter], gu[:, inter:], act_name, d_in, c_d)
         if res2 == (None, None):
             h2 = _C.gemm_nt(a, w_d, bias=b_d, residual=h1, operand_type=t_d)
         else:
@@ -419,9 +455,7 @@ def bert_layer_forward(layer, hidden_states, attention_mask):
         k4 = qk[:, hidden:].view(B, S, H, D).transpose(1, 2)
         scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                          # [B, H, S, S]
         probs = softmax(scores, scaling, attention_mask, sc_in, sm_in, p_in, c_pv)
-        ctx = torch.empty(B, S, hidden, dtype=torch.bfloat16, device=x.device)
-        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv)
-        ctx2 = fake_quant(ctx.view(T, hidden), o_in, c_o)
+        ctx2 = _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D)
         if res1 == (None, None):
             h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x, operand_type=t_o)
         else:

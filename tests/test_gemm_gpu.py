@@ -146,3 +146,68 @@ def test_argument_errors():
         _C.gemm_nt(a, torch.zeros(8, 20, dtype=torch.bfloat16, device=DEV))      # lda = 20 is not 16-byte aligned
     with pytest.raises(TypeError):
         _C.gemm_nt(a.float(), a.float())
+
+
+def _fq_table(oracle, dtype):
+    import numpy as np
+    table = torch.from_numpy(oracle.qmap(dtype).view(np.int16)).view(torch.bfloat16).to(DEV)
+    return lambda x: table[(x.contiguous().view(torch.int16).to(torch.int32) & 0xFFFF)].view(x.shape)
+
+
+@pytest.mark.parametrize("spec", ["posit8_1", "e4m3", "int8", "fp8_e5m2"])
+def test_epilogue_requantization_is_the_consumers_fake_quant(oracle, spec):
+    """C = fq(bf16(A B^T + bias)) in the epilogue == the separate fake-quant pass on the plain GEMM's output, bit for
+    bit (same accumulator, same rounding to bf16, same rounding engine); fp8 codes decode to the same values."""
+    g = torch.Generator().manual_seed(31)
+    M, N, K = 300, 328, 256
+    a = quantized_operand((M, K), "e4m3", g)
+    w = quantized_operand((N, K), "e4m3", g, 0.3)
+    bias = torch.randn(N, generator=g).to(torch.bfloat16).to(DEV)
+    m = qt.FusedAmaxObsFakeQuantize(spec, device=DEV)
+    plain = _C.gemm_nt(a, w, bias=bias)
+    want = _fq_table(oracle, spec)(plain)
+    got = _C.gemm_nt(a, w, bias=bias, fq=(m._fmt, m.lut))
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    if m.fp8_kind is not None:
+        codes = _C.gemm_nt(a[:, :], w[:320], bias=bias[:320].contiguous(), fq=(m._fmt, m.lut), out_codes=True)
+        tdt = torch.float8_e4m3fn if m.fp8_kind == "e4m3" else torch.float8_e5m2
+        assert codes.dtype == torch.uint8 and torch.equal(codes.view(tdt).to(torch.bfloat16).view(torch.int16),
+                                                          want[:, :320].contiguous().view(torch.int16))
+    # batched, strided destination (the PV product writing a fake-quantized context into [B, S, H*D])
+    B, H, S, D = 2, 4, 136, 64
+    p_ = quantized_operand((B, H, S, S), "e4m3", g, 0.1)
+    vt = quantized_operand((B, H, D, S), "e4m3", g)
+    ctx = torch.zeros(B, S, H * D, dtype=torch.bfloat16, device=DEV)
+    _C.gemm_nt(p_, vt, out=ctx.view(B, S, H, D).transpose(1, 2), fq=(m._fmt, m.lut))
+    ref = _fq_table(oracle, spec)(_C.gemm_nt(p_, vt))
+    assert torch.equal(ctx.view(B, S, H, D).transpose(1, 2).contiguous().view(torch.int16), ref.view(torch.int16))
+
+
+@pytest.mark.parametrize("spec,codes", [("posit8_1", False), ("e4m3", False), ("e4m3", True)])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_gated_epilogue_matches_the_mlp_op_chain(oracle, spec, codes, with_bias):
+    """silu(gate) * up + fake quant inside the gate|up GEMM (weights interleaved in blocks of 64 rows) vs the HF
+    LlamaMLP op chain on the two separate projections: act_fn(gate_proj(x)) * up_proj(x), then down_proj's input hook.
+    Tolerance: SiLU goes through exp, so as for qt_act_mul_fq >= 99.5 % of the values are bit-identical and none is
+    further than one grid step."""
+    g = torch.Generator().manual_seed(41)
+    M, K, I = 200, 256, 704                       # I % 64 == 0
+    x = quantized_operand((M, K), "e4m3", g)
+    wg = quantized_operand((I, K), "e4m3", g, 0.2)
+    wu = quantized_operand((I, K), "e4m3", g, 0.2)
+    bg = torch.randn(I, generator=g).to(torch.bfloat16).to(DEV) if with_bias else None
+    bu = torch.randn(I, generator=g).to(torch.bfloat16).to(DEV) if with_bias else None
+    inter = lambda t, u: torch.stack((t.view(I // 64, 64, *t.shape[1:]), u.view(I // 64, 64, *u.shape[1:])), 1).reshape(2 * I, *t.shape[1:])
+    w = inter(wg, wu).contiguous()
+    b = inter(bg, bu).contiguous() if with_bias else None
+    m = qt.FusedAmaxObsFakeQuantize(spec, device=DEV)
+    got = _C.gemm_nt(x, w, bias=b, activation="silu", glu=True, fq=(m._fmt, m.lut), out_codes=codes)
+    gate, up = _C.gemm_nt(x, wg, bias=bg), _C.gemm_nt(x, wu, bias=bu)
+    want = _fq_table(oracle, spec)(torch.nn.functional.silu(gate) * up)
+    if codes:
+        got = got.view(torch.float8_e4m3fn).to(torch.bfloat16)
+    assert got.shape == (M, I)
+    same = got.view(torch.int16) == want.view(torch.int16)
+    assert float(same.float().mean()) >= 0.995
+    gf, wf = got.float(), want.float()
+    assert not bool((~same & ((gf - wf).abs() > 0.26 * wf.abs().clamp_min(1e-30)) & ((gf - wf).abs() > 2.0 ** -14)).any())
