@@ -32,13 +32,12 @@
 
 #include "qt_internal.h"
 #include "qt_lut.h"
+#include "qt_tc.cuh"
 
 namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int MAX_BLOCK_N = 256;  // the tile width is a launch parameter: 64, 128 or 256 columns (see pick_block_n)
-constexpr int ROW_BYTES = 128;  // one k-block of a row: 64 bf16 or 128 fp8, = the swizzle span
-constexpr int MMA_K_BYTES = 32;  // K extent of one tcgen05.mma in bytes (16 bf16 / 32 fp8)
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * ROW_BYTES;  // 32 KB
@@ -75,102 +74,6 @@ struct GemmParams {
 };
 
 enum { OUT_PLAIN = 0, OUT_FQ = 1, OUT_GLU = 2 };
-
-// ----------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    for (uint32_t spins = 0;; ++spins) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (spins > (1u << 24)) __trap();  // try_wait itself blocks for a while; this is many seconds
-    }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
-            "r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-template <bool FP8>
-__device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate)
-{
-    if (FP8)
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-            : "memory");
-    else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-            : "memory");
-}
-// 32 TMEM lanes (one per thread of the warp) x 32 consecutive 32-bit columns
-// (asynchronous: the registers are valid after tcgen05.wait::ld)
-__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t *v)
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-
-// K-major operand tile in shared memory, 128-byte rows, 128-byte swizzle (what TMA wrote):
-// canonical UMMA layout ((8, n), 2) : ((8 x 16 B, SBO), 16 B) with SBO = 8 rows x 128 B = 1024 B.
-// Fields (cute/arch/mma_sm100_desc.hpp): start address >> 4 [0,14), LBO >> 4 [16,30) (ignored for swizzled
-// K-major; 1 like CUTLASS), SBO >> 4 [32,46), version = 1 [46,48), layout type SWIZZLE_128B = 2 [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 
 __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
@@ -523,55 +426,6 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ----------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    }
-    return fn;
-}
-
-// [outer, inner, rows, cols] tensor with a unit-stride last axis and arbitrary (16-byte aligned) strides on the other
-// three: dims {cols, rows, inner, outer}, box {box_cols, box_rows, 1, 1}, 128-byte swizzle (box_cols * esz == 128).
-// Loads: out-of-bounds elements (K tail, row tail) are filled with zeros.  Stores: they are not written.
-int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int64_t rows, int64_t inner, int64_t outer,
-             int64_t ld, int64_t stride_inner, int64_t stride_outer, int box_rows, int box_bytes = ROW_BYTES)
-{
-    EncodeTiledFn fn = encode_tiled();
-    if (!fn) {
-        qt_set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return QT_ERR_CUDA;
-    }
-    const int esz = one_byte ? 1 : 2;
-    // size-1 axes never move: give them a harmless, valid stride
-    if (inner <= 1) stride_inner = rows * ld;
-    if (outer <= 1) stride_outer = (inner <= 1 ? rows * ld : inner * stride_inner);
-    cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)stride_inner * esz, (cuuint64_t)stride_outer * esz};
-    cuuint32_t box[4] = {(cuuint32_t)(box_bytes / esz), (cuuint32_t)box_rows, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(map, one_byte ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                    const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        qt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld batch=%lldx%lld ld=%lld "
-                     "strides=%lld,%lld)", (int)r, (long long)cols, (long long)rows, (long long)outer, (long long)inner,
-                     (long long)ld, (long long)stride_inner, (long long)stride_outer);
-        return QT_ERR_INVALID_ARGUMENT;
-    }
-    return QT_OK;
-}
-
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D = F32 [4,6) = 1;
 // A/B format [7,10) / [10,13): kind::f16 BF16 = 1, kind::f8f6f4 E4M3 = 0 / E5M2 = 1; both K-major;
 // N >> 3 at [17,23); M >> 4 at [24,29).

@@ -265,6 +265,62 @@ def _usable(x):
     return _ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()
 
 
+_CAUSAL_CACHE = {}
+
+
+def _mask3(mask, B, Sq, Sk):
+    """(additive bf16 mask [Bm, rows, Sk] contiguous or None, is_standard_causal).  The causal test runs once per mask
+    tensor (every layer of a forward, and every replay of a captured graph, sees the same object)."""
+    if mask is None:
+        return None, False
+    if mask.dtype == torch.bool:
+        from .modules.quantizable._common import additive_mask
+        mask = additive_mask(mask, torch.bfloat16)
+    if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] not in (1, Sq) or mask.shape[0] not in (1, B) \
+            or not mask.dtype.is_floating_point or mask.shape[3] < Sk:
+        raise _NotFusable
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype)
+    hit = _CAUSAL_CACHE.get("last")
+    if hit is None or hit[0] != key:
+        m3 = mask[:, 0, :, :Sk]
+        if m3.dtype != torch.bfloat16:
+            m3 = m3.to(torch.bfloat16)
+        m3 = m3.contiguous()
+        causal = False
+        if m3.shape[1] == Sq and Sq == Sk and not torch.cuda.is_current_stream_capturing():
+            ref = torch.full((Sq, Sk), torch.finfo(torch.bfloat16).min, device=mask.device, dtype=torch.bfloat16).triu(1)
+            causal = bool((m3 == ref[None]).all())
+        hit = (key, m3, causal, mask)
+        _CAUSAL_CACHE["last"] = hit
+    return hit[1], hit[2]
+
+
+def attention(q4, k4, vt, scaling, mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c_o, B, S, H, D):
+    """The attention core: QK^T GEMM -> scale+mask+softmax+fq -> PV GEMM (three launches, default), or the single
+    kernel qt_attention_fq (QT_ATTENTION=fused) when every fake-quant step involved is a bare spec of one format, the
+    head dimension is 64 / 128 and the keys are a multiple of 16.  Measured on B200 at the Llama-2-7B window shape
+    (scripts/attn_micro.py): chain 80 us, single kernel 178 us -- it recomputes the element-wise chain in both of
+    its passes with 8 softmax warps per SM (one CTA per SM: 200 KB of shared memory) and is issue-bound there, so
+    the chain stays the default until the kernel gets more softmax warps and a balanced causal schedule."""
+    steps = [f for f in (sc_in, sm_in, p_in, o_in) if f is not None]
+    Sk = k4.shape[2]
+    one_kernel = (D in (64, 128) and Sk % 16 == 0 and (D * q4.element_size()) % 128 == 0
+                  and all(f.qscheme is None for f in steps) and len({f.dtype for f in steps}) <= 1
+                  and os.environ.get("QT_ATTENTION", "chain") == "fused")
+    if one_kernel:
+        m3, causal = _mask3(mask, B, S, Sk)
+        fmt, lut = (steps[0]._fmt, steps[0].lut) if steps else (_identity_fmt(), None)
+        points = (_C.FQ_PRE if sc_in is not None else 0) | (_C.FQ_MID if sm_in is not None else 0) | \
+            (_C.FQ_POST if p_in is not None else 0) | (_C.FQ_OUT if o_in is not None else 0)
+        ctx = torch.empty(B, S, H * D, dtype=torch.uint8 if c_o else torch.bfloat16, device=q4.device)
+        _C.attention_fq(q4, k4, vt, ctx.view(B, S, H, D).transpose(1, 2), scaling, m3, causal, points, fmt, lut,
+                        qk_type=t_qk, pv_type=t_pv)
+        return ctx.view(B * S, H * D)
+    scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                              # [B, H, S, S]
+    probs = softmax(scores, scaling, mask, sc_in, sm_in, p_in, t_pv != _C.GEMM_BF16)
+    return _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D)
+
+
 def _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D):
     """probabilities x values written straight into [B*S, H*D].  The output projection's input fake quant is applied
     by the product's epilogue only for long reductions: at S = 1024 the product is epilogue-bound (128 x 128 tiles,
@@ -353,9 +409,7 @@ def llama_layer_forward(layer, hidden_states, attention_mask, position_embedding
         _C.fq_transpose(v, vt, _flags(post=v_in), fmt, s_v, lut)
         q4 = qk[0].view(B, S, H, D).transpose(1, 2)
         k4 = qk[1].view(B, S, H, D).transpose(1, 2)
-        scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                           # [B, H, S, S]
-        probs = softmax(scores, attn.scaling, attention_mask, sc_in, sm_in, p_in, c_pv)
-        ctx2 = _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D)
+        ctx2 = attention(q4, k4, vt, attn.scaling, attention_mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c_o, B, S, H, D)
         if res1 == (None, None):
             h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x, operand_type=t_o)   # residual add in the epilogue
         else:
@@ -453,9 +507,7 @@ def bert_layer_forward(layer, hidden_states, attention_mask):
         _C.fq_transpose(qkv[:, 2 * hidden:].view(B, S, H, D), vt, _flags(post=v_in), fmt, s_v, lut)
         q4 = qk[:, :hidden].view(B, S, H, D).transpose(1, 2)
         k4 = qk[:, hidden:].view(B, S, H, D).transpose(1, 2)
-        scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                          # [B, H, S, S]
-        probs = softmax(scores, scaling, attention_mask, sc_in, sm_in, p_in, c_pv)
-        ctx2 = _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D)
+        ctx2 = attention(q4, k4, vt, scaling, attention_mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c_o, B, S, H, D)
         if res1 == (None, None):
             h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x, operand_type=t_o)
         else:
