@@ -163,7 +163,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    L = min(args.log2_numel, 24)
+    L = min(args.log2_numel, 26)   # 2^26 elements x 8 specs per step: ~0.1-0.2 s of CPU work per step
     for _ in range(args.warmup):
         cpu_port_gbs(L, 1, SWEEP[:1])
     t0 = time.perf_counter()
@@ -346,7 +346,7 @@ def run_gpu(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             gbs, threads, dt = cpu_port_gbs(24, 2)
-            reps = max(1, min(40, int(15.0 / max(dt / 2, 1e-3))))  # about 15 s of CPU work
+            reps = max(1, min(2000, int(12.0 / max(dt / 2, 1e-3))))  # about 12 s of CPU work
             gbs, threads, dt = cpu_port_gbs(24, reps)
             cpu = {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{reps} x {len(SWEEP)} specs x 2^24 bf16 elements, {dt:.1f} s"}
