@@ -38,6 +38,10 @@ def lib():
         L.qto_scale_update.argtypes = [vp, i32, sz, vp, vp, f32, i32]
         L.qto_fake_quant_bf16.argtypes = [vp, vp, sz, sz, sz, vp, vp]
         L.qto_fake_quant_f32.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+        L.qto_mx_fake_quant.argtypes = [vp, vp, i32, i32, vp, vp, i32, f32, i32, vp, vp, vp]
+        L.qto_gwa_fake_quant.argtypes = [vp, vp, i32, i32, vp, vp, i32, f32, f32, vp, vp, vp]
+        L.qto_mx_fake_quant.restype = None
+        L.qto_gwa_fake_quant.restype = None
         L.qto_num_threads.restype = i32
         L.qto_set_num_threads.argtypes = [i32]
         for f in (L.qto_vmap_bf16, L.qto_vmap_f32, L.qto_amax, L.qto_scale_update,
@@ -135,6 +139,41 @@ class FakeQuant:
         fn = L.qto_fake_quant_f32 if is_f32 else L.qto_fake_quant_bf16
         fn(_p(x), _p(y), outer, C, inner, _p(self.scale), _p(self.table))
         return y
+
+
+def _block_args(shape, axes, block_size):
+    shape = [int(d) for d in shape]
+    axes = [axes] if isinstance(axes, int) else list(axes)
+    axes = [a + len(shape) if a < 0 else a for a in axes]
+    flags = np.array([1 if d in axes else 0 for d in range(len(shape))], dtype=np.int32)
+    bshape = [-(-d // block_size) if f else d for d, f in zip(shape, flags)]
+    return np.array(shape, dtype=np.uint64), flags, bshape
+
+
+def mx_fake_quant(x, shape, axes, block_size, quant_max, table, force_pow2=False, scale_table=None):
+    """MXFakeQuantFunction.forward (fake_quantize.py:105-129) -> (y, scale[block grid] float32)."""
+    x = np.ascontiguousarray(x)
+    shp, flags, bshape = _block_args(shape, axes, block_size)
+    y = np.empty_like(x)
+    scale = np.empty(int(np.prod(bshape)) if bshape else 1, dtype=np.float32)
+    lib().qto_mx_fake_quant(_p(x), _p(y), int(x.dtype == np.float32), len(shape), _p(shp), _p(flags),
+                            int(block_size), float(quant_max), int(force_pow2),
+                            None if scale_table is None else _p(scale_table), _p(table), _p(scale))
+    return y, scale.reshape(bshape)
+
+
+def gwa_fake_quant(x, shape, axes, block_size, quant_min, quant_max, scale_table=None):
+    """GroupWiseAffineFakeQuantFunction.forward (fake_quantize.py:138-190) -> (y, scale, zero_point)."""
+    x = np.ascontiguousarray(x)
+    shp, flags, bshape = _block_args(shape, axes, block_size)
+    y = np.empty_like(x)
+    nb = int(np.prod(bshape)) if bshape else 1
+    scale = np.empty(nb, dtype=np.float32)
+    zp = np.empty(nb, dtype=np.float32)
+    lib().qto_gwa_fake_quant(_p(x), _p(y), int(x.dtype == np.float32), len(shape), _p(shp), _p(flags),
+                             int(block_size), float(quant_min), float(quant_max),
+                             None if scale_table is None else _p(scale_table), _p(scale), _p(zp))
+    return y, scale.reshape(bshape), zp.reshape(bshape)
 
 
 def num_threads():

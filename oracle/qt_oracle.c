@@ -431,6 +431,155 @@ void qto_fake_quant_f32(const float *x, float *y, size_t outer, size_t C, size_t
     }
 }
 
+/* ------------------------------------------------- block-scaled qschemes
+ * microscaling:      MXFakeQuantFunction.forward fake_quantize.py:105-129,
+ *                    calculate_mx_qparam decomposed.py:372-419, quantize :171-210, expand :127-140,
+ *                    _reshape_to_blocks mx_utils.py:62-121, _shared_exponents :16-59
+ * group_wise_affine: GroupWiseAffineFakeQuantFunction.forward fake_quantize.py:138-190
+ *
+ * The tensor is contiguous with `ndim` dims; axes flagged in is_block[] are tiled with
+ * `bs` (the reference pads with zeros to a multiple of bs, which changes nothing for
+ * amax but DOES enter the min / max of the affine scheme).  Parameters come out with
+ * shape[d] -> ceil(shape[d] / bs) on the block axes, as the reference's `scale` buffer.
+ * Every op of the reference runs in the tensor's dtype: for bf16 tensors each
+ * intermediate is rounded to bf16 (bfr), python scalars enter as fp32. */
+
+#define QTO_MAXD 8
+typedef struct {
+    int ndim;
+    size_t shape[QTO_MAXD], bshape[QTO_MAXD], bstride[QTO_MAXD];
+    int blocked[QTO_MAXD];
+    size_t n, nblocks;
+    int bs, padded;
+} blk_t;
+
+static void blk_init(blk_t *B, int ndim, const size_t *shape, const int *is_block, int bs)
+{
+    B->ndim = ndim; B->bs = bs; B->n = 1; B->nblocks = 1; B->padded = 0;
+    for (int d = 0; d < ndim; d++) {
+        B->shape[d] = shape[d];
+        B->blocked[d] = is_block[d] != 0;
+        B->bshape[d] = is_block[d] ? (shape[d] + (size_t)bs - 1) / (size_t)bs : shape[d];
+        if (is_block[d] && shape[d] % (size_t)bs) B->padded = 1;
+        B->n *= shape[d];
+    }
+    for (int d = ndim - 1; d >= 0; d--) { B->bstride[d] = B->nblocks; B->nblocks *= B->bshape[d]; }
+}
+static inline size_t blk_of(const blk_t *B, size_t i)
+{
+    size_t b = 0;
+    for (int d = B->ndim - 1; d >= 0; d--) {
+        size_t c = i % B->shape[d];
+        i /= B->shape[d];
+        b += (B->blocked[d] ? c / (size_t)B->bs : c) * B->bstride[d];
+    }
+    return b;
+}
+static inline float ld_elem(const void *x, int is_f32, size_t i)
+{
+    return is_f32 ? ((const float *)x)[i] : bf2f(((const uint16_t *)x)[i]);
+}
+/* an op result in the tensor's dtype */
+static inline float rnd(int is_f32, float v) { return is_f32 ? v : bfr(v); }
+/* vmap of one value of the tensor's dtype */
+static inline float vmap1(int is_f32, float v, const uint16_t *qmap)
+{
+    return bf2f(qmap[is_f32 ? rto_index(v) : f2bf(v)]);
+}
+
+/* scale of one block from its amax (decomposed.py:391-419) */
+static float mx_block_scale(int is_f32, float amax, float quant_max, int force_pow2, const uint16_t *scale_qmap)
+{
+    float s;
+    if (force_pow2) {
+        /* shared_exp = floor(log2(amax + FP32_MIN_NORMAL * (amax == 0))) - floor(log2(quant_max)); 2 ** shared_exp */
+        float a = rnd(is_f32, amax + (amax == 0.0f ? 0x1p-126f : 0.0f));
+        float e = floorf(rnd(is_f32, log2f(a)));
+        e = rnd(is_f32, e - (float)floor(log2((double)quant_max)));
+        s = rnd(is_f32, powf(2.0f, e));
+    } else {
+        s = rnd(is_f32, amax / quant_max);
+        if (scale_qmap) s = vmap1(is_f32, s, scale_qmap);
+    }
+    return s > 0.0f ? s : 1.0f; /* torch.where(scale > 0.0, scale, 1.0): NaN -> 1 */
+}
+
+void qto_mx_fake_quant(const void *x, void *y, int is_f32, int ndim, const size_t *shape, const int *is_block,
+                       int bs, float quant_max, int force_pow2, const uint16_t *scale_qmap,
+                       const uint16_t *qmap, float *scale_out)
+{
+    blk_t B;
+    blk_init(&B, ndim, shape, is_block, bs);
+    uint32_t *am = (uint32_t *)calloc(B.nblocks ? B.nblocks : 1, sizeof(uint32_t));
+    for (size_t i = 0; i < B.n; i++) { /* amax(|x|) per block; NaN patterns order above Inf */
+        uint32_t a = f2u(ld_elem(x, is_f32, i)) & 0x7fffffffu;
+        size_t b = blk_of(&B, i);
+        if (a > am[b]) am[b] = a;
+    }
+    for (size_t b = 0; b < B.nblocks; b++)
+        scale_out[b] = mx_block_scale(is_f32, u2f(am[b]), quant_max, force_pow2, scale_qmap);
+    free(am);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < B.n; i++) {
+        const float s = scale_out[blk_of(&B, i)];
+        const float q = vmap1(is_f32, rnd(is_f32, ld_elem(x, is_f32, i) / s), qmap); /* quantize(): input / scale, vmap */
+        const float r = q * s;                                                     /* input * expand(sf) */
+        if (is_f32) ((float *)y)[i] = r; else ((uint16_t *)y)[i] = f2bf(r);
+    }
+}
+
+/* torch.amin / amax: NaN propagates */
+static inline float nan_min(float a, float b) { return (isnan(a) || isnan(b)) ? NAN : (b < a ? b : a); }
+static inline float nan_max(float a, float b) { return (isnan(a) || isnan(b)) ? NAN : (b > a ? b : a); }
+
+void qto_gwa_fake_quant(const void *x, void *y, int is_f32, int ndim, const size_t *shape, const int *is_block,
+                        int bs, float quant_min, float quant_max, const uint16_t *scale_qmap,
+                        float *scale_out, float *zp_out)
+{
+    blk_t B;
+    blk_init(&B, ndim, shape, is_block, bs);
+    const size_t nb = B.nblocks ? B.nblocks : 1;
+    float *mn = (float *)malloc(nb * sizeof(float)), *mx = (float *)malloc(nb * sizeof(float));
+    /* a block cut by the tensor edge holds padding zeros (F.pad, mx_utils.py:94-96) */
+    for (size_t b = 0; b < nb; b++) mn[b] = mx[b] = NAN;
+    unsigned char *seen = (unsigned char *)calloc(nb, 1);
+    for (size_t i = 0; i < B.n; i++) {
+        const float v = ld_elem(x, is_f32, i);
+        const size_t b = blk_of(&B, i);
+        if (!seen[b]) { mn[b] = mx[b] = v; seen[b] = 1; }
+        else { mn[b] = nan_min(mn[b], v); mx[b] = nan_max(mx[b], v); }
+    }
+    if (B.padded) {
+        for (size_t b = 0; b < B.nblocks; b++) { /* is block b cut on any block axis? */
+            size_t r = b; int cut = 0;
+            for (int d = B.ndim - 1; d >= 0; d--) {
+                size_t c = r % B.bshape[d]; r /= B.bshape[d];
+                if (B.blocked[d] && (c + 1) * (size_t)B.bs > B.shape[d]) cut = 1;
+            }
+            if (cut) { mn[b] = nan_min(mn[b], 0.0f); mx[b] = nan_max(mx[b], 0.0f); }
+        }
+    }
+    const float range = quant_max - quant_min;
+    for (size_t b = 0; b < B.nblocks; b++) {
+        float sf = rnd(is_f32, rnd(is_f32, mx[b] - mn[b]) / range);
+        sf = sf > 0.0f ? sf : 1.0f;
+        float zp = rnd(is_f32, rnd(is_f32, -mn[b] / sf) + quant_min);
+        if (scale_qmap) { sf = vmap1(is_f32, sf, scale_qmap); zp = vmap1(is_f32, zp, scale_qmap); }
+        scale_out[b] = sf; zp_out[b] = zp;
+    }
+    free(mn); free(mx); free(seen);
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < B.n; i++) {
+        const size_t b = blk_of(&B, i);
+        const float sf = scale_out[b], zp = zp_out[b];
+        float q = rnd(is_f32, rnd(is_f32, ld_elem(x, is_f32, i) / sf) + zp);
+        q = nearbyintf(q);                        /* torch.round: half to even */
+        q = clampf_t(q, quant_min, quant_max);    /* torch.clamp */
+        const float r = rnd(is_f32, rnd(is_f32, q - zp) * sf);
+        if (is_f32) ((float *)y)[i] = r; else ((uint16_t *)y)[i] = f2bf(r);
+    }
+}
+
 int qto_num_threads(void)
 {
 #ifdef _OPENMP

@@ -41,8 +41,12 @@ def golden():
         pbits = np.load(os.path.join(GOLDEN, "pbits.npz"))
         vmap32 = np.load(os.path.join(GOLDEN, "vmap32.npz"))
         fq = np.load(os.path.join(GOLDEN, "fq_cases.npz"))
+        mx = np.load(os.path.join(GOLDEN, "mx_cases.npz"))
+        mx_scale = np.load(os.path.join(GOLDEN, "mx_scale.npz"))
         with open(os.path.join(GOLDEN, "manifest.json")) as f:
             manifest = json.load(f)
+        with open(os.path.join(GOLDEN, "mx_manifest.json")) as f:
+            mx_manifest = json.load(f)
     return G
 
 

@@ -63,3 +63,45 @@ def test_fake_quant_sequences(golden, oracle):
         yb = y.view(np.uint32) if f32 else y
         assert nan_eq(yb, golden.fq[f"{name}/y_obsoff"]).all(), (name, "obsoff")
         assert nan_eq32(fq.scale.view(np.uint32), golden.fq[f"{name}/scale_obsoff"]).all()
+
+
+def _as_input(bits, dtype):
+    return bits.view(np.float32) if dtype == "f32" else bits
+
+
+def test_block_scaled_cases(golden, oracle):
+    """microscaling / group_wise_affine forward: outputs, scale and zero_point of the reference run."""
+    assert len(golden.mx_manifest["cases"]) >= 20
+    for case in golden.mx_manifest["cases"]:
+        name = case["name"]
+        x = _as_input(golden.mx[f"{name}/x"], case["dtype"])
+        stab = oracle.qmap(case["scale_dtype"]) if case["scale_dtype"] else None
+        if case["qscheme"] == "microscaling":
+            y, s = oracle.mx_fake_quant(x, case["shape"], case["ch_axis"], case["block_size"], case["quant_max"],
+                                        oracle.qmap(case["element"]), case["force_scale_power_of_two"], stab)
+        else:
+            y, s, zp = oracle.gwa_fake_quant(x, case["shape"], case["ch_axis"], case["block_size"],
+                                             case["quant_min"], case["quant_max"], stab)
+            assert nan_eq32(zp.reshape(-1).view(np.uint32), golden.mx[f"{name}/zero_point"]).all(), (name, "zp")
+        assert list(s.shape) == case["scale_shape"], name
+        assert nan_eq32(s.reshape(-1).view(np.uint32), golden.mx[f"{name}/scale"]).all(), (name, "scale")
+        yb = y.view(np.uint32) if case["dtype"] == "f32" else y
+        assert nan_eq(yb.reshape(-1), golden.mx[f"{name}/y"].reshape(-1)).all(), name
+
+
+def test_mx_scale_function(golden, oracle):
+    """calculate_mx_qparam on one-element blocks: every positive bf16 amax, fp32 values around every power of
+    two -- pins the dtype-dependent floor(log2()) of force_scale_power_of_two."""
+    e5m3 = oracle.qmap("fp8_e5m3")
+    ident = np.arange(65536, dtype=np.uint16)  # get_quantization_map(None): identity table
+    allb = np.arange(0x8000, dtype=np.uint16)
+    fb = golden.mx_scale["f32_amax_bits"]
+    for qmax in golden.mx_manifest["scale_fn_quant_max"]:
+        for mode, pow2, stab in (("pow2", True, None), ("amax", False, None), ("e5m3", False, e5m3)):
+            _, s = oracle.mx_fake_quant(allb, (allb.size, 1), -1, 1, qmax, ident, pow2, stab)
+            # the bf16 reference returns the scale as bf16: compare through its fp32 widening
+            want = golden.mx_scale[f"bf16/{mode}/{qmax}"].astype(np.uint32) << 16
+            assert nan_eq32(s.reshape(-1).view(np.uint32), want).all(), ("bf16", mode, qmax)
+            _, s = oracle.mx_fake_quant(fb.view(np.float32), (fb.size, 1), -1, 1, qmax, ident, pow2, stab)
+            bad = np.nonzero(~nan_eq32(s.reshape(-1).view(np.uint32), golden.mx_scale[f"f32/{mode}/{qmax}"]))[0]
+            assert bad.size == 0, ("f32", mode, qmax, [hex(fb[i]) for i in bad[:8]])
