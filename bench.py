@@ -296,6 +296,22 @@ def run_gpu(args):
         extra["posit8_1 bf16 per-channel ax=0 [N/4096,4096] + amax"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
         ms = timed(lambda: qt._C.fq_forward(xs, ys, rows, 4096, 1, m._fmt, scc, torch.zeros(4096, device=dev), m.lut))
         extra["posit8_1 bf16 per-channel ax=-1 [N/4096,4096] + amax"] = 4.0 * nn_ / (ms * 1e-3) / 1e9
+        # block-scaled qschemes through the module API (scale buffer written per block: + 4 / bs bytes per element)
+        x2 = xs.view(rows, 4096)
+        for spec, ax in (("fp4_e2m1,qs=microscaling,bs=32", -1), ("fp8_e4m3,qs=microscaling,bs=32", -1),
+                         ("int6,qs=microscaling,bs=64,scale=fp8_e5m3", -1), ("int6,qs=microscaling,bs=64,scale=fp8_e5m3", 0)):
+            for pow2 in ((True,) if "fp" in spec.split(",")[0] else (False,)):
+                qs = qt.QuantizationSpec.from_str(spec + f",ax={ax}")
+                m = qt.FusedAmaxObsFakeQuantize(**qs.fake_quant_kwargs(), force_scale_power_of_two=pow2, device=dev)
+                ms = timed(lambda: m(x2))
+                extra[f"{spec} ax={ax}{' pow2' if pow2 else ''} bf16 [N/4096,4096]"] = \
+                    (4.0 + 4.0 / qs.block_size) * nn_ / (ms * 1e-3) / 1e9
+        qs = qt.QuantizationSpec.from_str("uint4,qs=group_wise_affine,bs=64,ax=-1")
+        m = qt.FusedAmaxObsFakeQuantize(**qs.fake_quant_kwargs(), device=dev)
+        ms = timed(lambda: m(x2))
+        extra["uint4,qs=group_wise_affine,bs=64 ax=-1 bf16 [N/4096,4096] (two-kernel generic path)"] = \
+            (4.0 + 8.0 / 64) * nn_ / (ms * 1e-3) / 1e9
+        del x2
         ms = timed(lambda: qt._C.amax(xs, 1, 1, nn_, hist))
         extra["amax only bf16 (read bytes)"] = 2.0 * nn_ / (ms * 1e-3) / 1e9
         x32 = xs[: nn_ // 2].float()

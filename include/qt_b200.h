@@ -123,6 +123,56 @@ int qt_quantize_codes(const void *x, void *codes, size_t n, int elem_type, const
 int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type,
             float *amax_out, void *stream);
 
+/* ---- block-scaled qschemes: microscaling and group_wise_affine (qt_block.cu) ---------------------------------
+ * One call = MXFakeQuantFunction.forward (fake_quantize.py:105-129: calculate_mx_qparam decomposed.py:372-419,
+ * quantize :171-210, expand :127-140, tiling of mx_utils.py:62-121) or GroupWiseAffineFakeQuantFunction.forward
+ * (fake_quantize.py:138-190).  The scale is a function of the block being quantized (no history, no delay):
+ *   microscaling       s = amax(|block|) / quant_max [through the scale_fmt codebook], or with
+ *                      force_scale_power_of_two 2^(floor(log2 amax) - floor(log2 quant_max)); s <= 0 or NaN -> 1;
+ *                      y = round_fmt(x / s) * s
+ *   group_wise_affine  sf = (max - min) / (quant_max - quant_min), <= 0 or NaN -> 1; zp = -min / sf + quant_min
+ *                      [both through the scale_fmt codebook]; y = (clamp(round(x / sf + zp), qmin, qmax) - zp) * sf
+ * with every intermediate rounded to the tensor's dtype as the reference's separate torch ops do.
+ * x, y: contiguous, seen as [d0, n1, d1, n2, d2].  Axis n1 is tiled with block_size; axis n2 is tiled too when
+ * block_axis2 != 0 (two-axis blocks, e.g. ax=(-2,-1)), else it is an ordinary axis (pass n2 = d2 = 1 for the
+ * usual [outer, n, inner] view of a single tiled axis).  Edge blocks are zero padded as in the reference (this
+ * matters for the min / max of the affine scheme only).
+ * scale (and zero_point for the affine scheme): OUTPUT, one float per block, row-major over the block grid
+ * [d0, ceil(n1/bs), d1, ceil(n2/bs) or n2, d2] -- what the reference leaves in the module's `scale` buffer.
+ * fmt / lut: element format as in qt_fq_forward (ignored by the affine scheme, which rounds to integers).
+ * scale_fmt: codebook of the parameters (`scale_dtype`, e.g. fp8_e5m3), or NULL.
+ * pow2_table: QT_POW2_TABLE_WORDS uint32 on the device from qt_block_pow2_table_host(elem_type, ...); needed
+ * when force_scale_power_of_two != 0. */
+#define QT_BLOCK_MX 0
+#define QT_BLOCK_AFFINE 1
+#define QT_POW2_TABLE_WORDS 288
+typedef struct qt_block_desc {
+    const void *x;
+    void *y;
+    int32_t elem_type; /* QT_BF16 / QT_F32 */
+    int32_t qscheme;   /* QT_BLOCK_MX / QT_BLOCK_AFFINE */
+    int64_t d0, n1, d1, n2, d2;
+    int32_t block_size;
+    int32_t block_axis2;
+    float quant_min, quant_max;
+    int32_t force_scale_power_of_two;
+    int32_t reserved;
+    const qt_format_t *fmt;
+    const void *lut;
+    const qt_format_t *scale_fmt;
+    const void *pow2_table;
+    float *scale;
+    float *zero_point;
+} qt_block_desc_t;
+int qt_fq_block(const qt_block_desc_t *desc, void *stream);
+
+/* HOST: the function  amax -> floor(log2(amax))  as the reference evaluates it in the tensor's dtype
+ * (mx_utils.py:44-48: for bf16 tensors log2() is rounded to bf16 before the floor).  table_host[e], e = 1..254:
+ * mantissa threshold (23-bit units) at or above which the result is e - 126 instead of e - 127;
+ * table_host[256 + k], k = 0..22: the same for subnormal amax with leading bit k (threshold on the whole pattern).
+ * QT_POW2_TABLE_WORDS uint32. */
+int qt_block_pow2_table_host(int elem_type, uint32_t *table_host);
+
 /* ---- quantized GEMM / batched GEMM (tcgen05 + TMEM + TMA) -------------------------------------------
  * C[b, m, n] = epilogue(alpha * sum_k A[b, m, k] * B[b, n, k]),  fp32 accumulation, C in bf16.
  * Replaces F.linear(x_q, W_q, bias) of the QAT Linear (modules/qat/linear.py:40-41; A = activations [M, K],

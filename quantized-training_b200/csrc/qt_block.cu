@@ -1,0 +1,548 @@
+// qt_block.cu -- block-scaled fake quant for sm_100a: the `microscaling` and `group_wise_affine` qschemes.
+//
+// Replaces (reference, src/quantized_training/): MXFakeQuantFunction.forward fake_quantize.py:105-129,
+// GroupWiseAffineFakeQuantFunction.forward :138-190, calculate_mx_qparam decomposed.py:372-419, quantize :171-210,
+// expand :127-140 and the pad / reshape of mx_utils.py:62-121 -- about 25 ATen launches with padded, tiled and
+// repeat_interleave-d temporaries -- with ONE pass over HBM: the block statistic, the scale, (x / s) -> round to the
+// format -> (* s) and the store happen while the block sits in registers.
+//
+// Unlike the per-tensor scheme (qt_fq.cu) the scale is NOT delayed: it is a function of the block being quantized,
+// so the statistic has to be complete before the first element is rounded.  A block is small (block_size elements,
+// or block_size^2 for two tiled axes), which is what makes the single pass possible:
+//   flat  kernel  blocks along the last axis (unit stride): block_size / VEC lanes of a warp hold one block, the
+//                 maximum is a log2(lanes)-step xor-shuffle.
+//   cols  kernel  blocks along an inner axis (stride = inner elements): a (32, 8) CTA holds 32 column groups of
+//                 one block row; every column is its own block, maxima of the 8 row phases meet in shared memory.
+//   generic       anything else (two tiled axes, ragged last axis, odd block sizes, misaligned views, and the
+//                 affine scheme): a statistic kernel (one warp per block) and an element-wise apply kernel.
+//
+// Scale arithmetic follows the reference op by op in the tensor's dtype (bf16 tensors: every intermediate is
+// rounded to bf16; python scalars enter as fp32).  force_scale_power_of_two evaluates floor(log2(amax)) *in the
+// tensor's dtype* (mx_utils.py:44-48): for a bf16 tensor log2() is rounded to 8 significant bits before the floor,
+// so e.g. amax = 1.98 * 2^60 has floor(bf16(60.98)) = 61.  That function of amax is one mantissa threshold per
+// exponent, tabulated on the host (qt_block_pow2_table_host) with the same libm call sequence and checked against
+// the reference on every bf16 value.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "qt_fq_common.cuh"
+
+namespace {
+
+struct BlockParams {
+    float quant_min, quant_max, range;  // range = quant_max - quant_min (affine)
+    int32_t pow2;                       // force_scale_power_of_two
+    int32_t qmax_exp;                   // floor(log2(quant_max))
+    int32_t has_scale_fmt;              // scale / zero point go through the scale_dtype codebook
+    QtRound scale_round;
+    const uint32_t *pow2_tab;  // QT_POW2_TABLE_WORDS words on the device (pow2 only)
+};
+
+template <bool F32>
+__device__ __forceinline__ float to_dtype(float v)
+{
+    return F32 ? v : __uint_as_float(bf16_rne_hi(v));
+}
+// vmap of one value of the tensor's dtype through the scale codebook
+template <bool F32>
+__device__ __forceinline__ float scale_codebook(const BlockParams &bp, float v)
+{
+    const uint32_t b = __float_as_uint(v);
+    return __uint_as_float(qt_round_dyn(bp.scale_round, F32 ? f32_to_bf16_rto_hi(b) : b));
+}
+
+// scale of one block from the bit pattern of its amax (decomposed.py:391-419); NaN patterns order above Inf
+template <bool F32>
+__device__ __forceinline__ float mx_scale_of(uint32_t a, const BlockParams &bp)
+{
+    float s;
+    if (bp.pow2) {
+        if (a > 0x7F800000u) return 1.0f;  // log2(NaN) -> NaN -> where(scale > 0) picks 1
+        if (a == 0x7F800000u) return __uint_as_float(a);
+        int E;
+        if (a == 0u)
+            E = -126;  // amax + FP32_MIN_NORMAL * (amax == 0)
+        else if (a >> 23) {
+            const uint32_t e = a >> 23;
+            E = (int)e - 127 + ((a & 0x7FFFFFu) >= bp.pow2_tab[e] ? 1 : 0);
+        } else {
+            const int k = 31 - __clz(a);
+            E = k - 149 + (a >= bp.pow2_tab[256 + k] ? 1 : 0);
+        }
+        E -= bp.qmax_exp;
+        if (E < (F32 ? -149 : -133)) return 1.0f;  // 2^E rounds to zero in the tensor's dtype
+        if (E > 127) return __uint_as_float(0x7F800000u);
+        s = __uint_as_float(E >= -126 ? (uint32_t)(E + 127) << 23 : 1u << (E + 149));
+    } else {
+        s = to_dtype<F32>(__fdiv_rn(__uint_as_float(a), bp.quant_max));
+        if (bp.has_scale_fmt) s = scale_codebook<F32>(bp, s);
+    }
+    return s > 0.0f ? s : 1.0f;
+}
+
+__device__ __forceinline__ ScaleBf16 make_scale(float s)
+{
+    ScaleBf16 sc;
+    sc.s = s;
+    sc.rs = __frcp_rn(s);
+    return sc;
+}
+
+// one 16-byte vector with one scale; the scale is already in the tensor's dtype
+template <class R, bool F32>
+__device__ __forceinline__ uint4 mx_apply_vec(const R &round, const uint4 &v, float s)
+{
+    const ScaleBf16 sc = make_scale(s);
+    uint32_t unused = 0u;
+    const int mode = classify_scale(s);
+    if (mode == DIV_UNIT) return fq_vec<R, F32, DIV_UNIT, false>(round, v, sc, unused);
+    if (F32 || mode == DIV_EXACT) return fq_vec<R, F32, DIV_EXACT, false>(round, v, sc, unused);
+    return fq_vec<R, F32, DIV_RECIP, false>(round, v, sc, unused);
+}
+
+// ----------------------------------------------------------------------------- flat kernel
+// Blocks of LANES consecutive 16-byte vectors (last axis, shape[-1] % block_size == 0): block b = vector i / LANES,
+// which is also its index in the row-major block grid.  nvec % LANES == 0.
+template <class R, bool F32, int LANES>
+__global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
+mx_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
+               const __grid_constant__ typename R::Params params, const __grid_constant__ BlockParams bp,
+               float *__restrict__ scale_out)
+{
+    const R round(params, stage_table<R>(params));
+    const size_t nthr = blockDim.x;
+    const size_t tile = nthr * kUnroll;
+    const size_t ntiles = (nvec + tile - 1) / tile;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t base = t * tile + threadIdx.x;
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * nthr;
+            v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * nthr;
+            uint32_t a = F32 ? amax_of_vec_f32(0u, v[j]) : amax_of_vec_bf16(0u, v[j]);
+#pragma unroll
+            for (int o = 1; o < LANES; o <<= 1) a = max(a, __shfl_xor_sync(0xFFFFFFFFu, a, o));
+            const float s = mx_scale_of<F32>(a, bp);
+            if (i < nvec) {
+                if ((i & (size_t)(LANES - 1)) == 0) scale_out[i / LANES] = s;
+                st_stream(y + i, mx_apply_vec<R, F32>(round, v[j], s));
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- cols kernel
+// Tensor [outer, n, inner], blocks of BS = 8 * RPT rows along n, inner % VEC == 0: every column is a block of its
+// own.  blockDim = (32, 8): threadIdx.x -> a 16-byte column group g of the flattened (outer, inner / VEC) space,
+// threadIdx.y -> row phase; a thread keeps its RPT rows in registers.  Rows past n read as zero (the reference pads).
+template <class R, bool F32, int RPT>
+__global__ void __launch_bounds__(256)
+mx_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer, size_t n, size_t inner_vec,
+               size_t nblk, const __grid_constant__ typename R::Params params,
+               const __grid_constant__ BlockParams bp, float *__restrict__ scale_out)
+{
+    constexpr int VEC = F32 ? 4 : 8;
+    constexpr int BS = 8 * RPT;
+    const R round(params, stage_table<R>(params));
+    __shared__ uint4 red[8][33];           // per row phase: packed maxima of a column group
+    __shared__ float col_scale[32][VEC + 1];
+    const size_t G = outer * inner_vec;
+    const size_t gchunks = (G + 31) / 32;
+    const size_t work = nblk * gchunks;
+    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const size_t b = w / gchunks, gc = w - b * gchunks;
+        const size_t g = gc * 32 + threadIdx.x;
+        const bool active = g < G;
+        const size_t o = active ? g / inner_vec : 0, cv = active ? g - o * inner_vec : 0;
+        const size_t row0 = b * BS + threadIdx.y;
+        const uint4 *xp = x + (o * n) * inner_vec + cv;
+        uint4 v[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const size_t r = row0 + (size_t)k * 8;
+            v[k] = (active && r < n) ? ld_stream(xp + r * inner_vec) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        // per-column maxima of |x| bit patterns: fp32 four 32-bit maxima, bf16 eight packed 16-bit maxima
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            if (F32) {
+                m.x = max(m.x, v[k].x & 0x7FFFFFFFu);
+                m.y = max(m.y, v[k].y & 0x7FFFFFFFu);
+                m.z = max(m.z, v[k].z & 0x7FFFFFFFu);
+                m.w = max(m.w, v[k].w & 0x7FFFFFFFu);
+            } else {
+                m.x = __vmaxu2(m.x, v[k].x & 0x7FFF7FFFu);
+                m.y = __vmaxu2(m.y, v[k].y & 0x7FFF7FFFu);
+                m.z = __vmaxu2(m.z, v[k].z & 0x7FFF7FFFu);
+                m.w = __vmaxu2(m.w, v[k].w & 0x7FFF7FFFu);
+            }
+        }
+        red[threadIdx.y][threadIdx.x] = m;
+        __syncthreads();
+        if (threadIdx.y < VEC) {  // row phase c computes the scale of column c of the group
+            const int c = threadIdx.y;
+            uint32_t a = 0u;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const uint4 q = red[p][threadIdx.x];
+                const uint32_t wsel = F32 ? (c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w)
+                                          : ((c >> 1) == 0 ? q.x : (c >> 1) == 1 ? q.y : (c >> 1) == 2 ? q.z : q.w);
+                a = max(a, F32 ? wsel : ((c & 1) ? (wsel & 0xFFFF0000u) : (wsel << 16)));
+            }
+            const float s = mx_scale_of<F32>(a, bp);
+            col_scale[threadIdx.x][c] = s;
+            if (active) scale_out[(o * nblk + b) * (inner_vec * VEC) + cv * VEC + c] = s;
+        }
+        __syncthreads();
+        ScaleBf16 sc[VEC];
+        bool recip_ok[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            sc[c] = make_scale(col_scale[threadIdx.x][c]);
+            recip_ok[c] = classify_scale(sc[c].s) != DIV_EXACT;
+        }
+        uint4 *yp = y + (o * n) * inner_vec + cv;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const size_t r = row0 + (size_t)k * 8;
+            const uint32_t win[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+            uint32_t out[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (F32) {
+                    out[q] = fq_f32<R, false>(round, win[q], sc[q].s);
+                } else {
+                    const uint32_t lo = win[q] << 16, hi = win[q] & 0xFFFF0000u;
+                    const float qlo = recip_ok[2 * q] ? bf16_quotient<DIV_RECIP>(lo, sc[2 * q])
+                                                      : bf16_quotient<DIV_EXACT>(lo, sc[2 * q]);
+                    const float qhi = recip_ok[2 * q + 1] ? bf16_quotient<DIV_RECIP>(hi, sc[2 * q + 1])
+                                                          : bf16_quotient<DIV_EXACT>(hi, sc[2 * q + 1]);
+                    const uint32_t uq = bf16x2_rne(qlo, qhi);
+                    out[q] = bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), sc[2 * q].s),
+                                        __fmul_rn(__uint_as_float(round.hi(uq)), sc[2 * q + 1].s));
+                }
+            }
+            if (active && r < n) st_stream(yp + r * inner_vec, make_uint4(out[0], out[1], out[2], out[3]));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- generic kernels
+// Tensor [d0, n1, d1, n2, d2]; n1 is tiled with bs, n2 is tiled with bs2 (bs or 1).  Block grid
+// [d0, nb1, d1, nb2, d2] row-major is the layout of scale / zero_point.
+struct BlockDims {
+    size_t d0, n1, d1, n2, d2;
+    size_t nb1, nb2;
+    uint32_t bs, bs2;
+};
+
+__device__ __forceinline__ float load_elem(const void *x, bool f32, size_t i)
+{
+    return f32 ? static_cast<const float *>(x)[i]
+               : __uint_as_float((uint32_t) static_cast<const uint16_t *>(x)[i] << 16);
+}
+
+// AFFINE = false: amax -> scale.  AFFINE = true: min / max (padding zeros of cut blocks included) -> scale, zp.
+template <bool F32, bool AFFINE>
+__global__ void __launch_bounds__(256)
+block_stat_kernel(const void *__restrict__ x, const __grid_constant__ BlockDims D,
+                  const __grid_constant__ BlockParams bp, float *__restrict__ scale_out,
+                  float *__restrict__ zp_out)
+{
+    const size_t nblocks = D.d0 * D.nb1 * D.d1 * D.nb2 * D.d2;
+    const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const uint32_t per_block = D.bs * D.bs2;
+    for (size_t bi = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bi < nblocks; bi += nwarps) {
+        size_t r = bi;
+        const size_t i4 = r % D.d2; r /= D.d2;
+        const size_t b2 = r % D.nb2; r /= D.nb2;
+        const size_t i2 = r % D.d1; r /= D.d1;
+        const size_t b1 = r % D.nb1;
+        const size_t i0 = r / D.nb1;
+        uint32_t amax = 0u;
+        float mn = __uint_as_float(0x7F800000u), mx = __uint_as_float(0xFF800000u);
+        bool nan = false, cut = false;
+        for (uint32_t e = lane; e < per_block; e += 32) {
+            const size_t j1 = b1 * D.bs + e / D.bs2, j2 = b2 * D.bs2 + e % D.bs2;
+            if (j1 < D.n1 && j2 < D.n2) {
+                const float v = load_elem(x, F32, (((i0 * D.n1 + j1) * D.d1 + i2) * D.n2 + j2) * D.d2 + i4);
+                if (AFFINE) {
+                    nan |= v != v;
+                    mn = fminf(mn, v);
+                    mx = fmaxf(mx, v);
+                } else {
+                    amax = max(amax, __float_as_uint(v) & 0x7FFFFFFFu);
+                }
+            } else {
+                cut = true;
+            }
+        }
+        if (AFFINE) {
+            if (cut) {
+                mn = fminf(mn, 0.0f);
+                mx = fmaxf(mx, 0.0f);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+            }
+            nan = __any_sync(0xFFFFFFFFu, nan);
+            if (lane == 0) {
+                if (nan) mn = mx = __uint_as_float(QT_NAN_BITS);
+                // sf = (max - min) / (quant_max - quant_min); sf = where(sf > 0, sf, 1); zp = -min / sf + quant_min
+                float sf = to_dtype<F32>(__fdiv_rn(to_dtype<F32>(__fsub_rn(mx, mn)), bp.range));
+                sf = sf > 0.0f ? sf : 1.0f;
+                float zp = to_dtype<F32>(__fadd_rn(to_dtype<F32>(__fdiv_rn(-mn, sf)), bp.quant_min));
+                if (bp.has_scale_fmt) {
+                    sf = scale_codebook<F32>(bp, sf);
+                    zp = scale_codebook<F32>(bp, zp);
+                }
+                scale_out[bi] = sf;
+                zp_out[bi] = zp;
+            }
+        } else {
+            amax = __reduce_max_sync(0xFFFFFFFFu, amax);
+            if (lane == 0) scale_out[bi] = mx_scale_of<F32>(amax, bp);
+        }
+    }
+}
+
+template <class R, bool F32, bool AFFINE>
+__global__ void __launch_bounds__(R::kThreads)
+block_apply_kernel(const void *__restrict__ x, void *__restrict__ y, size_t total,
+                   const __grid_constant__ BlockDims D, const __grid_constant__ typename R::Params params,
+                   const __grid_constant__ BlockParams bp, const float *__restrict__ scale,
+                   const float *__restrict__ zp)
+{
+    const R round(params, stage_table<R>(params));
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        size_t r = i;
+        const size_t i4 = r % D.d2; r /= D.d2;
+        const size_t j2 = r % D.n2; r /= D.n2;
+        const size_t i2 = r % D.d1; r /= D.d1;
+        const size_t j1 = r % D.n1;
+        const size_t i0 = r / D.n1;
+        const size_t bi = (((i0 * D.nb1 + j1 / D.bs) * D.d1 + i2) * D.nb2 + j2 / D.bs2) * D.d2 + i4;
+        const float s = scale[bi];
+        uint32_t out;
+        if (AFFINE) {
+            // q = clamp(round(x / sf + zp), qmin, qmax); y = (q - zp) * sf -- every op rounded to the tensor's dtype
+            const float z = zp[bi];
+            float q = to_dtype<F32>(__fadd_rn(to_dtype<F32>(__fdiv_rn(load_elem(x, F32, i), s)), z));
+            q = rintf(q);
+            q = (q < bp.quant_min) ? bp.quant_min : q;  // compare-select keeps NaN like torch.clamp
+            q = (q > bp.quant_max) ? bp.quant_max : q;
+            out = __float_as_uint(to_dtype<F32>(__fmul_rn(to_dtype<F32>(__fsub_rn(q, z)), s)));
+        } else if (F32) {
+            out = fq_f32<R, false>(round, static_cast<const uint32_t *>(x)[i], s);
+        } else {
+            out = fq_bf16<R, DIV_EXACT>(round, (uint32_t) static_cast<const uint16_t *>(x)[i] << 16, make_scale(s));
+        }
+        if (F32)
+            static_cast<uint32_t *>(y)[i] = out;
+        else
+            static_cast<uint16_t *>(y)[i] = (uint16_t)(out >> 16);
+    }
+}
+
+// ----------------------------------------------------------------------------- launch
+
+struct BlockJob {
+    const qt_block_desc_t *d;
+    BlockDims D;
+    BlockParams bp;
+    cudaStream_t stream;
+    bool f32;
+};
+
+template <class R, bool F32, int LANES>
+void launch_flat(const BlockJob &j, const typename R::Params &p, size_t nvec)
+{
+    allow_smem<mx_flat_kernel<R, F32, LANES>>(R::kSmemBytes);
+    const size_t tile = (size_t)R::kThreads * kUnroll;
+    const unsigned grid = grid_for((nvec + tile - 1) / tile, R::kCtasPerSm);
+    mx_flat_kernel<R, F32, LANES><<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(
+        static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), nvec, p, j.bp, j.d->scale);
+}
+template <class R, bool F32>
+bool try_flat(const BlockJob &j, const typename R::Params &p)
+{
+    constexpr size_t VEC = F32 ? 4 : 8;
+    const BlockDims &D = j.D;
+    // blocks along the unit-stride axis only: [d0, n1] with n1 % bs == 0 (d1 = n2 = d2 = 1)
+    if (D.d1 != 1 || D.n2 != 1 || D.d2 != 1 || D.bs2 != 1) return false;
+    if (D.n1 % D.bs != 0 || D.bs % VEC != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(j.d->x) | reinterpret_cast<uintptr_t>(j.d->y)) & 15u) return false;
+    const size_t lanes = D.bs / VEC;
+    const size_t nvec = D.d0 * D.n1 / VEC;
+    switch (lanes) {
+    case 1: launch_flat<R, F32, 1>(j, p, nvec); return true;
+    case 2: launch_flat<R, F32, 2>(j, p, nvec); return true;
+    case 4: launch_flat<R, F32, 4>(j, p, nvec); return true;
+    case 8: launch_flat<R, F32, 8>(j, p, nvec); return true;
+    case 16: launch_flat<R, F32, 16>(j, p, nvec); return true;
+    case 32: launch_flat<R, F32, 32>(j, p, nvec); return true;
+    default: return false;
+    }
+}
+
+template <class R, bool F32, int RPT>
+void launch_cols(const BlockJob &j, const typename R::Params &p, size_t outer, size_t n, size_t inner_vec)
+{
+    allow_smem<mx_cols_kernel<R, F32, RPT>>(R::kSmemBytes);
+    const size_t nblk = (n + 8 * RPT - 1) / (8 * RPT);
+    const size_t work = nblk * ((outer * inner_vec + 31) / 32);
+    const unsigned grid = grid_for(work, R::kTable ? 3 : 8);
+    mx_cols_kernel<R, F32, RPT><<<grid, dim3(32, 8), R::kSmemBytes, j.stream>>>(
+        static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), outer, n, inner_vec, nblk, p, j.bp,
+        j.d->scale);
+}
+template <class R, bool F32>
+bool try_cols(const BlockJob &j, const typename R::Params &p)
+{
+    constexpr size_t VEC = F32 ? 4 : 8;
+    const BlockDims &D = j.D;
+    // one tiled axis with a dense inner part: [d0, n1, d1] (n2 = d2 = 1), d1 % VEC == 0
+    if (D.n2 != 1 || D.d2 != 1 || D.bs2 != 1 || D.d1 < VEC || D.d1 % VEC != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(j.d->x) | reinterpret_cast<uintptr_t>(j.d->y)) & 15u) return false;
+    const size_t inner_vec = D.d1 / VEC;
+    switch (D.bs) {
+    case 8: launch_cols<R, F32, 1>(j, p, D.d0, D.n1, inner_vec); return true;
+    case 16: launch_cols<R, F32, 2>(j, p, D.d0, D.n1, inner_vec); return true;
+    case 32: launch_cols<R, F32, 4>(j, p, D.d0, D.n1, inner_vec); return true;
+    case 64: launch_cols<R, F32, 8>(j, p, D.d0, D.n1, inner_vec); return true;
+    case 128: launch_cols<R, F32, 16>(j, p, D.d0, D.n1, inner_vec); return true;
+    default: return false;
+    }
+}
+
+template <class R, bool F32, bool AFFINE>
+void launch_generic(const BlockJob &j, const typename R::Params &p)
+{
+    const BlockDims &D = j.D;
+    const size_t nblocks = D.d0 * D.nb1 * D.d1 * D.nb2 * D.d2;
+    const size_t total = D.d0 * D.n1 * D.d1 * D.n2 * D.d2;
+    block_stat_kernel<F32, AFFINE><<<grid_for((nblocks + 7) / 8, 8), 256, 0, j.stream>>>(j.d->x, D, j.bp, j.d->scale,
+                                                                                      j.d->zero_point);
+    allow_smem<block_apply_kernel<R, F32, AFFINE>>(R::kSmemBytes);
+    const unsigned grid = grid_for((total + R::kThreads - 1) / R::kThreads, R::kCtasPerSm);
+    block_apply_kernel<R, F32, AFFINE><<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(
+        j.d->x, j.d->y, total, D, p, j.bp, j.d->scale, j.d->zero_point);
+}
+
+template <class R, bool F32>
+void launch_mx(const BlockJob &j, const typename R::Params &p)
+{
+    if (try_flat<R, F32>(j, p)) return;
+    if (try_cols<R, F32>(j, p)) return;
+    launch_generic<R, F32, false>(j, p);
+}
+
+}  // namespace
+
+extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
+{
+    if (!d) {
+        qt_set_error("qt_fq_block: desc is NULL");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (d->elem_type != QT_BF16 && d->elem_type != QT_F32) {
+        qt_set_error("qt_fq_block: elem_type must be QT_BF16 or QT_F32, got %d", d->elem_type);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (d->qscheme != QT_BLOCK_MX && d->qscheme != QT_BLOCK_AFFINE) {
+        qt_set_error("qt_fq_block: qscheme must be QT_BLOCK_MX or QT_BLOCK_AFFINE, got %d", d->qscheme);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (d->block_size < 1) {
+        qt_set_error("qt_fq_block: block_size must be >= 1, got %d", d->block_size);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (d->d0 < 0 || d->n1 < 0 || d->d1 < 0 || d->n2 < 0 || d->d2 < 0) {
+        qt_set_error("qt_fq_block: negative dimension");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    const bool affine = d->qscheme == QT_BLOCK_AFFINE;
+    BlockJob j;
+    j.d = d;
+    j.stream = static_cast<cudaStream_t>(stream);
+    j.f32 = d->elem_type == QT_F32;
+    BlockDims &D = j.D;
+    D.d0 = (size_t)d->d0; D.n1 = (size_t)d->n1; D.d1 = (size_t)d->d1; D.n2 = (size_t)d->n2; D.d2 = (size_t)d->d2;
+    D.bs = (uint32_t)d->block_size;
+    D.bs2 = d->block_axis2 ? D.bs : 1u;
+    D.nb1 = (D.n1 + D.bs - 1) / D.bs;
+    D.nb2 = (D.n2 + D.bs2 - 1) / D.bs2;
+    const size_t total = D.d0 * D.n1 * D.d1 * D.n2 * D.d2;
+
+    QtRound P;
+    memset(&P, 0, sizeof(P));
+    if (!affine) {
+        if (!d->fmt) {
+            qt_set_error("qt_fq_block: fmt is NULL");
+            return QT_ERR_INVALID_ARGUMENT;
+        }
+        int rc = qt_make_round(d->fmt, &P);
+        if (rc != QT_OK) return rc;
+    }
+    BlockParams &bp = j.bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.quant_min = d->quant_min;
+    bp.quant_max = d->quant_max;
+    bp.range = d->quant_max - d->quant_min;
+    bp.pow2 = (!affine && d->force_scale_power_of_two) ? 1 : 0;
+    bp.qmax_exp = (int32_t)floor(log2((double)d->quant_max));
+    bp.pow2_tab = static_cast<const uint32_t *>(d->pow2_table);
+    if (d->scale_fmt) {
+        int rc = qt_make_round(d->scale_fmt, &bp.scale_round);
+        if (rc != QT_OK) return rc;
+        bp.has_scale_fmt = 1;
+    }
+    if (!(d->quant_max > 0.0f) && !affine) {
+        qt_set_error("qt_fq_block: quant_max must be positive, got %g", (double)d->quant_max);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (total == 0) return QT_OK;
+    if (!d->x || !d->y || !d->scale || (affine && !d->zero_point)) {
+        qt_set_error("qt_fq_block: x, y, scale%s must not be NULL", affine ? ", zero_point" : "");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (bp.pow2 && !bp.pow2_tab) {
+        qt_set_error("qt_fq_block: force_scale_power_of_two needs the device table of qt_block_pow2_table_host()");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    const size_t esz = j.f32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->y)) % esz) {
+        qt_set_error("qt_fq_block: x / y not aligned to the element size");
+        return QT_ERR_UNALIGNED;
+    }
+    if (num_sms() == 0) return no_device();
+
+    int rc = QT_OK;
+    if (affine) {
+        rc = dispatch_direct_small(P, [&](auto tag, const auto &p) {
+            using R = typename decltype(tag)::type;
+            j.f32 ? launch_generic<R, true, true>(j, p) : launch_generic<R, false, true>(j, p);
+        });
+    } else {
+        rc = dispatch_rounder(P, d->lut, [&](auto tag, const auto &p) {
+            using R = typename decltype(tag)::type;
+            j.f32 ? launch_mx<R, true>(j, p) : launch_mx<R, false>(j, p);
+        });
+    }
+    if (rc != QT_OK) return rc;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "block-scaled fake-quant kernel launch");
+    return QT_OK;
+}

@@ -294,3 +294,57 @@ extern "C" int qt_table_host(const qt_format_t *fmt, uint16_t *table_host)
     for (uint32_t i = 0; i < 65536u; ++i) table_host[i] = (uint16_t)(qt_round_dyn(P, i << 16) >> 16);
     return QT_OK;
 }
+
+// ---- force_scale_power_of_two of the microscaling qscheme --------------------------------------------------
+// shared_exp = floor(log2(amax)) evaluated in the tensor's dtype (mx_utils.py:44-48).  For each exponent the
+// result is e - 127 up to some mantissa and e - 126 from there on (log2 rounds up to the next integer); the
+// thresholds are found by bisection over the same libm call the reference's CPU kernel makes.
+static float floor_log2_in_dtype(uint32_t bits, bool f32)
+{
+    float a;
+    memcpy(&a, &bits, 4);
+    float l = log2f(a);
+    if (!f32) l = bf16_round(l);
+    return floorf(l);
+}
+
+extern "C" int qt_block_pow2_table_host(int elem_type, uint32_t *table_host)
+{
+    if (!table_host || (elem_type != QT_BF16 && elem_type != QT_F32)) {
+        qt_set_error("qt_block_pow2_table_host: invalid argument");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    const bool f32 = elem_type == QT_F32;
+    const uint32_t step = f32 ? 1u : 0x10000u;  // bf16 values have the low 16 bits clear
+    for (int i = 0; i < QT_POW2_TABLE_WORDS; ++i) table_host[i] = 0xFFFFFFFFu;
+    for (uint32_t e = 1; e <= 254; ++e) {
+        const float base = (float)((int)e - 127);
+        // first mantissa (multiple of step) with floor(log2) > e - 127, or 2^23 if none
+        uint32_t lo = 0, hi = 0x800000u / step;  // search over m / step in [lo, hi)
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (floor_log2_in_dtype((e << 23) | (mid * step), f32) > base)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        table_host[e] = lo * step;  // 0x800000 = never
+    }
+    for (int k = 0; k <= 22; ++k) {
+        // subnormal patterns [2^k, 2^(k+1)): value = pattern * 2^-149; bf16 subnormals use bits 16..22 only
+        const uint32_t first = 1u << k, last = (2u << k);
+        if (!f32 && k < 16) continue;
+        const float base = (float)(k - 149);
+        uint32_t lo = first / step, hi = last / step;
+        if (lo == 0) lo = 1;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (floor_log2_in_dtype(mid * step, f32) > base)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        table_host[256 + k] = lo * step;  // == last: never
+    }
+    return QT_OK;
+}

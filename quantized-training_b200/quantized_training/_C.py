@@ -68,6 +68,8 @@ EXPORTS = {
                         [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat),
                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qt_attention_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_fq_block": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_block_pow2_table_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "qt_amax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -199,6 +201,66 @@ def scale_update(history, ahl, channels, scale, quant_max, force_pow2):
     with torch.cuda.device(history.device):
         _check(lib().qt_scale_update(history.data_ptr(), ahl, channels, scale.data_ptr(), float(quant_max),
                                      int(bool(force_pow2)), _stream(history)))
+
+
+BLOCK_MX, BLOCK_AFFINE = 0, 1
+QT_POW2_TABLE_WORDS = 288
+
+
+class QtBlockDesc(ctypes.Structure):
+    """qt_block_desc_t"""
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("y", ctypes.c_void_p),
+        ("elem_type", ctypes.c_int32), ("qscheme", ctypes.c_int32),
+        ("d0", ctypes.c_int64), ("n1", ctypes.c_int64), ("d1", ctypes.c_int64), ("n2", ctypes.c_int64),
+        ("d2", ctypes.c_int64),
+        ("block_size", ctypes.c_int32), ("block_axis2", ctypes.c_int32),
+        ("quant_min", ctypes.c_float), ("quant_max", ctypes.c_float),
+        ("force_scale_power_of_two", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("fmt", ctypes.POINTER(QtFormat)), ("lut", ctypes.c_void_p),
+        ("scale_fmt", ctypes.POINTER(QtFormat)), ("pow2_table", ctypes.c_void_p),
+        ("scale", ctypes.c_void_p), ("zero_point", ctypes.c_void_p),
+    ]
+
+
+def pow2_table_host(elem_type):
+    """int32[288] CPU tensor: floor(log2(amax)) thresholds in the tensor's dtype (force_scale_power_of_two)."""
+    out = torch.empty(QT_POW2_TABLE_WORDS, dtype=torch.int32)
+    _check(lib().qt_block_pow2_table_host(int(elem_type), out.data_ptr()))
+    return out
+
+
+def fq_block(x, y, dims, block_size, block_axis2, qscheme, quant_min, quant_max, fmt, scale, zero_point=None,
+             lut=None, scale_fmt=None, force_pow2=False, pow2_table=None):
+    """Block-scaled fake quant (qt_fq_block).  dims = (d0, n1, d1, n2, d2) view of the contiguous x;
+    scale / zero_point: float32 outputs, one entry per block."""
+    _require_cuda(x, "input")
+    assert x.is_contiguous() and y.is_contiguous() and y.dtype == x.dtype and y.device == x.device
+    d0, n1, d1, n2, d2 = (int(v) for v in dims)
+    assert d0 * n1 * d1 * n2 * d2 == x.numel() == y.numel()
+    nb1 = -(-n1 // block_size)
+    nb2 = -(-n2 // block_size) if block_axis2 else n2
+    for t in (scale, zero_point):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.device == x.device and t.is_contiguous() \
+                and t.numel() == d0 * nb1 * d1 * nb2 * d2
+    d = QtBlockDesc()
+    d.x, d.y = x.data_ptr(), y.data_ptr()
+    d.elem_type, d.qscheme = _elem_type(x), int(qscheme)
+    d.d0, d.n1, d.d1, d.n2, d.d2 = d0, n1, d1, n2, d2
+    d.block_size, d.block_axis2 = int(block_size), int(bool(block_axis2))
+    d.quant_min, d.quant_max = float(quant_min), float(quant_max)
+    d.force_scale_power_of_two = int(bool(force_pow2))
+    d.fmt = ctypes.pointer(fmt) if fmt is not None else None
+    d.lut = lut.data_ptr() if lut is not None else None
+    d.scale_fmt = ctypes.pointer(scale_fmt) if scale_fmt is not None else None
+    if pow2_table is not None:
+        assert pow2_table.device == x.device and pow2_table.numel() == QT_POW2_TABLE_WORDS
+        d.pow2_table = pow2_table.data_ptr()
+    d.scale = scale.data_ptr()
+    d.zero_point = zero_point.data_ptr() if zero_point is not None else None
+    with torch.cuda.device(x.device):
+        _check(lib().qt_fq_block(ctypes.byref(d), _stream(x)))
 
 
 GEMM_BF16, GEMM_E4M3, GEMM_E5M2, GEMM_E4M3_E5M2, GEMM_E5M2_E4M3 = range(5)

@@ -112,6 +112,72 @@ def _run(mod, x, emit_codes=False):
     return y if perm is None else y.permute(perm)
 
 
+def _block_view(shape, axes, block_size):
+    """(d0, n1, d1, n2, d2), tiled-second-axis flag and the block-grid shape for tiling `axes` of a contiguous
+    tensor with block_size (mx_utils.py:62-121).  One or two tiled axes."""
+    nd = len(shape)
+    axes = [axes] if isinstance(axes, int) else list(axes)
+    axes = sorted({a + nd if a < 0 else a for a in axes})
+    if not axes or any(not 0 <= a < nd for a in axes):
+        raise IndexError(f"block axes {axes} out of range for a {nd}-d tensor")
+    if len(axes) > 2:
+        raise NotImplementedError("block-scaled qschemes tile one or two axes")
+
+    def prod(v):
+        r = 1
+        for d in v:
+            r *= d
+        return r
+
+    grid = [-(-d // block_size) if i in axes else d for i, d in enumerate(shape)]
+    a1 = axes[0]
+    if len(axes) == 1:
+        return (prod(shape[:a1]), shape[a1], prod(shape[a1 + 1:]), 1, 1), False, grid
+    a2 = axes[1]
+    return (prod(shape[:a1]), shape[a1], prod(shape[a1 + 1:a2]), shape[a2], prod(shape[a2 + 1:])), True, grid
+
+
+def _run_block(mod, x):
+    """microscaling / group_wise_affine: statistic, parameters and quantize-dequantize of every block in one
+    call; the parameters land in the module's `scale` (and `zero_point`) buffers, shaped like the block grid."""
+    if not mod._flags()[1]:  # only fake_quant_enabled gates these schemes (fake_quantize.py:116, 150)
+        return x
+    if not x.is_cuda:
+        raise RuntimeError(
+            f"FusedAmaxObsFakeQuantize got a tensor on {x.device}: the B200 build runs on CUDA only "
+            "(no CPU fallback)")
+    xc = x.detach().contiguous()
+    bs = mod.block_size
+    if not isinstance(bs, int) or bs <= 0:
+        raise AssertionError("block_size must be a positive integer")  # decomposed.py:381 `assert block_size > 0`
+    dims, axis2, grid = _block_view(tuple(xc.shape), mod.ch_axis, bs)
+    affine = mod.qscheme == QScheme.GROUP_WISE_AFFINE
+    mod.scale.resize_(grid)
+    if affine:
+        mod.zero_point.resize_(grid)
+    y = torch.empty_like(xc)
+    if xc.numel() == 0:
+        return y
+    pow2 = mod.force_scale_power_of_two and not affine
+    _C.fq_block(xc, y, dims, bs, axis2, _C.BLOCK_AFFINE if affine else _C.BLOCK_MX,
+                mod.quant_min if mod.quant_min is not None else 0.0, mod.quant_max, None if affine else mod._fmt,
+                mod.scale, mod.zero_point if affine else None, None if affine else mod.lut, mod._scale_fmt,
+                pow2, mod._pow2_table(xc) if pow2 else None)
+    return y
+
+
+class BlockScaledFakeQuantFunction(torch.autograd.Function):
+    """MXFakeQuantFunction / GroupWiseAffineFakeQuantFunction (fake_quantize.py:98-194); STE backward."""
+
+    @staticmethod
+    def forward(ctx, x, mod):
+        return _run_block(mod, x)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None
+
+
 class FusedAmaxObsFakeQuantFunction(torch.autograd.Function):
     """Delayed-scaling observer + quantize-dequantize, one fused pass; STE backward."""
 
@@ -155,12 +221,15 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         super().__init__()
         if isinstance(qscheme, str):
             qscheme = QScheme(qscheme)
-        if qscheme in (QScheme.MICROSCALING, QScheme.GROUP_WISE_AFFINE):
-            raise NotImplementedError(
-                f"qscheme={qscheme.value} is outside the B200 hot path built so far (SURVEY.md §8f, rank 1)")
+        self.is_block_scaled = qscheme in (QScheme.MICROSCALING, QScheme.GROUP_WISE_AFFINE)
         if outlier_threshold is not None:
             raise NotImplementedError("outlier_threshold belongs to the PT2E flow, outside the B200 hot path")
-        if qscheme is not None and (quant_max is None or amax_history_len is None):
+        if self.is_block_scaled:
+            if quant_max is None or block_size is None or ch_axis is None:
+                raise ValueError("quant_max, block_size and ch_axis are required for block-scaled qschemes")
+            if qscheme == QScheme.GROUP_WISE_AFFINE and quant_min is None:
+                raise ValueError("quant_min is required for group_wise_affine")
+        elif qscheme is not None and (quant_max is None or amax_history_len is None):
             raise ValueError("quant_max and amax_history_len are required when a qscheme is given")
         self.dtype = dtype
         self.qscheme = qscheme
@@ -177,7 +246,10 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         # back as the same view; set by `prepare` on the fake-quantizers that feed our own matmul.
         self.preserve_strides = False
         self._fmt = _C.format_from_string(dtype)  # ValueError("Unsupported dtype: ...")
+        self._scale_fmt = _C.format_from_string(scale_dtype) if scale_dtype is not None else None
         self._qmap = None
+        self._scale_qmap = None
+        self._pow2_tables = {}
         device = kwargs.get("device", None)
         f32 = dict(device=device, dtype=torch.float)
         self.register_buffer("amax_history", torch.tensor([], **f32))
@@ -213,10 +285,25 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
 
     @property
     def scale_qmap(self):
-        return None
+        if self.scale_dtype is None:
+            return None
+        if self._scale_qmap is None or self._scale_qmap.device != self.scale.device:
+            self._scale_qmap = get_quantization_map(self.scale_dtype, self.scale.device)
+        return self._scale_qmap
+
+    def _pow2_table(self, x):
+        """Device copy of the floor(log2()) thresholds for x's dtype (force_scale_power_of_two, block-scaled)."""
+        key = (x.dtype, x.device)
+        t = self._pow2_tables.get(key)
+        if t is None:
+            t = _C.pow2_table_host(_C.QT_F32 if x.dtype == torch.float32 else _C.QT_BF16).to(x.device)
+            self._pow2_tables[key] = t
+        return t
 
     @torch.jit.export
     def calculate_qparams(self):
+        if self.qscheme == QScheme.GROUP_WISE_AFFINE:
+            return self.scale, self.zero_point
         return self.scale
 
     @property
@@ -249,12 +336,14 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         if self.record_histogram:
             mag = X.detach().float().abs()
             self.histogram += torch.histc(torch.log2(mag).floor(), bins=254, min=-126, max=127)
+        if self.is_block_scaled:
+            return BlockScaledFakeQuantFunction.apply(X, self)
         return FusedAmaxObsFakeQuantFunction.apply(X, self)
 
     def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict,
                               missing_keys, unexpected_keys, error_msgs):
         # `scale` / `amax_history` are shaped lazily by the first observed call; adopt checkpoint shapes
-        for name in ("scale", "amax_history"):
+        for name in ("scale", "amax_history", "zero_point"):
             key = prefix + name
             if key in state_dict:
                 getattr(self, name).resize_(state_dict[key].shape)

@@ -129,3 +129,77 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cc", ".h", ".cuh")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def _pow2_scale_from_table(tab, amax_bits, qmax, f32):
+    """numpy restatement of mx_scale_of() (csrc/qt_block.cu) for the force_scale_power_of_two branch."""
+    import math
+    out = np.empty(amax_bits.size, dtype=np.uint32)
+    qe = math.floor(math.log2(qmax))
+    lo = -149 if f32 else -133
+    for i, a in enumerate(amax_bits.tolist()):
+        if a > 0x7F800000:
+            out[i] = 0x3F800000
+            continue
+        if a == 0x7F800000:
+            out[i] = a
+            continue
+        if a == 0:
+            E = -126
+        elif a >> 23:
+            e = a >> 23
+            E = e - 127 + (1 if (a & 0x7FFFFF) >= int(tab[e]) else 0)
+        else:
+            k = a.bit_length() - 1
+            E = k - 149 + (1 if a >= int(tab[256 + k]) else 0)
+        E -= qe
+        if E < lo:
+            out[i] = 0x3F800000
+        elif E > 127:
+            out[i] = 0x7F800000
+        else:
+            out[i] = (E + 127) << 23 if E >= -126 else 1 << (E + 149)
+    return out
+
+
+def test_block_pow2_thresholds_match_reference(golden):
+    """force_scale_power_of_two: the tabulated floor(log2(amax)) reproduces calculate_mx_qparam of the reference
+    on every positive bf16 amax and on fp32 values around every power of two."""
+    allb = np.arange(0x8000, dtype=np.uint32) << 16
+    fb = golden.mx_scale["f32_amax_bits"]
+    t16 = _C.pow2_table_host(_C.QT_BF16).numpy().view(np.uint32)
+    t32 = _C.pow2_table_host(_C.QT_F32).numpy().view(np.uint32)
+    for qmax in golden.mx_manifest["scale_fn_quant_max"]:
+        got = _pow2_scale_from_table(t16, allb, qmax, False)
+        want = golden.mx_scale[f"bf16/pow2/{qmax}"].astype(np.uint32) << 16
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, ("bf16", qmax, [(hex(allb[i]), hex(got[i]), hex(want[i])) for i in bad[:6]])
+        got = _pow2_scale_from_table(t32, fb, qmax, True)
+        want = golden.mx_scale[f"f32/pow2/{qmax}"]
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, ("f32", qmax, [(hex(fb[i]), hex(got[i]), hex(want[i])) for i in bad[:6]])
+
+
+def test_block_view():
+    from quantized_training.fake_quantize import _block_view
+    assert _block_view((4, 6, 128), -1, 64) == ((24, 128, 1, 1, 1), False, [4, 6, 2])
+    assert _block_view((3, 160, 64), -2, 64) == ((3, 160, 64, 1, 1), False, [3, 3, 64])
+    assert _block_view((2, 3, 40, 50), (-2, -1), 16) == ((6, 40, 1, 50, 1), True, [2, 3, 3, 4])
+    assert _block_view((5, 7, 9, 11), (0, 2), 4) == ((1, 5, 7, 9, 11), True, [2, 7, 3, 11])
+    assert _block_view((7,), 0, 32) == ((1, 7, 1, 1, 1), False, [1])
+    with pytest.raises(NotImplementedError):
+        _block_view((2, 2, 2), (0, 1, 2), 2)
+
+
+def test_block_scaled_module_surface():
+    spec = qt.QuantizationSpec.from_str("int6,qs=microscaling,bs=64,ax=-1,scale=fp8_e5m3")
+    m = spec.observer_or_fake_quant_ctr(**spec.fake_quant_kwargs())
+    assert m.is_block_scaled and m.quant_max == 31.0 and m.block_size == 64 and m.scale_dtype == "fp8_e5m3"
+    assert m.scale_qmap.shape == (65536,) and m.calculate_qparams() is m.scale
+    g = qt.QuantizationSpec.from_str("uint2,bs=64,qs=group_wise_affine,ax=-2,scale=fp8_e5m3")
+    gm = g.observer_or_fake_quant_ctr(**g.fake_quant_kwargs())
+    assert (gm.quant_min, gm.quant_max) == (0.0, 3.0) and len(gm.calculate_qparams()) == 2
+    with pytest.raises(ValueError, match="block_size is required"):
+        qt.QuantizationSpec.from_str("int6,qs=microscaling,ax=-1")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(4, 64, dtype=torch.bfloat16))
