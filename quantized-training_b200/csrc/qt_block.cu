@@ -36,6 +36,9 @@ struct BlockParams {
     int32_t pow2;                       // force_scale_power_of_two
     int32_t qmax_exp;                   // floor(log2(quant_max))
     int32_t has_scale_fmt;              // scale / zero point go through the scale_dtype codebook
+    int32_t fast_ok;                    // the element format is insensitive to sub-2^-120 quotients (qt_tiny_safe)
+    int32_t qmax_short;                 // quant_max has <= 8 significant bits: amax / quant_max by reciprocal multiply
+    float rqmax;                        // 1 / quant_max
     QtRound scale_round;
     const uint32_t *pow2_tab;  // QT_POW2_TABLE_WORDS words on the device (pow2 only)
 };
@@ -102,40 +105,135 @@ __device__ __forceinline__ uint4 mx_apply_vec(const R &round, const uint4 &v, fl
     return fq_vec<R, F32, DIV_RECIP, false>(round, v, sc, unused);
 }
 
+// The common case of mx_scale_of() with the rare inputs (zero, subnormal, Inf, NaN amax; scales outside the normal
+// range) sent to it: the power-of-two branch is an exponent-field lookup in the staged threshold table, the
+// amax / quant_max branch a reciprocal multiply (same argument as DIV_RECIP in qt_fq_common.cuh: a bf16 amax over a
+// quant_max of at most 8 significant bits is never within 2^-17 of a bf16 rounding tie).
+template <bool F32>
+__device__ __forceinline__ float mx_scale_fast(uint32_t a, const BlockParams &bp, const uint32_t *tab_smem)
+{
+    if (bp.pow2) {
+        const uint32_t e = a >> 23;
+        if (e - 1u < 254u) {
+            const int E = (int)e - 127 - bp.qmax_exp + ((a & 0x7FFFFFu) >= tab_smem[e] ? 1 : 0);
+            if ((unsigned)(E + 126) <= 253u) return __uint_as_float((uint32_t)(E + 127) << 23);
+        }
+    } else if (!F32 && bp.qmax_short) {
+        const float p = __fmul_rn(__uint_as_float(a), bp.rqmax);
+        if (p >= 0x1p-120f && a < 0x7F800000u) {
+            float s = __uint_as_float(bf16_rne_hi(p));
+            if (bp.has_scale_fmt) s = scale_codebook<false>(bp, s);
+            return s > 0.0f ? s : 1.0f;
+        }
+    }
+    return mx_scale_of<F32>(a, bp);
+}
+
+// The rounder of the fast path: the same table without the fpN_eXmY NaN-band test (quotients are bounded there).
+template <class R>
+struct FastOf {
+    using type = R;
+};
+template <bool C, bool M, int REPL>
+struct FastOf<TableRounder<C, M, REPL>> {
+    using type = TableRounder<C, false, REPL>;
+};
+
+// A block may take the fast path when every quotient is finite and below 2^126 and the scale allows the
+// reciprocal multiply; sub-2^-120 quotients need no care for formats with bp.fast_ok (see qt_tiny_safe()).
+__device__ __forceinline__ bool mx_block_is_fast(uint32_t a, float s, float rs, const BlockParams &bp)
+{
+    const uint32_t sb = __float_as_uint(s);
+    return bp.fast_ok && a < 0x7E800000u && (sb - 0x0D800000u) <= (0x71800000u - 0x0D800000u) &&
+           __fmul_rn(__uint_as_float(a), rs) < 0x1p126f;
+}
+// two bf16 values, each with its own scale
+template <class RF>
+__device__ __forceinline__ uint32_t mx_word_fast(const RF &round, uint32_t w, float s_lo, float rs_lo, float s_hi,
+                                                 float rs_hi)
+{
+    const uint32_t uq = bf16x2_rne(__fmul_rn(__uint_as_float(w << 16), rs_lo),
+                                   __fmul_rn(__uint_as_float(w & 0xFFFF0000u), rs_hi));
+    return bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), s_lo), __fmul_rn(__uint_as_float(round.hi(uq)), s_hi));
+}
+
+__device__ __forceinline__ const uint32_t *stage_pow2_table(const BlockParams &bp, size_t smem_offset)
+{
+    uint32_t *dst = reinterpret_cast<uint32_t *>(qt_dyn_smem + smem_offset);
+    if (bp.pow2) {
+        const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.x + threadIdx.y * blockDim.x;
+        for (int i = tid; i < QT_POW2_TABLE_WORDS; i += nthreads) dst[i] = bp.pow2_tab[i];
+        __syncthreads();
+    }
+    return dst;
+}
+constexpr size_t kPow2SmemBytes = QT_POW2_TABLE_WORDS * 4;
+
 // ----------------------------------------------------------------------------- flat kernel
 // Blocks of LANES consecutive 16-byte vectors (last axis, shape[-1] % block_size == 0): block b = vector i / LANES,
 // which is also its index in the row-major block grid.  nvec % LANES == 0.
+template <class R, bool F32, int LANES, bool CHECK>
+__device__ __forceinline__ void mx_flat_tile(const R &round, const typename FastOf<R>::type &fast_round,
+                                             const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
+                                             size_t base, const BlockParams &bp, const uint32_t *tab,
+                                             float *__restrict__ scale_out)
+{
+    const size_t nthr = blockDim.x;
+    uint4 v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const size_t i = base + (size_t)j * nthr;
+        v[j] = (!CHECK || i < nvec) ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+        const size_t i = base + (size_t)j * nthr;
+        uint32_t a = F32 ? amax_of_vec_f32(0u, v[j]) : amax_of_vec_bf16(0u, v[j]);
+#pragma unroll
+        for (int o = 1; o < LANES; o <<= 1) a = max(a, __shfl_xor_sync(0xFFFFFFFFu, a, o));
+        const float s = mx_scale_fast<F32>(a, bp, tab);
+        // an all-zero block gives +-0 whatever its scale is: apply it with 1 (its true scale may be below 2^-126,
+        // whose reciprocal overflows)
+        const float sa = a == 0u ? 1.0f : s;
+        uint4 r;
+        bool fast = false;
+        float rs = 0.0f;
+        if (!F32) {
+            rs = __frcp_rn(sa);
+            fast = __all_sync(0xFFFFFFFFu, mx_block_is_fast(a, sa, rs, bp));
+        }
+        if (fast) {
+            r.x = mx_word_fast(fast_round, v[j].x, sa, rs, sa, rs);
+            r.y = mx_word_fast(fast_round, v[j].y, sa, rs, sa, rs);
+            r.z = mx_word_fast(fast_round, v[j].z, sa, rs, sa, rs);
+            r.w = mx_word_fast(fast_round, v[j].w, sa, rs, sa, rs);
+        } else {
+            r = mx_apply_vec<R, F32>(round, v[j], sa);
+        }
+        if (!CHECK || i < nvec) {
+            if ((i & (size_t)(LANES - 1)) == 0) scale_out[i / LANES] = s;
+            st_stream(y + i, r);
+        }
+    }
+}
+
 template <class R, bool F32, int LANES>
 __global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
 mx_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
                const __grid_constant__ typename R::Params params, const __grid_constant__ BlockParams bp,
                float *__restrict__ scale_out)
 {
-    const R round(params, stage_table<R>(params));
-    const size_t nthr = blockDim.x;
-    const size_t tile = nthr * kUnroll;
-    const size_t ntiles = (nvec + tile - 1) / tile;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const size_t base = t * tile + threadIdx.x;
-        uint4 v[kUnroll];
-#pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * nthr;
-            v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
-        }
-#pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const size_t i = base + (size_t)j * nthr;
-            uint32_t a = F32 ? amax_of_vec_f32(0u, v[j]) : amax_of_vec_bf16(0u, v[j]);
-#pragma unroll
-            for (int o = 1; o < LANES; o <<= 1) a = max(a, __shfl_xor_sync(0xFFFFFFFFu, a, o));
-            const float s = mx_scale_of<F32>(a, bp);
-            if (i < nvec) {
-                if ((i & (size_t)(LANES - 1)) == 0) scale_out[i / LANES] = s;
-                st_stream(y + i, mx_apply_vec<R, F32>(round, v[j], s));
-            }
-        }
-    }
+    const unsigned char *lut_smem = stage_table<R>(params);
+    const R round(params, lut_smem);
+    const typename FastOf<R>::type fast_round(params, lut_smem);
+    const uint32_t *tab = stage_pow2_table(bp, R::kSmemBytes);
+    const size_t tile = (size_t)blockDim.x * kUnroll;
+    const size_t full_tiles = nvec / tile;
+    for (size_t t = blockIdx.x; t < full_tiles; t += gridDim.x)
+        mx_flat_tile<R, F32, LANES, false>(round, fast_round, x, y, nvec, t * tile + threadIdx.x, bp, tab, scale_out);
+    if (full_tiles * tile < nvec && blockIdx.x == full_tiles % gridDim.x)
+        mx_flat_tile<R, F32, LANES, true>(round, fast_round, x, y, nvec, full_tiles * tile + threadIdx.x, bp, tab,
+                                          scale_out);
 }
 
 // ----------------------------------------------------------------------------- cols kernel
@@ -150,7 +248,10 @@ mx_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer,
 {
     constexpr int VEC = F32 ? 4 : 8;
     constexpr int BS = 8 * RPT;
-    const R round(params, stage_table<R>(params));
+    const unsigned char *lut_smem = stage_table<R>(params);
+    const R round(params, lut_smem);
+    const typename FastOf<R>::type fast_round(params, lut_smem);
+    const uint32_t *tab = stage_pow2_table(bp, R::kSmemBytes);
     __shared__ uint4 red[8][33];           // per row phase: packed maxima of a column group
     __shared__ float col_scale[32][VEC + 1];
     const size_t G = outer * inner_vec;
@@ -197,18 +298,26 @@ mx_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer,
                                           : ((c >> 1) == 0 ? q.x : (c >> 1) == 1 ? q.y : (c >> 1) == 2 ? q.z : q.w);
                 a = max(a, F32 ? wsel : ((c & 1) ? (wsel & 0xFFFF0000u) : (wsel << 16)));
             }
-            const float s = mx_scale_of<F32>(a, bp);
-            col_scale[threadIdx.x][c] = s;
+            const float s = mx_scale_fast<F32>(a, bp, tab);
             if (active) scale_out[(o * nblk + b) * (inner_vec * VEC) + cv * VEC + c] = s;
+            // the scale the column is applied with (1 for an all-zero block, see mx_flat_tile); scales are
+            // positive, so the sign bit is free to carry "this column needs the careful path"
+            const float sa = a == 0u ? 1.0f : s;
+            const bool f = !F32 && mx_block_is_fast(a, sa, __frcp_rn(sa), bp);
+            col_scale[threadIdx.x][c] = f ? sa : -sa;
         }
         __syncthreads();
         ScaleBf16 sc[VEC];
         bool recip_ok[VEC];
+        bool mine_fast = !F32;
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
-            sc[c] = make_scale(col_scale[threadIdx.x][c]);
+            const float sv = col_scale[threadIdx.x][c];
+            mine_fast = mine_fast && !(__float_as_uint(sv) >> 31);
+            sc[c] = make_scale(fabsf(sv));
             recip_ok[c] = classify_scale(sc[c].s) != DIV_EXACT;
         }
+        const bool fast = __all_sync(0xFFFFFFFFu, mine_fast);
         uint4 *yp = y + (o * n) * inner_vec + cv;
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
@@ -217,7 +326,10 @@ mx_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer,
             uint32_t out[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (F32) {
+                if (!F32 && fast) {
+                    out[q] = mx_word_fast(fast_round, win[q], sc[(2 * q) % VEC].s, sc[(2 * q) % VEC].rs,
+                                          sc[(2 * q + 1) % VEC].s, sc[(2 * q + 1) % VEC].rs);
+                } else if (F32) {
                     out[q] = fq_f32<R, false>(round, win[q], sc[q].s);
                 } else {
                     const uint32_t lo = win[q] << 16, hi = win[q] & 0xFFFF0000u;
@@ -369,10 +481,10 @@ struct BlockJob {
 template <class R, bool F32, int LANES>
 void launch_flat(const BlockJob &j, const typename R::Params &p, size_t nvec)
 {
-    allow_smem<mx_flat_kernel<R, F32, LANES>>(R::kSmemBytes);
+    allow_smem<mx_flat_kernel<R, F32, LANES>>(R::kSmemBytes + kPow2SmemBytes);
     const size_t tile = (size_t)R::kThreads * kUnroll;
     const unsigned grid = grid_for((nvec + tile - 1) / tile, R::kCtasPerSm);
-    mx_flat_kernel<R, F32, LANES><<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(
+    mx_flat_kernel<R, F32, LANES><<<grid, R::kThreads, R::kSmemBytes + kPow2SmemBytes, j.stream>>>(
         static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), nvec, p, j.bp, j.d->scale);
 }
 template <class R, bool F32>
@@ -400,11 +512,11 @@ bool try_flat(const BlockJob &j, const typename R::Params &p)
 template <class R, bool F32, int RPT>
 void launch_cols(const BlockJob &j, const typename R::Params &p, size_t outer, size_t n, size_t inner_vec)
 {
-    allow_smem<mx_cols_kernel<R, F32, RPT>>(R::kSmemBytes);
+    allow_smem<mx_cols_kernel<R, F32, RPT>>(R::kSmemBytes + kPow2SmemBytes);
     const size_t nblk = (n + 8 * RPT - 1) / (8 * RPT);
     const size_t work = nblk * ((outer * inner_vec + 31) / 32);
     const unsigned grid = grid_for(work, R::kTable ? 3 : 8);
-    mx_cols_kernel<R, F32, RPT><<<grid, dim3(32, 8), R::kSmemBytes, j.stream>>>(
+    mx_cols_kernel<R, F32, RPT><<<grid, dim3(32, 8), R::kSmemBytes + kPow2SmemBytes, j.stream>>>(
         static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), outer, n, inner_vec, nblk, p, j.bp,
         j.d->scale);
 }
@@ -504,6 +616,13 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
     bp.pow2 = (!affine && d->force_scale_power_of_two) ? 1 : 0;
     bp.qmax_exp = (int32_t)floor(log2((double)d->quant_max));
     bp.pow2_tab = static_cast<const uint32_t *>(d->pow2_table);
+    bp.fast_ok = (!affine && qt_tiny_safe(P)) ? 1 : 0;
+    {
+        uint32_t qb;
+        memcpy(&qb, &d->quant_max, 4);
+        bp.qmax_short = ((qb & 0xFFFFu) == 0u && d->quant_max > 0x1p-60f && d->quant_max < 0x1p60f) ? 1 : 0;
+        bp.rqmax = 1.0f / d->quant_max;
+    }
     if (d->scale_fmt) {
         int rc = qt_make_round(d->scale_fmt, &bp.scale_round);
         if (rc != QT_OK) return rc;

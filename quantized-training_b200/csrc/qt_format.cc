@@ -348,3 +348,13 @@ extern "C" int qt_block_pow2_table_host(int elem_type, uint32_t *table_host)
     }
     return QT_OK;
 }
+
+int qt_tiny_safe(const QtRound &P)
+{
+    for (uint32_t sign = 0; sign < 2; ++sign) {
+        const uint32_t first = qt_round_dyn(P, (sign << 31) | (1u << 16));
+        for (uint32_t pat = 1; pat < 0x0380u; ++pat)  // bf16 patterns below 2^-120 (exponent field < 7)
+            if (qt_round_dyn(P, (sign << 31) | (pat << 16)) != first) return 0;
+    }
+    return 1;
+}
