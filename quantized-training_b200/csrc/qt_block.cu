@@ -347,6 +347,277 @@ mx_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer,
     }
 }
 
+// ----------------------------------------------------------------------------- affine scheme, single pass
+// sf = (max - min) / (quant_max - quant_min); sf = where(sf > 0, sf, 1); zp = -min / sf + quant_min, each op in
+// the tensor's dtype, both optionally through the scale codebook (fake_quantize.py:165-174).  NaN in the block:
+// amin / amax propagate it.
+template <bool F32>
+__device__ __forceinline__ void gwa_params(float mn, float mx, bool nan, const BlockParams &bp, float &sf, float &zp)
+{
+    if (nan) mn = mx = __uint_as_float(QT_NAN_BITS);
+    sf = to_dtype<F32>(__fdiv_rn(to_dtype<F32>(__fsub_rn(mx, mn)), bp.range));
+    sf = sf > 0.0f ? sf : 1.0f;
+    zp = to_dtype<F32>(__fadd_rn(to_dtype<F32>(__fdiv_rn(-mn, sf)), bp.quant_min));
+    if (bp.has_scale_fmt) {
+        sf = scale_codebook<F32>(bp, sf);
+        zp = scale_codebook<F32>(bp, zp);
+    }
+}
+// q = clamp(round(x / sf + zp), qmin, qmax); y = (q - zp) * sf -- every op rounded to the tensor's dtype
+template <bool F32>
+__device__ __forceinline__ float gwa_elem(float x, float sf, float zp, const BlockParams &bp)
+{
+    float q = to_dtype<F32>(__fadd_rn(to_dtype<F32>(__fdiv_rn(x, sf)), zp));
+    q = rintf(q);
+    q = (q < bp.quant_min) ? bp.quant_min : q;  // compare-select keeps NaN like torch.clamp
+    q = (q > bp.quant_max) ? bp.quant_max : q;
+    return to_dtype<F32>(__fmul_rn(to_dtype<F32>(__fsub_rn(q, zp)), sf));
+}
+// x / sf as a reciprocal multiply is legal when sf is a normal-range bf16 value, the quotients stay finite, and a
+// sub-2^-120 quotient cannot matter: it is absorbed by a zero point of ordinary size, or (zp == 0) only its sign
+// survives round().
+__device__ __forceinline__ bool gwa_block_is_fast(uint32_t amax_bits, float sf, float rsf, float zp)
+{
+    const uint32_t sb = __float_as_uint(sf), zb = __float_as_uint(zp) & 0x7FFFFFFFu;
+    return amax_bits < 0x7E800000u && (sb - 0x0D800000u) <= (0x71800000u - 0x0D800000u) &&
+           (zb == 0u || (zb - 0x0D800000u) <= (0x71800000u - 0x0D800000u)) &&
+           __fmul_rn(__uint_as_float(amax_bits), rsf) < 0x1p126f;
+}
+// two bf16 values of one word, each with its own parameters (fast path: no NaN, bounded quotients)
+__device__ __forceinline__ uint32_t gwa_word_fast(uint32_t w, float sf_lo, float rsf_lo, float zp_lo, float sf_hi,
+                                                 float rsf_hi, float zp_hi, const BlockParams &bp)
+{
+    uint32_t u = bf16x2_rne(__fmul_rn(__uint_as_float(w << 16), rsf_lo),
+                            __fmul_rn(__uint_as_float(w & 0xFFFF0000u), rsf_hi));
+    u = bf16x2_rne(__fadd_rn(__uint_as_float(u << 16), zp_lo), __fadd_rn(__uint_as_float(u & 0xFFFF0000u), zp_hi));
+    float qlo = rintf(__uint_as_float(u << 16)), qhi = rintf(__uint_as_float(u & 0xFFFF0000u));
+    qlo = fminf(fmaxf(qlo, bp.quant_min), bp.quant_max);
+    qhi = fminf(fmaxf(qhi, bp.quant_min), bp.quant_max);
+    u = bf16x2_rne(__fsub_rn(qlo, zp_lo), __fsub_rn(qhi, zp_hi));
+    return bf16x2_rne(__fmul_rn(__uint_as_float(u << 16), sf_lo), __fmul_rn(__uint_as_float(u & 0xFFFF0000u), sf_hi));
+}
+// fmaxf would turn -0 - 0 ... into the same values as the compare-select form for every non-NaN input: max(-0, 0)
+// may return either zero, but round() of it is then clamped against quant_min <= 0 <= quant_max and only enters
+// (q - zp): with zp != 0 the sign of a zero q is immaterial, with zp == 0 ... the sign could differ -- so when
+// zp == 0 and quant_min == 0 the careful path is taken (see gwa_fast_allowed).
+__device__ __forceinline__ bool gwa_fast_allowed(float zp, const BlockParams &bp)
+{
+    return !(zp == 0.0f && (bp.quant_min == 0.0f || bp.quant_max == 0.0f));
+}
+
+__device__ __forceinline__ uint32_t bf16x2_min(uint32_t a, uint32_t b)
+{
+    __nv_bfloat162 r = __hmin2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b)
+{
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+
+// Blocks of LANES consecutive 16-byte vectors along the last axis (same geometry as mx_flat_kernel).
+template <bool F32, int LANES>
+__global__ void __launch_bounds__(256, 4)
+gwa_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec, const __grid_constant__ BlockParams bp,
+                float *__restrict__ scale_out, float *__restrict__ zp_out)
+{
+    const size_t nthr = blockDim.x;
+    const size_t tile = nthr * kUnroll;
+    const size_t ntiles = (nvec + tile - 1) / tile;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const size_t base = t * tile + threadIdx.x;
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * nthr;
+            v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * nthr;
+            uint32_t a = F32 ? amax_of_vec_f32(0u, v[j]) : amax_of_vec_bf16(0u, v[j]);
+            float mn, mx;
+            if (F32) {
+                mn = fminf(fminf(__uint_as_float(v[j].x), __uint_as_float(v[j].y)),
+                           fminf(__uint_as_float(v[j].z), __uint_as_float(v[j].w)));
+                mx = fmaxf(fmaxf(__uint_as_float(v[j].x), __uint_as_float(v[j].y)),
+                           fmaxf(__uint_as_float(v[j].z), __uint_as_float(v[j].w)));
+            } else {
+                const uint32_t pmn = bf16x2_min(bf16x2_min(v[j].x, v[j].y), bf16x2_min(v[j].z, v[j].w));
+                const uint32_t pmx = bf16x2_max(bf16x2_max(v[j].x, v[j].y), bf16x2_max(v[j].z, v[j].w));
+                mn = fminf(__uint_as_float(pmn << 16), __uint_as_float(pmn & 0xFFFF0000u));
+                mx = fmaxf(__uint_as_float(pmx << 16), __uint_as_float(pmx & 0xFFFF0000u));
+            }
+#pragma unroll
+            for (int o = 1; o < LANES; o <<= 1) {
+                a = max(a, __shfl_xor_sync(0xFFFFFFFFu, a, o));
+                mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+            }
+            float sf, zp;
+            gwa_params<F32>(mn, mx, a > 0x7F800000u, bp, sf, zp);
+            const float rsf = __frcp_rn(sf);
+            const bool fast = !F32 && __all_sync(0xFFFFFFFFu, gwa_block_is_fast(a, sf, rsf, zp) && gwa_fast_allowed(zp, bp));
+            uint4 r;
+            if (fast) {
+                r.x = gwa_word_fast(v[j].x, sf, rsf, zp, sf, rsf, zp, bp);
+                r.y = gwa_word_fast(v[j].y, sf, rsf, zp, sf, rsf, zp, bp);
+                r.z = gwa_word_fast(v[j].z, sf, rsf, zp, sf, rsf, zp, bp);
+                r.w = gwa_word_fast(v[j].w, sf, rsf, zp, sf, rsf, zp, bp);
+            } else {
+                const uint32_t win[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                uint32_t out[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (F32) {
+                        out[q] = __float_as_uint(gwa_elem<true>(__uint_as_float(win[q]), sf, zp, bp));
+                    } else {
+                        const float lo = gwa_elem<false>(__uint_as_float(win[q] << 16), sf, zp, bp);
+                        const float hi = gwa_elem<false>(__uint_as_float(win[q] & 0xFFFF0000u), sf, zp, bp);
+                        out[q] = __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+                    }
+                }
+                r = make_uint4(out[0], out[1], out[2], out[3]);
+            }
+            if (i < nvec) {
+                if ((i & (size_t)(LANES - 1)) == 0) {
+                    scale_out[i / LANES] = sf;
+                    zp_out[i / LANES] = zp;
+                }
+                st_stream(y + i, r);
+            }
+        }
+    }
+}
+
+// Blocks along an inner axis (same geometry as mx_cols_kernel): rows past n are the reference's zero padding and
+// DO enter min / max.
+template <bool F32, int RPT>
+__global__ void __launch_bounds__(256)
+gwa_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer, size_t n, size_t inner_vec,
+                size_t nblk, const __grid_constant__ BlockParams bp, float *__restrict__ scale_out,
+                float *__restrict__ zp_out)
+{
+    constexpr int VEC = F32 ? 4 : 8;
+    constexpr int BS = 8 * RPT;
+    __shared__ uint4 red_mn[8][33], red_mx[8][33], red_am[8][33];
+    __shared__ float col_sf[32][VEC + 1], col_zp[32][VEC + 1];
+    const size_t G = outer * inner_vec;
+    const size_t gchunks = (G + 31) / 32;
+    const size_t work = nblk * gchunks;
+    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
+        const size_t b = w / gchunks, gc = w - b * gchunks;
+        const size_t g = gc * 32 + threadIdx.x;
+        const bool active = g < G;
+        const size_t o = active ? g / inner_vec : 0, cv = active ? g - o * inner_vec : 0;
+        const size_t row0 = b * BS + threadIdx.y;
+        const uint4 *xp = x + (o * n) * inner_vec + cv;
+        uint4 v[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const size_t r = row0 + (size_t)k * 8;
+            v[k] = (active && r < n) ? ld_stream(xp + r * inner_vec) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint4 mn = v[0], mx = v[0], am = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            if (F32) {
+                mn.x = __float_as_uint(fminf(__uint_as_float(mn.x), __uint_as_float(v[k].x)));
+                mn.y = __float_as_uint(fminf(__uint_as_float(mn.y), __uint_as_float(v[k].y)));
+                mn.z = __float_as_uint(fminf(__uint_as_float(mn.z), __uint_as_float(v[k].z)));
+                mn.w = __float_as_uint(fminf(__uint_as_float(mn.w), __uint_as_float(v[k].w)));
+                mx.x = __float_as_uint(fmaxf(__uint_as_float(mx.x), __uint_as_float(v[k].x)));
+                mx.y = __float_as_uint(fmaxf(__uint_as_float(mx.y), __uint_as_float(v[k].y)));
+                mx.z = __float_as_uint(fmaxf(__uint_as_float(mx.z), __uint_as_float(v[k].z)));
+                mx.w = __float_as_uint(fmaxf(__uint_as_float(mx.w), __uint_as_float(v[k].w)));
+                am.x = max(am.x, v[k].x & 0x7FFFFFFFu);
+                am.y = max(am.y, v[k].y & 0x7FFFFFFFu);
+                am.z = max(am.z, v[k].z & 0x7FFFFFFFu);
+                am.w = max(am.w, v[k].w & 0x7FFFFFFFu);
+            } else {
+                mn.x = bf16x2_min(mn.x, v[k].x); mn.y = bf16x2_min(mn.y, v[k].y);
+                mn.z = bf16x2_min(mn.z, v[k].z); mn.w = bf16x2_min(mn.w, v[k].w);
+                mx.x = bf16x2_max(mx.x, v[k].x); mx.y = bf16x2_max(mx.y, v[k].y);
+                mx.z = bf16x2_max(mx.z, v[k].z); mx.w = bf16x2_max(mx.w, v[k].w);
+                am.x = __vmaxu2(am.x, v[k].x & 0x7FFF7FFFu); am.y = __vmaxu2(am.y, v[k].y & 0x7FFF7FFFu);
+                am.z = __vmaxu2(am.z, v[k].z & 0x7FFF7FFFu); am.w = __vmaxu2(am.w, v[k].w & 0x7FFF7FFFu);
+            }
+        }
+        red_mn[threadIdx.y][threadIdx.x] = mn;
+        red_mx[threadIdx.y][threadIdx.x] = mx;
+        red_am[threadIdx.y][threadIdx.x] = am;
+        __syncthreads();
+        if (threadIdx.y < VEC) {
+            const int c = threadIdx.y;
+            float fmn = __uint_as_float(0x7F800000u), fmx = __uint_as_float(0xFF800000u);
+            uint32_t a = 0u;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const uint4 qn = red_mn[p][threadIdx.x], qx = red_mx[p][threadIdx.x], qa = red_am[p][threadIdx.x];
+                const int wi = F32 ? c : (c >> 1);
+                const uint32_t wn = wi == 0 ? qn.x : wi == 1 ? qn.y : wi == 2 ? qn.z : qn.w;
+                const uint32_t wx = wi == 0 ? qx.x : wi == 1 ? qx.y : wi == 2 ? qx.z : qx.w;
+                const uint32_t wa = wi == 0 ? qa.x : wi == 1 ? qa.y : wi == 2 ? qa.z : qa.w;
+                const bool hi = !F32 && (c & 1);
+                fmn = fminf(fmn, __uint_as_float(F32 ? wn : (hi ? (wn & 0xFFFF0000u) : (wn << 16))));
+                fmx = fmaxf(fmx, __uint_as_float(F32 ? wx : (hi ? (wx & 0xFFFF0000u) : (wx << 16))));
+                a = max(a, F32 ? wa : (hi ? (wa & 0xFFFF0000u) : (wa << 16)));
+            }
+            float sf, zp;
+            gwa_params<F32>(fmn, fmx, a > 0x7F800000u, bp, sf, zp);
+            if (active) {
+                const size_t si = (o * nblk + b) * (inner_vec * VEC) + cv * VEC + c;
+                scale_out[si] = sf;
+                zp_out[si] = zp;
+            }
+            // sf > 0 always (NaN or non-positive became 1; a codebook may return 0 or NaN: then not fast) -- the
+            // sign bit carries "careful path"
+            const bool f = !F32 && sf > 0.0f && gwa_block_is_fast(a, sf, __frcp_rn(sf), zp) && gwa_fast_allowed(zp, bp);
+            col_sf[threadIdx.x][c] = f ? sf : __uint_as_float(__float_as_uint(sf) | 0x80000000u);
+            col_zp[threadIdx.x][c] = zp;
+        }
+        __syncthreads();
+        float sf[VEC], rsf[VEC], zp[VEC];
+        bool mine_fast = !F32;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) {
+            const float sv = col_sf[threadIdx.x][c];
+            mine_fast = mine_fast && !(__float_as_uint(sv) >> 31);
+            sf[c] = mine_fast ? sv : sv;  // restored below for the careful path
+            zp[c] = col_zp[threadIdx.x][c];
+        }
+        const bool fast = __all_sync(0xFFFFFFFFu, mine_fast);
+        uint4 *yp = y + (o * n) * inner_vec + cv;
+        if (fast) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) rsf[c] = __frcp_rn(sf[c]);
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const size_t r = row0 + (size_t)k * 8;
+            const uint32_t win[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+            uint32_t out[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (F32) {
+                    out[q] = __float_as_uint(gwa_elem<true>(__uint_as_float(win[q]), col_sf_true<F32>(sf[q % VEC]), zp[q % VEC], bp));
+                } else if (fast) {
+                    out[q] = gwa_word_fast(win[q], sf[(2 * q) % VEC], rsf[(2 * q) % VEC], zp[(2 * q) % VEC],
+                                           sf[(2 * q + 1) % VEC], rsf[(2 * q + 1) % VEC], zp[(2 * q + 1) % VEC], bp);
+                } else {
+                    const float lo = gwa_elem<false>(__uint_as_float(win[q] << 16), col_sf_true<F32>(sf[(2 * q) % VEC]),
+                                                     zp[(2 * q) % VEC], bp);
+                    const float hi = gwa_elem<false>(__uint_as_float(win[q] & 0xFFFF0000u),
+                                                     col_sf_true<F32>(sf[(2 * q + 1) % VEC]), zp[(2 * q + 1) % VEC], bp);
+                    out[q] = __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+                }
+            }
+            if (active && r < n) st_stream(yp + r * inner_vec, make_uint4(out[0], out[1], out[2], out[3]));
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------- generic kernels
 // Tensor [d0, n1, d1, n2, d2]; n1 is tiled with bs, n2 is tiled with bs2 (bs or 1).  Block grid
 // [d0, nb1, d1, nb2, d2] row-major is the layout of scale / zero_point.
@@ -616,7 +887,7 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
     bp.pow2 = (!affine && d->force_scale_power_of_two) ? 1 : 0;
     bp.qmax_exp = (int32_t)floor(log2((double)d->quant_max));
     bp.pow2_tab = static_cast<const uint32_t *>(d->pow2_table);
-    bp.fast_ok = (!affine && qt_tiny_safe(P)) ? 1 : 0;
+    bp.fast_ok = (!affine && P.tiny_safe) ? 1 : 0;
     {
         uint32_t qb;
         memcpy(&qb, &d->quant_max, 4);

@@ -244,6 +244,7 @@ int qt_make_round(const qt_format_t *fmt, QtRound *P)
         P->kind = QTR_INT;
         P->qmin = bf16_round(fmt->min_value);
         P->qmax = bf16_round(fmt->max_value);
+        P->tiny_safe = (P->qmin <= 0.0f && P->qmax >= 0.0f) ? 1 : 0;
         return QT_OK;
     case QT_KIND_FP: {
         if (fmt->flavour == QT_FP_MX ? !qt_mx_supported(fmt->ebits, fmt->mbits)
@@ -259,6 +260,7 @@ int qt_make_round(const qt_format_t *fmt, QtRound *P)
         P->min_sub_bits = fbits(min_sub);
         // the bf16 value immediately below half the smallest subnormal rounds up (fp8.py:123-127 in bf16)
         P->quirk_bits = fmt->flavour == QT_FP_MX ? fbits(min_sub * 0.5f) - 0x10000u : 0u;
+        P->tiny_safe = 1;  // half the smallest subnormal is >= 2^-21 for every supported (ebits, mbits)
         return QT_OK;
     }
     case QT_KIND_POSIT: {
@@ -272,6 +274,7 @@ int qt_make_round(const qt_format_t *fmt, QtRound *P)
         P->minpos_bits = fbits((float)ldexp(1.0, -max_scale));
         double thr = floor(-(double)(n - 1) * (double)(1 << es) + pow(2.0, es - 1));
         P->flush_bits = fbits(bf16_round((float)ldexp(1.0, (int)thr)));
+        P->tiny_safe = P->flush_bits >= 0x03800000u ? 1 : 0;  // everything below 2^-120 is flushed to zero
         return QT_OK;
     }
     default:
@@ -284,6 +287,13 @@ int qt_make_round(const qt_format_t *fmt, QtRound *P)
 
 extern "C" int qt_table_host(const qt_format_t *fmt, uint16_t *table_host)
 {
+    {
+        QtRound chk;
+        if (fmt && qt_make_round(fmt, &chk) == QT_OK && chk.tiny_safe && !qt_tiny_safe(chk)) {
+            qt_set_error("internal: tiny_safe flag inconsistent for this format");
+            return QT_ERR_INVALID_ARGUMENT;
+        }
+    }
     if (!fmt || !table_host) {
         qt_set_error("qt_table_host: NULL argument");
         return QT_ERR_INVALID_ARGUMENT;
@@ -349,6 +359,8 @@ extern "C" int qt_block_pow2_table_host(int elem_type, uint32_t *table_host)
     return QT_OK;
 }
 
+// brute-force statement of QtRound::tiny_safe (the analytic flag set by qt_make_round is checked against it in
+// qt_lut_build_host and qt_table_host, i.e. once per module, never per launch)
 int qt_tiny_safe(const QtRound &P)
 {
     for (uint32_t sign = 0; sign < 2; ++sign) {

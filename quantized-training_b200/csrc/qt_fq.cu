@@ -47,7 +47,19 @@ __device__ __forceinline__ void fq_span(const R &round, const uint4 *__restrict_
             const size_t i = base + (size_t)j * nthr;
             v[j] = i < nvec ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
         }
-        if constexpr (!F32 && DIV == DIV_RECIP) {
+        if constexpr (!F32 && DIV == DIV_RECIP_NOTINY) {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const size_t i = base + (size_t)j * nthr;
+                if (AMAX) amax = amax_of_vec_bf16(amax, v[j]);
+                uint4 r;
+                r.x = fq_word_bf16_recip_notiny<R>(round, v[j].x, sc);
+                r.y = fq_word_bf16_recip_notiny<R>(round, v[j].y, sc);
+                r.z = fq_word_bf16_recip_notiny<R>(round, v[j].z, sc);
+                r.w = fq_word_bf16_recip_notiny<R>(round, v[j].w, sc);
+                if (i < nvec) st_stream(y + i, r);
+            }
+        } else if constexpr (!F32 && DIV == DIV_RECIP) {
             // Reciprocal path: the inputs are consumed as they are processed (no register is held back for a
             // fallback); the rare tile with a sub-2^-120 quotient is redone from memory with the true division.
             bool tiny = false;
@@ -97,6 +109,8 @@ fq_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
         fq_span<R, F32, DIV_UNIT, AMAX>(round, x, y, nvec, blockIdx.x, gridDim.x, sc, amax);
     else if (F32 || mode == DIV_EXACT)
         fq_span<R, F32, DIV_EXACT, AMAX>(round, x, y, nvec, blockIdx.x, gridDim.x, sc, amax);
+    else if (R::tiny_safe(params))
+        fq_span<R, F32, DIV_RECIP_NOTINY, AMAX>(round, x, y, nvec, blockIdx.x, gridDim.x, sc, amax);
     else
         fq_span<R, F32, DIV_RECIP, AMAX>(round, x, y, nvec, blockIdx.x, gridDim.x, sc, amax);
     if (AMAX) block_amax_commit(amax, amax_out);
@@ -213,6 +227,8 @@ fq_rows_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
                 fq_row_segment<R, F32, DIV_UNIT, AMAX>(round, xr, yr, v0, v1, sc, amax);
             else if (F32 || mode == DIV_EXACT)
                 fq_row_segment<R, F32, DIV_EXACT, AMAX>(round, xr, yr, v0, v1, sc, amax);
+            else if (R::tiny_safe(params))
+                fq_row_segment<R, F32, DIV_RECIP_NOTINY, AMAX>(round, xr, yr, v0, v1, sc, amax);
             else
                 fq_row_segment<R, F32, DIV_RECIP, AMAX>(round, xr, yr, v0, v1, sc, amax);
         } else {

@@ -30,6 +30,7 @@ struct DirectRounder {
     static constexpr bool kMxBand = KIND == QTR_FP_MX;
     static constexpr size_t kSmemBytes = 0;
     using Params = DirectParams<KIND>;
+    static __device__ __forceinline__ bool tiny_safe(const Params &p) { return p.P.tiny_safe != 0; }
     const QtRound &P;
     __device__ __forceinline__ DirectRounder(const Params &p, const unsigned char *) : P(p.P) {}
     __device__ __forceinline__ uint32_t operator()(uint32_t u) const { return qt_round<KIND>(P, u); }
@@ -49,6 +50,7 @@ struct TableRounder {
     static constexpr int kReplicas = REPL;
     static constexpr size_t kSmemBytes = (size_t)QT_LUT_BYTES * REPL;
     using Params = TableParams;
+    static __device__ __forceinline__ bool tiny_safe(const Params &p) { return p.cfg.tiny_safe != 0; }
     const unsigned char *tab;  // shared memory, 8 interleaved replicas (qt_lut.h)
     const uint32_t clamp_bits;
     const uint32_t slot16;
@@ -114,7 +116,7 @@ __device__ __forceinline__ uint32_t f32_to_bf16_rto_hi(uint32_t b)
 //          bf16(fp32(x / s)).  The argument needs a normal-range quotient: elements whose product is below
 //          2^-120 (other than exact zeros) take the true division.
 //   EXACT  __fdiv_rn (scale outside [2^-100, 2^100], or not finite).
-enum { DIV_UNIT = 0, DIV_RECIP = 1, DIV_EXACT = 2 };
+enum { DIV_UNIT = 0, DIV_RECIP = 1, DIV_EXACT = 2, DIV_RECIP_NOTINY = 3 };
 
 struct ScaleBf16 {
     float s, rs;
@@ -179,6 +181,18 @@ __device__ __forceinline__ uint32_t fq_word_bf16_recip(const R &round, uint32_t 
     return bf16x2_rne(__fmul_rn(__uint_as_float(qlo), sc.s), __fmul_rn(__uint_as_float(qhi), sc.s));
 }
 
+// The same without the range test: valid for formats with QtRound::tiny_safe, where a sub-2^-120 quotient only
+// has to come out with the right sign and zero-ness (x * rcp(s) underflows to zero exactly when bf16(x / s) does:
+// the two differ by a factor within 2^-22 of one, and a quotient of two 8-bit significands is either equal to the
+// bf16 underflow boundary 2^-134 -- then the product is exactly on it too -- or at least 2^-8 away from it).
+template <class R>
+__device__ __forceinline__ uint32_t fq_word_bf16_recip_notiny(const R &round, uint32_t w, const ScaleBf16 &sc)
+{
+    const uint32_t uq = bf16x2_rne(__fmul_rn(__uint_as_float(w << 16), sc.rs),
+                                   __fmul_rn(__uint_as_float(w & 0xFFFF0000u), sc.rs));
+    return bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), sc.s), __fmul_rn(__uint_as_float(round.hi(uq)), sc.s));
+}
+
 __device__ __forceinline__ uint32_t amax_of_vec_f32(uint32_t amax, const uint4 &v)
 {
     return max(max(amax, v.x & 0x7FFFFFFFu), max(max(v.y & 0x7FFFFFFFu, v.z & 0x7FFFFFFFu), v.w & 0x7FFFFFFFu));
@@ -216,7 +230,12 @@ __device__ __forceinline__ uint4 fq_vec(const R &round, uint4 v, const ScaleBf16
         r.w = fq_f32<R, DIV == DIV_UNIT>(round, v.w, sc.s);
     } else {
         if (AMAX) amax = amax_of_vec_bf16(amax, v);
-        if (DIV == DIV_RECIP) {
+        if (DIV == DIV_RECIP_NOTINY) {
+            r.x = fq_word_bf16_recip_notiny<R>(round, v.x, sc);
+            r.y = fq_word_bf16_recip_notiny<R>(round, v.y, sc);
+            r.z = fq_word_bf16_recip_notiny<R>(round, v.z, sc);
+            r.w = fq_word_bf16_recip_notiny<R>(round, v.w, sc);
+        } else if (DIV == DIV_RECIP) {
             bool tiny = false;
             r = fq_vec_bf16_recip_fast<R>(round, v, sc, tiny);
             if (tiny) {  // sub-2^-120 quotients: the reference's fp32 division rounds in the denormal range

@@ -110,6 +110,7 @@ int qt_lut_config(const QtRound &P, QtLutCfg *cfg)
 {
     cfg->clamp_bits = 0x7FFFFFFFu;
     cfg->mx_band = 0;
+    cfg->tiny_safe = (uint32_t)P.tiny_safe;
     switch (P.kind) {
     case QTR_FP_CUSTOM: cfg->clamp_bits = P.max_bits; return QT_OK;
     case QTR_FP_MX:

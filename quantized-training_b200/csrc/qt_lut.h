@@ -37,6 +37,7 @@ struct QtLutEntry {
 struct QtLutCfg {
     uint32_t clamp_bits;  // |x| is clamped to this bit pattern first (max_norm); 0x7FFFFFFF = no clamp
     uint32_t mx_band;     // 1: |x| >= 0x7F58 (bf16) other than Inf gives NaN -- fpN_eXmY only
+    uint32_t tiny_safe;   // QtRound::tiny_safe
 };
 
 QT_HD float qt_saturate(float x)

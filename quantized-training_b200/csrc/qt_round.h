@@ -55,6 +55,10 @@ struct QtRound {
     uint32_t minpos_bits;  // fp32 bits of 2^-max_scale
     uint32_t maxpos_bits;  // fp32 bits of 2^max_scale
     uint32_t flush_bits;   // |x| bits below which the result is 0
+    // 1: round(u) of a bf16 u with 0 < |u| < 2^-120 depends on the sign of u only, so a quotient in that range may
+    // be computed inexactly (x * rcp(s)) as long as its sign and zero-ness are right (checked by brute force in
+    // qt_lut_build_host / tests)
+    int32_t tiny_safe;
 };
 
 QT_HD float qt_bits2f(uint32_t u)
