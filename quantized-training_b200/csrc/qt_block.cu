@@ -396,10 +396,8 @@ __device__ __forceinline__ uint32_t gwa_word_fast(uint32_t w, float sf_lo, float
     u = bf16x2_rne(__fsub_rn(qlo, zp_lo), __fsub_rn(qhi, zp_hi));
     return bf16x2_rne(__fmul_rn(__uint_as_float(u << 16), sf_lo), __fmul_rn(__uint_as_float(u & 0xFFFF0000u), sf_hi));
 }
-// fmaxf would turn -0 - 0 ... into the same values as the compare-select form for every non-NaN input: max(-0, 0)
-// may return either zero, but round() of it is then clamped against quant_min <= 0 <= quant_max and only enters
-// (q - zp): with zp != 0 the sign of a zero q is immaterial, with zp == 0 ... the sign could differ -- so when
-// zp == 0 and quant_min == 0 the careful path is taken (see gwa_fast_allowed).
+// fminf / fmaxf may return either zero for (-0, +0), unlike the compare-select clamp of the careful path.  The sign of
+// a zero q matters only when it survives (q - zp), i.e. when zp == 0 and a clamp bound is zero: careful path then.
 __device__ __forceinline__ bool gwa_fast_allowed(float zp, const BlockParams &bp)
 {
     return !(zp == 0.0f && (bp.quant_min == 0.0f || bp.quant_max == 0.0f));
@@ -503,6 +501,7 @@ gwa_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer
     constexpr int BS = 8 * RPT;
     __shared__ uint4 red_mn[8][33], red_mx[8][33], red_am[8][33];
     __shared__ float col_sf[32][VEC + 1], col_zp[32][VEC + 1];
+    __shared__ unsigned char col_fast[32][VEC];
     const size_t G = outer * inner_vec;
     const size_t gchunks = (G + 31) / 32;
     const size_t work = nblk * gchunks;
@@ -571,28 +570,24 @@ gwa_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer
                 scale_out[si] = sf;
                 zp_out[si] = zp;
             }
-            // sf > 0 always (NaN or non-positive became 1; a codebook may return 0 or NaN: then not fast) -- the
-            // sign bit carries "careful path"
-            const bool f = !F32 && sf > 0.0f && gwa_block_is_fast(a, sf, __frcp_rn(sf), zp) && gwa_fast_allowed(zp, bp);
-            col_sf[threadIdx.x][c] = f ? sf : __uint_as_float(__float_as_uint(sf) | 0x80000000u);
+            col_sf[threadIdx.x][c] = sf;
             col_zp[threadIdx.x][c] = zp;
+            col_fast[threadIdx.x][c] =
+                !F32 && gwa_block_is_fast(a, sf, __frcp_rn(sf), zp) && gwa_fast_allowed(zp, bp) ? 1 : 0;
         }
         __syncthreads();
         float sf[VEC], rsf[VEC], zp[VEC];
         bool mine_fast = !F32;
 #pragma unroll
         for (int c = 0; c < VEC; ++c) {
-            const float sv = col_sf[threadIdx.x][c];
-            mine_fast = mine_fast && !(__float_as_uint(sv) >> 31);
-            sf[c] = mine_fast ? sv : sv;  // restored below for the careful path
+            mine_fast = mine_fast && col_fast[threadIdx.x][c] != 0;
+            sf[c] = col_sf[threadIdx.x][c];
             zp[c] = col_zp[threadIdx.x][c];
         }
         const bool fast = __all_sync(0xFFFFFFFFu, mine_fast);
         uint4 *yp = y + (o * n) * inner_vec + cv;
-        if (fast) {
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) rsf[c] = __frcp_rn(sf[c]);
-        }
+        for (int c = 0; c < VEC; ++c) rsf[c] = __frcp_rn(sf[c]);
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const size_t r = row0 + (size_t)k * 8;
@@ -601,15 +596,15 @@ gwa_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (F32) {
-                    out[q] = __float_as_uint(gwa_elem<true>(__uint_as_float(win[q]), col_sf_true<F32>(sf[q % VEC]), zp[q % VEC], bp));
+                    out[q] = __float_as_uint(gwa_elem<true>(__uint_as_float(win[q]), sf[q % VEC], zp[q % VEC], bp));
                 } else if (fast) {
                     out[q] = gwa_word_fast(win[q], sf[(2 * q) % VEC], rsf[(2 * q) % VEC], zp[(2 * q) % VEC],
                                            sf[(2 * q + 1) % VEC], rsf[(2 * q + 1) % VEC], zp[(2 * q + 1) % VEC], bp);
                 } else {
-                    const float lo = gwa_elem<false>(__uint_as_float(win[q] << 16), col_sf_true<F32>(sf[(2 * q) % VEC]),
+                    const float lo = gwa_elem<false>(__uint_as_float(win[q] << 16), sf[(2 * q) % VEC],
                                                      zp[(2 * q) % VEC], bp);
                     const float hi = gwa_elem<false>(__uint_as_float(win[q] & 0xFFFF0000u),
-                                                     col_sf_true<F32>(sf[(2 * q + 1) % VEC]), zp[(2 * q + 1) % VEC], bp);
+                                                     sf[(2 * q + 1) % VEC], zp[(2 * q + 1) % VEC], bp);
                     out[q] = __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
                 }
             }
@@ -681,15 +676,8 @@ block_stat_kernel(const void *__restrict__ x, const __grid_constant__ BlockDims 
             }
             nan = __any_sync(0xFFFFFFFFu, nan);
             if (lane == 0) {
-                if (nan) mn = mx = __uint_as_float(QT_NAN_BITS);
-                // sf = (max - min) / (quant_max - quant_min); sf = where(sf > 0, sf, 1); zp = -min / sf + quant_min
-                float sf = to_dtype<F32>(__fdiv_rn(to_dtype<F32>(__fsub_rn(mx, mn)), bp.range));
-                sf = sf > 0.0f ? sf : 1.0f;
-                float zp = to_dtype<F32>(__fadd_rn(to_dtype<F32>(__fdiv_rn(-mn, sf)), bp.quant_min));
-                if (bp.has_scale_fmt) {
-                    sf = scale_codebook<F32>(bp, sf);
-                    zp = scale_codebook<F32>(bp, zp);
-                }
+                float sf, zp;
+                gwa_params<F32>(mn, mx, nan, bp, sf, zp);
                 scale_out[bi] = sf;
                 zp_out[bi] = zp;
             }
@@ -721,12 +709,7 @@ block_apply_kernel(const void *__restrict__ x, void *__restrict__ y, size_t tota
         uint32_t out;
         if (AFFINE) {
             // q = clamp(round(x / sf + zp), qmin, qmax); y = (q - zp) * sf -- every op rounded to the tensor's dtype
-            const float z = zp[bi];
-            float q = to_dtype<F32>(__fadd_rn(to_dtype<F32>(__fdiv_rn(load_elem(x, F32, i), s)), z));
-            q = rintf(q);
-            q = (q < bp.quant_min) ? bp.quant_min : q;  // compare-select keeps NaN like torch.clamp
-            q = (q > bp.quant_max) ? bp.quant_max : q;
-            out = __float_as_uint(to_dtype<F32>(__fmul_rn(to_dtype<F32>(__fsub_rn(q, z)), s)));
+            out = __float_as_uint(gwa_elem<F32>(load_elem(x, F32, i), s, zp[bi], bp));
         } else if (F32) {
             out = fq_f32<R, false>(round, static_cast<const uint32_t *>(x)[i], s);
         } else {
@@ -822,6 +805,55 @@ void launch_generic(const BlockJob &j, const typename R::Params &p)
     const unsigned grid = grid_for((total + R::kThreads - 1) / R::kThreads, R::kCtasPerSm);
     block_apply_kernel<R, F32, AFFINE><<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(
         j.d->x, j.d->y, total, D, p, j.bp, j.d->scale, j.d->zero_point);
+}
+
+template <bool F32, int LANES>
+void launch_gwa_flat(const BlockJob &j, size_t nvec)
+{
+    const size_t tile = (size_t)256 * kUnroll;
+    gwa_flat_kernel<F32, LANES><<<grid_for((nvec + tile - 1) / tile, 4), 256, 0, j.stream>>>(
+        static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), nvec, j.bp, j.d->scale, j.d->zero_point);
+}
+template <bool F32, int RPT>
+void launch_gwa_cols(const BlockJob &j, size_t outer, size_t n, size_t inner_vec)
+{
+    const size_t nblk = (n + 8 * RPT - 1) / (8 * RPT);
+    const size_t work = nblk * ((outer * inner_vec + 31) / 32);
+    gwa_cols_kernel<F32, RPT><<<grid_for(work, 6), dim3(32, 8), 0, j.stream>>>(
+        static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), outer, n, inner_vec, nblk, j.bp, j.d->scale,
+        j.d->zero_point);
+}
+// single-pass kernels for the affine scheme; false = not expressible, use the generic pair
+template <bool F32>
+bool try_gwa_fast(const BlockJob &j)
+{
+    constexpr size_t VEC = F32 ? 4 : 8;
+    const BlockDims &D = j.D;
+    if ((reinterpret_cast<uintptr_t>(j.d->x) | reinterpret_cast<uintptr_t>(j.d->y)) & 15u) return false;
+    if (D.n2 != 1 || D.d2 != 1 || D.bs2 != 1) return false;
+    if (D.d1 == 1) {
+        if (D.n1 % D.bs != 0 || D.bs % VEC != 0) return false;
+        const size_t nvec = D.d0 * D.n1 / VEC;
+        switch (D.bs / VEC) {
+        case 1: launch_gwa_flat<F32, 1>(j, nvec); return true;
+        case 2: launch_gwa_flat<F32, 2>(j, nvec); return true;
+        case 4: launch_gwa_flat<F32, 4>(j, nvec); return true;
+        case 8: launch_gwa_flat<F32, 8>(j, nvec); return true;
+        case 16: launch_gwa_flat<F32, 16>(j, nvec); return true;
+        case 32: launch_gwa_flat<F32, 32>(j, nvec); return true;
+        default: return false;
+        }
+    }
+    if (D.d1 < VEC || D.d1 % VEC != 0) return false;
+    const size_t inner_vec = D.d1 / VEC;
+    switch (D.bs) {
+    case 8: launch_gwa_cols<F32, 1>(j, D.d0, D.n1, inner_vec); return true;
+    case 16: launch_gwa_cols<F32, 2>(j, D.d0, D.n1, inner_vec); return true;
+    case 32: launch_gwa_cols<F32, 4>(j, D.d0, D.n1, inner_vec); return true;
+    case 64: launch_gwa_cols<F32, 8>(j, D.d0, D.n1, inner_vec); return true;
+    case 128: launch_gwa_cols<F32, 16>(j, D.d0, D.n1, inner_vec); return true;
+    default: return false;
+    }
 }
 
 template <class R, bool F32>
@@ -923,6 +955,7 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
     if (affine) {
         rc = dispatch_direct_small(P, [&](auto tag, const auto &p) {
             using R = typename decltype(tag)::type;
+            if (j.f32 ? try_gwa_fast<true>(j) : try_gwa_fast<false>(j)) return;
             j.f32 ? launch_generic<R, true, true>(j, p) : launch_generic<R, false, true>(j, p);
         });
     } else {
