@@ -218,7 +218,7 @@ __device__ __forceinline__ void mx_flat_tile(const R &round, const typename Fast
 }
 
 template <class R, bool F32, int LANES>
-__global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
+__global__ void __launch_bounds__(R::kThreads, R::kTable ? R::kMinCtas : 4)
 mx_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
                const __grid_constant__ typename R::Params params, const __grid_constant__ BlockParams bp,
                float *__restrict__ scale_out)
@@ -492,7 +492,7 @@ gwa_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
 // Blocks along an inner axis (same geometry as mx_cols_kernel): rows past n are the reference's zero padding and
 // DO enter min / max.
 template <bool F32, int RPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, RPT <= 4 ? 4 : (RPT <= 8 ? 3 : 2))
 gwa_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer, size_t n, size_t inner_vec,
                 size_t nblk, const __grid_constant__ BlockParams bp, float *__restrict__ scale_out,
                 float *__restrict__ zp_out)

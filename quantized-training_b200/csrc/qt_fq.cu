@@ -268,6 +268,13 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
         recip_ok[k] = classify_scale(sc[k].s) != DIV_EXACT;  // x * rcp(1) is exact too
         am[k] = 0u;
     }
+    // every column of every lane on the reciprocal path, and the format indifferent to sub-2^-120 quotients:
+    // the warp takes the branch without per-element tests
+    bool mine_fast = !F32 && WRITE && R::tiny_safe(params);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) mine_fast = mine_fast && recip_ok[k];
+    const bool fast = __all_sync(0xFFFFFFFFu, mine_fast);
+    uint32_t amp[4] = {0u, 0u, 0u, 0u};  // bf16: packed running maxima of the eight columns
     if (active) {
         const size_t rstep = (size_t)gridDim.y * blockDim.y;
         for (size_t r0 = (size_t)blockIdx.y * blockDim.y + threadIdx.y; r0 < rows; r0 += rstep * kUnroll) {
@@ -289,11 +296,10 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
                         if (WRITE) o[k] = fq_f32<R, false>(round, w[k], sc[k].s);
                     } else {
                         const uint32_t lo = w[k] << 16, hi = w[k] & 0xFFFF0000u;
-                        if (AMAX) {
-                            am[2 * k] = max(am[2 * k], lo & 0x7FFFFFFFu);
-                            am[2 * k + 1] = max(am[2 * k + 1], hi & 0x7FFFFFFFu);
-                        }
-                        if (WRITE) {
+                        if (AMAX) amp[k] = __vmaxu2(amp[k], w[k] & 0x7FFF7FFFu);  // two 16-bit maxima per word
+                        if (WRITE && fast) {
+                            o[k] = fq_word_bf16_recip2_notiny<R>(round, w[k], sc[2 * k], sc[2 * k + 1]);
+                        } else if (WRITE) {
                             // per column: reciprocal multiply when its scale allows it, true division otherwise
                             const float qlo = recip_ok[2 * k] ? bf16_quotient<DIV_RECIP>(lo, sc[2 * k])
                                                               : bf16_quotient<DIV_EXACT>(lo, sc[2 * k]);
@@ -310,6 +316,13 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
         }
     }
     if (AMAX) {
+        if (!F32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                am[(2 * k) % VEC] = amp[k] << 16;
+                am[(2 * k + 1) % VEC] = amp[k] & 0xFFFF0000u;
+            }
+        }
         __shared__ uint32_t red[8][32][VEC + 1];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) red[threadIdx.y][threadIdx.x][k] = am[k];

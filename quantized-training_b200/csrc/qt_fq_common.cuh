@@ -193,6 +193,16 @@ __device__ __forceinline__ uint32_t fq_word_bf16_recip_notiny(const R &round, ui
     return bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), sc.s), __fmul_rn(__uint_as_float(round.hi(uq)), sc.s));
 }
 
+// ... and with one scale per half (per-channel along the last axis)
+template <class R>
+__device__ __forceinline__ uint32_t fq_word_bf16_recip2_notiny(const R &round, uint32_t w, const ScaleBf16 &lo,
+                                                               const ScaleBf16 &hi)
+{
+    const uint32_t uq = bf16x2_rne(__fmul_rn(__uint_as_float(w << 16), lo.rs),
+                                   __fmul_rn(__uint_as_float(w & 0xFFFF0000u), hi.rs));
+    return bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), lo.s), __fmul_rn(__uint_as_float(round.hi(uq)), hi.s));
+}
+
 __device__ __forceinline__ uint32_t amax_of_vec_f32(uint32_t amax, const uint4 &v)
 {
     return max(max(amax, v.x & 0x7FFFFFFFu), max(max(v.y & 0x7FFFFFFFu, v.z & 0x7FFFFFFFu), v.w & 0x7FFFFFFFu));
