@@ -23,18 +23,13 @@ class HostPipeline:
         self.xin = [torch.empty(self.chunk, dtype=dtype, device=self.device) for _ in range(depth)]
         self.yout = [torch.empty(self.chunk, dtype=dtype, device=self.device) for _ in range(depth)]
 
-    def run(self, mod: FusedAmaxObsFakeQuantize, x_host: torch.Tensor, out: torch.Tensor = None):
-        assert not x_host.is_cuda and x_host.is_contiguous() and x_host.dtype == self.xin[0].dtype
+    def _prepare(self, mod, n):
+        """Observer step of one module (once per call, like mod.forward): (quantize?, observe?, amax slot)."""
         if mod.scale.device != self.device:
             mod.to(self.device)
         observe, quantize = mod._flags()
-        if mod.is_per_channel:
+        if mod.is_per_channel or getattr(mod, "is_block_scaled", False):
             raise NotImplementedError("host streaming handles per-tensor and bare specs (chunks cut across channels)")
-        if out is None:
-            out = torch.empty_like(x_host).pin_memory() if quantize else x_host
-        n = x_host.numel()
-        xf, of = x_host.view(-1), out.view(-1)
-        main = torch.cuda.current_stream(self.device)
         amax_slot = None
         if observe:
             if n == 0:
@@ -45,6 +40,24 @@ class HostPipeline:
             _C.scale_update(mod.amax_history, mod.amax_history_len, 1, mod.scale, mod.quant_max,
                             mod.force_scale_power_of_two)
             amax_slot = mod.amax_history
+        return quantize, observe, amax_slot
+
+    def run(self, mod: FusedAmaxObsFakeQuantize, x_host: torch.Tensor, out: torch.Tensor = None):
+        quantize = mod._flags()[1]
+        if out is None:
+            out = torch.empty_like(x_host).pin_memory() if quantize else x_host
+        return self.run_many([mod], x_host, [out])[0]
+
+    def run_many(self, mods, x_host: torch.Tensor, outs):
+        """Several fake-quantizers over the SAME host tensor (a format sweep, or the activation quantizers of sibling
+        consumers): every chunk is uploaded once and each module's result is downloaded into its own `outs[k]`."""
+        assert not x_host.is_cuda and x_host.is_contiguous() and x_host.dtype == self.xin[0].dtype
+        assert len(mods) == len(outs)
+        n = x_host.numel()
+        xf = x_host.view(-1)
+        main = torch.cuda.current_stream(self.device)
+        plans = [self._prepare(m, n) for m in mods]
+        ofs = [o.view(-1) for o in outs]
         ready = torch.cuda.Event()
         ready.record(main)
         for c, start in enumerate(range(0, n, self.chunk)):
@@ -54,14 +67,17 @@ class HostPipeline:
                 self.streams[i].wait_event(ready)
                 xin, yout = self.xin[i][:m], self.yout[i][:m]
                 xin.copy_(xf[start:start + m], non_blocking=True)
-                if quantize:
-                    _C.fq_forward(xin, yout, 1, 1, m, mod._fmt, mod.scale.reshape(1), amax_slot, mod.lut)
-                    of[start:start + m].copy_(yout, non_blocking=True)
-                elif observe:
-                    _C.amax(xin, 1, 1, m, amax_slot)
+                for mod, of, (quantize, observe, amax_slot) in zip(mods, ofs, plans):
+                    if quantize:
+                        # same stream: the download of the previous module's chunk has drained `yout` before this
+                        # kernel overwrites it (the kernel is ~100x faster than the link, nothing is lost)
+                        _C.fq_forward(xin, yout, 1, 1, m, mod._fmt, mod.scale.reshape(1), amax_slot, mod.lut)
+                        of[start:start + m].copy_(yout, non_blocking=True)
+                    elif observe:
+                        _C.amax(xin, 1, 1, m, amax_slot)
         for s in self.streams:
             main.wait_stream(s)
-        return out
+        return outs
 
 
 def fake_quantize_host(mod, x_host, out=None, device="cuda:0", chunk_elems=1 << 23, depth=3):

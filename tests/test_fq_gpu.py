@@ -207,6 +207,18 @@ def test_host_streaming_matches_device_call():
             assert nan_eq32(bits_of(a.scale), bits_of(b.scale)).all()
             if a.qscheme is not None:
                 assert nan_eq32(bits_of(a.amax_history), bits_of(b.amax_history)).all()
+    # several modules over one host tensor: one upload per chunk, one result per module
+    specs = ("int8", "e4m3", "posit8_2", "fp8_e4m3,qs=per_tensor_symmetric,ahl=3")
+    mods = [module_for(sp)[0] for sp in specs]
+    refs = [module_for(sp)[0] for sp in specs]
+    pipe = qt.HostPipeline(DEV, torch.bfloat16, chunk_elems=1 << 18, depth=3)
+    for call in range(2):
+        xi = (x.float() * (call + 2)).to(torch.bfloat16).pin_memory()
+        outs = pipe.run_many(mods, xi, [torch.empty_like(xi).pin_memory() for _ in specs])
+        torch.cuda.synchronize()
+        for sp, got, r, m in zip(specs, outs, refs, mods):
+            assert nan_eq16(bits_of(got), bits_of(r(xi.to(DEV)))).all(), (sp, call)
+            assert nan_eq32(bits_of(r.scale), bits_of(m.scale)).all()
 
 
 @pytest.mark.parametrize("spec", ["e4m3", "e5m2", "fp8_e4m3", "fp8_e5m2", "fp8_e4m3,qs=per_tensor_symmetric,ahl=2"])
