@@ -227,7 +227,19 @@ typedef struct qt_gemm_desc {
     const void *fq_lut;
     int32_t out_type;
     int32_t glu;
+    /* Causal attention schedules (M x N tiles are 128 rows high).  QT_CAUSAL_OUT_LOWER (needs M == N): output tiles
+     * that lie entirely above the diagonal are neither computed nor written -- the consumer (qt_softmax_fq with
+     * QT_SOFTMAX_CAUSAL) does not read them.  QT_CAUSAL_A_LOWER (needs M == K): A[m, k] is known to be zero -- or
+     * unwritten, see qt_softmax_fq -- for k >= 128 * (m / 128 + 1), so the reduction of row tile mt stops there. */
+    int32_t causal;
+    int32_t reserved;
+    /* NULL: the schedule above applies.  Otherwise a device int32 written earlier on the same stream (e.g. by
+     * qt_causal_mask_check): the schedule applies only if it is non-zero, else the full product is computed -- the
+     * decision is made on the device, so a forward captured in a CUDA graph stays correct when the mask changes. */
+    const int32_t *causal_flag;
 } qt_gemm_desc_t;
+#define QT_CAUSAL_OUT_LOWER 1
+#define QT_CAUSAL_A_LOWER 2
 int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
 
 /* ---- ops between the GEMMs, fused with the fake-quant steps around them (qt_fused.cu) -------------------------
@@ -239,6 +251,12 @@ int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
 #define QT_FQ_PRE 1
 #define QT_FQ_MID 2
 #define QT_FQ_POST 4
+/* qt_softmax_fq only, OR-ed into fq_points: the mask is the standard causal one of a square attention
+ * (cols == mask_rows; mask[r, c] = finfo(bf16).min for c > r, 0 otherwise) and no QT_FQ_MID step exists.  Scores at
+ * c > r are then not read (they may be unwritten: QT_CAUSAL_OUT_LOWER), their probabilities are exactly 0, and
+ * probabilities at c >= 128 * (r / 128 + 1) are not written (consume them with QT_CAUSAL_A_LOWER).  With a non-NULL
+ * causal_flag (device int32) the bit takes effect only if *causal_flag != 0. */
+#define QT_SOFTMAX_CAUSAL 16
 /* out_type: what the op stores.  QT_OUT_BF16: the fake-quantized values.  QT_OUT_E4M3 / QT_OUT_E5M2: their one-byte
  * fp8 codes (operands of the QT_GEMM_E4M3.. products); allowed only when the output step (QT_FQ_POST) is an unscaled
  * e4m3 / e5m2 fake quant, so that decode(code) is exactly the value the bf16 form would hold. */
@@ -254,7 +272,14 @@ int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
 int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_t cols, float alpha, const void *mask,
                   size_t rows_per_batch, size_t mask_rows, size_t mask_batches, int fq_points, int out_type,
                   const qt_format_t *fmt, const float *scale_pre, const float *scale_mid, const float *scale_post,
-                  const void *lut, void *stream);
+                  const void *lut, const int32_t *causal_flag, void *stream);
+
+/* *flag_out = 1 if the additive bf16 mask [batches, rows, rows] is the standard causal mask (finfo(bf16).min strictly
+ * above the diagonal, zero elsewhere) for every batch entry, else 0.  Asynchronous on `stream`; feed the flag to
+ * qt_gemm_nt_ex (causal_flag) and qt_softmax_fq (QT_SOFTMAX_CAUSAL + causal_flag).  Replaces nothing in the
+ * reference: it is what lets the kernels exploit the structure of the mask HF hands to the attention blocks
+ * (modeling_llama.py:228-246) without a host round trip. */
+int qt_causal_mask_check(const void *mask, size_t batches, size_t rows, int32_t *flag_out, void *stream);
 
 /* y = fq_post(norm(fq_pre(x))), rows of `cols` <= 8192; y_raw (optional, bf16): norm(fq_pre(x)) before the output step,
  * for consumers that read the un-quantized tensor (BERT: the residual input of the next add).  kind 0: LlamaRMSNorm (x * rsqrt(mean x^2 + eps) rounded to

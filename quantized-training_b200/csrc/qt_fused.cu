@@ -23,6 +23,7 @@ namespace {
 
 constexpr int FQ_PRE = 1;   // fake-quantize the op's input  (hook of the op's own group: scaling / layernorm)
 constexpr int FQ_MID = 2;   // softmax only: fake-quantize scores * alpha + mask (the "activation" hook of nn.Softmax)
+constexpr int FQ_CAUSAL = 16;  // qt_softmax_fq: QT_SOFTMAX_CAUSAL
 constexpr int FQ_POST = 4;  // fake-quantize the op's output (input hook of the consuming GEMM)
 
 // Table rounder of the fused kernels: single-replica 8 KB table (staging 64 KB per CTA would dominate these small
@@ -240,10 +241,11 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
                   int has_alpha, const uint4 *__restrict__ mask, size_t rows_per_batch, size_t mask_rows,
                   size_t mask_batch_stride_vec, int flags, const __grid_constant__ typename R::Params params,
                   const float *__restrict__ scale_pre, const float *__restrict__ scale_mid,
-                  const float *__restrict__ scale_post)
+                  const float *__restrict__ scale_post, const int32_t *__restrict__ causal_flag)
 {
     const R round(params, stage_table<R>(params));
     const FqPoint pre = load_point(scale_pre), mid = load_point(scale_mid), post = load_point(scale_post);
+    if (causal_flag && *causal_flag == 0) flags &= ~FQ_CAUSAL;  // decided on the device (graph-safe)
     constexpr int RPC = ROW_THREADS / TPR;  // rows per CTA pass
     const int lane = threadIdx.x % TPR;
     const int nvec = cols >> 3;
@@ -252,6 +254,10 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
     for (size_t row0 = (size_t)blockIdx.x * RPC; row0 < rows; row0 += row_stride) {
         const size_t row = row0 + threadIdx.x / TPR;
         const bool live = row < rows;
+        // QT_SOFTMAX_CAUSAL: columns past the row's own position are masked by contract -- not read, probability 0;
+        // columns past the row tile's diagonal block are not even written (the P x V product stops there)
+        const int r_seq = (flags & FQ_CAUSAL) ? (int)(row % mask_rows) : 0x7FFFFFF0;
+        const int wr_end = (flags & FQ_CAUSAL) ? ((r_seq >> 7) + 1) << 7 : cols;
         const uint4 *srow = scores + (live ? row : 0) * nvec;
         const uint4 *mrow = nullptr;
         if (mask && live) mrow = mask + (row / rows_per_batch) * mask_batch_stride_vec + (row % mask_rows) * (size_t)nvec;
@@ -259,7 +265,7 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {  // all loads first: VPL (x2 with a mask) 16-byte requests in flight per thread
             const int i = lane + TPR * j;
-            const bool in = i < nvec && live;
+            const bool in = i < nvec && live && i * 8 <= r_seq;
             raw[j] = in ? __ldcs(srow + i) : make_uint4(0u, 0u, 0u, 0u);
             mraw[j] = (in && mrow) ? __ldg(mrow + i) : make_uint4(0u, 0u, 0u, 0u);
         }
@@ -268,7 +274,7 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int i = lane + TPR * j;
-            if (i < nvec && live) {
+            if (i < nvec && live && i * 8 <= r_seq) {
                 unpack8(raw[j], f[j]);
                 if (flags & FQ_PRE) fq8<R, SCALED>(round, f[j], pre);
                 if (has_alpha) {
@@ -319,7 +325,7 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int i = lane + TPR * j;
-            if (i < nvec && live) {
+            if (i < nvec && live && i * 8 < wr_end) {
                 if (alive & (1u << j)) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[j][k] *= inv;
@@ -714,7 +720,7 @@ int finish(const char *what)
 extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_t cols, float alpha, const void *mask,
                              size_t rows_per_batch, size_t mask_rows, size_t mask_batches, int fq_points,
                              int out_type, const qt_format_t *fmt, const float *scale_pre, const float *scale_mid,
-                             const float *scale_post, const void *lut, void *stream)
+                             const float *scale_post, const void *lut, const int32_t *causal_flag, void *stream)
 {
     QtRound P;
     int rc = check_common("qt_softmax_fq", fmt, &P);
@@ -722,6 +728,11 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
     rc = check_out_type("qt_softmax_fq", &out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
+    if ((fq_points & FQ_CAUSAL) && (!mask || mask_rows != cols || (fq_points & FQ_MID))) {
+        qt_set_error("qt_softmax_fq: QT_SOFTMAX_CAUSAL needs the causal mask of a square attention (mask_rows == cols) "
+                     "and no QT_FQ_MID step");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
     if (!scores || !probs || cols % 8 || cols > 4096 || !aligned16(scores) || !aligned16(probs) ||
         (mask && (!aligned16(mask) || mask_rows == 0 || rows_per_batch == 0 || mask_batches == 0))) {
         qt_set_error("qt_softmax_fq: needs 16-byte aligned contiguous bf16 rows, cols %% 8 == 0, cols <= 4096 (got %zu)",
@@ -741,7 +752,7 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
         kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                                \
             static_cast<const uint4 *>(scores), probs, out_type, rows, (int)cols, alpha, has_alpha,                  \
             static_cast<const uint4 *>(mask), rows_per_batch, mask_rows, mask_batch_stride_vec, fq_points, params,   \
-            scale_pre, scale_mid, scale_post);                                                                       \
+            scale_pre, scale_mid, scale_post, causal_flag);                                                          \
     } while (0)
         if (cols <= 256)
             QT_SOFTMAX_LAUNCH(32, 1);
@@ -913,4 +924,40 @@ extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int
     });
     if (rc != QT_OK) return rc;
     return finish("fq_transpose kernel launch");
+}
+
+// ----------------------------------------------------------------------------- causal mask detection
+namespace {
+// mask [batches, rows, rows] bf16: standard causal = finfo(bf16).min (0xFF7F) strictly above the diagonal, +-0 elsewhere
+__global__ void __launch_bounds__(256)
+causal_mask_check_kernel(const uint16_t *__restrict__ mask, size_t batches, size_t rows, int32_t *__restrict__ flag)
+{
+    const size_t total = batches * rows * rows;
+    bool ok = true;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i % rows, r = (i / rows) % rows;
+        const uint16_t v = mask[i];
+        ok = ok && (c > r ? v == 0xFF7Fu : (v & 0x7FFFu) == 0u);
+    }
+    if (!__all_sync(0xFFFFFFFFu, ok) && (threadIdx.x & 31) == 0) *flag = 0;
+}
+__global__ void set_flag_kernel(int32_t *flag, int32_t v) { *flag = v; }
+}  // namespace
+
+extern "C" int qt_causal_mask_check(const void *mask, size_t batches, size_t rows, int32_t *flag_out, void *stream)
+{
+    if (!flag_out) {
+        qt_set_error("qt_causal_mask_check: flag_out is NULL");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (num_sms() == 0) return no_device();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool possible = mask != nullptr && batches > 0 && rows > 0;
+    set_flag_kernel<<<1, 1, 0, st>>>(flag_out, possible ? 1 : 0);
+    if (possible) {
+        const size_t total = batches * rows * rows;
+        causal_mask_check_kernel<<<grid_for((total + 255) / 256, 8), 256, 0, st>>>(static_cast<const uint16_t *>(mask),
+                                                                                   batches, rows, flag_out);
+    }
+    return finish("causal mask check launch");
 }

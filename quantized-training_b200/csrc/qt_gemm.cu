@@ -58,6 +58,9 @@ struct GemmParams {
     int k_blocks;            // ceil(K * elem_bytes / 128)
     uint32_t m_tiles, n_tiles, num_tiles;  // < 2^31 (checked by the launcher)
     int block_n;             // 64, 128 or 256
+    const int32_t *causal_flag;  // device flag gating `causal` (null: unconditional)
+    int causal;              // 0 off; 1: tiles strictly above the diagonal are skipped (scores of a causal attention);
+                             // 2: A is lower triangular (its probabilities): the K loop of row tile mt stops at its diagonal
     int debug;               // QT_GEMM_DEBUG bit mask (timing experiments only; results are wrong when set)
     const __nv_bfloat16 *bias;      // [N] or null
     const __nv_bfloat16 *residual;  // same layout as C, or null
@@ -74,6 +77,21 @@ struct GemmParams {
 };
 
 enum { OUT_PLAIN = 0, OUT_FQ = 1, OUT_GLU = 2 };
+
+// Causal schedules (p.causal): the three roles of the kernel walk the same tile sequence, so they must agree on
+// which tiles exist and how many K blocks each has.
+__device__ __forceinline__ bool tile_skipped(int causal, uint32_t mt, uint32_t nt, int block_n)
+{
+    return causal == 1 && (int64_t)nt * block_n > (int64_t)mt * 128 + 127;  // first column past the last row
+}
+template <bool FP8>
+__device__ __forceinline__ int tile_k_blocks(const GemmParams &p, int causal, uint32_t mt)
+{
+    if (causal != 2) return p.k_blocks;
+    // rows of tile mt are < (mt + 1) * 128 and see k < (mt + 1) * 128: 128-byte K blocks hold 128 fp8 / 64 bf16 values
+    const int64_t kb = (int64_t)(mt + 1) * (FP8 ? 1 : 2);
+    return kb < p.k_blocks ? (int)kb : p.k_blocks;
+}
 
 __device__ __forceinline__ float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
@@ -153,6 +171,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int block_n = p.block_n;
+    // every thread reads the same (already final) flag: the three roles agree on the schedule
+    const int causal = (p.causal != 0 && (p.causal_flag == nullptr || *p.causal_flag != 0)) ? p.causal : 0;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -190,7 +210,9 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
                 const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
                 const int bi = (int)(b % p.batch_inner), bo = (int)(b / p.batch_inner);
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                if (tile_skipped(causal, mt, nt, block_n)) continue;
+                const int kbn = tile_k_blocks<FP8>(p, causal, mt);
+                for (int kb = 0; kb < kbn; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     trace(p, 0, tslot);
                     mbar_arrive_expect_tx(full_bar(stage), stage_tx);
@@ -213,11 +235,14 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int acc = 0, tslot = 0;
             uint32_t acc_phase = 0;
             for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const uint32_t mt = tile % p.m_tiles, nt = (tile / p.m_tiles) % p.n_tiles;
+                if (tile_skipped(causal, mt, nt, block_n)) continue;
+                const int kbn = tile_k_blocks<FP8>(p, causal, mt);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
                 trace(p, 1, tslot);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                for (int kb = 0; kb < kbn; ++kb) {
                     mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
                     trace(p, 1, tslot);
                     tcgen05_fence_after();
@@ -258,6 +283,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint32_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
             const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
             const int bi = (int)(b % p.batch_inner), bo = (int)(b / p.batch_inner);
+            if (tile_skipped(causal, mt, nt, block_n)) continue;
             const int64_t row0 = (int64_t)mt * BLOCK_M + quarter * 32;
             const int64_t row = row0 + lane;
             mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -568,6 +594,13 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.batch_inner = (uint32_t)inner;
     p.k_blocks = (int)((K * esz + ROW_BYTES - 1) / ROW_BYTES);
     p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, glu ? 128 : 64);
+    p.causal = d->causal;
+    p.causal_flag = d->causal_flag;
+    if (p.causal < 0 || p.causal > 2 || (p.causal == 1 && M != N) || (p.causal == 2 && M != K)) {
+        qt_set_error("qt_gemm_nt: causal = 1 needs a square output (M == N), causal = 2 a square A (M == K); got "
+                     "causal=%d M=%lld N=%lld K=%lld", p.causal, (long long)M, (long long)N, (long long)K);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
     if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
         p.debug = atoi(dbg);
         if (p.debug & 4) p.block_n = 128;

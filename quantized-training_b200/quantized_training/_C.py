@@ -50,7 +50,9 @@ EXPORTS = {
     "qt_softmax_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float,
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                      ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p,
-                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_causal_mask_check": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
     "qt_norm_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                   ctypes.c_int,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int,
@@ -282,6 +284,7 @@ class QtGemmDesc(ctypes.Structure):
         ("ldr", ctypes.c_int64), ("strideR_inner", ctypes.c_int64), ("strideR_outer", ctypes.c_int64),
         ("fq_fmt", ctypes.POINTER(QtFormat)), ("fq_lut", ctypes.c_void_p),
         ("out_type", ctypes.c_int32), ("glu", ctypes.c_int32),
+        ("causal", ctypes.c_int32), ("reserved", ctypes.c_int32), ("causal_flag", ctypes.c_void_p),
     ]
 
 
@@ -301,14 +304,16 @@ def _as4d(t, name, align):
 
 
 def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None,
-            fq=None, out_codes=False, glu=False):
+            fq=None, out_codes=False, glu=False, causal=0, causal_flag=None):
     """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
     a, b: bf16 (GEMM_BF16) or uint8 fp8 codes, up to two leading batch dimensions with arbitrary strides;
     bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional destination (any 16-byte
     aligned strides, e.g. a [B, H, S, D] view of a [B, S, H*D] buffer).
     fq: (fmt, lut) of a BARE fake-quantizer applied to the result in the epilogue (the consumer's input hook);
     out_codes: with an e4m3 / e5m2 `fq`, store one-byte fp8 codes (out is uint8); glu: b is a gate|up projection
-    interleaved in blocks of 64 rows and the result is activation(gate) * up with n / 2 columns."""
+    interleaved in blocks of 64 rows and the result is activation(gate) * up with n / 2 columns.
+    causal: CAUSAL_OUT_LOWER (skip output tiles above the diagonal) / CAUSAL_A_LOWER (a is lower triangular);
+    causal_flag: optional device int32 tensor (causal_mask_check) that gates the schedule on the device."""
     _require_cuda(a, "a")
     want = torch.uint8 if operand_type != GEMM_BF16 else torch.bfloat16
     if a.dtype != want or b.dtype != want:
@@ -345,6 +350,10 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     d.strideC_outer, d.strideC_inner = o4.stride(0), o4.stride(1)
     d.alpha = float(alpha)
     d.glu = 1 if glu else 0
+    d.causal = int(causal)
+    if causal_flag is not None:
+        assert causal_flag.dtype == torch.int32 and causal_flag.device == a.device
+        d.causal_flag = causal_flag.data_ptr()
     if fq is not None:
         fq_fmt, fq_lut = fq
         d.fq_fmt = ctypes.pointer(fq_fmt)
@@ -366,6 +375,8 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
 
 # ---- fused ops (qt_fused.cu): thin wrappers; argument checking beyond dtype/device lives in the C library --------
 FQ_PRE, FQ_MID, FQ_POST = 1, 2, 4
+SOFTMAX_CAUSAL = 16
+CAUSAL_OUT_LOWER, CAUSAL_A_LOWER = 1, 2
 NORM_RMS, NORM_LAYER = 0, 1
 OUT_BF16, OUT_E4M3, OUT_E5M2 = 0, 1, 2
 
@@ -402,8 +413,21 @@ def _resolve_out(out, fmt):
     return _codes_type(fmt) if t is None else t
 
 
+def causal_mask_check(mask3, flag=None):
+    """int32 device flag: 1 iff the additive bf16 mask [batches, rows, rows] is the standard causal mask.  Asynchronous
+    (no host read-back): hand the tensor to gemm_nt(causal_flag=...) / softmax_fq(causal_flag=...)."""
+    _bf16_cuda(mask3, "mask")
+    assert mask3.is_contiguous() and mask3.dim() == 3 and mask3.shape[1] == mask3.shape[2]
+    if flag is None:
+        flag = torch.empty(1, dtype=torch.int32, device=mask3.device)
+    with torch.cuda.device(mask3.device):
+        _check(lib().qt_causal_mask_check(mask3.data_ptr(), mask3.shape[0], mask3.shape[1], flag.data_ptr(),
+                                          _stream(mask3)))
+    return flag
+
+
 def softmax_fq(scores, probs, alpha, mask, rows_per_batch, mask_rows, mask_batches, fq_points, fmt,
-               scale_pre=None, scale_mid=None, scale_post=None, lut=None):
+               scale_pre=None, scale_mid=None, scale_post=None, lut=None, causal_flag=None):
     _bf16_cuda(scores, "scores")
     assert scores.is_contiguous() and probs.is_contiguous() and probs.shape == scores.shape
     cols = scores.shape[-1]
@@ -411,7 +435,7 @@ def softmax_fq(scores, probs, alpha, mask, rows_per_batch, mask_rows, mask_batch
         _check(lib().qt_softmax_fq(scores.data_ptr(), probs.data_ptr(), scores.numel() // cols, cols, float(alpha),
                                    _ptr(mask), rows_per_batch, mask_rows, mask_batches, fq_points,
                                    _resolve_out(probs, fmt), ctypes.byref(fmt), _ptr(scale_pre), _ptr(scale_mid),
-                                   _ptr(scale_post), _ptr(lut), _stream(scores)))
+                                   _ptr(scale_post), _ptr(lut), _ptr(causal_flag), _stream(scores)))
 
 
 def norm_fq(x, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale_post=None, lut=None, y_raw=None):

@@ -153,8 +153,10 @@ def norm(x2, weight, bias, eps, kind, pre, post, codes=False, want_raw=False):
     return y
 
 
-def softmax(scores, alpha, mask, pre, mid, post, codes=False):
-    """scores [B, H, Sq, Sk] contiguous; mask None or additive [Bm, 1, Sq or 1, >=Sk] (Bm in {1, B})."""
+def softmax(scores, alpha, mask, pre, mid, post, codes=False, causal=False, causal_flag=None):
+    """scores [B, H, Sq, Sk] contiguous; mask None or additive [Bm, 1, Sq or 1, >=Sk] (Bm in {1, B}).
+    causal=True: the caller has checked that `mask` is the standard causal mask (see _mask3) -- masked scores are not
+    read and probabilities beyond the row tile's diagonal block are not written."""
     B, H, Sq, Sk = scores.shape
     m3, mb, mrows = None, 1, Sq
     if mask is not None and mask.dtype == torch.bool:
@@ -171,7 +173,9 @@ def softmax(scores, alpha, mask, pre, mid, post, codes=False):
         mb, mrows = m3.shape[0], m3.shape[1]
     fmt, lut, (s_pre, s_mid, s_post) = _spec(pre, mid, post)
     probs = _out_like(scores, codes)
-    _C.softmax_fq(scores, probs, alpha, m3, H * Sq, mrows, mb, _flags(pre, mid, post), fmt, s_pre, s_mid, s_post, lut)
+    flags = _flags(pre, mid, post) | (_C.SOFTMAX_CAUSAL if causal else 0)
+    _C.softmax_fq(scores, probs, alpha, m3, H * Sq, mrows, mb, flags, fmt, s_pre, s_mid, s_post, lut,
+                  causal_flag=causal_flag)
     return probs
 
 
@@ -316,23 +320,52 @@ def attention(q4, k4, vt, scaling, mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c
         _C.attention_fq(q4, k4, vt, ctx.view(B, S, H, D).transpose(1, 2), scaling, m3, causal, points, fmt, lut,
                         qk_type=t_qk, pv_type=t_pv)
         return ctx.view(B * S, H * D)
-    scores = _C.gemm_nt(q4, k4, operand_type=t_qk)                              # [B, H, S, S]
-    probs = softmax(scores, scaling, mask, sc_in, sm_in, p_in, t_pv != _C.GEMM_BF16)
-    return _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D)
+    # Causal schedule: with the standard causal mask and no fake quant between the mask and the softmax, everything
+    # above the diagonal is exactly zero probability -- the score tiles there are not computed, the softmax neither
+    # reads nor writes them and the P x V reduction of a row tile stops at its diagonal block.
+    # Whether the mask IS the causal one is decided on the device (qt_causal_mask_check writes a flag the three kernels
+    # read): no host round trip, and a captured graph stays correct if a later replay carries a padding mask.
+    flag = None
+    if mask is not None and sm_in is None and Sk == S and S % 128 == 0 and os.environ.get("QT_CAUSAL", "1") != "0":
+        flag = _causal_flag(mask, S)
+    causal = flag is not None
+    scores = _C.gemm_nt(q4, k4, operand_type=t_qk, causal=_C.CAUSAL_OUT_LOWER if causal else 0, causal_flag=flag)
+    probs = softmax(scores, scaling, mask, sc_in, sm_in, p_in, t_pv != _C.GEMM_BF16, causal=causal, causal_flag=flag)
+    return _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D, flag)
 
 
-def _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D):
+_FLAG_CACHE = {}
+
+
+def _causal_flag(mask, S):
+    """Device flag for `mask` ([Bm, 1, S, S] additive bf16), computed once per mask tensor (all layers of a forward
+    see the same object); None when the mask cannot be the square causal one."""
+    if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] != S or mask.shape[3] != S \
+            or mask.dtype != torch.bfloat16 or not mask[:, 0].is_contiguous():
+        return None
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape))
+    hit = _FLAG_CACHE.get("last")
+    if hit is None or hit[0] != key:
+        hit = (key, _C.causal_mask_check(mask[:, 0]), mask)   # keeps the mask alive: its address is the key
+        _FLAG_CACHE["last"] = hit
+    return hit[1]
+
+
+def _attention_context(probs, vt, t_pv, o_in, c_o, B, S, H, D, causal_flag=None):
     """probabilities x values written straight into [B*S, H*D].  The output projection's input fake quant is applied
     by the product's epilogue only for long reductions: at S = 1024 the product is epilogue-bound (128 x 128 tiles,
     16 k-blocks) and the table lookups of the re-quantization cost more there than the separate 7 us pass
     (measured: 26.6 vs 14 + 6.7 us per Llama-2-7B layer)."""
+    causal = causal_flag is not None
     if o_in is None or (o_in.qscheme is None and S >= 4096):
         ctx = torch.empty(B, S, H * D, dtype=torch.uint8 if c_o else torch.bfloat16, device=probs.device)
         _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv,
-                   fq=_epilogue_fq(o_in), out_codes=c_o)
+                   fq=_epilogue_fq(o_in), out_codes=c_o, causal=_C.CAUSAL_A_LOWER if causal else 0,
+                   causal_flag=causal_flag)
         return ctx.view(B * S, H * D)
     ctx = torch.empty(B, S, H * D, dtype=torch.bfloat16, device=probs.device)
-    _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv)
+    _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_pv,
+               causal=_C.CAUSAL_A_LOWER if causal else 0, causal_flag=causal_flag)
     return fake_quant(ctx.view(B * S, H * D), o_in, c_o)
 
 

@@ -281,3 +281,83 @@ def test_attention_core_matches_the_three_kernel_chain(oracle, spec, codes, B, H
     rel = float((ctx.double() - ctx_ref.double()).norm() / ctx_ref.double().norm())
     assert rel <= 1e-2, f"relative error {rel:.4f}, identical {float(same.float().mean()):.4f}"
     assert float(same.float().mean()) >= 0.98
+
+
+@pytest.mark.parametrize("spec,codes", [("posit8_1", False), ("e4m3", False), ("e4m3", True)])
+@pytest.mark.parametrize("B,H,S,D", [(1, 4, 1024, 128), (2, 3, 384, 64), (1, 2, 128, 128), (1, 1, 2048, 64)])
+def test_causal_schedule_is_bit_identical(spec, codes, B, H, S, D):
+    """The causal schedule of the three-kernel chain (QT_CAUSAL_OUT_LOWER scores, QT_SOFTMAX_CAUSAL,
+    QT_CAUSAL_A_LOWER context) skips work whose contribution is exactly zero: the context equals the full
+    computation bit for bit, computed score tiles are identical, and so are the probabilities that get written."""
+    if codes and D != 128:
+        pytest.skip("fp8 q / k rows are kept a multiple of 128 bytes")
+    torch.manual_seed(S * 7 + D)
+    m = qt.FusedAmaxObsFakeQuantize(spec, device=DEV)
+    fmt, lut = m._fmt, m.lut
+    qkv = m((torch.randn(B, S, 3 * H * D, device=DEV) * 1.5).bfloat16())
+    vt = torch.empty(B, H, D, S, device=DEV, dtype=torch.bfloat16)
+    _C.fq_transpose(qkv[..., 2 * H * D:].view(B, S, H, D), vt, 0, fmt, lut=lut)
+    t_op = _C.GEMM_BF16
+    if codes:
+        tdt = torch.float8_e4m3fn
+        enc = lambda t: t.contiguous().to(tdt).view(torch.uint8)
+        qc = enc(qkv[..., :2 * H * D])
+        q = qc[..., :H * D].view(B, S, H, D).transpose(1, 2)
+        k = qc[..., H * D:].view(B, S, H, D).transpose(1, 2)
+        vt = enc(vt)
+        t_op = _C.GEMM_E4M3
+    else:
+        q = qkv[..., :H * D].view(B, S, H, D).transpose(1, 2)
+        k = qkv[..., H * D:2 * H * D].view(B, S, H, D).transpose(1, 2)
+    mask = torch.full((S, S), torch.finfo(torch.bfloat16).min, device=DEV, dtype=torch.bfloat16).triu(1)[None].contiguous()
+    alpha = D ** -0.5
+
+    def chain(causal, mask=mask, flag=None):
+        scores = torch.full((B, H, S, S), float("nan"), device=DEV, dtype=torch.bfloat16)  # poison what is skipped
+        _C.gemm_nt(q, k, out=scores, operand_type=t_op, causal=_C.CAUSAL_OUT_LOWER if causal else 0, causal_flag=flag)
+        probs = torch.full((B, H, S, S), 77 if codes else float("nan"), device=DEV,
+                           dtype=torch.uint8 if codes else torch.bfloat16)
+        _C.softmax_fq(scores, probs, alpha, mask, H * S, S, 1, _C.FQ_POST | (_C.SOFTMAX_CAUSAL if causal else 0),
+                      fmt, lut=lut, causal_flag=flag)
+        ctx = torch.empty(B, S, H * D, device=DEV, dtype=torch.bfloat16)
+        _C.gemm_nt(probs, vt, out=ctx.view(B, S, H, D).transpose(1, 2), operand_type=t_op,
+                   causal=_C.CAUSAL_A_LOWER if causal else 0, causal_flag=flag)
+        return scores, probs, ctx
+
+    s0, p0, c0 = chain(False)
+    flag = _C.causal_mask_check(mask)
+    assert int(flag.item()) == 1
+    s1, p1, c1 = chain(True, flag=flag)
+    # a mask that is NOT the causal one switches the schedule off on the device: same results as the full computation
+    other = mask.clone()
+    other[0, S // 2, 3] = torch.finfo(torch.bfloat16).min
+    flag0 = _C.causal_mask_check(other)
+    assert int(flag0.item()) == 0
+    sa, pa, ca = chain(False, mask=other)
+    sb, pb_, cb = chain(True, mask=other, flag=flag0)
+    assert torch.equal(bits(cb), bits(ca)) and torch.equal(bits(sb), bits(sa))
+    assert torch.equal(pb_ if codes else bits(pb_), pa if codes else bits(pa))
+    assert torch.equal(bits(c1), bits(c0))
+    assert not bool(torch.isnan(c1.float()).any())
+    rows = torch.arange(S, device=DEV)[:, None]
+    cols = torch.arange(S, device=DEV)[None, :]
+    lower = cols <= rows
+    assert torch.equal(bits(s1)[..., lower], bits(s0)[..., lower])
+    written = cols < ((rows // 128) + 1) * 128
+    pb = (lambda t: t) if codes else bits
+    assert torch.equal(pb(p1)[..., written], pb(p0)[..., written])
+    if S > 128:  # something was actually skipped
+        assert bool((pb(p1)[..., ~written] != pb(p0)[..., ~written]).any())
+
+
+def test_causal_flags_are_validated():
+    a = torch.zeros(2, 128, 256, device=DEV, dtype=torch.bfloat16)
+    b = torch.zeros(2, 256, 256, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="causal"):
+        _C.gemm_nt(a, b, causal=_C.CAUSAL_OUT_LOWER)          # M = 128, N = 256: not a square score matrix
+    with pytest.raises(ValueError, match="causal"):
+        _C.gemm_nt(a, b, causal=_C.CAUSAL_A_LOWER)            # A is 128 x 256: not a square probability matrix
+    m = qt.FusedAmaxObsFakeQuantize("e4m3", device=DEV)
+    sc = torch.zeros(1, 1, 128, 128, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="CAUSAL"):
+        _C.softmax_fq(sc, torch.empty_like(sc), 1.0, None, 128, 128, 1, _C.FQ_POST | _C.SOFTMAX_CAUSAL, m._fmt, lut=m.lut)
