@@ -173,6 +173,40 @@ int qt_fq_block(const qt_block_desc_t *desc, void *stream);
  * QT_POW2_TABLE_WORDS uint32. */
 int qt_block_pow2_table_host(int elem_type, uint32_t *table_host);
 
+/* ---- operator surface: torch.ops.quantized_ops.{vmap, quantize, dequantize} (decomposed.py:143-262) ----------
+ * The reference's PT2E graphs call these ops with an explicit 65 536-entry table tensor (`qmap`), so the table may
+ * be ANY codebook (e.g. NF4) -- this entry point therefore gathers from the caller's table instead of using the
+ * bitwise rounders.  x, y, scale, zero_point all have the element type `elem_type` (the result dtype of the
+ * reference's `input / scale` after torch's type promotion; the binding promotes).
+ *   QT_TABLE_QUANTIZE    u = x / s [+ zp];  y = table_a ? table_a[idx(u)] : u            (decomposed.py:171-210)
+ *   QT_TABLE_DEQUANTIZE  v = table_a ? table_a[idx(x)] : x;  d = zp ? (v - zp) * s : v * s;
+ *                        y = table_b ? table_b[idx(d)] : d                                (:218-262)
+ * idx(v) = the bf16 bit pattern of v; fp32 values are truncated to bf16 with round-to-odd first (vmap, :146-163).
+ * Tables: uint16[65536] of bf16 bit patterns on the device, or NULL.  NaN results of the arithmetic carry the bit
+ * pattern the reference's CPU run produces (bf16: 0x7FC0; fp32: first NaN operand quieted, else 0xFFC00000), so a
+ * table that tells NaN patterns apart is indexed identically.  scale / zero_point: one value (scalar_params != 0) or one value per block of the grid
+ * [d0, ceil(n1/bs), d1, ceil(n2/bs) or n2, d2] (`expand`, decomposed.py:127-140), tensor seen as [d0,n1,d1,n2,d2]
+ * like qt_fq_block. */
+#define QT_TABLE_QUANTIZE 0
+#define QT_TABLE_DEQUANTIZE 1
+#define QT_TABLE_LOOKUP 2 /* y = table_a[idx(x)] on the raw bits (vmap): scale / zero_point unused */
+typedef struct qt_table_op_desc {
+    const void *x;
+    void *y;
+    int32_t elem_type;
+    int32_t op;
+    int64_t d0, n1, d1, n2, d2;
+    int32_t block_size;
+    int32_t block_axis2;
+    int32_t scalar_params;
+    int32_t reserved;
+    const void *scale;
+    const void *zero_point; /* or NULL */
+    const void *table_a;
+    const void *table_b;
+} qt_table_op_desc_t;
+int qt_table_op(const qt_table_op_desc_t *desc, void *stream);
+
 /* ---- quantized GEMM / batched GEMM (tcgen05 + TMEM + TMA) -------------------------------------------
  * C[b, m, n] = epilogue(alpha * sum_k A[b, m, k] * B[b, n, k]),  fp32 accumulation, C in bf16.
  * Replaces F.linear(x_q, W_q, bias) of the QAT Linear (modules/qat/linear.py:40-41; A = activations [M, K],

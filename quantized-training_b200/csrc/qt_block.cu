@@ -864,6 +864,82 @@ void launch_mx(const BlockJob &j, const typename R::Params &p)
     launch_generic<R, F32, false>(j, p);
 }
 
+// ----------------------------------------------------------------------------- table ops (operator surface)
+// torch.ops.quantized_ops.{vmap, quantize, dequantize} of the reference (decomposed.py:143-262) with a caller-supplied
+// 65 536-entry table (any codebook, e.g. one this library has no bitwise rounder for):
+//   QUANT    u = x / s [+ zp];  y = table ? table[idx(u)] : u
+//   DEQUANT  v = table_in ? table_in[idx(x)] : x;  d = zp ? (v - zp) * s : v * s;  y = table_out ? table_out[idx(d)] : d
+// idx() = the bf16 bits (fp32: truncated with round-to-odd); s / zp per block of the grid `D` (or one value).
+// The 128 KB table is read through L1 / L2 (a gather; the formats of this library never need it).
+__device__ __forceinline__ float table_lookup(const uint16_t *table, bool f32, float v)
+{
+    if (!table) return v;
+    const uint32_t b = __float_as_uint(v);
+    const uint32_t idx = f32 ? (f32_to_bf16_rto_hi(b) >> 16) : (b >> 16);
+    return __uint_as_float((uint32_t)__ldg(table + idx) << 16);
+}
+
+// One arithmetic result in the tensor's dtype with the NaN the reference's CPU run produces, so that even a table
+// that distinguishes NaN patterns is indexed identically: bf16 tensors -- c10::BFloat16's conversion turns every
+// NaN into 0x7FC0; fp32 tensors -- SSE semantics: the first NaN operand, quieted, else the default NaN 0xFFC00000.
+template <bool F32>
+__device__ __forceinline__ float op_result(float a, float b, float r)
+{
+    if (r == r) return to_dtype<F32>(r);
+    if (!F32) return __uint_as_float(0x7FC00000u);
+    if (a != a) return __uint_as_float(__float_as_uint(a) | 0x00400000u);
+    if (b != b) return __uint_as_float(__float_as_uint(b) | 0x00400000u);
+    return __uint_as_float(0xFFC00000u);
+}
+
+template <bool F32, int OP>
+__global__ void __launch_bounds__(256)
+table_op_kernel(const void *__restrict__ x, void *__restrict__ y, size_t total, const __grid_constant__ BlockDims D,
+                const void *__restrict__ scale, const void *__restrict__ zp, int scalar_params,
+                const uint16_t *__restrict__ table_a, const uint16_t *__restrict__ table_b)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float v = load_elem(x, F32, i);
+        float out;
+        if (OP == QT_TABLE_LOOKUP) {
+            out = table_lookup(table_a, F32, v);
+        } else {
+            size_t bi = 0;
+            if (!scalar_params) {
+                size_t r = i;
+                const size_t i4 = r % D.d2; r /= D.d2;
+                const size_t j2 = r % D.n2; r /= D.n2;
+                const size_t i2 = r % D.d1; r /= D.d1;
+                const size_t j1 = r % D.n1;
+                const size_t i0 = r / D.n1;
+                bi = (((i0 * D.nb1 + j1 / D.bs) * D.d1 + i2) * D.nb2 + j2 / D.bs2) * D.d2 + i4;
+            }
+            const float s = load_elem(scale, F32, bi);
+            if (OP == QT_TABLE_DEQUANTIZE) {
+                float d = table_lookup(table_a, F32, v);
+                if (zp) {
+                    const float z = load_elem(zp, F32, bi);
+                    d = op_result<F32>(d, z, __fsub_rn(d, z));
+                }
+                d = op_result<F32>(d, s, __fmul_rn(d, s));
+                out = table_lookup(table_b, F32, d);
+            } else {
+                float u = op_result<F32>(v, s, __fdiv_rn(v, s));
+                if (zp) {
+                    const float z = load_elem(zp, F32, bi);
+                    u = op_result<F32>(u, z, __fadd_rn(u, z));
+                }
+                out = table_lookup(table_a, F32, u);
+            }
+        }
+        if (F32)
+            static_cast<float *>(y)[i] = out;
+        else
+            static_cast<uint16_t *>(y)[i] = (uint16_t)(__float_as_uint(out) >> 16);
+    }
+}
+
 }  // namespace
 
 extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
@@ -967,5 +1043,49 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
     if (rc != QT_OK) return rc;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "block-scaled fake-quant kernel launch");
+    return QT_OK;
+}
+
+extern "C" int qt_table_op(const qt_table_op_desc_t *d, void *stream)
+{
+    if (!d) {
+        qt_set_error("qt_table_op: desc is NULL");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if ((d->elem_type != QT_BF16 && d->elem_type != QT_F32) || (d->op != QT_TABLE_QUANTIZE && d->op != QT_TABLE_DEQUANTIZE && d->op != QT_TABLE_LOOKUP)) {
+        qt_set_error("qt_table_op: bad elem_type %d or op %d", d->elem_type, d->op);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (d->d0 < 0 || d->n1 < 0 || d->d1 < 0 || d->n2 < 0 || d->d2 < 0 || (!d->scalar_params && d->block_size < 1)) {
+        qt_set_error("qt_table_op: negative dimension or block_size < 1");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    BlockDims D;
+    D.d0 = (size_t)d->d0; D.n1 = (size_t)d->n1; D.d1 = (size_t)d->d1; D.n2 = (size_t)d->n2; D.d2 = (size_t)d->d2;
+    D.bs = d->scalar_params ? 1u : (uint32_t)d->block_size;
+    D.bs2 = d->block_axis2 ? D.bs : 1u;
+    D.nb1 = (D.n1 + D.bs - 1) / D.bs;
+    D.nb2 = (D.n2 + D.bs2 - 1) / D.bs2;
+    const size_t total = D.d0 * D.n1 * D.d1 * D.n2 * D.d2;
+    if (total == 0) return QT_OK;
+    if (!d->x || !d->y || (!d->scale && d->op != QT_TABLE_LOOKUP)) {
+        qt_set_error("qt_table_op: x, y and scale must not be NULL");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (num_sms() == 0) return no_device();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = grid_for((total + 255) / 256, 8);
+    const uint16_t *ta = static_cast<const uint16_t *>(d->table_a), *tb = static_cast<const uint16_t *>(d->table_b);
+    const bool f32 = d->elem_type == QT_F32;
+#define QT_TABLE_LAUNCH(F, O) \
+    table_op_kernel<F, O><<<grid, 256, 0, st>>>(d->x, d->y, total, D, d->scale, d->zero_point, d->scalar_params, ta, tb)
+    switch (d->op) {
+    case QT_TABLE_QUANTIZE: f32 ? QT_TABLE_LAUNCH(true, QT_TABLE_QUANTIZE) : QT_TABLE_LAUNCH(false, QT_TABLE_QUANTIZE); break;
+    case QT_TABLE_DEQUANTIZE: f32 ? QT_TABLE_LAUNCH(true, QT_TABLE_DEQUANTIZE) : QT_TABLE_LAUNCH(false, QT_TABLE_DEQUANTIZE); break;
+    default: f32 ? QT_TABLE_LAUNCH(true, QT_TABLE_LOOKUP) : QT_TABLE_LAUNCH(false, QT_TABLE_LOOKUP); break;
+    }
+#undef QT_TABLE_LAUNCH
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "table op kernel launch");
     return QT_OK;
 }

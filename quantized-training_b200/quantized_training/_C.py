@@ -72,6 +72,7 @@ EXPORTS = {
     "qt_attention_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qt_fq_block": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qt_block_pow2_table_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
+    "qt_table_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qt_amax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                ctypes.c_void_p, ctypes.c_void_p]),
 }
@@ -263,6 +264,47 @@ def fq_block(x, y, dims, block_size, block_axis2, qscheme, quant_min, quant_max,
     d.zero_point = zero_point.data_ptr() if zero_point is not None else None
     with torch.cuda.device(x.device):
         _check(lib().qt_fq_block(ctypes.byref(d), _stream(x)))
+
+
+class QtTableOpDesc(ctypes.Structure):
+    """qt_table_op_desc_t"""
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("elem_type", ctypes.c_int32), ("op", ctypes.c_int32),
+        ("d0", ctypes.c_int64), ("n1", ctypes.c_int64), ("d1", ctypes.c_int64), ("n2", ctypes.c_int64),
+        ("d2", ctypes.c_int64),
+        ("block_size", ctypes.c_int32), ("block_axis2", ctypes.c_int32), ("scalar_params", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("scale", ctypes.c_void_p), ("zero_point", ctypes.c_void_p), ("table_a", ctypes.c_void_p),
+        ("table_b", ctypes.c_void_p),
+    ]
+
+
+TABLE_QUANTIZE, TABLE_DEQUANTIZE, TABLE_LOOKUP = 0, 1, 2
+
+
+def _ptr_or_none(t):
+    return t.data_ptr() if t is not None else None
+
+
+def table_op(op, x, y, dims, block_size, block_axis2, scale, zero_point=None, table_a=None, table_b=None):
+    """qt_table_op: quantize / dequantize through caller-supplied 65 536-entry bf16 tables (int16 / bf16 tensors).
+    x, y, scale, zero_point share one dtype (bf16 or fp32); scale.numel() == 1 means a scalar scale."""
+    _require_cuda(x, "input")
+    assert x.is_contiguous() and y.is_contiguous() and y.dtype == x.dtype and scale.dtype == x.dtype
+    assert scale.is_contiguous() and (zero_point is None or (zero_point.dtype == x.dtype and zero_point.is_contiguous()
+                                                             and zero_point.numel() == scale.numel()))
+    for t in (table_a, table_b):
+        assert t is None or (t.numel() == 65536 and t.element_size() == 2 and t.is_contiguous() and t.device == x.device)
+    d = QtTableOpDesc()
+    d.x, d.y, d.elem_type, d.op = x.data_ptr(), y.data_ptr(), _elem_type(x), int(op)
+    d.d0, d.n1, d.d1, d.n2, d.d2 = (int(v) for v in dims)
+    d.block_size, d.block_axis2 = int(block_size), int(bool(block_axis2))
+    d.scalar_params = int(scale.numel() == 1)
+    d.scale = scale.data_ptr()
+    d.zero_point = _ptr_or_none(zero_point)
+    d.table_a, d.table_b = _ptr_or_none(table_a), _ptr_or_none(table_b)
+    with torch.cuda.device(x.device):
+        _check(lib().qt_table_op(ctypes.byref(d), _stream(x)))
 
 
 GEMM_BF16, GEMM_E4M3, GEMM_E5M2, GEMM_E4M3_E5M2, GEMM_E5M2_E4M3 = range(5)

@@ -6,6 +6,7 @@ executed by hand-written sm_100a kernels behind a C ABI (include/qt_b200.h).
 CUDA only: there is no CPU or eager fallback.
 """
 from . import _C
+from . import decomposed  # registers torch.ops.quantized_ops.{vmap, quantize, dequantize} (CUDA)
 from .fake_quantize import FusedAmaxObsFakeQuantize, get_quantization_map
 from .host_io import HostPipeline, fake_quantize_host
 from .qconfig import QConfig, get_qconfig

@@ -43,6 +43,7 @@ def golden():
         fq = np.load(os.path.join(GOLDEN, "fq_cases.npz"))
         mx = np.load(os.path.join(GOLDEN, "mx_cases.npz"))
         mx_scale = np.load(os.path.join(GOLDEN, "mx_scale.npz"))
+        ops = np.load(os.path.join(GOLDEN, "ops_cases.npz"))
         with open(os.path.join(GOLDEN, "manifest.json")) as f:
             manifest = json.load(f)
         with open(os.path.join(GOLDEN, "mx_manifest.json")) as f:

@@ -143,6 +143,64 @@ def gen_scale_fn(ref):
     return out
 
 
+def gen_ops(ref):
+    """torch.ops.quantized_ops.{vmap, quantize, dequantize} of the reference on CPU (decomposed.py:143-262):
+    inputs, parameters, tables and outputs of a few calls that cover block grids, type promotion, zero points,
+    both tables of dequantize and codebooks this library has no bitwise rounder for (NF4, a random table)."""
+    D = ref.decomposed
+    gen = torch.Generator().manual_seed(77)
+    out, manifest = {}, []
+
+    def table(name):
+        t = ref.fq.get_quantization_map(name)
+        if isinstance(t, tuple):
+            t = t[1][t[0]]
+        return t.to(torch.bfloat16)
+
+    rnd_table = torch.randint(0, 65536, (65536,), generator=gen, dtype=torch.int32).to(torch.int16).view(torch.bfloat16)
+    tabs = {"int6": table("int6"), "nf4": table("nf4"), "fp8_e4m3": table("fp8_e4m3"), "random": rnd_table}
+    for k, t in tabs.items():
+        out[f"table/{k}"] = G.bits16(t)
+
+    def rec(name, op, x, scale, zp, axes, bs, ta, tb, y):
+        out[f"{name}/x"] = G.tensor_bits(x)
+        out[f"{name}/scale"] = G.tensor_bits(scale)
+        if zp is not None:
+            out[f"{name}/zp"] = G.tensor_bits(zp)
+        out[f"{name}/y"] = G.tensor_bits(y)
+        dn = lambda t: "bf16" if t.dtype == torch.bfloat16 else "f32"
+        manifest.append({"name": name, "op": op, "x_dtype": dn(x), "x_shape": list(x.shape), "scale_dtype": dn(scale),
+                         "scale_shape": list(scale.shape), "zp": zp is not None, "zp_dtype": None if zp is None else dn(zp),
+                         "axes": axes, "block_size": bs, "table_a": ta, "table_b": tb, "y_dtype": dn(y)})
+
+    x = (torch.randn(8, 128, generator=gen) * 3).to(torch.bfloat16)
+    x[0, :5] = torch.tensor([float("nan"), float("inf"), -float("inf"), 0.0, -0.0]).to(torch.bfloat16)
+    s = (torch.rand(8, 4, generator=gen) * 0.2 + 0.01).to(torch.bfloat16)
+    rec("q_bf16_blocks_int6", "quantize", x, s, None, [-1], 32, "int6", None, D.quantize(x, s, None, [-1], 32, tabs["int6"]))
+    rec("q_bf16_blocks_nf4", "quantize", x, s * 20, None, [-1], 32, "nf4", None, D.quantize(x, s * 20, None, [-1], 32, tabs["nf4"]))
+    s32 = s.float() * 1.00123
+    zp32 = torch.rand(8, 4, generator=gen) * 4 - 2
+    rec("q_bf16_f32scale_zp", "quantize", x, s32, zp32, [-1], 32, "int6", None, D.quantize(x, s32, zp32, [-1], 32, tabs["int6"]))
+    xf = torch.randn(5, 70, generator=gen) * 40
+    s0 = torch.tensor(0.37)
+    rec("q_f32_scalar_fp8", "quantize", xf, s0, None, None, None, "fp8_e4m3", None, D.quantize(xf, s0, None, None, None, tabs["fp8_e4m3"]))
+    x3 = (torch.randn(2, 70, 16, generator=gen) * 2).to(torch.bfloat16)
+    sg = (torch.rand(2, 3, 16, generator=gen) * 0.5 + 0.05).to(torch.bfloat16)
+    zg = (torch.rand(2, 3, 16, generator=gen) * 3).to(torch.bfloat16)
+    rec("dq_bf16_ax1_tables", "dequantize", x3, sg, zg, [-2], 32, "int6", "fp8_e4m3",
+        D.dequantize(x3, sg, zg, [-2], 32, tabs["int6"], tabs["fp8_e4m3"]))
+    rec("dq_bf16_scalar", "dequantize", x3, torch.tensor(0.25, dtype=torch.bfloat16), None, None, None, None, None,
+        D.dequantize(x3, torch.tensor(0.25, dtype=torch.bfloat16)))
+    x2 = (torch.randn(40, 48, generator=gen)).to(torch.bfloat16)
+    s2 = (torch.rand(3, 3, generator=gen) * 0.3 + 0.02).to(torch.bfloat16)
+    rec("q_bf16_2d_blocks", "quantize", x2, s2, None, [-2, -1], 16, "int6", None, D.quantize(x2, s2, None, [-2, -1], 16, tabs["int6"]))
+    allb = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.bfloat16)
+    rec("vmap_bf16_random", "vmap", allb, torch.ones(1, dtype=torch.bfloat16), None, None, None, "random", None, D.vmap(allb, tabs["random"]))
+    xr = torch.randn(3001, generator=gen) * 100
+    rec("vmap_f32_random", "vmap", xr, torch.ones(1), None, None, None, "random", None, D.vmap(xr, tabs["random"]))
+    return out, manifest
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -151,11 +209,13 @@ def main():
     np.savez_compressed(os.path.join(HERE, "mx_cases.npz"), **cases)
     sc = gen_scale_fn(ref)
     np.savez_compressed(os.path.join(HERE, "mx_scale.npz"), **sc)
+    ops, ops_manifest = gen_ops(ref)
+    np.savez_compressed(os.path.join(HERE, "ops_cases.npz"), **ops)
     with open(os.path.join(HERE, "mx_manifest.json"), "w") as f:
-        json.dump({"generator": "tests/golden/gen_mx_golden.py",
+        json.dump({"ops": ops_manifest, "generator": "tests/golden/gen_mx_golden.py",
                    "reference": "jeffreyyu0602/quantized-training @ /root/reference (CPU, torch %s)" % torch.__version__,
                    "cases": manifest, "scale_fn_quant_max": [448.0, 31.0, 6.0, 7.5, 32767.0]}, f, indent=1)
-    for fn in ["mx_cases.npz", "mx_scale.npz", "mx_manifest.json"]:
+    for fn in ["mx_cases.npz", "mx_scale.npz", "ops_cases.npz", "mx_manifest.json"]:
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 
 

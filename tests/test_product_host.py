@@ -203,3 +203,14 @@ def test_block_scaled_module_surface():
         qt.QuantizationSpec.from_str("int6,qs=microscaling,ax=-1")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(4, 64, dtype=torch.bfloat16))
+
+
+def test_operator_surface_is_registered():
+    """torch.ops.quantized_ops.{vmap, quantize, dequantize}: same schemas as decomposed.py:143,166-169,213-216; CUDA
+    implementations only (a CPU call fails in the dispatcher, no silent fallback)."""
+    for name in ("vmap", "quantize", "dequantize"):
+        assert hasattr(torch.ops.quantized_ops, name)
+    s = str(torch.ops.quantized_ops.quantize.default._schema)
+    assert "Tensor? zero_point=None" in s and "int? block_size=None" in s and "Tensor? qmap=None" in s
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.quantized_ops.vmap(torch.zeros(8, dtype=torch.bfloat16), torch.zeros(65536, dtype=torch.bfloat16))
