@@ -218,7 +218,7 @@ __device__ __forceinline__ void mx_flat_tile(const R &round, const typename Fast
 }
 
 template <class R, bool F32, int LANES>
-__global__ void __launch_bounds__(R::kThreads, R::kTable ? R::kMinCtas : 4)
+__global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
 mx_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
                const __grid_constant__ typename R::Params params, const __grid_constant__ BlockParams bp,
                float *__restrict__ scale_out)
