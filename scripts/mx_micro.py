@@ -19,6 +19,8 @@ CASES = [
     ("int6,qs=microscaling,bs=64,ax=0,scale=fp8_e5m3", False),
     ("fp4_e2m1,qs=microscaling,bs=32,ax=0", True),
     ("int6,qs=microscaling,bs=16,ax=(0,1),scale=fp8_e5m3", False),
+    ("int6,qs=microscaling,bs=64,ax=(0,1),scale=fp8_e5m3", False),
+    ("fp4_e2m1,qs=microscaling,bs=32,ax=(0,1)", True),
     ("uint4,qs=group_wise_affine,bs=64,ax=-1", False),
     ("uint2,qs=group_wise_affine,bs=64,ax=0,scale=fp8_e5m3", False),
 ]

@@ -104,7 +104,9 @@ MX_SWEEP = [
     # cols kernel: RPT 1..16, ragged n, inner not a multiple of 32 vectors
     ((4, 64, 256), -2, 8), ((4, 64, 256), 1, 16), ((4, 96, 256), 1, 32), ((2, 200, 64), 1, 64),
     ((2, 300, 40), 1, 128), ((160, 1024), 0, 32), ((7, 70, 8), 1, 32),
-    # generic kernels: two tiled axes, ragged last axis, odd block sizes, tiny inner
+    # tile kernel: two tiled axes (the last two), ragged rows / columns
+    ((2, 3, 128, 256), (-2, -1), 64), ((3, 100, 72), (-2, -1), 32), ((1, 256, 512), (-2, -1), 128), ((4, 40, 64), (-2, -1), 8),
+    # generic kernels: ragged last axis, odd block sizes, tiny inner, non-adjacent tiled axes
     ((2, 3, 48, 64), (-2, -1), 16), ((2, 40, 50), (-2, -1), 16), ((5, 70), -1, 32), ((6, 40, 3), 1, 8),
     ((9, 33), -1, 5), ((3, 50, 6), (0, 2), 4), ((31,), 0, 64),
 ]
