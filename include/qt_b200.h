@@ -94,6 +94,10 @@ int qt_lut_build_host(const qt_format_t *fmt, void *lut_host);
  *   sf = amax / quant_max, kept only if amax > 0 and finite; optional 2^ceil(log2 sf)
  *   scale[c] = sf
  * Call it before qt_fq_forward / qt_amax with amax_out = history (slot 0). */
+/* HOST evaluation of the force_scale_power_of_two rounding the device applies: 2 ** ceil(log2(sf)) as the
+ * reference computes it in fp32 (fake_quantize.py:240-241), restated without log2 (see qt_round.h) -- for tests. */
+float qt_scale_pow2_host(float sf);
+
 int qt_scale_update(float *history, int amax_history_len, size_t channels, float *scale,
                     float quant_max, int force_scale_power_of_two, void *stream);
 

@@ -370,3 +370,9 @@ int qt_tiny_safe(const QtRound &P)
     }
     return 1;
 }
+
+extern "C" float qt_scale_pow2_host(float sf)
+{
+    const float p2 = qt_pow2_ceil(sf);
+    return p2 >= 0.0f ? p2 : exp2f(ceilf(log2f(sf)));
+}

@@ -481,7 +481,10 @@ __global__ void scale_update_kernel(float *__restrict__ history, int ahl, size_t
     float sf = __fdiv_rn(amax, quant_max);
     const bool keep = (amax > 0.0f) && (m < 0x7F800000u);
     if (!keep) sf = scale[c];
-    if (pow2) sf = exp2f(ceilf(log2f(sf)));
+    if (pow2) {
+        const float p2 = qt_pow2_ceil(sf);
+        sf = p2 >= 0.0f ? p2 : exp2f(ceilf(log2f(sf)));  // zero / subnormal / non-finite scales: libm semantics
+    }
     scale[c] = sf;
 }
 

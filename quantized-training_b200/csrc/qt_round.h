@@ -176,3 +176,32 @@ QT_HD uint32_t qt_round_dyn(const QtRound &P, uint32_t u)
     default: return u;
     }
 }
+
+// ---- force_scale_power_of_two of the per-tensor / per-channel scheme (fake_quantize.py:240-241) ---------------
+// scale = 2 ** ceil(log2(sf)) evaluated in fp32 by the reference.  log2() of sf = 2^e (1 + m 2^-23) is e + t with
+// t ~ 1.4427 m 2^-23, and fl32(e + t) == e whenever t is below half an ulp of e: for |e| >= 4 the first few
+// mantissas above a power of two come out as ceil = e, not e + 1.  Restated exactly (no log2 on the device, whose
+// last-ulp behaviour differs from the host's libm): with |e| in [2^k, 2^(k+1)), ceil = e iff m < ln2 * 2^(k-1)
+// (ln2 * 2^(k-2) when e is a negative power of two, where the spacing below |e| is half as wide).
+// Checked against libm on every exponent in tests (qt_scale_pow2_host).
+QT_HD float qt_pow2_ceil(float sf)
+{
+    const uint32_t b = qt_f2bits(sf);
+    const uint32_t ef = (b >> 23) & 0xFFu, m = b & 0x7FFFFFu;
+    if ((b >> 31) || ef == 0u || ef == 255u) return -1.0f;  // caller falls back (sign, zero / subnormal, Inf / NaN)
+    int e = (int)ef - 127;
+    if (m != 0u) {
+        const int ae = e < 0 ? -e : e;
+        bool stays = false;
+        if (ae >= 4) {
+            int k = 2;
+            while ((2 << k) <= ae) ++k;                       // ae in [2^k, 2^(k+1))
+            float thr = 0.69314718f * (float)(1 << (k - 1));  // ln2 * 2^(k-1)
+            if (e < 0 && ae == (1 << k)) thr *= 0.5f;
+            stays = (float)m < thr;
+        }
+        if (!stays) ++e;
+    }
+    if (e > 127) return qt_bits2f(0x7F800000u);
+    return qt_bits2f((uint32_t)(e + 127) << 23);  // e >= -126 here
+}

@@ -35,6 +35,7 @@ EXPORTS = {
                                          ctypes.POINTER(ctypes.c_double)]),
     "qt_table_host": (ctypes.c_int, [ctypes.POINTER(QtFormat), ctypes.c_void_p]),
     "qt_lut_build_host": (ctypes.c_int, [ctypes.POINTER(QtFormat), ctypes.c_void_p]),
+    "qt_scale_pow2_host": (ctypes.c_float, [ctypes.c_float]),
     "qt_scale_update": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
                                        ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
     "qt_fq_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,

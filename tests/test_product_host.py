@@ -214,3 +214,20 @@ def test_operator_surface_is_registered():
     assert "Tensor? zero_point=None" in s and "int? block_size=None" in s and "Tensor? qmap=None" in s
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.quantized_ops.vmap(torch.zeros(8, dtype=torch.bfloat16), torch.zeros(65536, dtype=torch.bfloat16))
+
+
+def test_per_tensor_pow2_scale_matches_libm():
+    """force_scale_power_of_two of the per-tensor scheme: the log2-free rule the device uses equals
+    2 ** ceil(log2(sf)) in fp32 (numpy / libm, what the reference's CPU run computes) on the first 64 and last 64
+    mantissas of every exponent and on random scales."""
+    L = _C.lib()
+    tails = np.concatenate([np.arange(0, 64), np.arange(0x7FFFC0, 0x800000), [0x400000, 0x123456]]).astype(np.uint32)
+    bits = (np.arange(1, 255, dtype=np.uint32)[:, None] << 23 | tails[None, :]).reshape(-1)
+    rng = np.random.default_rng(0)
+    bits = np.concatenate([bits, rng.integers(0x00800000, 0x7F800000, 20000, dtype=np.uint32)])
+    sf = bits.view(np.float32)
+    with np.errstate(over="ignore"):
+        want = np.power(np.float32(2.0), np.ceil(np.log2(sf)), dtype=np.float32)
+    got = np.array([L.qt_scale_pow2_host(float(v)) for v in sf], dtype=np.float32)
+    bad = np.nonzero(got.view(np.uint32) != want.view(np.uint32))[0]
+    assert bad.size == 0, [(hex(bits[i]), got[i], want[i]) for i in bad[:8]]
