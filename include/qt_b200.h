@@ -292,7 +292,9 @@ int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
 /* qt_softmax_fq only, OR-ed into fq_points: the mask is the standard causal one of a square attention
  * (cols == mask_rows; mask[r, c] = finfo(bf16).min for c > r, 0 otherwise) and no QT_FQ_MID step exists.  Scores at
  * c > r are then not read (they may be unwritten: QT_CAUSAL_OUT_LOWER), their probabilities are exactly 0, and
- * probabilities at c >= 128 * (r / 128 + 1) are not written (consume them with QT_CAUSAL_A_LOWER).  With a non-NULL
+ * probabilities at c >= 128 * (r / 128 + 1) are not written (consume them with QT_CAUSAL_A_LOWER); the mask tensor
+ * itself is not read either.  (A NaN / +Inf score at a masked position, which would poison the row in the reference,
+ * is therefore ignored: the schedule is for finite scores.)  With a non-NULL
  * causal_flag (device int32) the bit takes effect only if *causal_flag != 0. */
 #define QT_SOFTMAX_CAUSAL 16
 /* out_type: what the op stores.  QT_OUT_BF16: the fake-quantized values.  QT_OUT_E4M3 / QT_OUT_E5M2: their one-byte

@@ -267,7 +267,8 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
             const int i = lane + TPR * j;
             const bool in = i < nvec && live && i * 8 <= r_seq;
             raw[j] = in ? __ldcs(srow + i) : make_uint4(0u, 0u, 0u, 0u);
-            mraw[j] = (in && mrow) ? __ldg(mrow + i) : make_uint4(0u, 0u, 0u, 0u);
+            // causal by contract: the mask is known (0 up to the diagonal, finfo.min above it) and is not read
+            mraw[j] = (in && mrow && !(flags & FQ_CAUSAL)) ? __ldg(mrow + i) : make_uint4(0u, 0u, 0u, 0u);
         }
         float f[VPL][8];
         float mx = -INFINITY;
@@ -282,7 +283,15 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
                     for (int k = 0; k < 8; ++k) f[j][k] *= alpha;
                     round8(f[j]);
                 }
-                if (mrow) {
+                if (flags & FQ_CAUSAL) {
+                    // s + 0 == s up to the diagonal; bf16(s + finfo.min) is so far below the row maximum that its
+                    // exp is exactly 0, like -inf: only the vector holding the diagonal needs any work
+                    if (i * 8 + 7 > r_seq) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (i * 8 + k > r_seq) f[j][k] = -INFINITY;
+                    }
+                } else if (mrow) {
                     float m8[8];
                     unpack8(mraw[j], m8);
 #pragma unroll
