@@ -82,7 +82,7 @@ def point(module, arg="0"):
     if not isinstance(fq, FusedAmaxObsFakeQuantize):
         raise _NotFusable
     observe, quantize = fq._flags()
-    if observe or fq.is_per_channel or fq.record_histogram or fq.scale.numel() != 1:
+    if observe or fq.is_per_channel or fq.is_block_scaled or fq.record_histogram or fq.scale.numel() != 1:
         raise _NotFusable
     return fq if quantize else None
 
