@@ -167,6 +167,10 @@ typedef struct qt_block_desc {
     const void *pow2_table;
     float *scale;
     float *zero_point;
+    /* Optional: the parameter codebook as a 65 536-entry table (uint16 bf16 patterns, device) instead of scale_fmt --
+     * what torch.ops.quantized_ops.calculate_mx_qparam receives as `scale_qmap` (decomposed.py:366-419).  y == NULL:
+     * compute the parameters only. */
+    const void *scale_table;
 } qt_block_desc_t;
 int qt_fq_block(const qt_block_desc_t *desc, void *stream);
 

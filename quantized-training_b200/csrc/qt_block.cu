@@ -42,6 +42,7 @@ struct BlockParams {
     float rqmax;                        // 1 / quant_max
     QtRound scale_round;
     const uint32_t *pow2_tab;  // QT_POW2_TABLE_WORDS words on the device (pow2 only)
+    const uint16_t *scale_table;  // 65 536-entry codebook of the scale given as a TABLE (operator surface), or null
 };
 
 template <bool F32>
@@ -54,6 +55,10 @@ template <bool F32>
 __device__ __forceinline__ float scale_codebook(const BlockParams &bp, float v)
 {
     const uint32_t b = __float_as_uint(v);
+    if (bp.scale_table) {
+        const uint32_t idx = F32 ? (f32_to_bf16_rto_hi(b) >> 16) : (b >> 16);
+        return __uint_as_float((uint32_t)__ldg(bp.scale_table + idx) << 16);
+    }
     return __uint_as_float(qt_round_dyn(bp.scale_round, F32 ? f32_to_bf16_rto_hi(b) : b));
 }
 
@@ -903,6 +908,7 @@ void launch_generic(const BlockJob &j, const typename R::Params &p)
     const size_t total = D.d0 * D.n1 * D.d1 * D.n2 * D.d2;
     block_stat_kernel<F32, AFFINE><<<grid_for((nblocks + 7) / 8, 8), 256, 0, j.stream>>>(j.d->x, D, j.bp, j.d->scale,
                                                                                       j.d->zero_point);
+    if (!j.d->y) return;  // parameters only
     allow_smem<block_apply_kernel<R, F32, AFFINE>>(R::kSmemBytes);
     const unsigned grid = grid_for((total + R::kThreads - 1) / R::kThreads, R::kCtasPerSm);
     block_apply_kernel<R, F32, AFFINE><<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(
@@ -961,9 +967,10 @@ bool try_gwa_fast(const BlockJob &j)
 template <class R, bool F32>
 void launch_mx(const BlockJob &j, const typename R::Params &p)
 {
-    if (try_flat<R, F32>(j, p)) return;
-    if (try_cols<R, F32>(j, p)) return;
-    if (try_tile<R, F32>(j, p)) return;
+    const bool single_pass_ok = j.d->y != nullptr && j.bp.scale_table == nullptr;
+    if (single_pass_ok && try_flat<R, F32>(j, p)) return;
+    if (single_pass_ok && try_cols<R, F32>(j, p)) return;
+    if (single_pass_ok && try_tile<R, F32>(j, p)) return;
     launch_generic<R, F32, false>(j, p);
 }
 
@@ -1110,13 +1117,18 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
         if (rc != QT_OK) return rc;
         bp.has_scale_fmt = 1;
     }
+    if (d->scale_table) {  // the codebook as a table (torch.ops.quantized_ops.calculate_mx_qparam's scale_qmap)
+        bp.scale_table = static_cast<const uint16_t *>(d->scale_table);
+        bp.has_scale_fmt = 1;
+    }
     if (!(d->quant_max > 0.0f) && !affine) {
         qt_set_error("qt_fq_block: quant_max must be positive, got %g", (double)d->quant_max);
         return QT_ERR_INVALID_ARGUMENT;
     }
     if (total == 0) return QT_OK;
-    if (!d->x || !d->y || !d->scale || (affine && !d->zero_point)) {
-        qt_set_error("qt_fq_block: x, y, scale%s must not be NULL", affine ? ", zero_point" : "");
+    const bool stat_only = d->y == nullptr;  // parameters only (calculate_mx_qparam)
+    if (!d->x || !d->scale || (affine && !d->zero_point)) {
+        qt_set_error("qt_fq_block: x, scale%s must not be NULL", affine ? ", zero_point" : "");
         return QT_ERR_INVALID_ARGUMENT;
     }
     if (bp.pow2 && !bp.pow2_tab) {
@@ -1124,7 +1136,7 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
         return QT_ERR_INVALID_ARGUMENT;
     }
     const size_t esz = j.f32 ? 4 : 2;
-    if ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->y)) % esz) {
+    if ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->y)) % esz) {  // y == NULL passes
         qt_set_error("qt_fq_block: x / y not aligned to the element size");
         return QT_ERR_UNALIGNED;
     }
@@ -1134,7 +1146,7 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
     if (affine) {
         rc = dispatch_direct_small(P, [&](auto tag, const auto &p) {
             using R = typename decltype(tag)::type;
-            if (j.f32 ? try_gwa_fast<true>(j) : try_gwa_fast<false>(j)) return;
+            if (j.d->y && !j.bp.scale_table && (j.f32 ? try_gwa_fast<true>(j) : try_gwa_fast<false>(j))) return;
             j.f32 ? launch_generic<R, true, true>(j, p) : launch_generic<R, false, true>(j, p);
         });
     } else {

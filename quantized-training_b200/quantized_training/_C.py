@@ -223,7 +223,7 @@ class QtBlockDesc(ctypes.Structure):
         ("force_scale_power_of_two", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("fmt", ctypes.POINTER(QtFormat)), ("lut", ctypes.c_void_p),
         ("scale_fmt", ctypes.POINTER(QtFormat)), ("pow2_table", ctypes.c_void_p),
-        ("scale", ctypes.c_void_p), ("zero_point", ctypes.c_void_p),
+        ("scale", ctypes.c_void_p), ("zero_point", ctypes.c_void_p), ("scale_table", ctypes.c_void_p),
     ]
 
 
@@ -235,13 +235,14 @@ def pow2_table_host(elem_type):
 
 
 def fq_block(x, y, dims, block_size, block_axis2, qscheme, quant_min, quant_max, fmt, scale, zero_point=None,
-             lut=None, scale_fmt=None, force_pow2=False, pow2_table=None):
+             lut=None, scale_fmt=None, force_pow2=False, pow2_table=None, scale_table=None):
     """Block-scaled fake quant (qt_fq_block).  dims = (d0, n1, d1, n2, d2) view of the contiguous x;
-    scale / zero_point: float32 outputs, one entry per block."""
+    scale / zero_point: float32 outputs, one entry per block.  y = None: parameters only.  scale_table: the parameter
+    codebook as a 65 536-entry bf16 table instead of scale_fmt."""
     _require_cuda(x, "input")
-    assert x.is_contiguous() and y.is_contiguous() and y.dtype == x.dtype and y.device == x.device
+    assert x.is_contiguous() and (y is None or (y.is_contiguous() and y.dtype == x.dtype and y.device == x.device))
     d0, n1, d1, n2, d2 = (int(v) for v in dims)
-    assert d0 * n1 * d1 * n2 * d2 == x.numel() == y.numel()
+    assert d0 * n1 * d1 * n2 * d2 == x.numel() and (y is None or y.numel() == x.numel())
     nb1 = -(-n1 // block_size)
     nb2 = -(-n2 // block_size) if block_axis2 else n2
     for t in (scale, zero_point):
@@ -249,8 +250,11 @@ def fq_block(x, y, dims, block_size, block_axis2, qscheme, quant_min, quant_max,
             assert t.dtype == torch.float32 and t.device == x.device and t.is_contiguous() \
                 and t.numel() == d0 * nb1 * d1 * nb2 * d2
     d = QtBlockDesc()
-    d.x, d.y = x.data_ptr(), y.data_ptr()
+    d.x, d.y = x.data_ptr(), (y.data_ptr() if y is not None else None)
     d.elem_type, d.qscheme = _elem_type(x), int(qscheme)
+    if scale_table is not None:
+        assert scale_table.numel() == 65536 and scale_table.element_size() == 2 and scale_table.device == x.device
+        d.scale_table = scale_table.data_ptr()
     d.d0, d.n1, d.d1, d.n2, d.d2 = d0, n1, d1, n2, d2
     d.block_size, d.block_axis2 = int(block_size), int(bool(block_axis2))
     d.quant_min, d.quant_max = float(quant_min), float(quant_max)

@@ -15,7 +15,7 @@ import torch
 from . import _C
 from .fake_quantize import _block_view
 
-__all__ = ["vmap", "quantize", "dequantize", "expand"]
+__all__ = ["vmap", "quantize", "dequantize", "expand", "calculate_mx_qparam", "quantize_mx", "linear_mx", "matmul_mx"]
 
 _lib = torch.library.Library("quantized_ops", "DEF")
 _lib.define("vmap(Tensor self, Tensor other) -> Tensor")
@@ -23,6 +23,15 @@ _lib.define("quantize(Tensor input, Tensor scale, Tensor? zero_point=None, SymIn
             "int? block_size=None, Tensor? qmap=None, Tensor? output_code=None) -> Tensor")
 _lib.define("dequantize(Tensor input, Tensor scale, Tensor? zero_point=None, SymInt[]? axes=None, "
             "int? block_size=None, Tensor? input_qmap=None, Tensor? output_qmap=None) -> Tensor")
+_lib.define("calculate_mx_qparam(Tensor self, SymInt[] axes, int block_size, float quant_max, "
+            "bool force_scale_power_of_two=False, Tensor scale_qmap=None) -> Tensor")
+_lib.define("quantize_mx(Tensor self, Tensor qmap, SymInt[] axes, int block_size, float quant_max, "
+            "bool force_scale_power_of_two=False, Tensor scale_qmap=None, Tensor output_code=None) -> (Tensor, Tensor)")
+_lib.define("linear_mx(Tensor input, Tensor weight, Tensor? bias=None, *, Tensor? input_scale=None, "
+            "Tensor? weight_scale=None, int? block_size=None, Tensor? input_code=None, "
+            "Tensor? weight_code=None) -> Tensor")
+_lib.define("matmul_mx(Tensor self, Tensor other, *, Tensor? input_scale=None, Tensor? weight_scale=None, "
+            "int? block_size=None, Tensor? input_code=None, Tensor? weight_code=None) -> Tensor")
 
 
 def expand(input, shape, block_size):
@@ -113,6 +122,69 @@ def dequantize(input, scale, zero_point=None, axes=None, block_size=None, input_
     return _run(_C.TABLE_DEQUANTIZE, input, scale, zero_point, axes, block_size, input_qmap, output_qmap)
 
 
+_POW2_TABLES = {}
+
+
+def calculate_mx_qparam(input, axes, block_size, quant_max, force_scale_power_of_two=False, scale_qmap=None):
+    """Per-block scale of the microscaling scheme (decomposed.py:372-419): amax / quant_max [through scale_qmap], or
+    2^(floor(log2 amax) - floor(log2 quant_max)); non-positive / NaN -> 1.  Shape: the block grid; dtype: input's."""
+    if not input.is_cuda:
+        raise RuntimeError("quantized_ops: the B200 build runs on CUDA tensors only (no CPU fallback)")
+    if input.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError(f"quantized_ops kernels take bfloat16 / float32 tensors, got {input.dtype}")
+    x = input.contiguous()
+    axes = [axes] if isinstance(axes, int) else list(axes)
+    dims, axis2, grid = _block_view(tuple(x.shape), axes, block_size)
+    scale = torch.empty(grid, dtype=torch.float32, device=x.device)
+    pow2_tab = None
+    if force_scale_power_of_two:
+        key = (x.dtype, x.device)
+        if key not in _POW2_TABLES:
+            _POW2_TABLES[key] = _C.pow2_table_host(_C.QT_F32 if x.dtype == torch.float32 else _C.QT_BF16).to(x.device)
+        pow2_tab = _POW2_TABLES[key]
+    if x.numel():
+        _C.fq_block(x, None, dims, block_size, axis2, _C.BLOCK_MX, -float(quant_max), float(quant_max),
+                    _C.format_from_string("bfloat16"), scale, force_pow2=force_scale_power_of_two,
+                    pow2_table=pow2_tab, scale_table=_table(scale_qmap, x.device))
+    return scale.to(input.dtype)
+
+
+def quantize_mx(input, qmap, axes, block_size, quant_max, force_scale_power_of_two=False, scale_qmap=None,
+                output_code=None):
+    """(scale, vmap(input / expand(scale), qmap)) -- decomposed.py:428-448."""
+    scale = calculate_mx_qparam(input, axes, block_size, quant_max, force_scale_power_of_two, scale_qmap)
+    return scale, quantize(input, scale, None, axes, block_size, qmap)
+
+
+def _decode(t, scale, block_size, code):
+    """codebook decode + block-scale multiply of one *_mx operand (decomposed.py:291-300)."""
+    if code is not None:
+        t = code[t.to(torch.long)].to(t.dtype)
+    if scale is not None:
+        t = dequantize(t, scale, None, None, block_size)
+    return t
+
+
+def linear_mx(input, weight, bias=None, *, input_scale=None, weight_scale=None, block_size=None, input_code=None,
+              weight_code=None):
+    """F.linear on the dequantized operands (decomposed.py:311-331); the product runs on the tcgen05 GEMM."""
+    from . import ops
+    return ops.linear(_decode(input, input_scale, block_size, input_code),
+                      _decode(weight, weight_scale, block_size, weight_code), bias)
+
+
+def matmul_mx(self, other, *, input_scale=None, weight_scale=None, block_size=None, input_code=None,
+              weight_code=None):
+    """torch.matmul on the dequantized operands (decomposed.py:341-363)."""
+    from . import ops
+    return ops.matmul(_decode(self, input_scale, block_size, input_code),
+                      _decode(other, weight_scale, block_size, weight_code))
+
+
+_lib.impl("calculate_mx_qparam", calculate_mx_qparam, "CUDA")
+_lib.impl("quantize_mx", quantize_mx, "CUDA")
+_lib.impl("linear_mx", linear_mx, "CUDA")
+_lib.impl("matmul_mx", matmul_mx, "CUDA")
 _lib.impl("vmap", vmap, "CUDA")
 _lib.impl("quantize", quantize, "CUDA")
 _lib.impl("dequantize", dequantize, "CUDA")

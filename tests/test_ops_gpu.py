@@ -66,3 +66,75 @@ def test_cpu_tensors_are_rejected():
     x = torch.zeros(8, dtype=torch.bfloat16)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.quantized_ops.vmap(x, torch.zeros(65536, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_calculate_mx_qparam_op(golden, dtype):
+    """torch.ops.quantized_ops.calculate_mx_qparam against the reference's own function on every positive bf16 amax /
+    fp32 values around every power of two (tests/golden/mx_scale.npz), the codebook passed as a TABLE like the
+    reference does."""
+    amax_bits = np.arange(0x8000, dtype=np.uint16) if dtype == "bf16" else golden.mx_scale["f32_amax_bits"]
+    x = to_tensor(amax_bits, dtype, (amax_bits.size, 1))
+    e5m3 = to_tensor(golden.qmaps["fp8_e5m3"], "bf16", (65536,))
+    for qmax in golden.mx_manifest["scale_fn_quant_max"]:
+        for mode, pow2, tab in (("pow2", True, None), ("amax", False, None), ("e5m3", False, e5m3)):
+            s = torch.ops.quantized_ops.calculate_mx_qparam(x, [-1], 1, qmax, pow2, tab)
+            assert s.dtype == x.dtype and s.shape == x.shape
+            bad = np.nonzero(~nan_eq(bits_of(s), golden.mx_scale[f"{dtype}/{mode}/{qmax}"]))[0]
+            assert bad.size == 0, (dtype, mode, qmax, bad[:6])
+
+
+@pytest.mark.parametrize("element,sdt,pow2,shape,axes,bs", [
+    ("int6", "fp8_e5m3", False, (16, 256), [-1], 32), ("fp4_e2m1", None, True, (4, 96, 64), [-2], 32),
+    ("int6", "fp8_e5m3", False, (2, 48, 64), [-2, -1], 16), ("posit8_1", None, False, (5, 70), [-1], 32)])
+def test_quantize_mx_op_agrees_with_the_module(golden, element, sdt, pow2, shape, axes, bs):
+    """(scale, q) = quantize_mx(x, qmap, ...): scale is the module's `scale` buffer and q * expand(scale) its output
+    (MXFakeQuantFunction.forward = quantize_mx + one multiply, fake_quantize.py:118-129)."""
+    from quantized_training.decomposed import expand
+    from quantized_training.quantizer import get_quant_min_max
+    torch.manual_seed(5)
+    x = (torch.randn(shape, device=DEV) * 3 * torch.exp2(torch.randint(-5, 5, shape, device=DEV).float())).bfloat16()
+    qmin, qmax = (float(v) for v in get_quant_min_max(element))
+    qmap = qt.get_quantization_map(element, DEV)
+    smap = qt.get_quantization_map(sdt, DEV) if sdt else None
+    scale, q = torch.ops.quantized_ops.quantize_mx(x, qmap, axes, bs, qmax, pow2, smap)
+    mod = qt.FusedAmaxObsFakeQuantize(element, qscheme="microscaling", quant_min=qmin, quant_max=qmax,
+                                      ch_axis=tuple(axes) if len(axes) > 1 else axes[0], block_size=bs, scale_dtype=sdt,
+                                      force_scale_power_of_two=pow2, device=DEV)
+    y = mod(x)
+    assert scale.dtype == x.dtype and tuple(scale.shape) == tuple(mod.scale.shape)
+    assert torch.equal(scale.float(), mod.scale)
+    assert nan_eq(bits_of(q * expand(scale, x.shape, bs)), bits_of(y)).all()
+
+
+def test_linear_and_matmul_mx_ops():
+    """linear_mx / matmul_mx = dequantize the operands (codebook decode, block scales) and multiply on the tcgen05 GEMM:
+    against the reference's formula evaluated with torch on the same device (decomposed.py:311-363), relative error
+    <= 2^-7 (bf16 output, fp32 accumulation; the accumulation order differs from cuBLAS)."""
+    from quantized_training.decomposed import expand
+    torch.manual_seed(9)
+    M, K, N, bs = 64, 256, 128, 32
+    xq = torch.randint(-31, 32, (M, K), device=DEV).bfloat16()
+    wq = torch.randint(-31, 32, (N, K), device=DEV).bfloat16()
+    xs = (torch.rand(M, K // bs, device=DEV) * 0.1 + 0.01).bfloat16()
+    ws = (torch.rand(N, K // bs, device=DEV) * 0.1 + 0.01).bfloat16()
+    bias = torch.randn(N, device=DEV).bfloat16()
+    got = torch.ops.quantized_ops.linear_mx(xq, wq, bias, input_scale=xs, weight_scale=ws, block_size=bs)
+    want = torch.nn.functional.linear((xq * expand(xs, xq.shape, bs)).float(), (wq * expand(ws, wq.shape, bs)).float(),
+                                      bias.float())
+    assert got.dtype == torch.bfloat16 and got.shape == (M, N)
+    assert float((got.float() - want).norm() / want.norm()) <= 2 ** -7
+    # codebook operands: indices into a 16-entry code
+    code = torch.linspace(-1, 1, 16, device=DEV).bfloat16()
+    wi = torch.randint(0, 16, (N, K), device=DEV).bfloat16()
+    got = torch.ops.quantized_ops.linear_mx(xq, wi, None, input_scale=xs, weight_scale=ws, block_size=bs, weight_code=code)
+    want = torch.nn.functional.linear((xq * expand(xs, xq.shape, bs)).float(),
+                                      (code[wi.long()] * expand(ws, wq.shape, bs)).float())
+    assert float((got.float() - want).norm() / want.norm()) <= 2 ** -7
+    a = torch.randint(-7, 8, (2, 4, 64, 128), device=DEV).bfloat16()
+    b = torch.randint(-7, 8, (2, 4, 128, 64), device=DEV).bfloat16()
+    sa = (torch.rand(2, 4, 64, 4, device=DEV) + 0.5).bfloat16()
+    sb = (torch.rand(2, 4, 4, 64, device=DEV) + 0.5).bfloat16()
+    got = torch.ops.quantized_ops.matmul_mx(a, b, input_scale=sa, weight_scale=sb, block_size=32)
+    want = torch.matmul((a * expand(sa, a.shape, 32)).float(), (b * expand(sb, b.shape, 32)).float())
+    assert float((got.float() - want).norm() / want.norm()) <= 2 ** -7
