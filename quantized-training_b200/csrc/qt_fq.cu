@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include "qt_fq_common.cuh"
+#include "qt_launch.cuh"
 
 namespace {
 
@@ -101,6 +102,8 @@ fq_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
                float *__restrict__ amax_out)
 {
     const R round(params, stage_table<R>(params));
+    griddep_wait();  // PDL: the scale and the input may come from the kernel before this one
+    griddep_launch_dependents();
     ScaleBf16 sc = {1.0f, 1.0f};
     if (scale) sc = load_scale<F32>(scale, 0);
     uint32_t amax = 0u;
@@ -420,6 +423,8 @@ codes_flat_kernel(const uint4 *__restrict__ x, uint32_t *__restrict__ y, size_t 
                   float *__restrict__ amax_out)
 {
     const R round(params, stage_table<R>(params));
+    griddep_wait();  // PDL: the scale and the input may come from the kernel before this one
+    griddep_launch_dependents();
     ScaleBf16 sc = {1.0f, 1.0f};
     if (scale) sc = load_scale<F32>(scale, 0);
     uint32_t amax = 0u;
@@ -528,7 +533,7 @@ void launch_layout(const Job &j, const typename R::Params &p)
                 allow_smem<fq_flat_kernel<R, F32, AMAX>>(R::kSmemBytes);
                 const size_t tile = (size_t)R::kThreads * kUnroll;
                 const unsigned grid = grid_for((nvec + tile - 1) / tile, R::kCtasPerSm);
-                kernel<<<grid, R::kThreads, R::kSmemBytes, j.stream>>>(xv, yv, nvec, p, j.scale, j.amax);
+                qt_launch(kernel, dim3(grid), dim3(R::kThreads), R::kSmemBytes, j.stream, xv, yv, nvec, p, j.scale, j.amax);
             } else {
                 const size_t tile = (size_t)256 * kUnroll;
                 amax_flat_kernel<F32><<<grid_for((nvec + tile - 1) / tile, 8), 256, 0, j.stream>>>(xv, nvec, j.amax);
@@ -726,8 +731,8 @@ void launch_codes(const void *x, void *y, size_t n, const typename R::Params &p,
         allow_smem<codes_flat_kernel<R, F32, AMAX, E5M2>>(R::kSmemBytes);
         const size_t tile = (size_t)R::kThreads * kUnroll;
         const unsigned grid = grid_for((nvec + tile - 1) / tile, R::kCtasPerSm);
-        codes_flat_kernel<R, F32, AMAX, E5M2><<<grid, R::kThreads, R::kSmemBytes, stream>>>(
-            static_cast<const uint4 *>(x), static_cast<uint32_t *>(y), nvec, p, scale, amax);
+        qt_launch(codes_flat_kernel<R, F32, AMAX, E5M2>, dim3(grid), dim3(R::kThreads), R::kSmemBytes, stream,
+                  static_cast<const uint4 *>(x), static_cast<uint32_t *>(y), nvec, p, scale, amax);
     }
     const size_t rest = n - nvec * VEC;
     if (rest) {

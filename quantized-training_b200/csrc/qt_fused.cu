@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "qt_fq_common.cuh"
+#include "qt_launch.cuh"
 
 namespace {
 
@@ -244,6 +245,8 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
                   const float *__restrict__ scale_post, const int32_t *__restrict__ causal_flag)
 {
     const R round(params, stage_table<R>(params));
+    griddep_wait();  // PDL: the table is constant data; everything below reads what the predecessor wrote
+    griddep_launch_dependents();
     const FqPoint pre = load_point(scale_pre), mid = load_point(scale_mid), post = load_point(scale_post);
     if (causal_flag && *causal_flag == 0) flags &= ~FQ_CAUSAL;  // decided on the device (graph-safe)
     constexpr int RPC = ROW_THREADS / TPR;  // rows per CTA pass
@@ -364,6 +367,8 @@ norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, uint4 *__restr
                const float *__restrict__ scale_post)
 {
     const R round(params, stage_table<R>(params));
+    griddep_wait();  // PDL: the table is constant data; everything below reads what the predecessor wrote
+    griddep_launch_dependents();
     const FqPoint pre = load_point(scale_pre), post = load_point(scale_post);
     constexpr int RPC = ROW_THREADS / TPR;
     const int lane = threadIdx.x % TPR;
@@ -452,6 +457,8 @@ act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, 
                   const __grid_constant__ typename R::Params params, const float *__restrict__ scale_post)
 {
     const R round(params, stage_table<R>(params));
+    griddep_wait();  // PDL: the table is constant data; everything below reads what the predecessor wrote
+    griddep_launch_dependents();
     const FqPoint post = load_point(scale_post);
     const size_t total = rows * (size_t)vec_per_row;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -517,6 +524,8 @@ rope_fq_kernel(RopeTensor t0, RopeTensor t1, int out_type, size_t tokens, int he
                const float *__restrict__ scale1)
 {
     const R round(params, stage_table<R>(params));
+    griddep_wait();  // PDL: the table is constant data; everything below reads what the predecessor wrote
+    griddep_launch_dependents();
     const FqPoint p0 = load_point(scale0), p1 = load_point(scale1);
     const int hv = head_dim >> 4;  // vector pairs per head
     const int dv = head_dim >> 3;  // vectors per head
@@ -591,6 +600,8 @@ fq_transpose_kernel(const uint16_t *__restrict__ v, void *__restrict__ out_v, in
 {
     const unsigned char *tab = stage_table<R>(params);
     const R round(params, tab);
+    griddep_wait();  // PDL
+    griddep_launch_dependents();
     const FqPoint post = load_point(scale_post);
     // tile after the (optional) rounding table in dynamic shared memory: [TR_TOK][D + 2] bf16
     uint16_t *tile = reinterpret_cast<uint16_t *>(qt_dyn_smem + R::kSmemBytes);
@@ -758,7 +769,7 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
     do {                                                                                                             \
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                                  \
         auto kernel = scaled ? softmax_fq_kernel<R, true, TPR, VPL> : softmax_fq_kernel<R, false, TPR, VPL>;         \
-        kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                                \
+        qt_launch(kernel, dim3(grid_for(ctas, ROW_MIN_CTAS * 2)), dim3(ROW_THREADS), R::kSmemBytes, st,                                \
             static_cast<const uint4 *>(scores), probs, out_type, rows, (int)cols, alpha, has_alpha,                  \
             static_cast<const uint4 *>(mask), rows_per_batch, mask_rows, mask_batch_stride_vec, fq_points, params,   \
             scale_pre, scale_mid, scale_post, causal_flag);                                                          \
@@ -804,7 +815,7 @@ extern "C" int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size
     do {                                                                                                         \
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                              \
         auto kernel = scaled ? norm_fq_kernel<R, true, TPR, VPL> : norm_fq_kernel<R, false, TPR, VPL>;           \
-        kernel<<<grid_for(ctas, ROW_MIN_CTAS * 2), ROW_THREADS, R::kSmemBytes, st>>>(                            \
+        qt_launch(kernel, dim3(grid_for(ctas, ROW_MIN_CTAS * 2)), dim3(ROW_THREADS), R::kSmemBytes, st,                            \
             static_cast<const uint4 *>(x), y, static_cast<uint4 *>(y_raw), out_type, rows, (int)cols, kind,      \
             static_cast<const uint4 *>(weight), static_cast<const uint4 *>(bias), eps, fq_points, params,        \
             scale_pre, scale_post);                                                                              \
@@ -861,7 +872,7 @@ extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t
         case 6: kernel = act_mul_fq_kernel<R, false, FACT_SILU>; break;
         default: kernel = act_mul_fq_kernel<R, true, FACT_SILU>; break;
         }
-        kernel<<<grid, EW_THREADS, R::kSmemBytes, st>>>(
+        qt_launch(kernel, dim3(grid), dim3(EW_THREADS), R::kSmemBytes, st,
             static_cast<const uint4 *>(gate), static_cast<const uint4 *>(up), out, out_type, rows, (int)(cols / 8),
             ld_gate / 8, ld_up / 8, ld_out / 8, fq_points, params, scale_post);
     });
@@ -897,7 +908,7 @@ extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_o
         const size_t total = tokens * (size_t)(t0.heads + t1.heads) * (head_dim / 16);
         const unsigned grid = grid_for((total + EW_THREADS - 1) / EW_THREADS, EW_MIN_CTAS * 2);
         auto kernel = (scale_q || scale_k) ? rope_fq_kernel<R, true> : rope_fq_kernel<R, false>;
-        kernel<<<grid, EW_THREADS, R::kSmemBytes, st>>>(
+        qt_launch(kernel, dim3(grid), dim3(EW_THREADS), R::kSmemBytes, st,
             t0, t1, out_type, tokens, head_dim, static_cast<const uint4 *>(cos_table),
             static_cast<const uint4 *>(sin_table), cos_rows, fq_points, params, scale_q, scale_k);
     });
@@ -927,7 +938,7 @@ extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int
         const size_t smem = R::kSmemBytes + (size_t)TR_TOK * (head_dim + 2) * 2;
         const unsigned grid = grid_for(jobs, EW_MIN_CTAS * 2);
         auto kernel = scale_post ? fq_transpose_kernel<R, true> : fq_transpose_kernel<R, false>;
-        kernel<<<grid, EW_THREADS, smem, st>>>(static_cast<const uint16_t *>(v), out, out_type, batch, seq, heads,
+        qt_launch(kernel, dim3(grid), dim3(EW_THREADS), smem, st, static_cast<const uint16_t *>(v), out, out_type, batch, seq, heads,
                                                head_dim, ld_tok, batch_stride, fq_points, params,
                                                                 scale_post);
     });

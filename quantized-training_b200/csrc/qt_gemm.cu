@@ -33,6 +33,7 @@
 #include "qt_internal.h"
 #include "qt_lut.h"
 #include "qt_tc.cuh"
+#include "qt_launch.cuh"
 
 namespace {
 
@@ -171,8 +172,6 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int block_n = p.block_n;
-    // every thread reads the same (already final) flag: the three roles agree on the schedule
-    const int causal = (p.causal != 0 && (p.causal_flag == nullptr || *p.causal_flag != 0)) ? p.causal : 0;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -199,6 +198,12 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tcgen05_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // PDL: everything above touched only this CTA's shared memory / TMEM and the kernel parameters; the operands, the
+    // causal flag and the output buffers belong to the predecessor until it has completed
+    griddep_wait();
+    griddep_launch_dependents();
+    // every thread reads the same (already final) flag: the three roles agree on the schedule
+    const int causal = (p.causal != 0 && (p.causal_flag == nullptr || *p.causal_flag != 0)) ? p.causal : 0;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -494,7 +499,7 @@ void launch_variant(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &
                              (int)SMEM_BYTES);
         if (dev < 64) done[dev] = true;
     }
-    qt_gemm_kernel<FP8, ACT, AUX, OUT><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, map_c, p);
+    qt_launch(qt_gemm_kernel<FP8, ACT, AUX, OUT>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, map_a, map_b, map_c, p);
 }
 
 }  // namespace
