@@ -9,6 +9,7 @@
 // Unlike the per-tensor scheme (qt_fq.cu) the scale is NOT delayed: it is a function of the block being quantized,
 // so the statistic has to be complete before the first element is rounded.  A block is small (block_size elements,
 // or block_size^2 for two tiled axes), which is what makes the single pass possible:
+//   (the three single-pass families live in qt_block_flat.cu / _cols.cu / _tile.cu so that they compile in parallel)
 //   flat  kernel  blocks along the last axis (unit stride): block_size / VEC lanes of a warp hold one block, the
 //                 maximum is a log2(lanes)-step xor-shuffle.
 //   cols  kernel  blocks along an inner axis (stride = inner elements): a (32, 8) CTA holds 32 column groups of
@@ -23,406 +24,9 @@
 // so e.g. amax = 1.98 * 2^60 has floor(bf16(60.98)) = 61.  That function of amax is one mantissa threshold per
 // exponent, tabulated on the host (qt_block_pow2_table_host) with the same libm call sequence and checked against
 // the reference on every bf16 value.
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
-#include <math.h>
-#include <string.h>
-
-#include "qt_fq_common.cuh"
+#include "qt_block_common.cuh"
 
 namespace {
-
-struct BlockParams {
-    float quant_min, quant_max, range;  // range = quant_max - quant_min (affine)
-    int32_t pow2;                       // force_scale_power_of_two
-    int32_t qmax_exp;                   // floor(log2(quant_max))
-    int32_t has_scale_fmt;              // scale / zero point go through the scale_dtype codebook
-    int32_t fast_ok;                    // the element format is insensitive to sub-2^-120 quotients (qt_tiny_safe)
-    int32_t qmax_short;                 // quant_max has <= 8 significant bits: amax / quant_max by reciprocal multiply
-    float rqmax;                        // 1 / quant_max
-    QtRound scale_round;
-    const uint32_t *pow2_tab;  // QT_POW2_TABLE_WORDS words on the device (pow2 only)
-    const uint16_t *scale_table;  // 65 536-entry codebook of the scale given as a TABLE (operator surface), or null
-};
-
-template <bool F32>
-__device__ __forceinline__ float to_dtype(float v)
-{
-    return F32 ? v : __uint_as_float(bf16_rne_hi(v));
-}
-// vmap of one value of the tensor's dtype through the scale codebook
-template <bool F32>
-__device__ __forceinline__ float scale_codebook(const BlockParams &bp, float v)
-{
-    const uint32_t b = __float_as_uint(v);
-    if (bp.scale_table) {
-        const uint32_t idx = F32 ? (f32_to_bf16_rto_hi(b) >> 16) : (b >> 16);
-        return __uint_as_float((uint32_t)__ldg(bp.scale_table + idx) << 16);
-    }
-    return __uint_as_float(qt_round_dyn(bp.scale_round, F32 ? f32_to_bf16_rto_hi(b) : b));
-}
-
-// scale of one block from the bit pattern of its amax (decomposed.py:391-419); NaN patterns order above Inf
-template <bool F32>
-__device__ __forceinline__ float mx_scale_of(uint32_t a, const BlockParams &bp)
-{
-    float s;
-    if (bp.pow2) {
-        if (a > 0x7F800000u) return 1.0f;  // log2(NaN) -> NaN -> where(scale > 0) picks 1
-        if (a == 0x7F800000u) return __uint_as_float(a);
-        int E;
-        if (a == 0u)
-            E = -126;  // amax + FP32_MIN_NORMAL * (amax == 0)
-        else if (a >> 23) {
-            const uint32_t e = a >> 23;
-            E = (int)e - 127 + ((a & 0x7FFFFFu) >= bp.pow2_tab[e] ? 1 : 0);
-        } else {
-            const int k = 31 - __clz(a);
-            E = k - 149 + (a >= bp.pow2_tab[256 + k] ? 1 : 0);
-        }
-        E -= bp.qmax_exp;
-        if (E < (F32 ? -149 : -133)) return 1.0f;  // 2^E rounds to zero in the tensor's dtype
-        if (E > 127) return __uint_as_float(0x7F800000u);
-        s = __uint_as_float(E >= -126 ? (uint32_t)(E + 127) << 23 : 1u << (E + 149));
-    } else {
-        s = to_dtype<F32>(__fdiv_rn(__uint_as_float(a), bp.quant_max));
-        if (bp.has_scale_fmt) s = scale_codebook<F32>(bp, s);
-    }
-    return s > 0.0f ? s : 1.0f;
-}
-
-__device__ __forceinline__ ScaleBf16 make_scale(float s)
-{
-    ScaleBf16 sc;
-    sc.s = s;
-    sc.rs = __frcp_rn(s);
-    return sc;
-}
-
-// one 16-byte vector with one scale; the scale is already in the tensor's dtype
-template <class R, bool F32>
-__device__ __forceinline__ uint4 mx_apply_vec(const R &round, const uint4 &v, float s)
-{
-    const ScaleBf16 sc = make_scale(s);
-    uint32_t unused = 0u;
-    const int mode = classify_scale(s);
-    if (mode == DIV_UNIT) return fq_vec<R, F32, DIV_UNIT, false>(round, v, sc, unused);
-    if (F32 || mode == DIV_EXACT) return fq_vec<R, F32, DIV_EXACT, false>(round, v, sc, unused);
-    return fq_vec<R, F32, DIV_RECIP, false>(round, v, sc, unused);
-}
-
-// The common case of mx_scale_of() with the rare inputs (zero, subnormal, Inf, NaN amax; scales outside the normal
-// range) sent to it: the power-of-two branch is an exponent-field lookup in the staged threshold table, the
-// amax / quant_max branch a reciprocal multiply (same argument as DIV_RECIP in qt_fq_common.cuh: a bf16 amax over a
-// quant_max of at most 8 significant bits is never within 2^-17 of a bf16 rounding tie).
-template <bool F32>
-__device__ __forceinline__ float mx_scale_fast(uint32_t a, const BlockParams &bp, const uint32_t *tab_smem)
-{
-    if (bp.pow2) {
-        const uint32_t e = a >> 23;
-        if (e - 1u < 254u) {
-            const int E = (int)e - 127 - bp.qmax_exp + ((a & 0x7FFFFFu) >= tab_smem[e] ? 1 : 0);
-            if ((unsigned)(E + 126) <= 253u) return __uint_as_float((uint32_t)(E + 127) << 23);
-        }
-    } else if (!F32 && bp.qmax_short) {
-        const float p = __fmul_rn(__uint_as_float(a), bp.rqmax);
-        if (p >= 0x1p-120f && a < 0x7F800000u) {
-            float s = __uint_as_float(bf16_rne_hi(p));
-            if (bp.has_scale_fmt) s = scale_codebook<false>(bp, s);
-            return s > 0.0f ? s : 1.0f;
-        }
-    }
-    return mx_scale_of<F32>(a, bp);
-}
-
-// The rounder of the fast path: the same table without the fpN_eXmY NaN-band test (quotients are bounded there).
-template <class R>
-struct FastOf {
-    using type = R;
-};
-template <bool C, bool M, int REPL>
-struct FastOf<TableRounder<C, M, REPL>> {
-    using type = TableRounder<C, false, REPL>;
-};
-
-// A block may take the fast path when every quotient is finite and below 2^126 and the scale allows the
-// reciprocal multiply; sub-2^-120 quotients need no care for formats with bp.fast_ok (see qt_tiny_safe()).
-__device__ __forceinline__ bool mx_block_is_fast(uint32_t a, float s, float rs, const BlockParams &bp)
-{
-    const uint32_t sb = __float_as_uint(s);
-    return bp.fast_ok && a < 0x7E800000u && (sb - 0x0D800000u) <= (0x71800000u - 0x0D800000u) &&
-           __fmul_rn(__uint_as_float(a), rs) < 0x1p126f;
-}
-// two bf16 values, each with its own scale
-template <class RF>
-__device__ __forceinline__ uint32_t mx_word_fast(const RF &round, uint32_t w, float s_lo, float rs_lo, float s_hi,
-                                                 float rs_hi)
-{
-    const uint32_t uq = bf16x2_rne(__fmul_rn(__uint_as_float(w << 16), rs_lo),
-                                   __fmul_rn(__uint_as_float(w & 0xFFFF0000u), rs_hi));
-    return bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), s_lo), __fmul_rn(__uint_as_float(round.hi(uq)), s_hi));
-}
-
-__device__ __forceinline__ const uint32_t *stage_pow2_table(const BlockParams &bp, size_t smem_offset)
-{
-    uint32_t *dst = reinterpret_cast<uint32_t *>(qt_dyn_smem + smem_offset);
-    if (bp.pow2) {
-        const int nthreads = blockDim.x * blockDim.y, tid = threadIdx.x + threadIdx.y * blockDim.x;
-        for (int i = tid; i < QT_POW2_TABLE_WORDS; i += nthreads) dst[i] = bp.pow2_tab[i];
-        __syncthreads();
-    }
-    return dst;
-}
-constexpr size_t kPow2SmemBytes = QT_POW2_TABLE_WORDS * 4;
-
-// ----------------------------------------------------------------------------- flat kernel
-// Blocks of LANES consecutive 16-byte vectors (last axis, shape[-1] % block_size == 0): block b = vector i / LANES,
-// which is also its index in the row-major block grid.  nvec % LANES == 0.
-template <class R, bool F32, int LANES, bool CHECK>
-__device__ __forceinline__ void mx_flat_tile(const R &round, const typename FastOf<R>::type &fast_round,
-                                             const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
-                                             size_t base, const BlockParams &bp, const uint32_t *tab,
-                                             float *__restrict__ scale_out)
-{
-    const size_t nthr = blockDim.x;
-    uint4 v[kUnroll];
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-        const size_t i = base + (size_t)j * nthr;
-        v[j] = (!CHECK || i < nvec) ? ld_stream(x + i) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int j = 0; j < kUnroll; ++j) {
-        const size_t i = base + (size_t)j * nthr;
-        uint32_t a = F32 ? amax_of_vec_f32(0u, v[j]) : amax_of_vec_bf16(0u, v[j]);
-#pragma unroll
-        for (int o = 1; o < LANES; o <<= 1) a = max(a, __shfl_xor_sync(0xFFFFFFFFu, a, o));
-        const float s = mx_scale_fast<F32>(a, bp, tab);
-        // an all-zero block gives +-0 whatever its scale is: apply it with 1 (its true scale may be below 2^-126,
-        // whose reciprocal overflows)
-        const float sa = a == 0u ? 1.0f : s;
-        uint4 r;
-        bool fast = false;
-        float rs = 0.0f;
-        if (!F32) {
-            rs = __frcp_rn(sa);
-            fast = __all_sync(0xFFFFFFFFu, mx_block_is_fast(a, sa, rs, bp));
-        }
-        if (fast) {
-            r.x = mx_word_fast(fast_round, v[j].x, sa, rs, sa, rs);
-            r.y = mx_word_fast(fast_round, v[j].y, sa, rs, sa, rs);
-            r.z = mx_word_fast(fast_round, v[j].z, sa, rs, sa, rs);
-            r.w = mx_word_fast(fast_round, v[j].w, sa, rs, sa, rs);
-        } else {
-            r = mx_apply_vec<R, F32>(round, v[j], sa);
-        }
-        if (!CHECK || i < nvec) {
-            if ((i & (size_t)(LANES - 1)) == 0) scale_out[i / LANES] = s;
-            st_stream(y + i, r);
-        }
-    }
-}
-
-template <class R, bool F32, int LANES>
-__global__ void __launch_bounds__(R::kThreads, R::kMinCtas)
-mx_flat_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t nvec,
-               const __grid_constant__ typename R::Params params, const __grid_constant__ BlockParams bp,
-               float *__restrict__ scale_out)
-{
-    const unsigned char *lut_smem = stage_table<R>(params);
-    const R round(params, lut_smem);
-    const typename FastOf<R>::type fast_round(params, lut_smem);
-    const uint32_t *tab = stage_pow2_table(bp, R::kSmemBytes);
-    const size_t tile = (size_t)blockDim.x * kUnroll;
-    const size_t full_tiles = nvec / tile;
-    for (size_t t = blockIdx.x; t < full_tiles; t += gridDim.x)
-        mx_flat_tile<R, F32, LANES, false>(round, fast_round, x, y, nvec, t * tile + threadIdx.x, bp, tab, scale_out);
-    if (full_tiles * tile < nvec && blockIdx.x == full_tiles % gridDim.x)
-        mx_flat_tile<R, F32, LANES, true>(round, fast_round, x, y, nvec, full_tiles * tile + threadIdx.x, bp, tab,
-                                          scale_out);
-}
-
-// ----------------------------------------------------------------------------- cols kernel
-// Tensor [outer, n, inner], blocks of BS = 8 * RPT rows along n, inner % VEC == 0: every column is a block of its
-// own.  blockDim = (32, 8): threadIdx.x -> a 16-byte column group g of the flattened (outer, inner / VEC) space,
-// threadIdx.y -> row phase; a thread keeps its RPT rows in registers.  Rows past n read as zero (the reference pads).
-template <class R, bool F32, int RPT>
-__global__ void __launch_bounds__(256)
-mx_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer, size_t n, size_t inner_vec,
-               size_t nblk, const __grid_constant__ typename R::Params params,
-               const __grid_constant__ BlockParams bp, float *__restrict__ scale_out)
-{
-    constexpr int VEC = F32 ? 4 : 8;
-    constexpr int BS = 8 * RPT;
-    const unsigned char *lut_smem = stage_table<R>(params);
-    const R round(params, lut_smem);
-    const typename FastOf<R>::type fast_round(params, lut_smem);
-    const uint32_t *tab = stage_pow2_table(bp, R::kSmemBytes);
-    __shared__ uint4 red[8][33];           // per row phase: packed maxima of a column group
-    __shared__ float col_scale[32][VEC + 1];
-    const size_t G = outer * inner_vec;
-    const size_t gchunks = (G + 31) / 32;
-    const size_t work = nblk * gchunks;
-    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
-        const size_t b = w / gchunks, gc = w - b * gchunks;
-        const size_t g = gc * 32 + threadIdx.x;
-        const bool active = g < G;
-        const size_t o = active ? g / inner_vec : 0, cv = active ? g - o * inner_vec : 0;
-        const size_t row0 = b * BS + threadIdx.y;
-        const uint4 *xp = x + (o * n) * inner_vec + cv;
-        uint4 v[RPT];
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const size_t r = row0 + (size_t)k * 8;
-            v[k] = (active && r < n) ? ld_stream(xp + r * inner_vec) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        // per-column maxima of |x| bit patterns: fp32 four 32-bit maxima, bf16 eight packed 16-bit maxima
-        uint4 m = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            if (F32) {
-                m.x = max(m.x, v[k].x & 0x7FFFFFFFu);
-                m.y = max(m.y, v[k].y & 0x7FFFFFFFu);
-                m.z = max(m.z, v[k].z & 0x7FFFFFFFu);
-                m.w = max(m.w, v[k].w & 0x7FFFFFFFu);
-            } else {
-                m.x = __vmaxu2(m.x, v[k].x & 0x7FFF7FFFu);
-                m.y = __vmaxu2(m.y, v[k].y & 0x7FFF7FFFu);
-                m.z = __vmaxu2(m.z, v[k].z & 0x7FFF7FFFu);
-                m.w = __vmaxu2(m.w, v[k].w & 0x7FFF7FFFu);
-            }
-        }
-        red[threadIdx.y][threadIdx.x] = m;
-        __syncthreads();
-        if (threadIdx.y < VEC) {  // row phase c computes the scale of column c of the group
-            const int c = threadIdx.y;
-            uint32_t a = 0u;
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const uint4 q = red[p][threadIdx.x];
-                const uint32_t wsel = F32 ? (c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w)
-                                          : ((c >> 1) == 0 ? q.x : (c >> 1) == 1 ? q.y : (c >> 1) == 2 ? q.z : q.w);
-                a = max(a, F32 ? wsel : ((c & 1) ? (wsel & 0xFFFF0000u) : (wsel << 16)));
-            }
-            const float s = mx_scale_fast<F32>(a, bp, tab);
-            if (active) scale_out[(o * nblk + b) * (inner_vec * VEC) + cv * VEC + c] = s;
-            // the scale the column is applied with (1 for an all-zero block, see mx_flat_tile); scales are
-            // positive, so the sign bit is free to carry "this column needs the careful path"
-            const float sa = a == 0u ? 1.0f : s;
-            const bool f = !F32 && mx_block_is_fast(a, sa, __frcp_rn(sa), bp);
-            col_scale[threadIdx.x][c] = f ? sa : -sa;
-        }
-        __syncthreads();
-        ScaleBf16 sc[VEC];
-        bool recip_ok[VEC];
-        bool mine_fast = !F32;
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) {
-            const float sv = col_scale[threadIdx.x][c];
-            mine_fast = mine_fast && !(__float_as_uint(sv) >> 31);
-            sc[c] = make_scale(fabsf(sv));
-            recip_ok[c] = classify_scale(sc[c].s) != DIV_EXACT;
-        }
-        const bool fast = __all_sync(0xFFFFFFFFu, mine_fast);
-        uint4 *yp = y + (o * n) * inner_vec + cv;
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const size_t r = row0 + (size_t)k * 8;
-            const uint32_t win[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-            uint32_t out[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (!F32 && fast) {
-                    out[q] = mx_word_fast(fast_round, win[q], sc[(2 * q) % VEC].s, sc[(2 * q) % VEC].rs,
-                                          sc[(2 * q + 1) % VEC].s, sc[(2 * q + 1) % VEC].rs);
-                } else if (F32) {
-                    out[q] = fq_f32<R, false>(round, win[q], sc[q].s);
-                } else {
-                    const uint32_t lo = win[q] << 16, hi = win[q] & 0xFFFF0000u;
-                    const float qlo = recip_ok[2 * q] ? bf16_quotient<DIV_RECIP>(lo, sc[2 * q])
-                                                      : bf16_quotient<DIV_EXACT>(lo, sc[2 * q]);
-                    const float qhi = recip_ok[2 * q + 1] ? bf16_quotient<DIV_RECIP>(hi, sc[2 * q + 1])
-                                                          : bf16_quotient<DIV_EXACT>(hi, sc[2 * q + 1]);
-                    const uint32_t uq = bf16x2_rne(qlo, qhi);
-                    out[q] = bf16x2_rne(__fmul_rn(__uint_as_float(round.lo(uq)), sc[2 * q].s),
-                                        __fmul_rn(__uint_as_float(round.hi(uq)), sc[2 * q + 1].s));
-                }
-            }
-            if (active && r < n) st_stream(yp + r * inner_vec, make_uint4(out[0], out[1], out[2], out[3]));
-        }
-    }
-}
-
-// ----------------------------------------------------------------------------- tile kernel (two tiled axes)
-// Tensor [outer, n1, n2], square blocks of BS x BS (BS = 8 * RPT) over the last two axes (ax = (-2, -1)),
-// n2 % VEC == 0.  blockDim = (32, 8): a CTA holds BS rows x 32 column groups; a block is BS / VEC adjacent lanes wide
-// (xor-shuffle) and 8 row phases x RPT register rows high (shared memory).  Rows / columns past the edge read as zero.
-template <class R, bool F32, int RPT>
-__global__ void __launch_bounds__(256)
-mx_tile_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer, size_t n1, size_t n2_vec, size_t nb1,
-               size_t nb2, const __grid_constant__ typename R::Params params, const __grid_constant__ BlockParams bp,
-               float *__restrict__ scale_out)
-{
-    constexpr int VEC = F32 ? 4 : 8;
-    constexpr int BS = 8 * RPT;
-    constexpr int LANES = BS / VEC >= 1 ? BS / VEC : 1;
-    static_assert(BS % VEC == 0 && LANES <= 32, "block width must be whole 16-byte vectors within a warp");
-    const unsigned char *lut_smem = stage_table<R>(params);
-    const R round(params, lut_smem);
-    const typename FastOf<R>::type fast_round(params, lut_smem);
-    const uint32_t *tab = stage_pow2_table(bp, R::kSmemBytes);
-    __shared__ uint32_t red[8][33];
-    const size_t cchunks = (n2_vec + 31) / 32;
-    const size_t work = outer * nb1 * cchunks;
-    for (size_t w = blockIdx.x; w < work; w += gridDim.x) {
-        const size_t cc = w % cchunks, rest = w / cchunks;
-        const size_t b1 = rest % nb1, o = rest / nb1;
-        const size_t cv = cc * 32 + threadIdx.x;
-        const bool active = cv < n2_vec;
-        const size_t row0 = b1 * BS + threadIdx.y;
-        const uint4 *xp = x + (o * n1) * n2_vec + cv;
-        uint4 v[RPT];
-        uint32_t a = 0u;
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const size_t r = row0 + (size_t)k * 8;
-            v[k] = (active && r < n1) ? ld_stream(xp + r * n2_vec) : make_uint4(0u, 0u, 0u, 0u);
-            a = F32 ? amax_of_vec_f32(a, v[k]) : amax_of_vec_bf16(a, v[k]);
-        }
-#pragma unroll
-        for (int off = 1; off < LANES; off <<= 1) a = max(a, __shfl_xor_sync(0xFFFFFFFFu, a, off));
-        red[threadIdx.y][threadIdx.x] = a;
-        __syncthreads();
-#pragma unroll
-        for (int p = 0; p < 8; ++p) a = max(a, red[p][threadIdx.x]);
-        __syncthreads();  // the next work item overwrites red[]
-        const float s = mx_scale_fast<F32>(a, bp, tab);
-        if (threadIdx.y == 0 && active && (threadIdx.x & (LANES - 1)) == 0)
-            scale_out[(o * nb1 + b1) * nb2 + cv / LANES] = s;
-        const float sa = a == 0u ? 1.0f : s;
-        float rs = 0.0f;
-        bool fast = false;
-        if (!F32) {
-            rs = __frcp_rn(sa);
-            fast = __all_sync(0xFFFFFFFFu, mx_block_is_fast(a, sa, rs, bp));
-        }
-        uint4 *yp = y + (o * n1) * n2_vec + cv;
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const size_t r = row0 + (size_t)k * 8;
-            uint4 out;
-            if (fast) {
-                out.x = mx_word_fast(fast_round, v[k].x, sa, rs, sa, rs);
-                out.y = mx_word_fast(fast_round, v[k].y, sa, rs, sa, rs);
-                out.z = mx_word_fast(fast_round, v[k].z, sa, rs, sa, rs);
-                out.w = mx_word_fast(fast_round, v[k].w, sa, rs, sa, rs);
-            } else {
-                out = mx_apply_vec<R, F32>(round, v[k], sa);
-            }
-            if (active && r < n1) st_stream(yp + r * n2_vec, out);
-        }
-    }
-}
 
 // ----------------------------------------------------------------------------- affine scheme, single pass
 // sf = (max - min) / (quant_max - quant_min); sf = where(sf > 0, sf, 1); zp = -min / sf + quant_min, each op in
@@ -693,18 +297,6 @@ gwa_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t outer
 // ----------------------------------------------------------------------------- generic kernels
 // Tensor [d0, n1, d1, n2, d2]; n1 is tiled with bs, n2 is tiled with bs2 (bs or 1).  Block grid
 // [d0, nb1, d1, nb2, d2] row-major is the layout of scale / zero_point.
-struct BlockDims {
-    size_t d0, n1, d1, n2, d2;
-    size_t nb1, nb2;
-    uint32_t bs, bs2;
-};
-
-__device__ __forceinline__ float load_elem(const void *x, bool f32, size_t i)
-{
-    return f32 ? static_cast<const float *>(x)[i]
-               : __uint_as_float((uint32_t) static_cast<const uint16_t *>(x)[i] << 16);
-}
-
 // AFFINE = false: amax -> scale.  AFFINE = true: min / max (padding zeros of cut blocks included) -> scale, zp.
 template <bool F32, bool AFFINE>
 __global__ void __launch_bounds__(256)
@@ -801,105 +393,6 @@ block_apply_kernel(const void *__restrict__ x, void *__restrict__ y, size_t tota
 
 // ----------------------------------------------------------------------------- launch
 
-struct BlockJob {
-    const qt_block_desc_t *d;
-    BlockDims D;
-    BlockParams bp;
-    cudaStream_t stream;
-    bool f32;
-};
-
-template <class R, bool F32, int LANES>
-void launch_flat(const BlockJob &j, const typename R::Params &p, size_t nvec)
-{
-    allow_smem<mx_flat_kernel<R, F32, LANES>>(R::kSmemBytes + kPow2SmemBytes);
-    const size_t tile = (size_t)R::kThreads * kUnroll;
-    const unsigned grid = grid_for((nvec + tile - 1) / tile, R::kCtasPerSm);
-    mx_flat_kernel<R, F32, LANES><<<grid, R::kThreads, R::kSmemBytes + kPow2SmemBytes, j.stream>>>(
-        static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), nvec, p, j.bp, j.d->scale);
-}
-template <class R, bool F32>
-bool try_flat(const BlockJob &j, const typename R::Params &p)
-{
-    constexpr size_t VEC = F32 ? 4 : 8;
-    const BlockDims &D = j.D;
-    // blocks along the unit-stride axis only: [d0, n1] with n1 % bs == 0 (d1 = n2 = d2 = 1)
-    if (D.d1 != 1 || D.n2 != 1 || D.d2 != 1 || D.bs2 != 1) return false;
-    if (D.n1 % D.bs != 0 || D.bs % VEC != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(j.d->x) | reinterpret_cast<uintptr_t>(j.d->y)) & 15u) return false;
-    const size_t lanes = D.bs / VEC;
-    const size_t nvec = D.d0 * D.n1 / VEC;
-    switch (lanes) {
-    case 1: launch_flat<R, F32, 1>(j, p, nvec); return true;
-    case 2: launch_flat<R, F32, 2>(j, p, nvec); return true;
-    case 4: launch_flat<R, F32, 4>(j, p, nvec); return true;
-    case 8: launch_flat<R, F32, 8>(j, p, nvec); return true;
-    case 16: launch_flat<R, F32, 16>(j, p, nvec); return true;
-    case 32: launch_flat<R, F32, 32>(j, p, nvec); return true;
-    default: return false;
-    }
-}
-
-template <class R, bool F32, int RPT>
-void launch_cols(const BlockJob &j, const typename R::Params &p, size_t outer, size_t n, size_t inner_vec)
-{
-    allow_smem<mx_cols_kernel<R, F32, RPT>>(R::kSmemBytes + kPow2SmemBytes);
-    const size_t nblk = (n + 8 * RPT - 1) / (8 * RPT);
-    const size_t work = nblk * ((outer * inner_vec + 31) / 32);
-    const unsigned grid = grid_for(work, R::kTable ? 3 : 8);
-    mx_cols_kernel<R, F32, RPT><<<grid, dim3(32, 8), R::kSmemBytes + kPow2SmemBytes, j.stream>>>(
-        static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), outer, n, inner_vec, nblk, p, j.bp,
-        j.d->scale);
-}
-template <class R, bool F32>
-bool try_cols(const BlockJob &j, const typename R::Params &p)
-{
-    constexpr size_t VEC = F32 ? 4 : 8;
-    const BlockDims &D = j.D;
-    // one tiled axis with a dense inner part: [d0, n1, d1] (n2 = d2 = 1), d1 % VEC == 0
-    if (D.n2 != 1 || D.d2 != 1 || D.bs2 != 1 || D.d1 < VEC || D.d1 % VEC != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(j.d->x) | reinterpret_cast<uintptr_t>(j.d->y)) & 15u) return false;
-    const size_t inner_vec = D.d1 / VEC;
-    switch (D.bs) {
-    case 8: launch_cols<R, F32, 1>(j, p, D.d0, D.n1, inner_vec); return true;
-    case 16: launch_cols<R, F32, 2>(j, p, D.d0, D.n1, inner_vec); return true;
-    case 32: launch_cols<R, F32, 4>(j, p, D.d0, D.n1, inner_vec); return true;
-    case 64: launch_cols<R, F32, 8>(j, p, D.d0, D.n1, inner_vec); return true;
-    case 128: launch_cols<R, F32, 16>(j, p, D.d0, D.n1, inner_vec); return true;
-    default: return false;
-    }
-}
-
-template <class R, bool F32, int RPT>
-void launch_tile(const BlockJob &j, const typename R::Params &p, size_t n2_vec)
-{
-    allow_smem<mx_tile_kernel<R, F32, RPT>>(R::kSmemBytes + kPow2SmemBytes);
-    const BlockDims &D = j.D;
-    const size_t work = D.d0 * D.nb1 * ((n2_vec + 31) / 32);
-    const unsigned grid = grid_for(work, R::kTable ? 3 : 8);
-    mx_tile_kernel<R, F32, RPT><<<grid, dim3(32, 8), R::kSmemBytes + kPow2SmemBytes, j.stream>>>(
-        static_cast<const uint4 *>(j.d->x), static_cast<uint4 *>(j.d->y), D.d0, D.n1, n2_vec, D.nb1, D.nb2, p, j.bp,
-        j.d->scale);
-}
-template <class R, bool F32>
-bool try_tile(const BlockJob &j, const typename R::Params &p)
-{
-    constexpr size_t VEC = F32 ? 4 : 8;
-    const BlockDims &D = j.D;
-    // two tiled axes, adjacent and last: [d0, n1, n2] (d1 = d2 = 1), n2 in whole vectors
-    if (D.bs2 != D.bs || D.d1 != 1 || D.d2 != 1 || D.n2 % VEC != 0 || D.bs % VEC != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(j.d->x) | reinterpret_cast<uintptr_t>(j.d->y)) & 15u) return false;
-    const size_t n2_vec = D.n2 / VEC;
-    switch (D.bs) {
-    case 8: launch_tile<R, F32, 1>(j, p, n2_vec); return true;
-    case 16: launch_tile<R, F32, 2>(j, p, n2_vec); return true;
-    case 32: launch_tile<R, F32, 4>(j, p, n2_vec); return true;
-    case 64: launch_tile<R, F32, 8>(j, p, n2_vec); return true;
-    case 128: launch_tile<R, F32, 16>(j, p, n2_vec); return true;
-    default: return false;
-    }
-}
-
 template <class R, bool F32, bool AFFINE>
 void launch_generic(const BlockJob &j, const typename R::Params &p)
 {
@@ -964,15 +457,6 @@ bool try_gwa_fast(const BlockJob &j)
     }
 }
 
-template <class R, bool F32>
-void launch_mx(const BlockJob &j, const typename R::Params &p)
-{
-    const bool single_pass_ok = j.d->y != nullptr && j.bp.scale_table == nullptr;
-    if (single_pass_ok && try_flat<R, F32>(j, p)) return;
-    if (single_pass_ok && try_cols<R, F32>(j, p)) return;
-    if (single_pass_ok && try_tile<R, F32>(j, p)) return;
-    launch_generic<R, F32, false>(j, p);
-}
 
 // ----------------------------------------------------------------------------- table ops (operator surface)
 // torch.ops.quantized_ops.{vmap, quantize, dequantize} of the reference (decomposed.py:143-262) with a caller-supplied
@@ -1150,10 +634,13 @@ extern "C" int qt_fq_block(const qt_block_desc_t *d, void *stream)
             j.f32 ? launch_generic<R, true, true>(j, p) : launch_generic<R, false, true>(j, p);
         });
     } else {
-        rc = dispatch_rounder(P, d->lut, [&](auto tag, const auto &p) {
-            using R = typename decltype(tag)::type;
-            j.f32 ? launch_mx<R, true>(j, p) : launch_mx<R, false>(j, p);
-        });
+        // single-pass kernels (one translation unit per family); anything they cannot express takes the generic pair
+        const bool single_pass_ok = d->y != nullptr && bp.scale_table == nullptr;
+        if (!(single_pass_ok && (qtblk::try_flat(j, P) || qtblk::try_cols(j, P) || qtblk::try_tile(j, P))))
+            rc = dispatch_rounder(P, d->lut, [&](auto tag, const auto &p) {
+                using R = typename decltype(tag)::type;
+                j.f32 ? launch_generic<R, true, false>(j, p) : launch_generic<R, false, false>(j, p);
+            });
     }
     if (rc != QT_OK) return rc;
     cudaError_t e = cudaGetLastError();
