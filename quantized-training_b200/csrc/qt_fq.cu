@@ -53,11 +53,7 @@ __device__ __forceinline__ void fq_span(const R &round, const uint4 *__restrict_
             for (int j = 0; j < kUnroll; ++j) {
                 const size_t i = base + (size_t)j * nthr;
                 if (AMAX) amax = amax_of_vec_bf16(amax, v[j]);
-                uint4 r;
-                r.x = fq_word_bf16_recip_notiny<R>(round, v[j].x, sc);
-                r.y = fq_word_bf16_recip_notiny<R>(round, v[j].y, sc);
-                r.z = fq_word_bf16_recip_notiny<R>(round, v[j].z, sc);
-                r.w = fq_word_bf16_recip_notiny<R>(round, v[j].w, sc);
+                const uint4 r = fq_vec_bf16_recip_notiny<R>(round, v[j], sc);
                 if (i < nvec) st_stream(y + i, r);
             }
         } else if constexpr (!F32 && DIV == DIV_RECIP) {
