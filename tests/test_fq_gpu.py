@@ -246,3 +246,35 @@ def test_codes_decode_to_the_fake_quant_values(spec, elem):
             # e4m3 has no Inf: fpN_eXmY's Inf pass-through becomes the NaN code (documented), everything else is exact
             assert nan_eq(got[finite_codes], want[finite_codes]).all(), (spec, elem, call)
             assert nan_eq32(bits_of(a.scale), bits_of(b.scale)).all()
+
+
+def test_more_than_four_giga_elements():
+    """BASELINE's sweep goes up to 4 G elements: one call on 2^32 + 2^20 bf16 elements (8 GiB in, 8 GiB out; element
+    and byte offsets beyond 32 bits).  The input is a 2^20-element block repeated, so every block of the output must
+    equal the output of that block alone (position independence), the amax must be the block's, and the block-scaled
+    kernel must write the same scales for every repetition."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs ~40 GiB of free device memory")
+    g = torch.Generator(device=DEV).manual_seed(11)
+    blk = (torch.randn(1 << 20, generator=g, device=DEV) * 7).to(torch.bfloat16)
+    reps = (1 << 12) + 1
+    x = blk.repeat(reps)
+    assert x.numel() == (1 << 32) + (1 << 20)
+    for spec in ("posit8_1", "fp8_e4m3,qs=per_tensor_symmetric,ahl=2", "int8"):
+        mod, _ = module_for(spec)
+        small, _ = module_for(spec)
+        for _ in range(2):                      # second call: the delayed scale is live
+            y = mod(x)
+            want = small(blk)
+            assert torch.equal(y.view(reps, -1).view(torch.int16), want.view(torch.int16).expand(reps, -1)), spec
+            del y
+        if mod.qscheme is not None:
+            assert torch.equal(mod.amax_history, small.amax_history) and torch.equal(mod.scale, small.scale)
+    mx = qt.FusedAmaxObsFakeQuantize("fp4_e2m1", qscheme="microscaling", quant_min=-6.0, quant_max=6.0, ch_axis=-1,
+                                     block_size=32, force_scale_power_of_two=True, device=DEV)
+    y = mx(x)
+    s_all = mx.scale.clone()
+    want = mx(blk)
+    assert torch.equal(y.view(reps, -1).view(torch.int16), want.view(torch.int16).expand(reps, -1))
+    assert torch.equal(s_all.view(reps, -1), mx.scale.view(1, -1).expand(reps, -1))
