@@ -35,15 +35,14 @@ _lib.define("matmul_mx(Tensor self, Tensor other, *, Tensor? input_scale=None, T
 
 
 def expand(input, shape, block_size):
-    """decomposed.py:127-140 (host-side helper of the reference, kept for drivers that import it)."""
-    while input.ndim < len(shape):
-        input = input.unsqueeze(0)
-    for dim in range(len(shape)):
-        if input.shape[dim] != shape[dim]:
-            input = torch.repeat_interleave(input, block_size, dim)
-    if list(input.shape) != list(shape):
-        input = input[tuple(slice(0, x) for x in shape)]
-    return input
+    """Per-block parameters -> one value per element of a tensor of `shape` (the host-side helper drivers import from
+    the reference, decomposed.py:127-140): leading axes are added, every axis whose extent differs is repeated
+    block_size times and cut back to the tensor's extent (edge blocks)."""
+    t = input.reshape((1,) * (len(shape) - input.ndim) + tuple(input.shape))
+    for d, want in enumerate(shape):
+        if t.shape[d] != want:
+            t = t.repeat_interleave(block_size, dim=d).narrow(d, 0, want)
+    return t
 
 
 def _table(t, device):

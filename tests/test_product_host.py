@@ -231,3 +231,16 @@ def test_per_tensor_pow2_scale_matches_libm():
     got = np.array([L.qt_scale_pow2_host(float(v)) for v in sf], dtype=np.float32)
     bad = np.nonzero(got.view(np.uint32) != want.view(np.uint32))[0]
     assert bad.size == 0, [(hex(bits[i]), got[i], want[i]) for i in bad[:8]]
+
+
+def test_expand_helper():
+    from quantized_training.decomposed import expand
+    s = torch.arange(6.0).reshape(2, 3)
+    e = expand(s, (2, 70), 32)
+    assert e.shape == (2, 70) and torch.equal(e[:, 0], s[:, 0]) and torch.equal(e[:, 31], s[:, 0])
+    assert torch.equal(e[:, 32], s[:, 1]) and torch.equal(e[:, 69], s[:, 2])
+    e3 = expand(s, (5, 2, 96), 32)           # a leading axis is added and repeated like any other
+    assert e3.shape == (5, 2, 96) and torch.equal(e3[4], e3[0]) and torch.equal(e3[0, :, 64], s[:, 2])
+    g = torch.arange(4.0).reshape(2, 2)
+    e2 = expand(g, (40, 50), 32)
+    assert e2.shape == (40, 50) and e2[31, 31] == 0 and e2[32, 31] == 2 and e2[31, 32] == 1 and e2[39, 49] == 3
