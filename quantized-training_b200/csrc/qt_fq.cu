@@ -247,8 +247,12 @@ fq_rows_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
 // inner == 1 per-channel (channel = last dim), channels % VEC == 0, 16-byte aligned rows.
 // blockDim = (32, 8): threadIdx.x -> a 16-byte column group, threadIdx.y -> row phase.
 // Scales and running maxima for the thread's VEC columns stay in registers over all rows.
+// kColsY row phases per CTA: 16 with a table rounder (512 threads, two CTAs per SM next to 2 x 64 KB of table = 1024
+// resident threads instead of 3 x 256), 8 otherwise.
+template <class R>
+constexpr int kColsY = R::kTable ? 16 : 8;
 template <class R, bool F32, bool AMAX, bool WRITE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kColsY<R>, R::kTable ? 2 : 1)
 fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, size_t vec_per_row,
                const __grid_constant__ typename R::Params params, const float *__restrict__ scale,
                float *__restrict__ amax_out)
@@ -322,7 +326,7 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
                 am[(2 * k + 1) % VEC] = amp[k] & 0xFFFF0000u;
             }
         }
-        __shared__ uint32_t red[8][32][VEC + 1];
+        __shared__ uint32_t red[kColsY<R>][32][VEC + 1];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) red[threadIdx.y][threadIdx.x][k] = am[k];
         __syncthreads();
@@ -330,7 +334,7 @@ fq_cols_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, size_t rows, 
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
                 uint32_t m = 0u;
-                for (int yy = 0; yy < 8; ++yy) m = max(m, red[yy][threadIdx.x][k]);
+                for (int yy = 0; yy < kColsY<R>; ++yy) m = max(m, red[yy][threadIdx.x][k]);
                 if (m != 0u) atomicMax(reinterpret_cast<unsigned int *>(amax_out) + cg * VEC + k, m);
             }
         }
@@ -542,14 +546,14 @@ void launch_layout(const Job &j, const typename R::Params &p)
     if (aligned && j.inner == 1 && j.channels % VEC == 0) {
         const size_t rows = j.outer, vec_per_row = j.channels / VEC;
         const unsigned gx = (unsigned)((vec_per_row + 31) / 32);
-        size_t want_y = ((size_t)num_sms() * (R::kTable ? 3 : 8) + gx - 1) / gx;
-        const size_t max_y = (rows + 7) / 8;
+        size_t want_y = ((size_t)num_sms() * (R::kTable ? 2 : 8) + gx - 1) / gx;
+        const size_t max_y = (rows + kColsY<R> - 1) / kColsY<R>;
         if (want_y > max_y) want_y = max_y;
         if (want_y < 1) want_y = 1;
         if (want_y > 65535) want_y = 65535;
         auto kernel = fq_cols_kernel<R, F32, AMAX, WRITE>;
         allow_smem<fq_cols_kernel<R, F32, AMAX, WRITE>>(R::kSmemBytes);
-        kernel<<<dim3(gx, (unsigned)want_y), dim3(32, 8), R::kSmemBytes, j.stream>>>(xv, yv, rows, vec_per_row, p,
+        kernel<<<dim3(gx, (unsigned)want_y), dim3(32, kColsY<R>), R::kSmemBytes, j.stream>>>(xv, yv, rows, vec_per_row, p,
                                                                                   j.scale, j.amax);
         return;
     }
