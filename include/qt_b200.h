@@ -279,7 +279,19 @@ typedef struct qt_gemm_desc {
      * qt_causal_mask_check): the schedule applies only if it is non-zero, else the full product is computed -- the
      * decision is made on the device, so a forward captured in a CUDA graph stays correct when the mask changes. */
     const int32_t *causal_flag;
+    /* Operand storage order.  QT_MAJOR_K (0, default): A is [M, K], B is [N, K], unit-stride K axis, lda / ldb =
+     * row strides.  QT_MAJOR_MN: the operand is stored transposed -- A as [K, M], B as [K, N], unit-stride row axis,
+     * lda / ldb = the stride between K lines -- and is read by the tensor cores as it lies (MN-major shared-memory
+     * descriptors), so the backward products of a Linear y = x W^T need no transpose copies
+     * (autograd of F.linear, modules/qat/linear.py:40-41):
+     *   dgrad  gx[M, K] = g[M, N] W[N, K]      A = g  (K-major), B = W (MN-major: contraction over its row axis)
+     *   wgrad  gW[N, K] = g[M, N]^T x[M, K]    A = g  (MN-major), B = x (MN-major)
+     * and torch.matmul(x, y) with y [K, N] row-major is A = x, B = y (MN-major).  With one-byte operands an MN-major
+     * B needs N tiles of 128 rows (chosen automatically).  The causal schedules take K-major operands. */
+    int32_t a_major, b_major;
 } qt_gemm_desc_t;
+#define QT_MAJOR_K 0
+#define QT_MAJOR_MN 1
 #define QT_CAUSAL_OUT_LOWER 1
 #define QT_CAUSAL_A_LOWER 2
 int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);

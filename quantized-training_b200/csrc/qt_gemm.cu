@@ -63,6 +63,7 @@ struct GemmParams {
     int causal;              // 0 off; 1: tiles strictly above the diagonal are skipped (scores of a causal attention);
                              // 2: A is lower triangular (its probabilities): the K loop of row tile mt stops at its diagonal
     int debug;               // QT_GEMM_DEBUG bit mask (timing experiments only; results are wrong when set)
+    int a_mn, b_mn;          // operand is MN-major: stored [K, rows] with a unit-stride row axis (backward products)
     const __nv_bfloat16 *bias;      // [N] or null
     const __nv_bfloat16 *residual;  // same layout as C, or null
     int64_t ldr, strideR_inner, strideR_outer;
@@ -172,6 +173,10 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int block_n = p.block_n;
+    // MN-major operand tiles: one TMA box = 128 bytes of rows (64 bf16 / 128 fp8) x the K lines of a k-block
+    constexpr int MN_BOX_ROWS = FP8 ? 128 : 64;
+    constexpr int MN_BOX_BYTES = (FP8 ? 128 : 64) * ROW_BYTES;        // K lines per k-block x 128 bytes
+    constexpr int MN_K_STEP_BYTES = (FP8 ? 32 : 16) * ROW_BYTES;      // K lines per tcgen05.mma x 128 bytes
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -223,8 +228,22 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_arrive_expect_tx(full_bar(stage), stage_tx);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     const int kcoord = kb * (FP8 ? ROW_BYTES : ROW_BYTES / 2);
-                    tma_load_4d(sa, &map_a, full_bar(stage), kcoord, (int)(mt * BLOCK_M), bi, bo);
-                    tma_load_4d(sb, &map_b, full_bar(stage), kcoord, (int)(nt * block_n), bi, bo);
+                    // K-major operand: one box, rows x 128 bytes of K.  MN-major operand: boxes of 128 bytes of rows
+                    // x one k-block of K lines (64 bf16 / 128 fp8), side by side: the canonical MN-major layout
+                    if (!p.a_mn) {
+                        tma_load_4d(sa, &map_a, full_bar(stage), kcoord, (int)(mt * BLOCK_M), bi, bo);
+                    } else {
+                        for (int j = 0; j < BLOCK_M / MN_BOX_ROWS; ++j)
+                            tma_load_4d(sa + j * MN_BOX_BYTES, &map_a, full_bar(stage),
+                                        (int)(mt * BLOCK_M) + j * MN_BOX_ROWS, kcoord, bi, bo);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_4d(sb, &map_b, full_bar(stage), kcoord, (int)(nt * block_n), bi, bo);
+                    } else {
+                        for (int j = 0; j < block_n / MN_BOX_ROWS; ++j)
+                            tma_load_4d(sb + j * MN_BOX_BYTES, &map_b, full_bar(stage),
+                                        (int)(nt * block_n) + j * MN_BOX_ROWS, kcoord, bi, bo);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -252,13 +271,15 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     trace(p, 1, tslot);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+                    const uint64_t da = p.a_mn ? make_smem_desc_mn(sa, MN_BOX_BYTES) : make_smem_desc(sa);
+                    const uint64_t db = p.b_mn ? make_smem_desc_mn(sb, MN_BOX_BYTES) : make_smem_desc(sb);
+                    // advancing K = advancing the start address (16-byte units): 32 bytes inside the swizzle atom of
+                    // a K-major tile; 16 (bf16) / 32 (fp8) K lines of 128 bytes in an MN-major tile
+                    const uint64_t ka = p.a_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
+                    const uint64_t kbs = p.b_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k) {
-                        // advancing K inside the swizzle atom = advancing the start address (16-byte units)
-                        const uint64_t koff = (uint64_t)((k * MMA_K_BYTES) >> 4);
-                        tcgen05_mma<FP8>(tmem_d, da + koff, db + koff, p.idesc, (kb | k) != 0);
-                    }
+                    for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k)
+                        tcgen05_mma<FP8>(tmem_d, da + k * ka, db + k * kbs, p.idesc, (kb | k) != 0);
                     tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) {
                         stage = 0;
@@ -459,11 +480,11 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ----------------------------------------------------------------------------- host side
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D = F32 [4,6) = 1;
 // A/B format [7,10) / [10,13): kind::f16 BF16 = 1, kind::f8f6f4 E4M3 = 0 / E5M2 = 1; both K-major;
-// N >> 3 at [17,23); M >> 4 at [24,29).
-uint32_t make_idesc(int a_fmt, int b_fmt, int block_n)
+// A / B major-ness at bit 15 / 16 (0 K-major, 1 MN-major); N >> 3 at [17,23); M >> 4 at [24,29).
+uint32_t make_idesc(int a_fmt, int b_fmt, int block_n, int a_mn = 0, int b_mn = 0)
 {
-    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(block_n >> 3) << 17) |
-           ((uint32_t)(BLOCK_M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(a_mn != 0) << 15) |
+           ((uint32_t)(b_mn != 0) << 16) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
 // Tile width.  The persistent grid runs ceil(tiles / SMs) rounds; a round costs the larger of the tile's MMA time
@@ -533,6 +554,12 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     const int esz = fp8 ? 1 : 2;
     const int64_t k_align = 16 / esz;
     auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0; };
+    const int a_mn = d->a_major != 0, b_mn = d->b_major != 0;
+    if ((d->a_major & ~1) || (d->b_major & ~1) || ((a_mn || b_mn) && d->causal)) {
+        qt_set_error("qt_gemm_nt: a_major / b_major are QT_MAJOR_K or QT_MAJOR_MN; the causal schedules take K-major "
+                     "operands");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
     const bool bad_ab = d->lda % k_align || d->ldb % k_align || (inner > 1 && (d->strideA_inner % k_align ||
                         d->strideB_inner % k_align)) || (outer > 1 && (d->strideA_outer % k_align ||
                         d->strideB_outer % k_align));
@@ -598,7 +625,10 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.K = K;
     p.batch_inner = (uint32_t)inner;
     p.k_blocks = (int)((K * esz + ROW_BYTES - 1) / ROW_BYTES);
-    p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, glu ? 128 : 64);
+    p.a_mn = a_mn;
+    p.b_mn = b_mn;
+    // an MN-major B tile is made of boxes of 128 bytes of rows: 64 bf16 rows, 128 fp8 rows
+    p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, (glu || (b_mn && fp8)) ? 128 : 64);
     p.causal = d->causal;
     p.causal_flag = d->causal_flag;
     if (p.causal < 0 || p.causal > 2 || (p.causal == 1 && M != N) || (p.causal == 2 && M != K)) {
@@ -609,7 +639,7 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
         p.debug = atoi(dbg);
         if (p.debug & 4) p.block_n = 128;
-        if ((p.debug & 8) && !glu) p.block_n = 64;
+        if ((p.debug & 8) && !glu && !(b_mn && fp8)) p.block_n = 64;
         if (p.debug & 16) p.block_n = 256;
     }
     const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + p.block_n - 1) / p.block_n;
@@ -623,9 +653,14 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.num_tiles = (uint32_t)(m_tiles * n_tiles * batch);
 
     CUtensorMap map_a, map_b, map_c;
-    int rc = make_map(&map_a, d->A, fp8, K, M, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, BLOCK_M);
+    // K-major: [rows, K] boxes of rows x 128 bytes of K.  MN-major: [K, rows] boxes of one k-block of K lines x 128
+    // bytes of rows; K lines / rows past the end read as zero either way.
+    const int k_lines = fp8 ? 128 : 64;
+    int rc = a_mn ? make_map(&map_a, d->A, fp8, M, K, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, k_lines)
+                  : make_map(&map_a, d->A, fp8, K, M, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, BLOCK_M);
     if (rc != QT_OK) return rc;
-    rc = make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n);
+    rc = b_mn ? make_map(&map_b, d->B, fp8, N, K, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, k_lines)
+              : make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n);
     if (rc != QT_OK) return rc;
     rc = make_map(&map_c, d->C, c_esz == 1, n_out, M, inner, outer, d->ldc, d->strideC_inner, d->strideC_outer, 32,
                   c_esz == 1 ? 64 : ROW_BYTES);
@@ -639,11 +674,11 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.alpha = d->alpha;
     p.act = d->activation;
     switch (operand_type) {
-    case QT_GEMM_BF16: p.idesc = make_idesc(1, 1, p.block_n); break;
-    case QT_GEMM_E4M3: p.idesc = make_idesc(0, 0, p.block_n); break;
-    case QT_GEMM_E5M2: p.idesc = make_idesc(1, 1, p.block_n); break;
-    case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1, p.block_n); break;
-    default: p.idesc = make_idesc(1, 0, p.block_n); break;  // QT_GEMM_E5M2_E4M3
+    case QT_GEMM_BF16: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn); break;
+    case QT_GEMM_E4M3: p.idesc = make_idesc(0, 0, p.block_n, a_mn, b_mn); break;
+    case QT_GEMM_E5M2: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn); break;
+    case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1, p.block_n, a_mn, b_mn); break;
+    default: p.idesc = make_idesc(1, 0, p.block_n, a_mn, b_mn); break;  // QT_GEMM_E5M2_E4M3
     }
     const unsigned grid = p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

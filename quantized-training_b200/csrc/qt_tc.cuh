@@ -110,6 +110,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
     return d;
 }
 
+// MN-major operand tile (the operand is stored [K, rows] with a unit-stride row axis): TMA boxes of 128 bytes of rows
+// x `k lines`, 128-byte swizzle, placed side by side `box_bytes` apart.  Canonical UMMA layout (units of 16 bytes)
+// ((8, n), (8, k)) : ((1, LBO), (8, SBO)): 8 K lines of 128 bytes form a swizzle atom (SBO = 1024 B between atoms
+// along K), the next 128 bytes of rows start LBO = box_bytes further (cute/atom/mma_traits_sm100.hpp,
+// make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t box_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((box_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 // ----------------------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,

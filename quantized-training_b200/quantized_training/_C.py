@@ -332,6 +332,7 @@ class QtGemmDesc(ctypes.Structure):
         ("fq_fmt", ctypes.POINTER(QtFormat)), ("fq_lut", ctypes.c_void_p),
         ("out_type", ctypes.c_int32), ("glu", ctypes.c_int32),
         ("causal", ctypes.c_int32), ("reserved", ctypes.c_int32), ("causal_flag", ctypes.c_void_p),
+        ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32),
     ]
 
 
@@ -351,7 +352,7 @@ def _as4d(t, name, align):
 
 
 def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None,
-            fq=None, out_codes=False, glu=False, causal=0, causal_flag=None):
+            fq=None, out_codes=False, glu=False, causal=0, causal_flag=None, a_mn=False, b_mn=False):
     """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
     a, b: bf16 (GEMM_BF16) or uint8 fp8 codes, up to two leading batch dimensions with arbitrary strides;
     bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional destination (any 16-byte
@@ -360,21 +361,24 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     out_codes: with an e4m3 / e5m2 `fq`, store one-byte fp8 codes (out is uint8); glu: b is a gate|up projection
     interleaved in blocks of 64 rows and the result is activation(gate) * up with n / 2 columns.
     causal: CAUSAL_OUT_LOWER (skip output tiles above the diagonal) / CAUSAL_A_LOWER (a is lower triangular);
-    causal_flag: optional device int32 tensor (causal_mask_check) that gates the schedule on the device."""
+    causal_flag: optional device int32 tensor (causal_mask_check) that gates the schedule on the device.
+    a_mn / b_mn: the operand is handed over as it is stored, transposed -- a as [..., k, m], b as [..., k, n] with a
+    unit-stride last axis -- and read MN-major by the tensor cores (dgrad / wgrad / x @ y without transpose copies)."""
     _require_cuda(a, "a")
     want = torch.uint8 if operand_type != GEMM_BF16 else torch.bfloat16
     if a.dtype != want or b.dtype != want:
         raise TypeError(f"operand_type {operand_type} takes {want} operands, got {a.dtype} and {b.dtype}")
-    if b.dim() == 2 and a.dim() > 2:   # one weight for every batch entry: the batch is just more rows
+    if b.dim() == 2 and a.dim() > 2 and not a_mn:   # one weight for every batch entry: the batch is just more rows
         a = a.reshape(-1, a.shape[-1])
     align = 16 if operand_type != GEMM_BF16 else 8
     a4, b4 = _as4d(a, "a", align), _as4d(b, "b", align)
     if a4.shape[:2] != b4.shape[:2]:
         raise ValueError(f"batch mismatch: {tuple(a.shape)} x {tuple(b.shape)}")
-    outer, inner, M, K = a4.shape
-    N = b4.shape[2]
-    if b4.shape[3] != K:
-        raise ValueError(f"inner dimensions differ: {tuple(a.shape)} x {tuple(b.shape)}^T")
+    outer, inner = a4.shape[:2]
+    (K, M) = a4.shape[2:] if a_mn else a4.shape[:1:-1]
+    (Kb, N) = b4.shape[2:] if b_mn else b4.shape[:1:-1]
+    if Kb != K:
+        raise ValueError(f"inner dimensions differ: {tuple(a.shape)} (a_mn={a_mn}) x {tuple(b.shape)} (b_mn={b_mn})")
     lead = a.shape[:-2] if a.dim() >= b.dim() else b.shape[:-2]
     out_shape = (*lead, M, N // 2 if glu else N)
     out_dtype = torch.uint8 if out_codes else torch.bfloat16
@@ -398,6 +402,7 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     d.alpha = float(alpha)
     d.glu = 1 if glu else 0
     d.causal = int(causal)
+    d.a_major, d.b_major = int(bool(a_mn)), int(bool(b_mn))
     if causal_flag is not None:
         assert causal_flag.dtype == torch.int32 and causal_flag.device == a.device
         d.causal_flag = causal_flag.data_ptr()

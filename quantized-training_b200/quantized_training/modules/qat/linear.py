@@ -29,7 +29,7 @@ class Linear(nn.Linear):
         kind = ops.fp8_route(self, input, self.weight_fake_quant)
         if kind is not None:  # bare e4m3/e5m2 on both sides: operands go to the FP8 tensor cores as codes
             return ops.linear_fp8(input, self.weight, self.bias, self.weight_fake_quant, kind,
-                                  codes=self._quantized_weight(codes=True))
+                                  codes=self._quantized_weight(codes=True), g_kind=ops.fp8_grad_kind(self))
         return ops.linear(input, self._quantized_weight(), self.bias)
 
     def _quantized_weight(self, codes=False):

@@ -27,7 +27,7 @@ class Linear(_FloatLora):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         in_dtype = x.dtype
         if self.disable_adapters or self.merged:
-            return F.linear(x, _t(self.weight, self.fan_in_fan_out), self.bias).to(in_dtype)
+            return ops.linear(x, _t(self.weight, self.fan_in_fan_out), self.bias).to(in_dtype)
         merged = self.weight.data.clone()
         for name in self.active_adapters:
             if name in self.lora_A:

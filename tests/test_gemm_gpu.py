@@ -211,3 +211,143 @@ def test_gated_epilogue_matches_the_mlp_op_chain(oracle, spec, codes, with_bias)
     assert float(same.float().mean()) >= 0.995
     gf, wf = got.float(), want.float()
     assert not bool((~same & ((gf - wf).abs() > 0.26 * wf.abs().clamp_min(1e-30)) & ((gf - wf).abs() > 2.0 ** -14)).any())
+
+
+# ---- MN-major operands: the backward products of a Linear and x @ y, read as the tensors lie (no transpose copies)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 192), (2048, 768, 768), (2048, 3072, 768),
+                                   (100, 264, 72), (8, 8, 8), (333, 1000, 1112), (1024, 4096, 4096)])
+def test_dgrad_wgrad_mn_major(M, N, K):
+    """y = x W^T with x [M, K], W [N, K], g = dL/dy [M, N].
+    dgrad gx = g W       : A = g K-major (contraction over N), B = W stored [N, K] = [k', n'] -> MN-major
+    wgrad gW = g^T x     : A = g stored [M, N] = [k', m'] -> MN-major, B = x stored [M, K] = [k', n'] -> MN-major"""
+    gen = torch.Generator().manual_seed(M + 3 * N + 5 * K)
+    x = quantized_operand((M, K), "e4m3", gen)
+    w = quantized_operand((N, K), "e4m3", gen, 0.05)
+    g = quantized_operand((M, N), "e5m2", gen, 0.01)
+    gx = _C.gemm_nt(g, w, b_mn=True)
+    assert gx.shape == (M, K)
+    check(gx, g.double() @ w.double())
+    gw = _C.gemm_nt(g, x, a_mn=True, b_mn=True)
+    assert gw.shape == (N, K)
+    check(gw, g.double().t() @ x.double())
+    # A MN-major alone (x^T @ B^T with B K-major)
+    if M % 8 == 0:   # row stride of a K-major B = M elements: the raw entry point wants 16-byte multiples
+        b = quantized_operand((N, M), "e4m3", gen, 0.1)      # [n', k'] K-major, contraction over M
+        out = _C.gemm_nt(x, b, a_mn=True)                    # x stored [k'=M, m'=K]
+        assert out.shape == (K, N)
+        check(out, x.double().t() @ b.double().t())
+
+
+@pytest.mark.parametrize("op,ta,tb", [(_C.GEMM_E4M3, "e4m3", "e4m3"), (_C.GEMM_E5M2_E4M3, "e5m2", "e4m3"),
+                                      (_C.GEMM_E4M3_E5M2, "e4m3", "e5m2")])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 384), (208, 272, 144), (1024, 4096, 1024)])
+def test_fp8_codes_mn_major(op, ta, tb, M, N, K):
+    """One-byte operands read MN-major (fp8 dgrad / wgrad): same products as the bf16 path."""
+    f8 = {"e4m3": torch.float8_e4m3fn, "e5m2": torch.float8_e5m2}
+    gen = torch.Generator().manual_seed(M + N + K)
+    a = quantized_operand((M, K), ta, gen)               # [m, k]
+    bt = quantized_operand((K, N), tb, gen, 0.1)         # B stored [k, n]: MN-major
+    at = quantized_operand((K, M), ta, gen)              # A stored [k, m]: MN-major
+    codes = lambda t, kind: t.to(f8[kind]).view(torch.uint8)
+    if N % 16 == 0:
+        check(_C.gemm_nt(codes(a, ta), codes(bt, tb), operand_type=op, b_mn=True), a.double() @ bt.double())
+    if M % 16 == 0 and N % 16 == 0:
+        check(_C.gemm_nt(codes(at, ta), codes(bt, tb), operand_type=op, a_mn=True, b_mn=True),
+              at.double().t() @ bt.double())
+
+
+def test_batched_mn_major_matmul_backward():
+    """torch.matmul(x, y) with x [B, H, S, S'], y [B, H, S', D] (attention P V): forward reads y MN-major;
+    gx = g y^T is K-major on both; gy = x^T g reads both MN-major.  Strided [B, S, H, D] views included."""
+    gen = torch.Generator().manual_seed(9)
+    B, H, S, D = 2, 3, 136, 64
+    p = quantized_operand((B, H, S, S), "e4m3", gen, 0.1)
+    v = quantized_operand((B, S, H * D), "e4m3", gen).view(B, S, H, D).transpose(1, 2)   # [B, H, S, D] strided
+    g = quantized_operand((B, H, S, D), "e5m2", gen, 0.01)
+    check(_C.gemm_nt(p, v, b_mn=True), p.double() @ v.double())
+    check(_C.gemm_nt(g, v), g.double() @ v.double().transpose(-1, -2))
+    gy = _C.gemm_nt(p, g, a_mn=True, b_mn=True)
+    assert gy.shape == (B, H, S, D)
+    check(gy, p.double().transpose(-1, -2) @ g.double())
+
+
+def _grad_check(got, ref):
+    check(got, ref)
+
+
+@pytest.mark.parametrize("shape,N,bias", [((4, 128, 768), 768, True), ((2048, 768), 3072, True), ((16, 768), 3, True),
+                                           ((3, 50, 72), 40, False), ((2, 7, 20), 12, True)])
+def test_ops_linear_autograd_on_kernel(shape, N, bias):
+    """ops.linear forward + dgrad + wgrad on the tcgen05 kernel (MN-major operands, zero-padded odd shapes such as a
+    3-class classifier head) against fp64 autograd of the same operands."""
+    from quantized_training import ops
+    gen = torch.Generator().manual_seed(sum(shape) + N)
+    K = shape[-1]
+    x = quantized_operand(shape, "e4m3", gen).requires_grad_(True)
+    w = quantized_operand((N, K), "e4m3", gen, 0.05).requires_grad_(True)
+    b = torch.randn(N, generator=gen).to(torch.bfloat16).to(DEV).requires_grad_(True) if bias else None
+    g = quantized_operand((*shape[:-1], N), "e5m2", gen, 0.01)
+    y = ops.linear(x, w, b)
+    y.backward(g)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd.backward(g.double())
+    check(y.detach(), yd.detach())
+    check(x.grad, xd.grad)
+    check(w.grad, wd.grad)
+    if bias:
+        check(b.grad, bd.grad)
+
+
+@pytest.mark.parametrize("transposed_y", [False, True])
+def test_ops_matmul_autograd_on_kernel(transposed_y):
+    from quantized_training import ops
+    gen = torch.Generator().manual_seed(77 + transposed_y)
+    B, H, S, D = 2, 4, 136, 64
+    if transposed_y:   # scores = q @ k^T
+        x = quantized_operand((B, H, S, D), "e4m3", gen).requires_grad_(True)
+        yb = quantized_operand((B, H, S, D), "e4m3", gen).requires_grad_(True)
+        y = yb.transpose(-1, -2)
+    else:              # context = p @ v
+        x = quantized_operand((B, H, S, S), "e4m3", gen, 0.1).requires_grad_(True)
+        yb = quantized_operand((B, H, S, D), "e4m3", gen).requires_grad_(True)
+        y = yb
+    out = ops.matmul(x, y)
+    g = quantized_operand(tuple(out.shape), "e5m2", gen, 0.01)
+    out.backward(g)
+    xd, ybd = x.detach().double().requires_grad_(True), yb.detach().double().requires_grad_(True)
+    outd = xd @ (ybd.transpose(-1, -2) if transposed_y else ybd)
+    outd.backward(g.double())
+    check(out.detach(), outd.detach())
+    check(x.grad, xd.grad)
+    check(yb.grad, ybd.grad)
+
+
+def test_fp8_linear_backward_on_fp8_tensor_cores():
+    """Bare e4m3 forward + bare e5m2 gradient: dgrad / wgrad as QT_GEMM_E5M2_E4M3 products of one-byte codes."""
+    from quantized_training import ops
+    gen = torch.Generator().manual_seed(123)
+    M, N, K = 256, 384, 512
+    x = quantized_operand((M, K), "e4m3", gen).requires_grad_(True)
+    w = (torch.randn(N, K, generator=gen) * 0.05).to(torch.bfloat16).to(DEV).requires_grad_(True)
+    wq = qt.FusedAmaxObsFakeQuantize("e4m3", device=DEV)
+    g = quantized_operand((M, N), "e5m2", gen, 0.01)
+    y = ops.linear_fp8(x, w, None, wq, "e4m3", g_kind="e5m2")
+    y.backward(g)
+    wv = wq(w.detach()).double()
+    check(y.detach(), x.detach().double() @ wv.t())
+    check(x.grad, g.double() @ wv)
+    check(w.grad, g.double().t() @ x.detach().double())
+
+
+def test_ops_raise_instead_of_falling_back():
+    from quantized_training import ops
+    x = torch.randn(8, 16, device=DEV)
+    w = torch.randn(8, 16, device=DEV)
+    with pytest.raises(TypeError):
+        ops.linear(x, w)
+    with pytest.raises(TypeError):
+        ops.matmul(x, w.t())
+    with pytest.raises(RuntimeError):
+        ops.linear(x.cpu().bfloat16(), w.cpu().bfloat16())
