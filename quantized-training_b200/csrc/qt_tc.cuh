@@ -155,6 +155,19 @@ int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int
         qt_set_error("cuTensorMapEncodeTiled is not available from this driver");
         return QT_ERR_CUDA;
     }
+    // cuTensorMapEncodeTiled is a DRIVER entry point: it needs a context current on the calling thread.  Runtime
+    // calls bind the primary context lazily, and a thread that has only ever inherited its device from a guard --
+    // autograd's backward worker, where dgrad / wgrad are launched -- may not have one yet (CUDA_ERROR_INVALID_CONTEXT).
+    // cudaSetDevice (CUDA 12) initialises and binds the primary context of the device; once per thread and device.
+    {
+        static thread_local int bound_device = -1;
+        int dev = -1;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_device) {
+            cudaSetDevice(dev);
+            cudaFree(nullptr);
+            bound_device = dev;
+        }
+    }
     const int esz = one_byte ? 1 : 2;
     // size-1 axes never move: give them a harmless, valid stride
     if (inner <= 1) stride_inner = rows * ld;

@@ -54,6 +54,24 @@ for name, b, M, N, K in shapes:
                  "out_GBps_qt_bf16": 2.0 * b * M * N / ms_q / 1e6}
     print(f"{name:38s} qt bf16 {fl/ms_q/1e9:6.0f} TF {ms_q*1e3:7.1f} us | cuBLAS bf16 {fl/ms_c/1e9:6.0f} TF {ms_c*1e3:7.1f} us | "
           f"qt fp8 {fl/ms_8/1e9:6.0f} TF {ms_8*1e3:7.1f} us", flush=True)
+# backward products (MN-major operands) vs the torch.matmul calls autograd would issue
+bwd = [("roberta 2048x768x768", 2048, 768, 768), ("roberta ffn1 2048x3072x768", 2048, 3072, 768),
+       ("roberta ffn2 2048x768x3072", 2048, 768, 3072), ("llama o 1024x4096x4096", 1024, 4096, 4096),
+       ("llama down 1024x4096x11008", 1024, 4096, 11008)]
+for name, M, N, K in bwd:
+    x = torch.randn(M, K, device=dev).to(torch.bfloat16); w = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    g = torch.randn(M, N, device=dev).to(torch.bfloat16)
+    gx = torch.empty(M, K, device=dev, dtype=torch.bfloat16); gw = torch.empty(N, K, device=dev, dtype=torch.bfloat16)
+    fl = 2.0 * M * N * K
+    t = {"dgrad_qt": timed(lambda: _C.gemm_nt(g, w, b_mn=True, out=gx)), "dgrad_cublas": timed(lambda: torch.matmul(g, w, out=gx)),
+         "wgrad_qt": timed(lambda: _C.gemm_nt(g, x, a_mn=True, b_mn=True, out=gw)),
+         "wgrad_cublas": timed(lambda: torch.matmul(g.t(), x, out=gw))}
+    g8 = g.to(torch.float8_e5m2).view(torch.uint8); w8 = w.to(torch.float8_e4m3fn).view(torch.uint8)
+    x8 = x.to(torch.float8_e4m3fn).view(torch.uint8)
+    t["dgrad_qt_fp8"] = timed(lambda: _C.gemm_nt(g8, w8, operand_type=_C.GEMM_E5M2_E4M3, b_mn=True, out=gx))
+    t["wgrad_qt_fp8"] = timed(lambda: _C.gemm_nt(g8, x8, operand_type=_C.GEMM_E5M2_E4M3, a_mn=True, b_mn=True, out=gw))
+    out["bwd " + name] = {k + "_TF": fl / v / 1e9 for k, v in t.items()}
+    print(f"bwd {name:30s} " + " | ".join(f"{k} {fl/v/1e9:6.0f} TF {v*1e3:6.1f} us" for k, v in t.items()), flush=True)
 print(json.dumps(out))
 if "--json" in sys.argv:
     with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
