@@ -75,8 +75,8 @@ class MobileBertOutput(_WithResidual, hf.MobileBertOutput):
 
     def forward(self, intermediate_states, residual_tensor_1, residual_tensor_2):
         out = self.dense(intermediate_states)
-        if not self.use_bottleneck:
-            return self.LayerNorm(self.residual(self.dropout(out), residual_tensor_1))
+        if not self.use_bottleneck:   # a bare `+` in the reference (modeling_mobilebert.py:165-166): never hooked
+            return self.LayerNorm(self.dropout(out) + residual_tensor_1)
         out = self.LayerNorm(self.residual(out, residual_tensor_1))
         return self.bottleneck(out, residual_tensor_2)
 

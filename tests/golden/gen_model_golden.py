@@ -39,8 +39,12 @@ CASES = [
 ]
 
 
-def load_reference_quantize():
+def load_reference_quantize(lora_linear=None):
+    """lora_linear: a functional stand-in for peft.tuners.lora.Linear (peft is absent from this image) that the
+    reference's qat.LoraLinear subclasses; None keeps the inert placeholder."""
     ref = load_reference()
+    if lora_linear is not None:
+        sys.modules["peft.tuners.lora"].Linear = lora_linear
     pkg = sys.modules["quantized_training"]
 
     def synth(name, path):
