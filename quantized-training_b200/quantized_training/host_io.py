@@ -42,15 +42,20 @@ class HostPipeline:
             amax_slot = mod.amax_history
         return quantize, observe, amax_slot
 
-    def run(self, mod: FusedAmaxObsFakeQuantize, x_host: torch.Tensor, out: torch.Tensor = None):
+    def run(self, mod: FusedAmaxObsFakeQuantize, x_host: torch.Tensor, out: torch.Tensor = None, wait: bool = True):
         quantize = mod._flags()[1]
         if out is None:
             out = torch.empty_like(x_host).pin_memory() if quantize else x_host
-        return self.run_many([mod], x_host, [out])[0]
+        return self.run_many([mod], x_host, [out], wait=wait)[0]
 
-    def run_many(self, mods, x_host: torch.Tensor, outs):
+    def run_many(self, mods, x_host: torch.Tensor, outs, wait: bool = True):
         """Several fake-quantizers over the SAME host tensor (a format sweep, or the activation quantizers of sibling
-        consumers): every chunk is uploaded once and each module's result is downloaded into its own `outs[k]`."""
+        consumers): every chunk is uploaded once and each module's result is downloaded into its own `outs[k]`.
+        wait=True (default): returns when the results ARE in `outs` -- the host blocks on one event per side stream,
+        recorded after its last download -- so the caller may read `outs` and reuse `x_host` immediately, like
+        `mod(x.cuda()).cpu()`.  wait=False: returns right after enqueueing; the copies are ordered before later work
+        on the current CUDA stream only, and the caller must `self.synchronize()` (or synchronize the device)
+        before touching `outs` or modifying `x_host` on the host."""
         assert not x_host.is_cuda and x_host.is_contiguous() and x_host.dtype == self.xin[0].dtype
         assert len(mods) == len(outs)
         n = x_host.numel()
@@ -75,11 +80,24 @@ class HostPipeline:
                         of[start:start + m].copy_(yout, non_blocking=True)
                     elif observe:
                         _C.amax(xin, 1, 1, m, amax_slot)
+        self._done = []
         for s in self.streams:
             main.wait_stream(s)
+            ev = torch.cuda.Event()
+            ev.record(s)
+            self._done.append(ev)
+        if wait:
+            self.synchronize()
         return outs
+
+    def synchronize(self):
+        """Block the host until every download of the last run()/run_many() call has landed in host memory."""
+        for ev in getattr(self, "_done", ()):
+            ev.synchronize()
+        self._done = []
 
 
 def fake_quantize_host(mod, x_host, out=None, device="cuda:0", chunk_elems=1 << 23, depth=3):
-    """One-shot convenience wrapper (allocates the staging buffers each call; keep a HostPipeline to reuse them)."""
-    return HostPipeline(device, x_host.dtype, chunk_elems, depth).run(mod, x_host, out)
+    """One-shot convenience wrapper (allocates the staging buffers each call; keep a HostPipeline to reuse them).
+    Synchronous: the result is in host memory when it returns."""
+    return HostPipeline(device, x_host.dtype, chunk_elems, depth).run(mod, x_host, out, wait=True)

@@ -32,8 +32,30 @@ def _worker(rank, world, port, out):
         x = torch.full((2, 4), float(rank + 1))
         model(x).sum().backward()
         nb = dp.allreduce_grads_(model.parameters())
+        # overlapped reducer: buckets fire from grad hooks during backward, finish() before the optimizer step
+        torch.manual_seed(1)
+        net = nn.Sequential(nn.Linear(4, 8), nn.ReLU(), nn.Linear(8, 8), nn.ReLU(), nn.Linear(8, 2))
+        net[0].weight.requires_grad_(False)
+        red = dp.GradReducer(net.parameters(), bucket_bytes=64)      # tiny buckets: several per backward
+        sums = []
+        for step in range(2):
+            red.zero_grad()
+            xin = torch.full((3, 4), float(rank + 1 + step))
+            net(xin).square().sum().backward()
+            nbk = red.finish()
+            sums.append([float(p.grad.sum()) for p in net.parameters() if p.requires_grad])
+        # reference: the same gradients computed locally for both ranks' inputs, averaged
+        want = []
+        for step in range(2):
+            acc = None
+            for r in range(world):
+                net.zero_grad(set_to_none=True)
+                net(torch.full((3, 4), float(r + 1 + step))).square().sum().backward()
+                g = [float(p.grad.sum()) for p in net.parameters() if p.requires_grad]
+                acc = g if acc is None else [a + b for a, b in zip(acc, g)]
+            want.append([a / world for a in acc])
         out[rank] = dict(units=units, t=t, n_units=n_units, nll=nll, bias_grad=model.bias.grad.tolist(), buckets=nb,
-                         weight_grad=model.weight.grad)
+                         weight_grad=model.weight.grad, reducer_sums=sums, reducer_want=want, reducer_buckets=nbk)
     finally:
         dist.destroy_process_group()
 
@@ -50,6 +72,10 @@ def test_two_rank_sharding_and_reductions():
     assert r0["n_units"] == r1["n_units"] == 11 and r0["nll"] == r1["nll"] == 0.5 * sum(range(11))
     assert r0["bias_grad"] == r1["bias_grad"] == [2.0, 2.0, 2.0]   # each rank's bias grad is 2 (two rows); mean is 2
     assert r0["buckets"] == 1 and r0["weight_grad"] is None
+    assert r0["reducer_buckets"] > 1
+    for r in (r0, r1):
+        for got, want in zip(r["reducer_sums"], r["reducer_want"]):
+            assert len(got) == 5 and all(abs(a - b) <= 1e-4 * max(1.0, abs(b)) for a, b in zip(got, want)), (got, want)
 
 
 def test_single_process_is_a_no_op():
