@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log2-numel L]
 
 A step = one pass of the fake-quant hot path over one batch: a resident bf16 tensor of 2^L
-elements per GPU (default 2^30 = 2 GiB in + 2 GiB out, far larger than the 126 MB L2) is
+elements per GPU (default 2^32 = 8 GiB in + 8 GiB out, the top of BASELINE's 1M-4G range) is
 quantized once with every spec of the sweep (int4, int8, e4m3, e5m2, fp6_e3m2, fp4_e2m1,
 posit8_1, posit8_2: 8 launches of the same kernel family).  Algorithmic bytes per launch
 = 2 * 2 B * 2^L.  `value` is whole-job algorithmic GB/s with inputs resident
@@ -102,6 +102,107 @@ def run_llama(args, dev, rank, world, dist, barrier):
 
 
 
+def run_size_sweep(dev, qt):
+    """BASELINE configs[2] size axis: 2^20 .. 2^32 bf16 elements on one GPU, L2 defeated by cycling through a pool of
+    distinct buffers larger than the 126 MB L2.  `device`: launches replayed from a CUDA graph (device time, what a
+    captured model step sees); `api`: the public module call issued eagerly from Python, wall clock (host overhead of
+    the ctypes boundary included).  GB/s of algorithmic read + write bytes."""
+    import torch
+    out = {"unit": "GB/s", "l2": "pool of distinct in/out buffers > 256 MB cycled between launches (2^26 and up: a "
+                                 "single launch already exceeds L2)", "sizes": {}}
+    unit = torch.ones(1, device=dev)
+    sc = torch.full((1,), 0.0123, device=dev)
+    free_b = torch.cuda.mem_get_info(dev)[0]
+    for L in range(20, 33, 2):
+        n = 1 << L
+        if 4 * n * 2 + (1 << 30) > free_b:
+            out["sizes"][str(L)] = {"skipped": "not enough free memory"}
+            continue
+        k = max(1, min(64, (256 << 20) // (4 * n) + 1)) if L < 26 else 1
+        xs = [(torch.randn(min(n, 1 << 24), device=dev) * 3).to(torch.bfloat16) for _ in range(min(k, 4))]
+        xs = [x.repeat(n // x.numel()) if n > x.numel() else x for x in xs]
+        xs = [xs[i % len(xs)].clone() if i >= len(xs) else xs[i] for i in range(k)]
+        ys = [torch.empty_like(x) for x in xs]
+        row = {"buffers": k}
+        for label, spec, scaled in (("e4m3 bare", "e4m3", False), ("posit8_1 bare", "posit8_1", False),
+                                    ("e4m3 per-tensor scale + amax", "e4m3", True)):
+            m = qt.FusedAmaxObsFakeQuantize(spec, device=dev)
+            hist = torch.zeros(1, device=dev)
+
+            def launch(i):
+                qt._C.fq_forward(xs[i], ys[i], 1, 1, n, m._fmt, sc if scaled else unit, hist if scaled else None, m.lut)
+
+            for i in range(k):
+                launch(i)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(k):
+                    launch(i)
+            g.replay()
+            reps = max(2, min(20, (1 << 30) // (n * k) + 1))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            row[label + " (device)"] = 4.0 * n * k * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+            del g
+        qs = qt.QuantizationSpec.from_str("fp8_e4m3,qs=per_tensor_symmetric")
+        mod = qt.FusedAmaxObsFakeQuantize(**qs.fake_quant_kwargs(), device=dev)
+        for i in range(k):
+            mod(xs[i])
+        torch.cuda.synchronize()
+        reps = max(2, min(20, (1 << 30) // (n * k) + 1))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for i in range(k):
+                mod(xs[i])
+        torch.cuda.synchronize()
+        row["fp8_e4m3 per-tensor scale + amax (api, eager module call)"] = 4.0 * n * k * reps / (time.perf_counter() - t0) / 1e9
+        out["sizes"][str(L)] = row
+        del xs, ys
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_gemm(dev):
+    """BASELINE metric (ii): quantized GEMM / BMM TFLOP/s on the configs' shapes, bf16 operands and e4m3 codes, with
+    cuBLAS (torch.matmul) on the same box beside it, against the measured dense bf16 peak (burst: kernels timed alone)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gemm_bench as GB
+    m = _measured()
+    peak = float(m["bf16_tflops"]) if m and "bf16_tflops" in m else FALLBACK_BF16_TFLOPS
+    src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if m and "bf16_tflops" in m else "fallback (B200_PROFILING.md)"
+    res = GB.run(str(dev), verbose=False, quick=True)
+    shapes = {}
+    for name, r in res.items():
+        if name.startswith("bwd "):
+            shapes[name] = {k: round(v, 1) for k, v in r.items()}
+            continue
+        shapes[name] = {"qt_bf16_TFLOPs": round(r["qt_bf16_TF"], 1), "cublas_bf16_TFLOPs": round(r["cublas_bf16_TF"], 1),
+                        "qt_fp8_TFLOPs": round(r["qt_fp8_TF"], 1), "frac_bf16": r["qt_bf16_TF"] / peak,
+                        "frac_fp8_of_2x": r["qt_fp8_TF"] / (2 * peak), "vs_cublas_bf16": r["qt_bf16_TF"] / r["cublas_bf16_TF"]}
+    return {"bound": "tensor", "unit": "TFLOP/s", "peak_bf16": peak, "peak_source": src,
+            "timing": "20 launches per CUDA-graph replay, CUDA events, operands rotate through L2-resident buffers "
+                      "(GEMM operands are re-read from L2 by design)", "shapes": shapes}
+
+
+def run_finetune(args, dev, rank, world, dist):
+    """BASELINE configs[3] at N GPUs: RoBERTa-base LoRA fine-tune step, NCCL all-reduce of the trainable gradients
+    overlapped with backward, whole step in one CUDA graph; plus the same step without the all-reduce (its cost)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import finetune_step as FT
+    rec = FT.run(dev, rank, world, dist, steps=args.finetune_steps, warmup=3, graph=True, allreduce=True)
+    if world > 1:
+        no_ar = FT.run(dev, rank, world, dist, steps=args.finetune_steps, warmup=3, graph=True, allreduce=False)
+        rec["ms_per_step_without_allreduce"] = no_ar["ms_per_step"]
+        rec["allreduce_cost_ms"] = rec["ms_per_step"] - no_ar["ms_per_step"]
+    return rec
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -143,6 +244,8 @@ def cpu_port_gbs(log2_numel, reps, specs=SWEEP):
     import numpy as np
     from oracle import oracle as O
 
+    # all host threads, whatever the launcher exported: torch.distributed.run sets OMP_NUM_THREADS=1 for its workers
+    O.set_num_threads(os.cpu_count() or 1)
     n = 1 << log2_numel
     rng = np.random.default_rng(0)
     x = (rng.standard_normal(n, dtype=np.float32) * 4.0)
@@ -358,6 +461,14 @@ def run_gpu(args):
     llama = None
     if not args.no_llama:
         llama = run_llama(args, dev, rank, world, dist, barrier)
+    finetune = None
+    if not args.no_finetune:
+        finetune = run_finetune(args, dev, rank, world, dist)
+    sizes = gemm = None
+    if rank == 0 and not args.no_extras:
+        sizes = run_size_sweep(dev, qt)
+        gemm = run_gemm(dev)
+    barrier()
 
     if rank == 0:
         cpu = None
@@ -394,7 +505,8 @@ def run_gpu(args):
                            f"host results): {2 << (args.e2e_log2_chunk - 20)} MB chunks, each uploaded once, H2D / "
                            "8 kernels / 8 D2H overlapped on 4 streams; value counts the algorithmic read+write bytes "
                            "of the 8 specs like the device-timed figure"},
-            "gpu_launches": launches, "clocks": clocks, "other_shapes_GBps": extra, "llama_forward": llama,
+            "gpu_launches": launches, "clocks": clocks, "other_shapes_GBps": extra, "size_sweep": sizes,
+            "gemm": gemm, "llama_forward": llama, "finetune": finetune,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -407,13 +519,15 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log2-numel", type=int, default=30)
+    ap.add_argument("--log2-numel", type=int, default=32)
     ap.add_argument("--e2e-log2-numel", type=int, default=26)
     ap.add_argument("--e2e-log2-chunk", type=int, default=22, help="log2 elements per staged chunk of the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-llama", action="store_true")
     ap.add_argument("--llama-steps", type=int, default=10)
+    ap.add_argument("--no-finetune", action="store_true")
+    ap.add_argument("--finetune-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
