@@ -353,6 +353,16 @@ int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t rows, size
                   size_t ld_out, int activation, int fq_points, int out_type, const qt_format_t *fmt,
                   const float *scale_post, const void *lut, void *stream);
 
+/* Merged LoRA weight of the QAT LoRA Linear (modules/qat/lora.py:44-52), one pass over W:
+ *   out = fq_post( bf16( W + bf16( bf16(Bq @ Aq) * scaling ) ) ),  Aq = fq(A), Bq = fq(B) when QT_FQ_PRE is set.
+ * W / out: bf16 [N, K] contiguous (out may alias neither input); A: bf16 [r, K] (lora_A.weight); B: bf16 [N, r]
+ * (lora_B.weight); K % 8 == 0.  QT_FQ_PRE fake-quantizes A and B with the BARE format (scale 1: use it only for
+ * un-observed specs -- with a live observer the reference updates the amax history on each of its three calls, so the
+ * caller quantizes A and B through the module and passes them in already quantized); QT_FQ_POST quantizes the merged
+ * weight, scale_post NULL = bare or a frozen per-tensor scale.  Replaces clone + 3 fake-quants + matmul + mul + add. */
+int qt_lora_merge_fq(const void *W, const void *A, const void *B, void *out, size_t N, size_t K, int r, float scaling,
+                     int fq_points, const qt_format_t *fmt, const float *scale_post, const void *lut, void *stream);
+
 /* Rotary position embedding + the qk_matmul input hooks, q and k (k may be NULL) in one launch:
  * out = fq(x * cos + rotate_half(x) * sin).  x: [tokens, heads, head_dim] with token stride ld (elements);
  * cos/sin: [cos_rows, head_dim], token t reads row t % cos_rows.  Replaces HF apply_rotary_pos_emb + two hooks. */

@@ -509,6 +509,72 @@ act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, 
     }
 }
 
+// ----------------------------------------------------------------------------- LoRA merged weight + fq
+// qat.LoraLinear (reference modules/qat/lora.py:44-52):  W' = fq( W + transpose(fq(B) @ fq(A)) * scaling ), as one pass
+// over W.  The reference's chain is clone -> fq(A) -> fq(B) -> matmul (bf16 out, fp32 accumulate) -> * scaling (bf16)
+// -> += (bf16) -> fq: the three bf16 roundings are reproduced in registers.  A [r, K] is staged once per CTA in shared
+// memory (fake-quantized on the way in when FQ_PRE is set); B [N, r] is read per output row.
+template <class R, bool SCALED>
+__global__ void __launch_bounds__(EW_THREADS, EW_MIN_CTAS)
+lora_merge_fq_kernel(const uint4 *__restrict__ W, const uint4 *__restrict__ A, const uint16_t *__restrict__ B,
+                     uint4 *__restrict__ out, size_t N, int k_vecs, int r, float scaling, int flags,
+                     const __grid_constant__ typename R::Params params, const float *__restrict__ scale_post)
+{
+    const R round(params, stage_table<R>(params));
+    griddep_wait();
+    griddep_launch_dependents();
+    const FqPoint post = load_point(scale_post);
+    FqPoint bare;
+    bare.sc.s = bare.sc.rs = 1.0f;
+    bare.mode = DIV_UNIT;
+    uint4 *sA = reinterpret_cast<uint4 *>(qt_dyn_smem + R::kSmemBytes);
+    for (int i = threadIdx.x; i < r * k_vecs; i += blockDim.x) {
+        uint4 v = __ldg(A + i);
+        if (flags & FQ_PRE) {
+            float f[8];
+            unpack8(v, f);
+            fq8<R, false>(round, f, bare);
+            v = pack8(f);
+        }
+        sA[i] = v;
+    }
+    __syncthreads();
+    const size_t total = N * (size_t)k_vecs;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t n = t / k_vecs;
+        const int kv = (int)(t - n * k_vecs);
+        const uint4 wv = __ldcs(W + t);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int j0 = 0; j0 < r; j0 += 8) {
+            float b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                b[j] = (j0 + j < r) ? __uint_as_float((uint32_t)__ldg(B + n * r + j0 + j) << 16) : 0.0f;
+            if (flags & FQ_PRE) fq8<R, false>(round, b, bare);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j0 + j < r) {
+                    float a[8];
+                    unpack8(sA[(j0 + j) * k_vecs + kv], a);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(b[j], a[k], acc[k]);
+                }
+            }
+        }
+        round8(acc);  // the matmul's bf16 output
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= scaling;
+        round8(acc);  // * scaling
+        float w[8];
+        unpack8(wv, w);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += w[k];
+        round8(acc);  // += into the cloned weight
+        if (flags & FQ_POST) fq8<R, SCALED>(round, acc, post);
+        __stcs(out + t, pack8(acc));
+    }
+}
+
 // ----------------------------------------------------------------------------- rotary embedding + fq
 // HF apply_rotary_pos_emb: x_embed = (x * cos) + (rotate_half(x) * sin), three bf16 ops.  x: [tokens, heads, D] with a
 // token stride (projection output [B*S, heads*D], possibly a slice of a fused QKV buffer); cos/sin: [cos_rows, D],
@@ -882,6 +948,37 @@ extern "C" int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t
     });
     if (rc != QT_OK) return rc;
     return finish("act_mul_fq kernel launch");
+}
+
+extern "C" int qt_lora_merge_fq(const void *W, const void *A, const void *B, void *out, size_t N, size_t K, int r,
+                                float scaling, int fq_points, const qt_format_t *fmt, const float *scale_post,
+                                const void *lut, void *stream)
+{
+    QtRound P;
+    int rc = check_common("qt_lora_merge_fq", fmt, &P);
+    if (rc != QT_OK) return rc;
+    if (N == 0 || K == 0) return QT_OK;
+    const size_t a_bytes = (size_t)r * K * 2;
+    if (!W || !A || !B || !out || K % 8 || r < 1 || r > 256 || a_bytes > 160 * 1024 || !aligned16(W) || !aligned16(A) ||
+        !aligned16(out) || (reinterpret_cast<uintptr_t>(B) & 1u) || (fq_points & ~(FQ_PRE | FQ_POST))) {
+        qt_set_error("qt_lora_merge_fq: needs contiguous 16-byte aligned bf16 W / out [N, K], A [r, K], B [N, r], "
+                     "K %% 8 == 0, r * K * 2 <= 160 KB; fq_points in {QT_FQ_PRE, QT_FQ_POST}");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
+        using R = typename decltype(tag)::type;
+        const size_t total = N * (K / 8);
+        const size_t smem = R::kSmemBytes + a_bytes;
+        const unsigned grid = grid_for((total + EW_THREADS - 1) / EW_THREADS, EW_MIN_CTAS);
+        auto kernel = scale_post ? lora_merge_fq_kernel<R, true> : lora_merge_fq_kernel<R, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        qt_launch(kernel, dim3(grid), dim3(EW_THREADS), smem, st, static_cast<const uint4 *>(W),
+                  static_cast<const uint4 *>(A), static_cast<const uint16_t *>(B), static_cast<uint4 *>(out), N,
+                  (int)(K / 8), r, scaling, fq_points, params, scale_post);
+    });
+    if (rc != QT_OK) return rc;
+    return finish("lora_merge_fq kernel launch");
 }
 
 extern "C" int qt_rope_fq(const void *q, void *q_out, size_t ld_q, size_t ld_q_out, int q_heads, const void *k,

@@ -62,6 +62,9 @@ EXPORTS = {
     "qt_act_mul_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_size_t] * 5 +
                       [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
                        ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_lora_merge_fq": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                        ctypes.c_float, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p]),
     "qt_rope_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                   ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
@@ -512,6 +515,20 @@ def act_mul_fq(gate, up, out, activation, fq_points, fmt, scale_post=None, lut=N
                                    gate.stride(0), up.stride(0) if up is not None else 0, out.stride(0),
                                    ACTIVATIONS[activation], fq_points, _resolve_out(out, fmt), ctypes.byref(fmt),
                                    _ptr(scale_post), _ptr(lut), _stream(gate)))
+
+
+def lora_merge_fq(w, a, b, out, scaling, fq_points, fmt, scale_post=None, lut=None):
+    """out = fq_post(w + (fq(b) @ fq(a)) * scaling) with the reference's bf16 roundings (qt_lora_merge_fq)."""
+    for t, what in ((w, "w"), (a, "a"), (b, "b"), (out, "out")):
+        _bf16_cuda(t, what)
+        assert t.is_contiguous(), what
+    n, k = w.shape
+    r = a.shape[0]
+    assert a.shape == (r, k) and b.shape == (n, r) and out.shape == w.shape
+    with torch.cuda.device(w.device):
+        _check(lib().qt_lora_merge_fq(w.data_ptr(), a.data_ptr(), b.data_ptr(), out.data_ptr(), n, k, r, float(scaling),
+                                      int(fq_points), ctypes.byref(fmt), _ptr(scale_post), _ptr(lut), _stream(w)))
+    return out
 
 
 def rope_fq(q, q_out, k, k_out, cos, sin, fq_points, fmt, scale_q=None, scale_k=None, lut=None):

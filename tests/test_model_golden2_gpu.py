@@ -237,3 +237,40 @@ def test_qat_lora_linear_forward_backward_against_reference_formula(G):
     for ours, ref in ((q.lora_A["default"].weight.grad, A.grad), (q.lora_B["default"].weight.grad, Bm.grad)):
         rel = float((ours.double() - ref.double()).norm() / ref.double().norm())
         assert rel < 1e-2, rel
+
+
+@pytest.mark.parametrize("spec", ["fp8_e4m3", "posit8_1", "int8,qs=per_tensor_symmetric,ahl=4", "e4m3"])
+@pytest.mark.parametrize("N,K,r", [(768, 768, 8), (64, 72, 4), (256, 1024, 16)])
+def test_lora_merge_kernel_is_the_reference_op_chain(spec, N, K, r):
+    """qt_lora_merge_fq vs clone -> fq(A) -> fq(B) -> B @ A -> * scaling -> += -> fq in torch bf16 ops (the reference's
+    chain, modules/qat/lora.py:44-52) with this repo's bit-exact fake-quant as `fq`: BIT-EXACT (r <= 16 products of
+    8-bit values are exact in fp32, so the accumulation order cannot matter), inference and observed-training modes."""
+    gen = torch.Generator().manual_seed(N + K + r)
+    w = (torch.randn(N, K, generator=gen) * 0.05).to(DEV).bfloat16()
+    a = (torch.randn(r, K, generator=gen) * 0.1).to(DEV).bfloat16()
+    b = (torch.randn(N, r, generator=gen) * 0.1).to(DEV).bfloat16()
+    scaling = 8 / r
+    qs = qt.QuantizationSpec.from_str(spec)
+    for mode in ("infer", "train"):
+        f1 = qt.FusedAmaxObsFakeQuantize(**qs.fake_quant_kwargs(), device=DEV)
+        f2 = qt.FusedAmaxObsFakeQuantize(**qs.fake_quant_kwargs(), device=DEV)
+        lin = torch.nn.Linear(K, N, bias=False)
+        lo = LoraLinear.from_linear(lin, r=r, lora_alpha=8).to(DEV).bfloat16()
+        lo.weight.data.copy_(w); lo.lora_A["default"].weight.data.copy_(a); lo.lora_B["default"].weight.data.copy_(b)
+        lo.qconfig = qt.get_qconfig(spec, spec, None)
+        q = qt.modules.qat.LoraLinear.from_float(lo)
+        q.weight_fake_quant = f1
+        x = torch.eye(K, device=DEV, dtype=torch.bfloat16)      # y = W'^T: reads the merged weight back exactly
+        for call in range(2):
+            if mode == "infer":
+                with torch.no_grad():
+                    y = q(x)
+            else:
+                y = q(x)
+            merged = w.clone()
+            aq = f2(a)                      # the reference quantizes A first, then B (lora.py:47-48)
+            bq = f2(b)
+            merged += (bq @ aq) * scaling
+            want = f2(merged)
+            assert torch.equal(y.detach().t().contiguous(), want), (spec, mode, call)
+        assert torch.equal(f1.scale, f2.scale) and torch.equal(f1.amax_history, f2.amax_history)
