@@ -123,6 +123,31 @@ int qt_fq_forward(const void *x, void *y, size_t outer, size_t channels, size_t 
 int qt_quantize_codes(const void *x, void *codes, size_t n, int elem_type, const qt_format_t *fmt,
                       const float *scale, float *amax_out, const void *lut, void *stream);
 
+/* ---- one-byte codes of ANY <= 8-bit format: the storage form of quantized GEMM operands (qt_codes.h) ---------------
+ * The reference emits codes for posits only (`return_pbits`, posit.py:60-65) and keeps every other format as bf16
+ * values; the layouts here follow it for posits and define the rest subject to decode(code) == qmap[idx]
+ * (SURVEY.md App. A):
+ *   QT_CODE_NATIVE  positN_ES: the N-bit posit word, two's complement for negative values, sign-extended to a byte
+ *                   (== the reference's pbits; NaR for NaN); intN: the two's-complement integer; uintN: the integer;
+ *                   fp formats: sign | biased exponent | mantissa (OCP E4M3 / E5M2 / E3M2 / E2M3 / E2M1 layouts).
+ *   QT_CODE_E4M3 / QT_CODE_E5M2  the OCP fp8 encoding of the same value, legal when every value of the format is an
+ *                   e4m3 (e5m2) value -- fp6_e3m2, fp6_e2m3, fp4_e2m1, int2..int5 are subsets of e4m3 -- so those
+ *                   operands run on the FP8 tensor cores (QT_GEMM_E4M3...) with no decode step.
+ * Exceptions to decode(encode(q)) == q, all outside what a GEMM operand can meaningfully hold: the sign of zero; NaN
+ * in formats without a NaN code (-> +0); +-Inf in formats without an Inf code (-> +-max).
+ * qt_code_table_host: table256_host[b] = bf16 bits of decode(byte b) -- what the GEMM's decode warps look up
+ * (QT_GEMM_CODE8); fails with QT_ERR_UNSUPPORTED_DTYPE if the format has more than 8 bits or does not fit the container.
+ * qt_encode_codes_host: HOST evaluation of round_fmt + encode on bf16 bit patterns (tests, API parity).
+ * qt_quantize_codes8: codes[i] = encode(round_fmt(x[i] / s)), per tensor, amax_out as in qt_fq_forward. */
+#define QT_CODE_NATIVE 0
+#define QT_CODE_E4M3 1
+#define QT_CODE_E5M2 2
+int qt_code_table_host(const qt_format_t *fmt, int code_kind, uint16_t *table256_host);
+int qt_encode_codes_host(const qt_format_t *fmt, int code_kind, const uint16_t *bf16_bits_host, uint8_t *codes_host,
+                         size_t n);
+int qt_quantize_codes8(const void *x, void *codes, size_t n, int elem_type, const qt_format_t *fmt, int code_kind,
+                       const float *scale, float *amax_out, void *stream);
+
 /* Observer only (fake quant disabled, e.g. calibration): amax_out[c] = max(amax_out[c], max|x|). */
 int qt_amax(const void *x, size_t outer, size_t channels, size_t inner, int elem_type,
             float *amax_out, void *stream);
@@ -230,6 +255,15 @@ int qt_table_op(const qt_table_op_desc_t *desc, void *stream);
 #define QT_GEMM_E5M2 2      /* A and B are e5m2 codes */
 #define QT_GEMM_E4M3_E5M2 3 /* A e4m3, B e5m2 */
 #define QT_GEMM_E5M2_E4M3 4 /* A e5m2, B e4m3 (gradient x weight in the backward pass) */
+/* Operands stored as ONE-BYTE CODES of any <= 8-bit format (posit8, int8, ...: qt_quantize_codes8, QT_CODE_NATIVE) and
+ * decoded exactly to bf16 INSIDE the kernel: eight decode warps fetch the codes, look them up in a bank-conflict-free
+ * copy of `code_lut` (qt_code_table_host: 256 bf16 values) and write the 128-byte-swizzled bf16 tiles the tensor cores
+ * read -- weights cost 1 byte of HBM traffic instead of 2 and the products are bit-identical to the bf16-operand path.
+ * CODE8_B: A bf16 (TMA), B codes [N, K]; CODE8_AB: both codes (same format).  K-major, K % 16 == 0, strides % 16 == 0,
+ * plain epilogue (alpha, bias, residual).  The decode costs shared-memory bandwidth the MMA also needs: use it where
+ * the product is bound by the weight traffic (small M), not for compute-bound shapes. */
+#define QT_GEMM_CODE8_B 5
+#define QT_GEMM_CODE8_AB 6
 #define QT_ACT_NONE 0
 #define QT_ACT_RELU 1
 #define QT_ACT_GELU 2 /* exact erf GELU (BERT / RoBERTa) */
@@ -289,6 +323,7 @@ typedef struct qt_gemm_desc {
      * and torch.matmul(x, y) with y [K, N] row-major is A = x, B = y (MN-major).  With one-byte operands an MN-major
      * B needs N tiles of 128 rows (chosen automatically).  The causal schedules take K-major operands. */
     int32_t a_major, b_major;
+    const void *code_lut; /* QT_GEMM_CODE8*: device uint16[256], bf16 bits of decode(byte) */
 } qt_gemm_desc_t;
 #define QT_MAJOR_K 0
 #define QT_MAJOR_MN 1

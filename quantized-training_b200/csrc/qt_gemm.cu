@@ -39,17 +39,26 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int MAX_BLOCK_N = 256;  // the tile width is a launch parameter: 64, 128 or 256 columns (see pick_block_n)
-constexpr int STAGES = 4;
+constexpr int BASE_STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * ROW_BYTES;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter, splitting the tile's 64-column chunks between them
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+// QT_GEMM_CODE8 variant: operands stored as one-byte codes are decoded to bf16 on their way into shared memory by
+// eight more warps.  Warp roles are aligned to warpgroups (setmaxnreg works per warpgroup): 0-3 producer / MMA / idle,
+// 4-11 epilogue, 12-19 decode; three ring stages make room for the 32 KB conflict-free decode table.
+constexpr int DEC_WARPS = 8;
+constexpr int CODE_NUM_THREADS = 128 + 32 * EPI_WARPS + 32 * DEC_WARPS;
+constexpr int CODE_STAGES = 3;
+constexpr int CODE_LUT_BYTES = 256 * 32 * 4;  // [code][lane] 32-bit entries: lane l always reads bank l
 constexpr int EPI_CHUNK_COLS = 64;                      // one TMA store box: 32 rows x 64 bf16 (128-byte rows)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK_COLS * 2;  // 4 KB per epilogue warp
 constexpr size_t SMEM_BYTES =
-    (size_t)STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_BUF_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+    (size_t)BASE_STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_BUF_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr size_t CODE_SMEM_BYTES = (size_t)CODE_STAGES * STAGE_BYTES + (size_t)EPI_WARPS * EPI_BUF_BYTES +
+                                   CODE_LUT_BYTES + 1024 + 256;
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3 };
 
@@ -64,6 +73,11 @@ struct GemmParams {
                              // 2: A is lower triangular (its probabilities): the K loop of row tile mt stops at its diagonal
     int debug;               // QT_GEMM_DEBUG bit mask (timing experiments only; results are wrong when set)
     int a_mn, b_mn;          // operand is MN-major: stored [K, rows] with a unit-stride row axis (backward products)
+    // QT_GEMM_CODE8*: operands held as one-byte codes (K-major, strides in bytes), decoded through code_lut
+    int a_code, b_code;
+    const uint8_t *a_codes, *b_codes;
+    int64_t lda_c, strideA_inner_c, strideA_outer_c, ldb_c, strideB_inner_c, strideB_outer_c;
+    const uint16_t *code_lut;  // 256 bf16 bit patterns (qt_code_table_host), device memory
     const __nv_bfloat16 *bias;      // [N] or null
     const __nv_bfloat16 *residual;  // same layout as C, or null
     int64_t ldr, strideR_inner, strideR_outer;
@@ -155,15 +169,18 @@ __device__ __forceinline__ void trace(const GemmParams &, int, int &) {}
 // ACT: activation; AUX: the problem has a bias and / or a residual (pointers checked at run time);
 // OUT: OUT_PLAIN bf16 result | OUT_FQ result fake-quantized (bf16 values or fp8 codes) | OUT_GLU act(gate) * up of a
 // column-interleaved gate|up projection (64 gate columns, then the 64 up columns of the same features), fake-quantized.
-template <bool FP8, int ACT, bool AUX, int OUT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool FP8, int ACT, bool AUX, int OUT, bool CODE = false>
+__global__ void __launch_bounds__(CODE ? CODE_NUM_THREADS : NUM_THREADS, 1)
 qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p)
 {
     extern __shared__ unsigned char smem_raw[];
+    constexpr int STAGES = CODE ? CODE_STAGES : BASE_STAGES;
+    constexpr int EPI_WARP0 = CODE ? 4 : 2;                              // first epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;         // EPI_WARPS x 4 KB store staging
-    const uint32_t bars = epi_base + EPI_WARPS * EPI_BUF_BYTES;
+    const uint32_t lut_base = epi_base + EPI_WARPS * EPI_BUF_BYTES;     // CODE: [256][32] decode table
+    const uint32_t bars = lut_base + (CODE ? CODE_LUT_BYTES : 0);
     // barrier slots (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base slot
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -180,7 +197,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), CODE ? 1 + DEC_WARPS : 1);  // CODE: + one arrival per decode warp
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -210,12 +227,118 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // every thread reads the same (already final) flag: the three roles agree on the schedule
     const int causal = (p.causal != 0 && (p.causal_flag == nullptr || *p.causal_flag != 0)) ? p.causal : 0;
 
-    if (warp == 0) {
+    // CODE8 register budget per warpgroup (setmaxnreg, first statement of each role's branch so that ptxas allocates
+    // the role's code against it).  Registers can only move between the warpgroups of this CTA: the pool is what the
+    // launch allocated, 640 x 96 = 61440, and 128 x 32 + 256 x 152 + 256 x 72 = 61440 uses it exactly (asking for more
+    // than the others release blocks forever).
+    if (CODE && warp >= 4 + EPI_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        // ===== decode warps (CODE8): codes (global / L2) -> registers -> table -> bf16 -> swizzled operand tile =====
+        // A thread owns 16-byte code vectors (16 elements of one row): vector v of the B tile is row v / 4, 16-byte
+        // chunk v % 4 of the row's 64-byte k-block; decoded it is two 16-byte chunks (2c, 2c + 1) of the row's 128-byte
+        // line, stored at chunk ^ (row & 7) -- the 128-byte swizzle TMA would have applied.  Quarter-warps write 8
+        // distinct chunks of two rows: conflict-free.  The vectors of k-block i + 1 are in flight while k-block i is
+        // decoded.
+        const int dt = threadIdx.x - 32 * (4 + EPI_WARPS);                    // 0 .. 255
+        const uint32_t my_lut = lut_base + ((uint32_t)lane << 2);
+        constexpr int NT = 32 * DEC_WARPS;
+        constexpr int MAXV = (BLOCK_M + MAX_BLOCK_N) * 4 / NT;                // 6 vectors per thread per k-block
+        const int va = p.a_code ? BLOCK_M * 4 / NT : 0, vb = p.b_code ? block_n * 4 / NT : 0;
+        struct It {
+            uint32_t tile;
+            int kb;
+        };
+        auto valid = [&](const It &it) { return it.tile < p.num_tiles; };
+        auto advance = [&](It &it) {
+            if (++it.kb == p.k_blocks) {
+                it.kb = 0;
+                it.tile += gridDim.x;
+            }
+        };
+        auto load = [&](const It &it, uint4 (&v)[MAXV]) {
+            const uint32_t mt = it.tile % p.m_tiles, rest = it.tile / p.m_tiles;
+            const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
+            const int64_t bi = b % p.batch_inner, bo = b / p.batch_inner;
+            const int64_t k0 = (int64_t)it.kb * 64;
+#pragma unroll
+            for (int j = 0; j < MAXV; ++j) {
+                v[j] = make_uint4(0u, 0u, 0u, 0u);
+                const bool is_a = j < va;
+                if (!is_a && j - va >= vb) continue;
+                const int idx = (is_a ? j : j - va) * NT + dt;
+                const int64_t row = (is_a ? (int64_t)mt * BLOCK_M : (int64_t)nt * block_n) + (idx >> 2);
+                const int64_t k = k0 + (idx & 3) * 16;
+                if (k >= p.K || row >= (is_a ? p.M : p.N)) continue;          // zero codes must decode to zero: see below
+                const uint8_t *src = is_a ? p.a_codes + bo * p.strideA_outer_c + bi * p.strideA_inner_c + row * p.lda_c + k
+                                          : p.b_codes + bo * p.strideB_outer_c + bi * p.strideB_inner_c + row * p.ldb_c + k;
+                v[j] = __ldg(reinterpret_cast<const uint4 *>(src));
+            }
+        };
+        auto lookup2 = [&](uint32_t w, int sel) -> uint32_t {   // two codes (bytes sel, sel + 1 of w) -> packed bf16 x 2
+            uint32_t lo, hi;
+            const uint32_t c0 = __byte_perm(w, 0u, 0x4440 + sel), c1 = __byte_perm(w, 0u, 0x4441 + sel);
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(my_lut + (c0 << 7)));
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hi) : "r"(my_lut + (c1 << 7)));
+            return __byte_perm(lo, hi, 0x5410);
+        };
+        auto store = [&](const uint4 (&v)[MAXV], int stage) {
+            const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < MAXV; ++j) {
+                const bool is_a = j < va;
+                if (!is_a && j - va >= vb) continue;
+                const int idx = (is_a ? j : j - va) * NT + dt;
+                const uint32_t r = (uint32_t)(idx >> 2), c = (uint32_t)(idx & 3);
+                const uint32_t line = (is_a ? sa : sb) + r * ROW_BYTES;
+                const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t d0 = lookup2(w[2 * h], 0), d1 = lookup2(w[2 * h], 2);
+                    const uint32_t d2 = lookup2(w[2 * h + 1], 0), d3 = lookup2(w[2 * h + 1], 2);
+                    const uint32_t dst = line + (((2 * c + h) ^ (r & 7u)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(d0), "r"(d1), "r"(d2), "r"(d3)
+                                 : "memory");
+                }
+            }
+        };
+        // the table: [code][lane] 32-bit entries (bf16 in the low half), replicated so that lane l only touches bank l
+        for (int i = dt; i < 256 * 32; i += NT)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(lut_base + ((uint32_t)i << 2)), "r"((uint32_t)__ldg(p.code_lut + (i >> 5)))
+                         : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");                 // decode warps only
+        It cur = {blockIdx.x, 0};
+        uint4 va_regs[MAXV], vb_regs[MAXV];
+        if (valid(cur)) load(cur, va_regs);
+        int stage = 0;
+        uint32_t phase = 0;
+        bool flip = false;
+        while (valid(cur)) {
+            It nxt = cur;
+            advance(nxt);
+            if (valid(nxt)) {
+                if (flip) load(nxt, va_regs); else load(nxt, vb_regs);
+            }
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (flip) store(vb_regs, stage); else store(va_regs, stage);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));
+            if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+            }
+            flip = !flip;
+            cur = nxt;
+        }
+    } else if (warp < EPI_WARP0) {
+      if constexpr (CODE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+      if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0, tslot = 0;
             uint32_t phase = 0;
-            const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES);
+            const uint32_t stage_tx = CODE ? (uint32_t)((p.a_code ? 0 : A_STAGE_BYTES) + (p.b_code ? 0 : block_n * ROW_BYTES))
+                                           : (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES);
             for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const uint32_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
                 const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
@@ -230,14 +353,17 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int kcoord = kb * (FP8 ? ROW_BYTES : ROW_BYTES / 2);
                     // K-major operand: one box, rows x 128 bytes of K.  MN-major operand: boxes of 128 bytes of rows
                     // x one k-block of K lines (64 bf16 / 128 fp8), side by side: the canonical MN-major layout
-                    if (!p.a_mn) {
+                    if (CODE && p.a_code) {
+                        // decoded into place by the decode warps
+                    } else if (!p.a_mn) {
                         tma_load_4d(sa, &map_a, full_bar(stage), kcoord, (int)(mt * BLOCK_M), bi, bo);
                     } else {
                         for (int j = 0; j < BLOCK_M / MN_BOX_ROWS; ++j)
                             tma_load_4d(sa + j * MN_BOX_BYTES, &map_a, full_bar(stage),
                                         (int)(mt * BLOCK_M) + j * MN_BOX_ROWS, kcoord, bi, bo);
                     }
-                    if (!p.b_mn) {
+                    if (CODE && p.b_code) {
+                    } else if (!p.b_mn) {
                         tma_load_4d(sb, &map_b, full_bar(stage), kcoord, (int)(nt * block_n), bi, bo);
                     } else {
                         for (int j = 0; j < block_n / MN_BOX_ROWS; ++j)
@@ -293,13 +419,15 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
+      }
     } else {
-        // ===== epilogue warps 2..9 =====
+        if constexpr (CODE) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        // ===== epilogue warps (2..9; 4..11 in the CODE8 variant) =====
         // A warp may touch only the TMEM lanes of its quarter (warp id % 4); the two warps of a quarter take
         // alternate 64-column chunks.  Per chunk: 2 x tcgen05.ld (thread = row, registers = columns) -> fp32 math
         // -> bf16 -> the warp's 4 KB staging buffer in the 128-byte-swizzle layout -> one TMA store of the
         // 32 x 64 box (full 128-byte rows in HBM; rows / columns outside C are clipped by the TMA unit).
-        const int e = warp - 2;
+        const int e = warp - EPI_WARP0;
         const int quarter = warp & 3, half = e >> 2;
         const uint32_t buf = epi_base + (uint32_t)e * EPI_BUF_BYTES;
         const int chunks = block_n / EPI_CHUNK_COLS;
@@ -510,17 +638,19 @@ int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int
     return best;
 }
 
-template <bool FP8, int ACT, bool AUX, int OUT = OUT_PLAIN>
+template <bool FP8, int ACT, bool AUX, int OUT = OUT_PLAIN, bool CODE = false>
 void launch_variant(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
                     const CUtensorMap &map_c, const GemmParams &p)
 {
     static bool done[64] = {};
+    constexpr size_t smem = CODE ? CODE_SMEM_BYTES : SMEM_BYTES;
     if (dev >= 64 || !done[dev]) {
-        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_BYTES);
+        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
         if (dev < 64) done[dev] = true;
     }
-    qt_launch(qt_gemm_kernel<FP8, ACT, AUX, OUT>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, map_a, map_b, map_c, p);
+    qt_launch(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE>, dim3(grid), dim3(CODE ? CODE_NUM_THREADS : NUM_THREADS), smem, st,
+              map_a, map_b, map_c, p);
 }
 
 }  // namespace
@@ -540,8 +670,10 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
         return QT_ERR_INVALID_ARGUMENT;
     }
     const int operand_type = d->operand_type;
-    const bool fp8 = operand_type != QT_GEMM_BF16;
-    if (operand_type < QT_GEMM_BF16 || operand_type > QT_GEMM_E5M2_E4M3) {
+    const bool b_code = operand_type == QT_GEMM_CODE8_B || operand_type == QT_GEMM_CODE8_AB;
+    const bool a_code = operand_type == QT_GEMM_CODE8_AB;
+    const bool fp8 = operand_type != QT_GEMM_BF16 && !b_code;
+    if (operand_type < QT_GEMM_BF16 || operand_type > QT_GEMM_CODE8_AB) {
         qt_set_error("qt_gemm_nt: unknown operand_type %d", operand_type);
         return QT_ERR_INVALID_ARGUMENT;
     }
@@ -555,6 +687,16 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     const int64_t k_align = 16 / esz;
     auto misaligned = [](const void *ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0; };
     const int a_mn = d->a_major != 0, b_mn = d->b_major != 0;
+    if (b_code) {
+        const bool bad_a = a_code && (d->lda % 16 || (inner > 1 && d->strideA_inner % 16) || (outer > 1 && d->strideA_outer % 16));
+        if (!d->code_lut || K % 16 || d->ldb % 16 || (inner > 1 && d->strideB_inner % 16) || bad_a ||
+            (outer > 1 && d->strideB_outer % 16) || a_mn || b_mn || d->causal || d->fq_fmt || d->glu ||
+            d->activation != ACT_NONE) {
+            qt_set_error("qt_gemm_nt: QT_GEMM_CODE8* needs code_lut (qt_code_table_host on the device), K-major code "
+                         "operands with K and every stride a multiple of 16, and the plain epilogue (alpha, bias, residual)");
+            return QT_ERR_INVALID_ARGUMENT;
+        }
+    }
     if ((d->a_major & ~1) || (d->b_major & ~1) || ((a_mn || b_mn) && d->causal)) {
         qt_set_error("qt_gemm_nt: a_major / b_major are QT_MAJOR_K or QT_MAJOR_MN; the causal schedules take K-major "
                      "operands");
@@ -627,6 +769,17 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.k_blocks = (int)((K * esz + ROW_BYTES - 1) / ROW_BYTES);
     p.a_mn = a_mn;
     p.b_mn = b_mn;
+    p.a_code = a_code;
+    p.b_code = b_code;
+    p.a_codes = static_cast<const uint8_t *>(d->A);
+    p.b_codes = static_cast<const uint8_t *>(d->B);
+    p.lda_c = d->lda;
+    p.strideA_inner_c = inner > 1 ? d->strideA_inner : 0;
+    p.strideA_outer_c = outer > 1 ? d->strideA_outer : 0;
+    p.ldb_c = d->ldb;
+    p.strideB_inner_c = inner > 1 ? d->strideB_inner : 0;
+    p.strideB_outer_c = outer > 1 ? d->strideB_outer : 0;
+    p.code_lut = static_cast<const uint16_t *>(d->code_lut);
     // an MN-major B tile is made of boxes of 128 bytes of rows: 64 bf16 rows, 128 fp8 rows
     p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, (glu || (b_mn && fp8)) ? 128 : 64);
     p.causal = d->causal;
@@ -656,15 +809,20 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     // K-major: [rows, K] boxes of rows x 128 bytes of K.  MN-major: [K, rows] boxes of one k-block of K lines x 128
     // bytes of rows; K lines / rows past the end read as zero either way.
     const int k_lines = fp8 ? 128 : 64;
-    int rc = a_mn ? make_map(&map_a, d->A, fp8, M, K, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, k_lines)
+    int rc = make_map(&map_c, d->C, c_esz == 1, n_out, M, inner, outer, d->ldc, d->strideC_inner, d->strideC_outer, 32,
+                      c_esz == 1 ? 64 : ROW_BYTES);
+    if (rc != QT_OK) return rc;
+    map_a = map_b = map_c;  // placeholders for operands the decode warps fetch themselves (QT_GEMM_CODE8*)
+    if (!a_code) {
+        rc = a_mn ? make_map(&map_a, d->A, fp8, M, K, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, k_lines)
                   : make_map(&map_a, d->A, fp8, K, M, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, BLOCK_M);
-    if (rc != QT_OK) return rc;
-    rc = b_mn ? make_map(&map_b, d->B, fp8, N, K, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, k_lines)
-              : make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n);
-    if (rc != QT_OK) return rc;
-    rc = make_map(&map_c, d->C, c_esz == 1, n_out, M, inner, outer, d->ldc, d->strideC_inner, d->strideC_outer, 32,
-                  c_esz == 1 ? 64 : ROW_BYTES);
-    if (rc != QT_OK) return rc;
+        if (rc != QT_OK) return rc;
+    }
+    if (!b_code) {
+        rc = b_mn ? make_map(&map_b, d->B, fp8, N, K, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, k_lines)
+                  : make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n);
+        if (rc != QT_OK) return rc;
+    }
 
     p.bias = static_cast<const __nv_bfloat16 *>(d->bias);
     p.residual = static_cast<const __nv_bfloat16 *>(d->residual);
@@ -674,7 +832,9 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.alpha = d->alpha;
     p.act = d->activation;
     switch (operand_type) {
-    case QT_GEMM_BF16: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn); break;
+    case QT_GEMM_BF16:
+    case QT_GEMM_CODE8_B:
+    case QT_GEMM_CODE8_AB: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn); break;
     case QT_GEMM_E4M3: p.idesc = make_idesc(0, 0, p.block_n, a_mn, b_mn); break;
     case QT_GEMM_E5M2: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn); break;
     case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1, p.block_n, a_mn, b_mn); break;
@@ -683,7 +843,10 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     const unsigned grid = p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool aux = d->bias != nullptr || d->residual != nullptr;
-    if (glu) {
+    if (b_code) {
+        aux ? launch_variant<false, ACT_NONE, true, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p)
+            : launch_variant<false, ACT_NONE, false, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p);
+    } else if (glu) {
         if (d->activation != ACT_SILU) {
             qt_set_error("qt_gemm_nt: the gated epilogue is built for SiLU (Llama-style MLP)");
             return QT_ERR_INVALID_ARGUMENT;

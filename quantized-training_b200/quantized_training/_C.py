@@ -62,6 +62,12 @@ EXPORTS = {
     "qt_act_mul_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_size_t] * 5 +
                       [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
                        ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_code_table_host": (ctypes.c_int, [ctypes.POINTER(QtFormat), ctypes.c_int, ctypes.c_void_p]),
+    "qt_encode_codes_host": (ctypes.c_int, [ctypes.POINTER(QtFormat), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_size_t]),
+    "qt_quantize_codes8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                          ctypes.POINTER(QtFormat), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p]),
     "qt_lora_merge_fq": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                         ctypes.c_float, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p]),
@@ -194,6 +200,34 @@ def quantize_codes(x, codes, fmt, scale=None, amax_out=None, lut=None):
                                        _stream(x)))
 
 
+CODE_NATIVE, CODE_E4M3, CODE_E5M2 = 0, 1, 2
+
+
+def code_table_host(fmt, code_kind=CODE_NATIVE):
+    """bf16 tensor [256]: decode(byte) of the format's one-byte codes (ValueError if it has none of that kind)."""
+    t = torch.empty(256, dtype=torch.int16)
+    _check(lib().qt_code_table_host(ctypes.byref(fmt), int(code_kind), t.data_ptr()))
+    return t.view(torch.bfloat16)
+
+
+def encode_codes_host(fmt, bf16_bits, code_kind=CODE_NATIVE):
+    """HOST: uint8 codes of round_fmt(value) for an int16/uint16 numpy-or-torch array of bf16 bit patterns."""
+    b = torch.as_tensor(bf16_bits).contiguous().view(torch.int16)
+    out = torch.empty(b.numel(), dtype=torch.uint8)
+    _check(lib().qt_encode_codes_host(ctypes.byref(fmt), int(code_kind), b.data_ptr(), out.data_ptr(), b.numel()))
+    return out
+
+
+def quantize_codes8(x, codes, fmt, code_kind=CODE_NATIVE, scale=None, amax_out=None):
+    """codes (uint8, same numel) = encode(round_fmt(x / s)) for any <= 8-bit format; per tensor."""
+    _require_cuda(x, "input")
+    assert x.is_contiguous() and codes.is_contiguous() and codes.dtype == torch.uint8 and codes.numel() == x.numel()
+    with torch.cuda.device(x.device):
+        _check(lib().qt_quantize_codes8(x.data_ptr(), codes.data_ptr(), x.numel(), _elem_type(x), ctypes.byref(fmt),
+                                        int(code_kind), _ptr_or_none(scale), _ptr_or_none(amax_out), _stream(x)))
+    return codes
+
+
 def amax(x, outer, channels, inner, amax_out):
     _require_cuda(x, "input")
     assert x.is_contiguous() and amax_out.dtype == torch.float32 and amax_out.device == x.device
@@ -315,7 +349,7 @@ def table_op(op, x, y, dims, block_size, block_axis2, scale, zero_point=None, ta
         _check(lib().qt_table_op(ctypes.byref(d), _stream(x)))
 
 
-GEMM_BF16, GEMM_E4M3, GEMM_E5M2, GEMM_E4M3_E5M2, GEMM_E5M2_E4M3 = range(5)
+GEMM_BF16, GEMM_E4M3, GEMM_E5M2, GEMM_E4M3_E5M2, GEMM_E5M2_E4M3, GEMM_CODE8_B, GEMM_CODE8_AB = range(7)
 ACTIVATIONS = {None: 0, "none": 0, "relu": 1, "gelu": 2, "silu": 3}
 
 
@@ -335,7 +369,7 @@ class QtGemmDesc(ctypes.Structure):
         ("fq_fmt", ctypes.POINTER(QtFormat)), ("fq_lut", ctypes.c_void_p),
         ("out_type", ctypes.c_int32), ("glu", ctypes.c_int32),
         ("causal", ctypes.c_int32), ("reserved", ctypes.c_int32), ("causal_flag", ctypes.c_void_p),
-        ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32),
+        ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32), ("code_lut", ctypes.c_void_p),
     ]
 
 
@@ -355,7 +389,7 @@ def _as4d(t, name, align):
 
 
 def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None,
-            fq=None, out_codes=False, glu=False, causal=0, causal_flag=None, a_mn=False, b_mn=False):
+            fq=None, out_codes=False, glu=False, causal=0, causal_flag=None, a_mn=False, b_mn=False, code_lut=None):
     """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
     a, b: bf16 (GEMM_BF16) or uint8 fp8 codes, up to two leading batch dimensions with arbitrary strides;
     bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional destination (any 16-byte
@@ -368,13 +402,16 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     a_mn / b_mn: the operand is handed over as it is stored, transposed -- a as [..., k, m], b as [..., k, n] with a
     unit-stride last axis -- and read MN-major by the tensor cores (dgrad / wgrad / x @ y without transpose copies)."""
     _require_cuda(a, "a")
-    want = torch.uint8 if operand_type != GEMM_BF16 else torch.bfloat16
-    if a.dtype != want or b.dtype != want:
-        raise TypeError(f"operand_type {operand_type} takes {want} operands, got {a.dtype} and {b.dtype}")
+    want_a = torch.bfloat16 if operand_type in (GEMM_BF16, GEMM_CODE8_B) else torch.uint8
+    want_b = torch.bfloat16 if operand_type == GEMM_BF16 else torch.uint8
+    if a.dtype != want_a or b.dtype != want_b:
+        raise TypeError(f"operand_type {operand_type} takes {want_a} x {want_b} operands, got {a.dtype} and {b.dtype}")
+    if operand_type in (GEMM_CODE8_B, GEMM_CODE8_AB):
+        if code_lut is None or code_lut.numel() != 256 or code_lut.element_size() != 2 or code_lut.device != a.device:
+            raise ValueError("GEMM_CODE8* needs code_lut: the format's 256-entry decode table on the device")
     if b.dim() == 2 and a.dim() > 2 and not a_mn:   # one weight for every batch entry: the batch is just more rows
         a = a.reshape(-1, a.shape[-1])
-    align = 16 if operand_type != GEMM_BF16 else 8
-    a4, b4 = _as4d(a, "a", align), _as4d(b, "b", align)
+    a4, b4 = _as4d(a, "a", 16 if a.dtype == torch.uint8 else 8), _as4d(b, "b", 16 if b.dtype == torch.uint8 else 8)
     if a4.shape[:2] != b4.shape[:2]:
         raise ValueError(f"batch mismatch: {tuple(a.shape)} x {tuple(b.shape)}")
     outer, inner = a4.shape[:2]
@@ -406,6 +443,8 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     d.glu = 1 if glu else 0
     d.causal = int(causal)
     d.a_major, d.b_major = int(bool(a_mn)), int(bool(b_mn))
+    if code_lut is not None:
+        d.code_lut = code_lut.data_ptr()
     if causal_flag is not None:
         assert causal_flag.dtype == torch.int32 and causal_flag.device == a.device
         d.causal_flag = causal_flag.data_ptr()

@@ -351,3 +351,46 @@ def test_ops_raise_instead_of_falling_back():
         ops.matmul(x, w.t())
     with pytest.raises(RuntimeError):
         ops.linear(x.cpu().bfloat16(), w.cpu().bfloat16())
+
+
+# ---- one-byte code operands decoded to bf16 inside the kernel (QT_GEMM_CODE8_B / _AB)
+@pytest.mark.parametrize("spec", ["posit8_1", "posit8_0", "int8", "fp6_e3m2", "posit6_1", "uint4"])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1024, 4096, 1024), (100, 264, 80), (8, 4096, 4096), (333, 1000, 1104),
+                                   (256, 64, 512), (130, 136, 4096)])
+def test_code8_operands_are_bit_identical_to_bf16_operands(spec, M, N, K):
+    """Weights (and activations) stored as one-byte codes, decoded exactly to bf16 in shared memory by the kernel's
+    decode warps: the tensor cores see the same bf16 tiles as on the bf16-operand path, so the results are
+    BIT-IDENTICAL, not merely close -- and codes decode to the fake-quantized values exactly."""
+    gen = torch.Generator().manual_seed(M + N + K)
+    fqm = qt.FusedAmaxObsFakeQuantize(spec, device=DEV)
+    scale_x = 4.0 if spec in ("int8", "uint4") else 1.0
+    x = ((torch.randn(M, K, generator=gen) * scale_x).to(torch.bfloat16)).to(DEV)
+    w = ((torch.randn(N, K, generator=gen) * scale_x * 0.5).to(torch.bfloat16)).to(DEV)
+    xq, wq = fqm(x), fqm(w)
+    lut = _C.code_table_host(fqm._fmt).to(DEV)
+    wc = _C.quantize_codes8(w, torch.empty(N, K, dtype=torch.uint8, device=DEV), fqm._fmt)
+    xc = _C.quantize_codes8(x, torch.empty(M, K, dtype=torch.uint8, device=DEV), fqm._fmt)
+    # decode(code) == the fake-quantized value (sign of zero aside)
+    dec = lut[wc.long()]
+    assert bool(((dec == wq) | ((dec == 0) & (wq == 0))).all())
+    bias = torch.randn(N, generator=gen).to(torch.bfloat16).to(DEV)
+    want = _C.gemm_nt(xq, wq, bias=bias, alpha=0.5)
+    got_b = _C.gemm_nt(xq, wc, bias=bias, alpha=0.5, operand_type=_C.GEMM_CODE8_B, code_lut=lut)
+    assert torch.equal(got_b, want), float((got_b.double() - want.double()).abs().max())
+    got_ab = _C.gemm_nt(xc, wc, bias=bias, alpha=0.5, operand_type=_C.GEMM_CODE8_AB, code_lut=lut)
+    assert torch.equal(got_ab, want)
+    check(got_b, (xq.double() @ wq.double().t()) * 0.5 + bias.double())
+
+
+def test_code8_batched_and_residual():
+    gen = torch.Generator().manual_seed(5)
+    fqm = qt.FusedAmaxObsFakeQuantize("posit8_1", device=DEV)
+    B, M, N, K = 3, 200, 136, 144
+    x = fqm(torch.randn(B, M, K, generator=gen).to(torch.bfloat16).to(DEV))
+    w = torch.randn(B, N, K, generator=gen).to(torch.bfloat16).to(DEV)
+    res = torch.randn(B, M, N, generator=gen).to(torch.bfloat16).to(DEV)
+    lut = _C.code_table_host(fqm._fmt).to(DEV)
+    wc = _C.quantize_codes8(w, torch.empty(B, N, K, dtype=torch.uint8, device=DEV), fqm._fmt)
+    want = _C.gemm_nt(x, fqm(w), residual=res)
+    got = _C.gemm_nt(x, wc, residual=res, operand_type=_C.GEMM_CODE8_B, code_lut=lut)
+    assert torch.equal(got, want)
