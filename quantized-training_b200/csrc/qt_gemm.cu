@@ -52,6 +52,7 @@ constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int DEC_WARPS = 8;
 constexpr int CODE_NUM_THREADS = 128 + 32 * EPI_WARPS + 32 * DEC_WARPS;
 constexpr int CODE_STAGES = 3;
+constexpr int CODE_PREFETCH = 8;  // k-blocks of codes the producer keeps ahead of the decode warps in L2
 constexpr int CODE_LUT_BYTES = 256 * 32 * 4;  // [code][lane] 32-bit entries: lane l always reads bank l
 constexpr int EPI_CHUNK_COLS = 64;                      // one TMA store box: 32 rows x 64 bf16 (128-byte rows)
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK_COLS * 2;  // 4 KB per epilogue warp
@@ -229,7 +230,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     // CODE8 register budget per warpgroup (setmaxnreg, first statement of each role's branch so that ptxas allocates
     // the role's code against it).  Registers can only move between the warpgroups of this CTA: the pool is what the
-    // launch allocated, 640 x 96 = 61440, and 128 x 32 + 256 x 152 + 256 x 72 = 61440 uses it exactly (asking for more
+    // launch allocated, 640 x 96 = 61440, and 128 x 40 + 256 x 144 + 256 x 72 = 60416 fits (asking for more
     // than the others release blocks forever).
     if (CODE && warp >= 4 + EPI_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -269,6 +270,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int64_t row = (is_a ? (int64_t)mt * BLOCK_M : (int64_t)nt * block_n) + (idx >> 2);
                 const int64_t k = k0 + (idx & 3) * 16;
                 if (k >= p.K || row >= (is_a ? p.M : p.N)) continue;          // zero codes must decode to zero: see below
+                if (p.debug & 128) continue;                                  // timing experiment: no global loads
                 const uint8_t *src = is_a ? p.a_codes + bo * p.strideA_outer_c + bi * p.strideA_inner_c + row * p.lda_c + k
                                           : p.b_codes + bo * p.strideB_outer_c + bi * p.strideB_inner_c + row * p.ldb_c + k;
                 v[j] = __ldg(reinterpret_cast<const uint4 *>(src));
@@ -293,18 +295,32 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const uint32_t d0 = lookup2(w[2 * h], 0), d1 = lookup2(w[2 * h], 2);
-                    const uint32_t d2 = lookup2(w[2 * h + 1], 0), d3 = lookup2(w[2 * h + 1], 2);
+                    uint32_t d0, d1, d2, d3;
+                    if (p.debug & 64) {                                       // timing experiment: no table lookups
+                        d0 = w[2 * h], d1 = w[2 * h] >> 8, d2 = w[2 * h + 1], d3 = w[2 * h + 1] >> 8;
+                    } else {
+                        d0 = lookup2(w[2 * h], 0), d1 = lookup2(w[2 * h], 2);
+                        d2 = lookup2(w[2 * h + 1], 0), d3 = lookup2(w[2 * h + 1], 2);
+                    }
                     const uint32_t dst = line + (((2 * c + h) ^ (r & 7u)) << 4);
+                    if (p.debug & 256) continue;                              // timing experiment: no stores
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(d0), "r"(d1), "r"(d2), "r"(d3)
                                  : "memory");
                 }
             }
         };
-        // the table: [code][lane] 32-bit entries (bf16 in the low half), replicated so that lane l only touches bank l
-        for (int i = dt; i < 256 * 32; i += NT)
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(lut_base + ((uint32_t)i << 2)), "r"((uint32_t)__ldg(p.code_lut + (i >> 5)))
-                         : "memory");
+        // the table: [code][lane] 32-bit entries (bf16 in the low half), replicated so that lane l only touches bank l.
+        // One global load per thread (thread t holds entry t); each warp then broadcasts its 32 entries by shuffle and
+        // writes them as conflict-free rows.  (A loop of dependent global loads here cost 30+ us per CTA.)
+        {
+            const uint32_t mine = p.code_lut ? (uint32_t)__ldg(p.code_lut + dt) : 0u;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, mine, i);
+                const uint32_t code = (uint32_t)(dt & ~31) + (uint32_t)i;
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(my_lut + (code << 7)), "r"(v) : "memory");
+            }
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");                 // decode warps only
         It cur = {blockIdx.x, 0};
         uint4 va_regs[MAXV], vb_regs[MAXV];
@@ -320,7 +336,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (flip) store(vb_regs, stage); else store(va_regs, stage);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core reads
+            if (!(p.debug & 512))
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
             __syncwarp();
             if (lane == 0) mbar_arrive(full_bar(stage));
             if (++stage == STAGES) {
@@ -331,7 +348,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             cur = nxt;
         }
     } else if (warp < EPI_WARP0) {
-      if constexpr (CODE) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+      if constexpr (CODE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
       if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
@@ -354,7 +371,10 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // K-major operand: one box, rows x 128 bytes of K.  MN-major operand: boxes of 128 bytes of rows
                     // x one k-block of K lines (64 bf16 / 128 fp8), side by side: the canonical MN-major layout
                     if (CODE && p.a_code) {
-                        // decoded into place by the decode warps
+                        // fetched and decoded into place by the decode warps; this warp only pulls the code tile of a
+                        // later k-block into L2 (one bulk tensor prefetch), so that their loads see L2 latency, not HBM's
+                        if (kb + CODE_PREFETCH < kbn && !(p.debug & 1024))
+                            tma_prefetch_4d(&map_a, (kb + CODE_PREFETCH) * 64, (int)(mt * BLOCK_M), bi, bo);
                     } else if (!p.a_mn) {
                         tma_load_4d(sa, &map_a, full_bar(stage), kcoord, (int)(mt * BLOCK_M), bi, bo);
                     } else {
@@ -363,6 +383,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                         (int)(mt * BLOCK_M) + j * MN_BOX_ROWS, kcoord, bi, bo);
                     }
                     if (CODE && p.b_code) {
+                        if (kb + CODE_PREFETCH < kbn && !(p.debug & 1024))
+                            tma_prefetch_4d(&map_b, (kb + CODE_PREFETCH) * 64, (int)(nt * block_n), bi, bo);
                     } else if (!p.b_mn) {
                         tma_load_4d(sb, &map_b, full_bar(stage), kcoord, (int)(nt * block_n), bi, bo);
                     } else {
@@ -421,7 +443,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     } else {
-        if constexpr (CODE) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        if constexpr (CODE) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         // ===== epilogue warps (2..9; 4..11 in the CODE8 variant) =====
         // A warp may touch only the TMEM lanes of its quarter (warp id % 4); the two warps of a quarter take
         // alternate 64-column chunks.  Per chunk: 2 x tcgen05.ld (thread = row, registers = columns) -> fp32 math
@@ -812,7 +834,16 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     int rc = make_map(&map_c, d->C, c_esz == 1, n_out, M, inner, outer, d->ldc, d->strideC_inner, d->strideC_outer, 32,
                       c_esz == 1 ? 64 : ROW_BYTES);
     if (rc != QT_OK) return rc;
-    map_a = map_b = map_c;  // placeholders for operands the decode warps fetch themselves (QT_GEMM_CODE8*)
+    map_a = map_b = map_c;
+    // code operands: the decode warps fetch them with plain loads; the maps serve the producer's L2 prefetches
+    if (a_code) {
+        rc = make_map(&map_a, d->A, true, K, M, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, BLOCK_M, 64);
+        if (rc != QT_OK) return rc;
+    }
+    if (b_code) {
+        rc = make_map(&map_b, d->B, true, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n, 64);
+        if (rc != QT_OK) return rc;
+    }
     if (!a_code) {
         rc = a_mn ? make_map(&map_a, d->A, fp8, M, K, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, k_lines)
                   : make_map(&map_a, d->A, fp8, K, M, inner, outer, d->lda, d->strideA_inner, d->strideA_outer, BLOCK_M);
@@ -843,7 +874,7 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     const unsigned grid = p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool aux = d->bias != nullptr || d->residual != nullptr;
-    if (b_code) {
+    if (b_code || ((p.debug & 4096) && operand_type == QT_GEMM_BF16 && !glu && !requant && d->activation == ACT_NONE)) {
         aux ? launch_variant<false, ACT_NONE, true, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p)
             : launch_variant<false, ACT_NONE, false, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p);
     } else if (glu) {
