@@ -412,41 +412,6 @@ int qt_fq_transpose(const void *v, void *out, int batch, int seq, int heads, int
                     size_t batch_stride, int fq_points, int out_type, const qt_format_t *fmt,
                     const float *scale_post, const void *lut, void *stream);
 
-/* ---- quantized attention core in one kernel (qt_attn.cu) ----------------------------------------------------
- * ctx = fq_out( fq_post(softmax(fq_mid(fq_pre(q k^T) * alpha + mask))) v ) per (batch, head); scores and
- * probabilities never reach HBM (two passes over the keys: row statistics, then probabilities -> P V).
- * Replaces qk_matmul -> attn_scaling -> (+ mask) -> nn.Softmax -> av_matmul -> permute and the fake-quant hooks on
- * them (modules/quantizable/modeling_bert.py:118-162, modeling_llama.py:228-263).
- * q, k: [batch, heads, seq, head_dim] views with a unit-stride last axis (ld_*: row stride, stride_*_head / _batch in
- * elements), already fake-quantized: bf16 values (qk_type QT_GEMM_BF16) or fp8 codes; vt: the values K-major,
- * contiguous [batch, heads, head_dim, seq_k] (qt_fq_transpose), bf16 or codes per pv_type -- with a code pv_type the
- * probabilities are turned into codes of the A format too (they must then leave an unscaled fp8 QT_FQ_POST step).
- * out: [batch, heads, seq_q, head_dim] view (e.g. of a [batch, seq, heads * head_dim] buffer); out_type QT_OUT_*
- * (codes need QT_FQ_OUT of that format).  mask: NULL or additive bf16 [mask_batches, mask_rows, seq_k]
- * (mask_rows 1 or seq_q, mask_batches 1 or batch); causal != 0 promises that the mask is the standard causal one
- * (key blocks above the diagonal are then skipped, not just masked).  fq_points: QT_FQ_PRE | QT_FQ_MID |
- * QT_FQ_POST | QT_FQ_OUT, all of the one format `fmt` (bare: scale 1).  head_dim 64 or 128 (rows of q / k a
- * multiple of 128 bytes), seq_k % 16 == 0. */
-#define QT_FQ_OUT 8
-typedef struct qt_attn_desc {
-    const void *q, *k, *vt;
-    void *out;
-    const void *mask;
-    int64_t batch, heads, seq_q, seq_k, head_dim;
-    int64_t ld_q, stride_q_head, stride_q_batch;
-    int64_t ld_k, stride_k_head, stride_k_batch;
-    int64_t ld_out, stride_out_head, stride_out_batch;
-    int64_t mask_rows, mask_batches;
-    float alpha;
-    int32_t qk_type, pv_type; /* QT_GEMM_* */
-    int32_t out_type;         /* QT_OUT_* */
-    int32_t fq_points;
-    int32_t causal;
-    const qt_format_t *fmt;
-    const void *lut;
-} qt_attn_desc_t;
-int qt_attention_fq(const qt_attn_desc_t *desc, void *stream);
-
 #ifdef __cplusplus
 }
 #endif

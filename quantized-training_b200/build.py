@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "quantized_training", "_lib")
 LIB = os.path.join(OUT_DIR, "libqt_b200.so")
-SOURCES = ["qt_format.cc", "qt_lut.cc", "qt_fq.cu", "qt_codes.cu", "qt_block.cu", "qt_block_flat.cu", "qt_block_cols.cu", "qt_block_tile.cu", "qt_gemm.cu", "qt_fused.cu", "qt_attn.cu"]
+SOURCES = ["qt_format.cc", "qt_lut.cc", "qt_fq.cu", "qt_codes.cu", "qt_block.cu", "qt_block_flat.cu", "qt_block_cols.cu", "qt_block_tile.cu", "qt_gemm.cu", "qt_fused.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

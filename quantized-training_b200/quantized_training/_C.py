@@ -79,7 +79,6 @@ EXPORTS = {
     "qt_fq_transpose": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
                         [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat),
                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "qt_attention_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qt_fq_block": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "qt_block_pow2_table_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "qt_table_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -598,53 +597,3 @@ def fq_transpose(v, out, fq_points, fmt, scale_post=None, lut=None):
         _check(lib().qt_fq_transpose(v.data_ptr(), out.data_ptr(), b, s_, h, d, v.stride(1), v.stride(0), fq_points,
                                      _resolve_out(out, fmt), ctypes.byref(fmt), _ptr(scale_post), _ptr(lut),
                                      _stream(v)))
-
-
-# ---- fused attention core (qt_attn.cu) ---------------------------------------------------------------------------
-FQ_OUT = 8
-
-
-class QtAttnDesc(ctypes.Structure):
-    """qt_attn_desc_t"""
-    _fields_ = [
-        ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("vt", ctypes.c_void_p), ("out", ctypes.c_void_p),
-        ("mask", ctypes.c_void_p),
-        ("batch", ctypes.c_int64), ("heads", ctypes.c_int64), ("seq_q", ctypes.c_int64), ("seq_k", ctypes.c_int64),
-        ("head_dim", ctypes.c_int64),
-        ("ld_q", ctypes.c_int64), ("stride_q_head", ctypes.c_int64), ("stride_q_batch", ctypes.c_int64),
-        ("ld_k", ctypes.c_int64), ("stride_k_head", ctypes.c_int64), ("stride_k_batch", ctypes.c_int64),
-        ("ld_out", ctypes.c_int64), ("stride_out_head", ctypes.c_int64), ("stride_out_batch", ctypes.c_int64),
-        ("mask_rows", ctypes.c_int64), ("mask_batches", ctypes.c_int64),
-        ("alpha", ctypes.c_float), ("qk_type", ctypes.c_int32), ("pv_type", ctypes.c_int32),
-        ("out_type", ctypes.c_int32), ("fq_points", ctypes.c_int32), ("causal", ctypes.c_int32),
-        ("fmt", ctypes.POINTER(QtFormat)), ("lut", ctypes.c_void_p),
-    ]
-
-
-def attention_fq(q, k, vt, out, alpha, mask, causal, fq_points, fmt, lut=None, qk_type=GEMM_BF16, pv_type=GEMM_BF16):
-    """out[b, h] = fq_out(fq_post(softmax(fq_mid(fq_pre(q k^T) * alpha + mask))) v): one kernel, no score tensor.
-    q, k: [B, H, S, D] views (unit-stride D), bf16 values or uint8 fp8 codes; vt: [B, H, D, Sk] contiguous; out:
-    [B, H, Sq, D] view, bf16 or uint8 (codes: needs FQ_OUT); mask: None or bf16 [Bm, rows, Sk] contiguous."""
-    _require_cuda(q, "q")
-    B, H, Sq, D = q.shape
-    Sk = k.shape[2]
-    assert k.shape == (B, H, Sk, D) and tuple(vt.shape) == (B, H, D, Sk) and vt.is_contiguous()
-    assert tuple(out.shape) == (B, H, Sq, D) and q.stride(3) == 1 and k.stride(3) == 1 and out.stride(3) == 1
-    d = QtAttnDesc()
-    d.q, d.k, d.vt, d.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
-    d.batch, d.heads, d.seq_q, d.seq_k, d.head_dim = B, H, Sq, Sk, D
-    d.ld_q, d.stride_q_head, d.stride_q_batch = q.stride(2), q.stride(1), q.stride(0)
-    d.ld_k, d.stride_k_head, d.stride_k_batch = k.stride(2), k.stride(1), k.stride(0)
-    d.ld_out, d.stride_out_head, d.stride_out_batch = out.stride(2), out.stride(1), out.stride(0)
-    if mask is not None:
-        assert mask.dtype == torch.bfloat16 and mask.is_contiguous() and mask.dim() == 3 and mask.shape[2] == Sk
-        d.mask, d.mask_batches, d.mask_rows = mask.data_ptr(), mask.shape[0], mask.shape[1]
-    d.alpha = float(alpha)
-    d.qk_type, d.pv_type = qk_type, pv_type
-    d.out_type = OUT_BF16 if out.dtype == torch.bfloat16 else _codes_type(fmt)
-    d.fq_points, d.causal = fq_points, 1 if causal else 0
-    d.fmt = ctypes.pointer(fmt)
-    d.lut = lut.data_ptr() if lut is not None else None
-    with torch.cuda.device(q.device):
-        _check(lib().qt_attention_fq(ctypes.addressof(d), _stream(q)))
-    return out

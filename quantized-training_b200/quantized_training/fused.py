@@ -155,7 +155,7 @@ def norm(x2, weight, bias, eps, kind, pre, post, codes=False, want_raw=False):
 
 def softmax(scores, alpha, mask, pre, mid, post, codes=False, causal=False, causal_flag=None):
     """scores [B, H, Sq, Sk] contiguous; mask None or additive [Bm, 1, Sq or 1, >=Sk] (Bm in {1, B}).
-    causal=True: the caller has checked that `mask` is the standard causal mask (see _mask3) -- masked scores are not
+    causal=True: the caller has a device flag saying whether `mask` is the standard causal mask (see _causal_flag) -- masked scores are not
     read and probabilities beyond the row tile's diagonal block are not written."""
     B, H, Sq, Sk = scores.shape
     m3, mb, mrows = None, 1, Sq
@@ -269,57 +269,12 @@ def _usable(x):
     return _ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()
 
 
-_CAUSAL_CACHE = {}
-
-
-def _mask3(mask, B, Sq, Sk):
-    """(additive bf16 mask [Bm, rows, Sk] contiguous or None, is_standard_causal).  The causal test runs once per mask
-    tensor (every layer of a forward, and every replay of a captured graph, sees the same object)."""
-    if mask is None:
-        return None, False
-    if mask.dtype == torch.bool:
-        from .modules.quantizable._common import additive_mask
-        mask = additive_mask(mask, torch.bfloat16)
-    if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] not in (1, Sq) or mask.shape[0] not in (1, B) \
-            or not mask.dtype.is_floating_point or mask.shape[3] < Sk:
-        raise _NotFusable
-    key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype)
-    hit = _CAUSAL_CACHE.get("last")
-    if hit is None or hit[0] != key:
-        m3 = mask[:, 0, :, :Sk]
-        if m3.dtype != torch.bfloat16:
-            m3 = m3.to(torch.bfloat16)
-        m3 = m3.contiguous()
-        causal = False
-        if m3.shape[1] == Sq and Sq == Sk and not torch.cuda.is_current_stream_capturing():
-            ref = torch.full((Sq, Sk), torch.finfo(torch.bfloat16).min, device=mask.device, dtype=torch.bfloat16).triu(1)
-            causal = bool((m3 == ref[None]).all())
-        hit = (key, m3, causal, mask)
-        _CAUSAL_CACHE["last"] = hit
-    return hit[1], hit[2]
-
-
 def attention(q4, k4, vt, scaling, mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c_o, B, S, H, D):
-    """The attention core: QK^T GEMM -> scale+mask+softmax+fq -> PV GEMM (three launches, default), or the single
-    kernel qt_attention_fq (QT_ATTENTION=fused) when every fake-quant step involved is a bare spec of one format, the
-    head dimension is 64 / 128 and the keys are a multiple of 16.  Measured on B200 at the Llama-2-7B window shape
-    (scripts/attn_micro.py): chain 80 us, single kernel 178 us -- it recomputes the element-wise chain in both of
-    its passes with 8 softmax warps per SM (one CTA per SM: 200 KB of shared memory) and is issue-bound there, so
-    the chain stays the default until the kernel gets more softmax warps and a balanced causal schedule."""
-    steps = [f for f in (sc_in, sm_in, p_in, o_in) if f is not None]
+    """The attention core: QK^T GEMM -> scale+mask+softmax+fq -> PV GEMM, three launches.  (Round 1 also carried a
+    single-kernel two-pass attention, qt_attention_fq; it recomputed the element-wise chain in both passes with 8
+    softmax warps per SM and ran 2.2x slower than this chain -- 176 vs 80 us at the Llama-2-7B window -- so it was
+    removed in round 2 rather than kept as dead weight.)"""
     Sk = k4.shape[2]
-    one_kernel = (D in (64, 128) and Sk % 16 == 0 and (D * q4.element_size()) % 128 == 0
-                  and all(f.qscheme is None for f in steps) and len({f.dtype for f in steps}) <= 1
-                  and os.environ.get("QT_ATTENTION", "chain") == "fused")
-    if one_kernel:
-        m3, causal = _mask3(mask, B, S, Sk)
-        fmt, lut = (steps[0]._fmt, steps[0].lut) if steps else (_identity_fmt(), None)
-        points = (_C.FQ_PRE if sc_in is not None else 0) | (_C.FQ_MID if sm_in is not None else 0) | \
-            (_C.FQ_POST if p_in is not None else 0) | (_C.FQ_OUT if o_in is not None else 0)
-        ctx = torch.empty(B, S, H * D, dtype=torch.uint8 if c_o else torch.bfloat16, device=q4.device)
-        _C.attention_fq(q4, k4, vt, ctx.view(B, S, H, D).transpose(1, 2), scaling, m3, causal, points, fmt, lut,
-                        qk_type=t_qk, pv_type=t_pv)
-        return ctx.view(B * S, H * D)
     # Causal schedule: with the standard causal mask and no fake quant between the mask and the softmax, everything
     # above the diagonal is exactly zero probability -- the score tiles there are not computed, the softmax neither
     # reads nor writes them and the P x V reduction of a row tile stops at its diagonal block.
@@ -343,6 +298,10 @@ def _causal_flag(mask, S):
     if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] != S or mask.shape[3] != S \
             or mask.dtype != torch.bfloat16 or not mask[:, 0].is_contiguous():
         return None
+    if torch.cuda.is_current_stream_capturing():
+        # the check kernel must be PART of the captured graph: a replay may carry a padding mask in the same static
+        # buffer, and a flag computed (and cached) at warm-up would then keep skipping tiles
+        return _C.causal_mask_check(mask[:, 0])
     key = (mask.data_ptr(), mask._version, tuple(mask.shape))
     hit = _FLAG_CACHE.get("last")
     if hit is None or hit[0] != key:

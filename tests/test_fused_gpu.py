@@ -227,62 +227,6 @@ def test_fp8_code_outputs_decode_to_the_bf16_outputs(spec, tdt):
         _C.norm_fq(x, yc, _C.NORM_RMS, w, None, 1e-5, _C.FQ_POST, pfmt, lut=plut)
 
 
-@pytest.mark.parametrize("spec,codes", [("posit8_1", False), ("e4m3", False), ("e4m3", True), ("int8", False)])
-@pytest.mark.parametrize("B,H,S,D,masked", [(1, 4, 1024, 128, "causal"), (2, 3, 384, 64, "padding"), (1, 2, 208, 128, "none"),
-                                             (2, 2, 144, 64, "causal")])
-def test_attention_core_matches_the_three_kernel_chain(oracle, spec, codes, B, H, S, D, masked):
-    """qt_attention_fq (scores stay on the SM) vs QK^T GEMM -> qt_softmax_fq -> PV GEMM -> fq on the same operands.
-    The chain's kernels are themselves checked against torch above.  Tolerance: both round to bf16 at the same points,
-    but the row sum is accumulated per 64-key chunk here (two-pass, rescaled) and per row there, and the exp is the same
-    ex2.approx: >= 98 % of the context values bit-identical, relative Frobenius error <= 1 %."""
-    if codes and D != 128:
-        pytest.skip("fp8 q / k rows must be a multiple of 128 bytes")
-    torch.manual_seed(S + D)
-    m = qt.FusedAmaxObsFakeQuantize(spec, device=DEV)
-    fmt, lut = m._fmt, m.lut
-    fqm = lambda t: m(t)
-    qkv = fqm((torch.randn(B, S, 3 * H * D, device=DEV) * 1.5).bfloat16())
-    q = qkv[..., :H * D].view(B, S, H, D).transpose(1, 2)
-    k = qkv[..., H * D:2 * H * D].view(B, S, H, D).transpose(1, 2)
-    v = qkv[..., 2 * H * D:].view(B, S, H, D)
-    vt = torch.empty(B, H, D, S, device=DEV, dtype=torch.bfloat16)
-    _C.fq_transpose(v, vt, 0, fmt, lut=lut)
-    mask, causal = None, False
-    if masked == "causal":
-        mask = torch.full((S, S), torch.finfo(torch.bfloat16).min, device=DEV, dtype=torch.bfloat16).triu(1)[None].contiguous()
-        causal = True
-    elif masked == "padding":
-        mask = torch.zeros(B, 1, S, device=DEV, dtype=torch.bfloat16)
-        mask[1, :, S - 100:] = torch.finfo(torch.bfloat16).min
-    alpha = D ** -0.5
-    # the chain
-    scores = _C.gemm_nt(q, k)
-    probs = torch.empty_like(scores)
-    _C.softmax_fq(scores, probs, alpha, mask, H * S, mask.shape[1] if mask is not None else S,
-                  mask.shape[0] if mask is not None else 1, _C.FQ_POST, fmt, lut=lut)
-    ctx_ref = torch.empty(B, S, H * D, device=DEV, dtype=torch.bfloat16)
-    _C.gemm_nt(probs, vt, out=ctx_ref.view(B, S, H, D).transpose(1, 2))
-    ctx_ref = fqm(ctx_ref)
-    # one kernel
-    if codes:
-        tdt = torch.float8_e4m3fn
-        enc = lambda t: t.contiguous().to(tdt).view(torch.uint8)
-        qc = enc(qkv[..., :2 * H * D])                                 # q | k codes, [B, S, 2 H D]
-        q8 = qc[..., :H * D].view(B, S, H, D).transpose(1, 2)
-        k8 = qc[..., H * D:].view(B, S, H, D).transpose(1, 2)
-        ctx = torch.empty(B, S, H * D, device=DEV, dtype=torch.uint8)
-        _C.attention_fq(q8, k8, enc(vt), ctx.view(B, S, H, D).transpose(1, 2), alpha, mask, causal,
-                        _C.FQ_POST | _C.FQ_OUT, fmt, lut, qk_type=_C.GEMM_E4M3, pv_type=_C.GEMM_E4M3)
-        ctx = ctx.view(tdt).to(torch.bfloat16)
-    else:
-        ctx = torch.empty(B, S, H * D, device=DEV, dtype=torch.bfloat16)
-        _C.attention_fq(q, k, vt, ctx.view(B, S, H, D).transpose(1, 2), alpha, mask, causal, _C.FQ_POST | _C.FQ_OUT, fmt, lut)
-    same = bits(ctx) == bits(ctx_ref)
-    rel = float((ctx.double() - ctx_ref.double()).norm() / ctx_ref.double().norm())
-    assert rel <= 1e-2, f"relative error {rel:.4f}, identical {float(same.float().mean()):.4f}"
-    assert float(same.float().mean()) >= 0.98
-
-
 @pytest.mark.parametrize("spec,codes", [("posit8_1", False), ("e4m3", False), ("e4m3", True)])
 @pytest.mark.parametrize("B,H,S,D", [(1, 4, 1024, 128), (2, 3, 384, 64), (1, 2, 128, 128), (1, 1, 2048, 64)])
 def test_causal_schedule_is_bit_identical(spec, codes, B, H, S, D):
