@@ -372,6 +372,10 @@ int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_t cols, flo
  * (modeling_llama.py:228-246) without a host round trip. */
 int qt_causal_mask_check(const void *mask, size_t batches, size_t rows, int32_t *flag_out, void *stream);
 
+/* 0 when `stream` is not being captured into a CUDA graph, otherwise the id of the capture in progress: host-side
+ * caches of per-forward launches (the flag above) key on it so that every captured graph contains its own check. */
+unsigned long long qt_stream_capture_id(void *stream);
+
 /* y = fq_post(norm(fq_pre(x))), rows of `cols` <= 8192; y_raw (optional, bf16): norm(fq_pre(x)) before the output step,
  * for consumers that read the un-quantized tensor (BERT: the residual input of the next add).  kind 0: LlamaRMSNorm (x * rsqrt(mean x^2 + eps) rounded to
  * bf16, then * weight); kind 1: nn.LayerNorm (weight, bias may be NULL for no bias).  Replaces the norm module plus the

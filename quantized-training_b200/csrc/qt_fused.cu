@@ -1047,6 +1047,20 @@ extern "C" int qt_fq_transpose(const void *v, void *out, int batch, int seq, int
     return finish("fq_transpose kernel launch");
 }
 
+// ----------------------------------------------------------------------------- stream capture identity
+// 0 when `stream` is not capturing, else the id of the capture in progress (cudaStreamGetCaptureInfo): lets the host
+// side cache "one launch per captured graph" work (the causal-mask check) without leaking it across graphs.
+extern "C" unsigned long long qt_stream_capture_id(void *stream)
+{
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(static_cast<cudaStream_t>(stream), &status, &id) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return status == cudaStreamCaptureStatusActive ? (id ? id : 1ull) : 0ull;
+}
+
 // ----------------------------------------------------------------------------- causal mask detection
 namespace {
 // mask [batches, rows, rows] bf16: standard causal = finfo(bf16).min (0xFF7F) strictly above the diagonal, +-0 elsewhere

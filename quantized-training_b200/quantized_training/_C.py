@@ -29,6 +29,7 @@ _lib = None
 # every symbol include/qt_b200.h declares; tests check the .so exports all of them
 EXPORTS = {
     "qt_version": (ctypes.c_char_p, []),
+    "qt_stream_capture_id": (ctypes.c_ulonglong, [ctypes.c_void_p]),
     "qt_last_error": (ctypes.c_char_p, []),
     "qt_format_from_string": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(QtFormat)]),
     "qt_format_min_max": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),
@@ -504,6 +505,11 @@ def _codes_type(fmt):
 def _resolve_out(out, fmt):
     t = _out_type(out)
     return _codes_type(fmt) if t is None else t
+
+
+def stream_capture_id(t):
+    """0 if the current stream of t's device is not capturing, else the id of the CUDA-graph capture in progress."""
+    return int(lib().qt_stream_capture_id(_stream(t)))
 
 
 def causal_mask_check(mask3, flag=None):

@@ -85,6 +85,9 @@ def _run(mod, x, emit_codes=False):
             mod.scale.resize_(stat_shape).fill_(1.0)
         _C.scale_update(mod.amax_history, mod.amax_history_len, channels, mod.scale, mod.quant_max,
                         mod.force_scale_power_of_two)
+        # the kernel writes `scale` through a raw pointer, which torch's version counter does not see: consumers that
+        # cache something derived from the scale (quantized weights) key on this epoch instead
+        mod._scale_epoch += 1
         amax_slot = mod.amax_history
     if not quantize:
         _C.amax(xc, outer, channels, inner, amax_slot)
@@ -261,6 +264,7 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         self.register_buffer("lut", _C.lut_host(self._fmt), persistent=False)
         self.is_per_channel = qscheme == QScheme.PER_CHANNEL_SYMMETRIC
         self._flag_versions = None
+        self._scale_epoch = 0   # bumped by every observer update and every external write to `scale` (state_key())
         self.enable_observer(qscheme is not None)
         if device is not None:
             self.to(device)
@@ -276,6 +280,13 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
             self._quantize = bool(self.fake_quant_enabled[0].item() == 1)
             self._flag_versions = versions
         return self._observe, self._quantize
+
+    def state_key(self):
+        """Hashable token that changes whenever the function this module computes may have changed: the observer
+        updated the scale (epoch), the scale buffer was written or replaced by torch (version / storage), or the
+        enable flags moved.  Used to key caches of quantized weights (qat.Linear, fused.py)."""
+        observe, quantize = self._flags()
+        return (self._scale_epoch, self.scale.data_ptr(), self.scale._version, observe, quantize)
 
     @property
     def qmap(self):
@@ -352,3 +363,4 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict,
                                       missing_keys, unexpected_keys, error_msgs)
         self._flag_versions = None
+        self._scale_epoch += 1

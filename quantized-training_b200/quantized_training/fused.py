@@ -227,7 +227,7 @@ def _quantized_cat(owner, tag, linears, codes=False, interleave=0):
             observe, quantize = fq._flags()
             if observe:
                 raise _NotFusable
-            key += [w.data_ptr(), w._version, fq.scale.data_ptr(), fq.scale._version, quantize]
+            key += [w.data_ptr(), w._version, fq.state_key()]
         elif isinstance(fq, nn.Identity):
             key += [w.data_ptr(), w._version]
         else:
@@ -298,11 +298,10 @@ def _causal_flag(mask, S):
     if mask.dim() != 4 or mask.shape[1] != 1 or mask.shape[2] != S or mask.shape[3] != S \
             or mask.dtype != torch.bfloat16 or not mask[:, 0].is_contiguous():
         return None
-    if torch.cuda.is_current_stream_capturing():
-        # the check kernel must be PART of the captured graph: a replay may carry a padding mask in the same static
-        # buffer, and a flag computed (and cached) at warm-up would then keep skipping tiles
-        return _C.causal_mask_check(mask[:, 0])
-    key = (mask.data_ptr(), mask._version, tuple(mask.shape))
+    # Under CUDA-graph capture the check kernel must be PART of the graph (a replay may carry a padding mask in the
+    # same static buffer, and a flag computed at warm-up would then keep skipping tiles): the capture id is part of
+    # the key, so each captured graph runs the check once, for all of its layers.
+    key = (mask.data_ptr(), mask._version, tuple(mask.shape), _C.stream_capture_id(mask))
     hit = _FLAG_CACHE.get("last")
     if hit is None or hit[0] != key:
         hit = (key, _C.causal_mask_check(mask[:, 0]), mask)   # keeps the mask alive: its address is the key

@@ -44,13 +44,22 @@ class Linear(nn.Linear):
         if flags is None or (torch.is_grad_enabled() and w.requires_grad):
             return None if codes else run()
         observe, quantize = flags()
-        if observe:
+        if observe or not getattr(self, "cache_quantized_weight", True):
             return None if codes else run()
-        key = (codes, w.data_ptr(), w._version, fq.scale.data_ptr(), fq.scale._version, quantize, w.dtype, w.device)
+        # fq.state_key(): observer epoch + scale version + flags -- a scale updated by a later calibration pass (the
+        # kernel writes it through a raw pointer) invalidates the cache.  The weight side uses torch's version counter,
+        # which in-place ops bump but writes through `.data` do NOT: after such writes call invalidate_weight_cache()
+        # or set `cache_quantized_weight = False` on the module (the reference re-quantizes on every forward).
+        key = (codes, w.data_ptr(), w._version, fq.state_key(), w.dtype, w.device)
         if self.__dict__.get("_wq_key") != key:
             self.__dict__["_wq"] = run().detach()
             self.__dict__["_wq_key"] = key
         return self.__dict__["_wq"]
+
+    def invalidate_weight_cache(self):
+        """Drop the cached quantized weight (needed only after writing the weight through `.data`)."""
+        self.__dict__.pop("_wq", None)
+        self.__dict__.pop("_wq_key", None)
 
     @classmethod
     def from_float(cls, mod):

@@ -178,3 +178,41 @@ def test_bert_fused_layer_matches_module_by_module(spec, ops_str, monkeypatch):
         fused.set_enabled(True)
     assert rel_err(got.start_logits, want.start_logits) < 2e-2
     assert rel_err(got.end_logits, want.end_logits) < 2e-2
+
+
+def test_quantized_weight_cache_follows_recalibration():
+    """The eval-time cache of fq(W) must not outlive the scale it was computed with: calibrate -> freeze -> eval ->
+    calibrate again (the kernel writes `scale` through a raw pointer, invisible to torch's version counter) -> freeze
+    -> eval has to re-quantize with the NEW scale, as the reference does on every forward (modules/qat/linear.py:41)."""
+    torch.manual_seed(0)
+    lin = nn.Linear(64, 32).to(DEV).bfloat16()
+    lin.qconfig = qt.get_qconfig(None, "int8,qs=per_tensor_symmetric,ahl=1", None)
+    q = qt.modules.qat.Linear.from_float(lin)
+    fq = q.weight_fake_quant
+    x = torch.randn(8, 64, device=DEV).bfloat16()
+
+    def frozen_eval():
+        fq.disable_observer()
+        with torch.no_grad():
+            y = q(x)
+            want = torch.nn.functional.linear(x, fq(q.weight), q.bias)
+        return y, want
+
+    with torch.no_grad():
+        q(x); q(x)                          # calibration: scale <- amax(W) / 127
+    y1, w1 = frozen_eval()
+    assert torch.equal(y1, w1)
+    s1 = float(fq.scale)
+    fq.enable_observer()
+    with torch.no_grad():
+        q.weight.mul_(3.0)                  # in-place: version counter moves, cache invalid
+        q(x); q(x)                          # re-calibration on the new weights: the scale moves
+    y2, w2 = frozen_eval()
+    assert float(fq.scale) != s1 and torch.equal(y2, w2)
+    # scale rewritten by a further observed pass WITHOUT touching the weight: only the epoch tells
+    fq.enable_observer()
+    fq.amax_history.fill_(50.0)             # pretend an outlier batch went through
+    with torch.no_grad():
+        q(x)
+    y3, w3 = frozen_eval()
+    assert torch.equal(y3, w3) and not torch.equal(y3, y2)
