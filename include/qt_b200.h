@@ -378,7 +378,8 @@ unsigned long long qt_stream_capture_id(void *stream);
 
 /* y = fq_post(norm(fq_pre(x))), rows of `cols` <= 8192; y_raw (optional, bf16): norm(fq_pre(x)) before the output step,
  * for consumers that read the un-quantized tensor (BERT: the residual input of the next add).  kind 0: LlamaRMSNorm (x * rsqrt(mean x^2 + eps) rounded to
- * bf16, then * weight); kind 1: nn.LayerNorm (weight, bias may be NULL for no bias).  Replaces the norm module plus the
+ * bf16, then * weight); kind 1: nn.LayerNorm (weight, bias may be NULL for no bias); kind 2: MobileBERT NoNorm
+ * (x * weight + bias, two bf16 ops, no row statistics; transformers modeling_mobilebert.NoNorm).  Replaces the norm module plus the
  * input hooks of the Linear layers that read it (same tensor quantized once instead of once per consumer). */
 int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size_t cols, int kind, const void *weight,
                const void *bias,

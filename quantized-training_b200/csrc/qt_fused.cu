@@ -434,6 +434,15 @@ norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, uint4 *__restr
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[k] *= w[k];
                     round8(f);
+                } else if (kind == 2) {  // MobileBERT NoNorm: input * weight + bias, two bf16 ops, no statistics
+                    float b[8];
+                    unpack8(__ldg(bias + i), b);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] *= w[k];
+                    round8(f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] += b[k];
+                    round8(f);
                 } else {
                     float b[8];
                     if (bias) unpack8(__ldg(bias + i), b);
@@ -870,7 +879,8 @@ extern "C" int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size
     rc = check_out_type("qt_norm_fq", &out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
-    if (!x || !y || !weight || cols % 8 || cols > 8192 || (kind != 0 && kind != 1) || !aligned16(x) || !aligned16(y) ||
+    if (!x || !y || !weight || cols % 8 || cols > 8192 || kind < 0 || kind > 2 || (kind == 2 && !bias) || !aligned16(x) ||
+        !aligned16(y) ||
         (y_raw && !aligned16(y_raw)) ||
         !aligned16(weight) || (bias && !aligned16(bias))) {
         qt_set_error("qt_norm_fq: needs 16-byte aligned contiguous bf16 rows, cols %% 8 == 0, cols <= 8192 (got %zu), "

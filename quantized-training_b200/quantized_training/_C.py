@@ -471,7 +471,7 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
 FQ_PRE, FQ_MID, FQ_POST = 1, 2, 4
 SOFTMAX_CAUSAL = 16
 CAUSAL_OUT_LOWER, CAUSAL_A_LOWER = 1, 2
-NORM_RMS, NORM_LAYER = 0, 1
+NORM_RMS, NORM_LAYER, NORM_NONE = 0, 1, 2
 OUT_BF16, OUT_E4M3, OUT_E5M2 = 0, 1, 2
 
 

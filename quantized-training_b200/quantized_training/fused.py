@@ -522,3 +522,140 @@ def bert_layer_forward(layer, hidden_states, attention_mask):
     except (_NotReady, _NotFusable, AttributeError):
         _why("layer")
         return None
+
+
+# ---- MobileBERT encoder layer ---------------------------------------------------------------------------------
+
+def _linear_block(owner, tag, x_q, in_fq, lin, res_mod=None, res=None, act=None, act_mod=None):
+    """y = act(x_q W_q^T + b) [+ res]: one GEMM; the residual add and a plain activation ride in its epilogue when no
+    fake-quant hook sits on them (their op group is "fused" in the paper's terms), otherwise the hooked module runs."""
+    t, codes = gemm_operands(in_fq, _weight_fq(lin), lin.weight.shape[1])
+    w, b = _quantized_cat(owner, tag, (lin,), codes)
+    if codes and x_q.dtype != torch.uint8:
+        x_q = x_q.to(_FP8_TORCH[in_fq.fp8_kind]).view(torch.uint8)   # exact: x_q already holds that format's values
+    epi_act = act if (act is not None and (act_mod is None or point(act_mod) is None)) else None
+    epi_res = res if (res is not None and (point(res_mod, "0"), point(res_mod, "1")) == (None, None)) else None
+    y = _C.gemm_nt(x_q, w, bias=b, activation=epi_act, residual=epi_res, operand_type=t)
+    if act is not None and epi_act is None:
+        y = act_mod(y)                       # hooked activation module: its own fake quant, then the op
+    if res is not None and epi_res is None:
+        y = res_mod(y, res)                  # hooked AddFunctional: fake quant of both inputs, then the add
+    return y
+
+
+_FP8_TORCH = {"e4m3": torch.float8_e4m3fn, "e5m2": torch.float8_e5m2}
+
+
+def _nonorm(norm_mod, y, post, want_raw=True):
+    """NoNorm (x * weight + bias) with its input hook and the consumer's input hook in one pass; LayerNorm likewise."""
+    kind = _C.NORM_LAYER if isinstance(norm_mod, nn.LayerNorm) else _C.NORM_NONE
+    if kind == _C.NORM_NONE and type(norm_mod).__name__ != "NoNorm":
+        raise _NotFusable
+    eps = getattr(norm_mod, "eps", 0.0)
+    codes = False
+    return norm(y, norm_mod.weight, norm_mod.bias, eps, kind, point(norm_mod), post, codes, want_raw=want_raw)
+
+
+def mobilebert_layer_forward(layer, hidden_states, attention_mask):
+    """Fused forward of a MobileBERT encoder layer whose blocks are the quantizable ones, or None.
+    Structure: transformers MobileBertLayer (bottleneck -> self-attention -> self-output -> (num_ffn - 1) x FFN ->
+    intermediate -> output + output bottleneck) around the reference's blocks (modules/quantizable/
+    modeling_mobilebert.py:38-206).  Same weights, same fake-quantizers, same rounding points as the module-by-module
+    execution: the three consumers of the layer input share one fake quant, every NoNorm runs with its input hook and
+    the next Linear's input hook in one pass, query | key are one GEMM, the attention core is the three-kernel chain,
+    and the residual adds / ReLU ride in GEMM epilogues wherever their op group is not hooked."""
+    if not _usable(hidden_states) or hidden_states.dim() != 3:
+        return None
+    try:
+        if not getattr(layer, "use_bottleneck", False):
+            return None
+        bn, att, so, out = layer.bottleneck, layer.attention.self, layer.attention.output, layer.output
+        if bn.use_bottleneck_attention or not bn.key_query_shared_bottleneck or not out.use_bottleneck:
+            return None
+        ffns = list(layer.ffn) if layer.num_feedforward_networks > 1 else []
+        mods = [layer, layer.attention, bn, bn.input, bn.attention, att, so, out, out.bottleneck, layer.intermediate,
+                att.attn_scaling, att.softmax, att.qk_matmul, att.av_matmul] + ffns + [f.intermediate for f in ffns] + \
+               [f.output for f in ffns]
+        for m in mods:
+            if len(m._forward_hooks) or len(m._backward_hooks):
+                return None
+        if layer.training and (att.dropout.p > 0.0 or out.bottleneck.dropout.p > 0.0):
+            return None
+
+        def act_of(inter):
+            am = inter.intermediate_act_fn
+            name = {"ReLU": "relu", "GELUActivation": "gelu", "GELU": "gelu"}.get(type(am).__name__)
+            if name is None or not isinstance(am, nn.Module):
+                raise _NotFusable
+            return name, am
+
+        B, S, hidden = hidden_states.shape
+        T = B * S
+        H, D = att.num_attention_heads, att.attention_head_size
+        th = att.query.weight.shape[1]                     # true hidden size
+        x = hidden_states.reshape(T, hidden)
+        if not x.is_contiguous():
+            x = x.contiguous()
+
+        # the layer input feeds three Linears (bottleneck.input, bottleneck.attention, value): one fake quant
+        x_in = same_points(point(bn.input.dense), point(bn.attention.dense), point(att.value))
+        xq = x if x_in is None else x_in(x)
+        layer_in = _linear_block(layer, "bn_in", xq, x_in, bn.input.dense)
+        layer_in = _nonorm(bn.input.LayerNorm, layer_in, None, want_raw=False)              # residual of self-output
+        qk_in = same_points(point(att.query), point(att.key))
+        shared = _linear_block(layer, "bn_att", xq, x_in, bn.attention.dense)
+        shared_q = _nonorm(bn.attention.LayerNorm, shared, qk_in, want_raw=False)            # input of query and key
+
+        # self-attention: query | key in one GEMM, value from the layer input
+        t_qkp, c_qkp = gemm_operands(qk_in, _common_weight_fq(att.query, att.key), th)
+        w_qk, b_qk = _quantized_cat(layer, "qk", (att.query, att.key), c_qkp)
+        if c_qkp:
+            shared_q = shared_q.to(_FP8_TORCH[qk_in.fp8_kind]).view(torch.uint8)
+        qk = _C.gemm_nt(shared_q, w_qk, bias=b_qk, operand_type=t_qkp)                       # [T, 2 * H * D]
+        v = _linear_block(layer, "v", xq, x_in, att.value)                                   # [T, H * D]
+        q_in, k_in = point(att.qk_matmul, "0"), point(att.qk_matmul, "1")
+        p_in, v_in = point(att.av_matmul, "0"), point(att.av_matmul, "1")
+        sc_in, sm_in = point(att.attn_scaling), point(att.softmax)
+        o_in = point(so.dense)
+        if (q_in is None) != (k_in is None) or (q_in is not None and (q_in.dtype != k_in.dtype or q_in.qscheme is not None
+                                                                      or k_in.qscheme is not None)):
+            raise _NotFusable
+        t_qk, c_qk = gemm_operands(q_in, k_in, D)
+        t_pv, c_pv = gemm_operands(p_in, v_in, S)
+        t_o, c_o = gemm_operands(o_in, _weight_fq(so.dense), H * D)
+        qkq = strided_fq(qk, q_in, c_qk)
+        fmt, lut, (s_v,) = _spec(v_in)
+        vt = _out_like(x, c_pv, (B, H, D, S))
+        _C.fq_transpose(v.view(B, S, H, D), vt, _flags(post=v_in), fmt, s_v, lut)
+        q4 = qkq[:, :H * D].view(B, S, H, D).transpose(1, 2)
+        k4 = qkq[:, H * D:].view(B, S, H, D).transpose(1, 2)
+        scaling = getattr(att, "scaling", D ** -0.5)
+        ctx2 = attention(q4, k4, vt, scaling, attention_mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c_o, B, S, H, D)
+
+        # self-output: dense + residual(layer_in) + NoNorm
+        a = _linear_block(layer, "so", ctx2, o_in, so.dense, so.residual, layer_in)
+        first_ffn = ffns[0].intermediate.dense if ffns else layer.intermediate.dense
+        a_q, a_raw = _nonorm(so.LayerNorm, a, point(first_ffn))
+
+        # feed-forward stacks: intermediate (dense + act) -> output dense + residual + NoNorm
+        stacks = [(f.intermediate, f.output, f"ffn{i}") for i, f in enumerate(ffns)] + [(layer.intermediate, out, "ffn_last")]
+        for i, (inter, outp, tag) in enumerate(stacks):
+            act_name, act_mod = act_of(inter)
+            mid = _linear_block(layer, tag + "_i", a_q, point(inter.dense), inter.dense, act=act_name, act_mod=act_mod)
+            o_fq = point(outp.dense)
+            mid_q = fake_quant(mid, o_fq, gemm_operands(o_fq, _weight_fq(outp.dense), mid.shape[1])[1])
+            h = _linear_block(layer, tag + "_o", mid_q, o_fq, outp.dense, outp.residual, a_raw)
+            if i + 1 < len(stacks):
+                nxt = point(stacks[i + 1][0].dense)
+            else:
+                nxt = point(out.bottleneck.dense)
+            a_q, a_raw = _nonorm(outp.LayerNorm, h, nxt)
+
+        # output bottleneck: dense (true hidden -> hidden) + residual(layer input) + NoNorm
+        ob = out.bottleneck
+        y = _linear_block(layer, "ob", a_q, point(ob.dense), ob.dense, ob.residual, x)
+        y = _nonorm(ob.LayerNorm, y, None, want_raw=False)
+        return y.view(B, S, hidden)
+    except (_NotReady, _NotFusable, AttributeError):
+        _why("layer")
+        return None

@@ -1,11 +1,11 @@
 from .functional_modules import AddFunctional, MatmulFunctional, MulFunctional
 from .modeling_bert import BertLayer, BertOutput, BertSelfAttention, BertSelfOutput
 from .modeling_llama import LlamaAttention, LlamaDecoderLayer
-from .modeling_mobilebert import (FFNOutput, MobileBertOutput, MobileBertSelfAttention, MobileBertSelfOutput,
-                                  OutputBottleneck)
+from .modeling_mobilebert import (FFNOutput, MobileBertLayer, MobileBertOutput, MobileBertSelfAttention,
+                                  MobileBertSelfOutput, OutputBottleneck)
 
 __all__ = [
     "AddFunctional", "BertLayer", "BertOutput", "BertSelfAttention", "BertSelfOutput", "FFNOutput", "LlamaAttention",
-    "LlamaDecoderLayer", "MatmulFunctional", "MobileBertOutput", "MobileBertSelfAttention",
+    "LlamaDecoderLayer", "MatmulFunctional", "MobileBertLayer", "MobileBertOutput", "MobileBertSelfAttention",
     "MobileBertSelfOutput", "MulFunctional", "OutputBottleneck",
 ]

@@ -2,10 +2,29 @@
 from torch import nn
 from transformers.models.mobilebert import modeling_mobilebert as hf
 
+from ... import fused
 from ._common import attention_ops, hooked_attention, rebrand
 from .functional_modules import AddFunctional
 
-__all__ = ["MobileBertSelfAttention", "MobileBertSelfOutput", "MobileBertOutput", "FFNOutput", "OutputBottleneck"]
+__all__ = ["MobileBertSelfAttention", "MobileBertSelfOutput", "MobileBertOutput", "FFNOutput", "OutputBottleneck",
+           "MobileBertLayer"]
+
+
+class MobileBertLayer(hf.MobileBertLayer):
+    """The HF encoder layer, unchanged in structure and parameter names; in inference with observer-free
+    fake-quantizers its forward runs as fused launches (fused.mobilebert_layer_forward) instead of module by module.
+    (Not in the reference's mapping: the reference has no fused execution; module names and state-dict keys are those
+    of the HF layer, so checkpoints and hooks are unaffected.)"""
+
+    def forward(self, hidden_states, attention_mask=None, **kwargs):
+        out = fused.mobilebert_layer_forward(self, hidden_states, attention_mask)
+        if out is not None:
+            return out
+        return super().forward(hidden_states, attention_mask, **kwargs)
+
+    @classmethod
+    def from_observed(cls, other):
+        return rebrand(other, cls, {})
 
 
 class MobileBertSelfAttention(hf.MobileBertSelfAttention):

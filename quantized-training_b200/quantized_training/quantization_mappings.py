@@ -38,6 +38,7 @@ TRANSFORMER_MODULE_MAPPINGS: Dict[Callable, Any] = {
     _R.RobertaSelfAttention: quantizable.BertSelfAttention,
     _R.RobertaSelfOutput: quantizable.BertSelfOutput,
     _R.RobertaOutput: quantizable.BertOutput,
+    _M.MobileBertLayer: quantizable.MobileBertLayer,
     _M.MobileBertSelfAttention: quantizable.MobileBertSelfAttention,
     _M.MobileBertSelfOutput: quantizable.MobileBertSelfOutput,
     _M.FFNOutput: quantizable.FFNOutput,

@@ -216,3 +216,55 @@ def test_quantized_weight_cache_follows_recalibration():
         q(x)
     y3, w3 = frozen_eval()
     assert torch.equal(y3, w3) and not torch.equal(y3, y2)
+
+
+@pytest.mark.parametrize("spec", ["e4m3", "posit8_1"])
+@pytest.mark.parametrize("ops_str", ["gemm,residual,layernorm,activation,scaling", "gemm", "gemm,layernorm"])
+def test_mobilebert_fused_layer_matches_module_by_module(spec, ops_str, monkeypatch):
+    """BASELINE configs[0] host model: the fused MobileBERT layer (fused.mobilebert_layer_forward) against the same
+    model executed module by module through the hooks (the reference's structure, itself pinned to the reference's own
+    run by tests/test_model_golden2_gpu.py).  Same weights, same fake-quantizers, same rounding points: the logits
+    must agree to <= 1 % relative Frobenius error with >= 98 % of the elements bit-identical, and the fused path must
+    actually have run."""
+    from transformers import MobileBertConfig, MobileBertForQuestionAnswering
+    from quantized_training import fused
+    torch.manual_seed(6)
+    cfg = MobileBertConfig(vocab_size=600, hidden_size=512, intra_bottleneck_size=128, num_attention_heads=4,
+                           intermediate_size=512, num_feedforward_networks=2, num_hidden_layers=2, embedding_size=128,
+                           hidden_act="relu", normalization_type="no_norm", hidden_dropout_prob=0.0,
+                           attention_probs_dropout_prob=0.0, attn_implementation="eager")
+    model = MobileBertForQuestionAnswering(cfg).to(DEV).eval()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "LayerNorm.weight" in n:
+                p.add_(0.2 * torch.randn_like(p))
+            elif "LayerNorm.bias" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    qt.quantize(model, parse("--activation", spec, "--weight", spec, "--quantize_forward", ops_str, "--bf16",
+                             "--op_fusion", "qa_outputs"))
+    assert isinstance(model.mobilebert.encoder.layer[0], qt.modules.quantizable.MobileBertLayer)
+    ids = torch.randint(0, 600, (2, 96), device=DEV)
+    am = torch.ones(2, 96, dtype=torch.long, device=DEV)
+    am[1, 80:] = 0
+    calls = {"n": 0}
+    real = fused.mobilebert_layer_forward
+
+    def counting(*a, **k):
+        out = real(*a, **k)
+        calls["n"] += out is not None
+        return out
+
+    with torch.no_grad():
+        model(input_ids=ids, attention_mask=am)     # first call: the hook fake-quantizers are created lazily
+    monkeypatch.setattr(fused, "mobilebert_layer_forward", counting)
+    with torch.no_grad():
+        got = model(input_ids=ids, attention_mask=am)
+        assert calls["n"] == 2, "the fused MobileBERT layer did not run"
+        fused.set_enabled(False)
+        try:
+            want = model(input_ids=ids, attention_mask=am)
+        finally:
+            fused.set_enabled(True)
+    for g, w in ((got.start_logits, want.start_logits), (got.end_logits, want.end_logits)):
+        same = float((g.view(torch.int16) == w.view(torch.int16)).float().mean())
+        assert rel_err(g, w) < 1e-2 and same >= 0.98, (rel_err(g, w), same)
