@@ -386,9 +386,21 @@ int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size_t cols, in
                float eps, int fq_points, int out_type, const qt_format_t *fmt, const float *scale_pre,
                const float *scale_post, const void *lut, void *stream);
 
+/* The same with the residual add in front: x' = bf16(fq_a(x) + fq_b(res)), then y = fq_post(norm(fq_pre(x'))).
+ * QT_FQ_RES_A / QT_FQ_RES_B: the hooks `prepare` puts on the two inputs of the block's AddFunctional (op group
+ * `residual`), bare specs of `fmt`.  kind 3: no norm (the hooked add alone).  One pass replaces dense-output hook,
+ * residual hook, add, norm-input hook, norm and the consumer's input hook (modeling_bert.py:187-191,
+ * modeling_mobilebert.py:118-124): six launches of the reference's structure. */
+#define QT_FQ_RES_A 32
+#define QT_FQ_RES_B 64
+int qt_add_norm_fq(const void *x, const void *res, void *y, void *y_raw, size_t rows, size_t cols, int kind,
+                   const void *weight, const void *bias, float eps, int fq_points, int out_type, const qt_format_t *fmt,
+                   const float *scale_pre, const float *scale_post, const void *lut, void *stream);
+
 /* out = fq_post(act(gate) * up)  (up == NULL: fq_post(act(gate))); rows with independent strides ld_* (elements), so
- * gate and up can be the two halves of one fused projection.  activation: QT_ACT_*.  Replaces act_fn, the product
- * and down_proj's input hook of the HF MLP blocks. */
+ * gate and up can be the two halves of one fused projection.  activation: QT_ACT_*.  QT_FQ_PRE: the activation module's
+ * own input hook (op group `activation`, bare spec) applied to gate first.  Replaces act_fn, the product and down_proj's
+ * input hook of the HF MLP blocks. */
 int qt_act_mul_fq(const void *gate, const void *up, void *out, size_t rows, size_t cols, size_t ld_gate, size_t ld_up,
                   size_t ld_out, int activation, int fq_points, int out_type, const qt_format_t *fmt,
                   const float *scale_post, const void *lut, void *stream);

@@ -26,6 +26,8 @@ constexpr int FQ_PRE = 1;   // fake-quantize the op's input  (hook of the op's o
 constexpr int FQ_MID = 2;   // softmax only: fake-quantize scores * alpha + mask (the "activation" hook of nn.Softmax)
 constexpr int FQ_CAUSAL = 16;  // qt_softmax_fq: QT_SOFTMAX_CAUSAL
 constexpr int FQ_POST = 4;  // fake-quantize the op's output (input hook of the consuming GEMM)
+constexpr int FQ_RES_A = 32;  // qt_add_norm_fq: fake-quantize x before the residual add (AddFunctional input 0 hook)
+constexpr int FQ_RES_B = 64;  // qt_add_norm_fq: fake-quantize the residual operand (AddFunctional input 1 hook)
 
 // Table rounder of the fused kernels: single-replica 8 KB table (staging 64 KB per CTA would dominate these small
 // launches), clamp / NaN-band switches read at run time so that ONE instantiation serves every fp / posit format.
@@ -364,8 +366,8 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
 // + b), fp32 inside.
 template <class R, bool SCALED, int TPR, int VPL>
 __global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
-norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, uint4 *__restrict__ y_raw, int out_type, size_t rows,
-               int cols, int kind,
+norm_fq_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ res, void *__restrict__ y,
+               uint4 *__restrict__ y_raw, int out_type, size_t rows, int cols, int kind,
                const uint4 *__restrict__ weight, const uint4 *__restrict__ bias, float eps, int flags,
                const __grid_constant__ typename R::Params params, const float *__restrict__ scale_pre,
                const float *__restrict__ scale_post)
@@ -387,6 +389,25 @@ norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, uint4 *__restr
         for (int j = 0; j < VPL; ++j) {
             const int i = lane + TPR * j;
             v[j] = (i < nvec && live) ? __ldcs(x + row * nvec + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (res) {  // the residual add in front of the norm (AddFunctional), with the hooks on its two inputs
+            FqPoint bare;
+            bare.sc.s = bare.sc.rs = 1.0f;
+            bare.mode = DIV_UNIT;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                const int i = lane + TPR * j;
+                if (i < nvec && live) {
+                    float a[8], b[8];
+                    unpack8(v[j], a);
+                    unpack8(__ldcs(res + row * nvec + i), b);
+                    if (flags & FQ_RES_A) fq8<R, false>(round, a, bare);
+                    if (flags & FQ_RES_B) fq8<R, false>(round, b, bare);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a[k] += b[k];
+                    v[j] = round_pack8(a);
+                }
+            }
         }
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
@@ -426,7 +447,7 @@ norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, uint4 *__restr
             if (i < nvec && live) {
                 float f[8], w[8];
                 unpack8(v[j], f);
-                unpack8(__ldg(weight + i), w);
+                if (kind != 3) unpack8(__ldg(weight + i), w);
                 if (kind == 0) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[k] *= rstd;
@@ -434,6 +455,7 @@ norm_fq_kernel(const uint4 *__restrict__ x, void *__restrict__ y, uint4 *__restr
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[k] *= w[k];
                     round8(f);
+                } else if (kind == 3) {  // no norm at all: the (hooked) residual add alone
                 } else if (kind == 2) {  // MobileBERT NoNorm: input * weight + bias, two bf16 ops, no statistics
                     float b[8];
                     unpack8(__ldg(bias + i), b);
@@ -493,6 +515,12 @@ act_mul_fq_kernel(const uint4 *__restrict__ gate, const uint4 *__restrict__ up, 
         for (int i = 0; i < U; ++i) {
             float g[8];
             unpack8(gv[i], g);
+            if (flags & FQ_PRE) {  // the activation module's own input hook (bare spec)
+                FqPoint bare;
+                bare.sc.s = bare.sc.rs = 1.0f;
+                bare.mode = DIV_UNIT;
+                fq8<R, false>(round, g, bare);
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 float a = g[k];
@@ -873,16 +901,30 @@ extern "C" int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size
                           const void *bias, float eps, int fq_points, int out_type, const qt_format_t *fmt,
                           const float *scale_pre, const float *scale_post, const void *lut, void *stream)
 {
+    if (kind == 3 || (fq_points & (FQ_RES_A | FQ_RES_B))) {
+        qt_set_error("qt_norm_fq: kind 3 and QT_FQ_RES_* belong to qt_add_norm_fq");
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    return qt_add_norm_fq(x, nullptr, y, y_raw, rows, cols, kind, weight, bias, eps, fq_points, out_type, fmt, scale_pre,
+                          scale_post, lut, stream);
+}
+
+extern "C" int qt_add_norm_fq(const void *x, const void *res, void *y, void *y_raw, size_t rows, size_t cols, int kind,
+                              const void *weight, const void *bias, float eps, int fq_points, int out_type,
+                              const qt_format_t *fmt, const float *scale_pre, const float *scale_post, const void *lut,
+                              void *stream)
+{
     QtRound P;
     int rc = check_common("qt_norm_fq", fmt, &P);
     if (rc != QT_OK) return rc;
     rc = check_out_type("qt_norm_fq", &out_type, fq_points, fmt, scale_post);
     if (rc != QT_OK) return rc;
     if (rows == 0 || cols == 0) return QT_OK;
-    if (!x || !y || !weight || cols % 8 || cols > 8192 || kind < 0 || kind > 2 || (kind == 2 && !bias) || !aligned16(x) ||
+    if (!x || !y || (!weight && kind != 3) || cols % 8 || cols > 8192 || kind < 0 || kind > 3 || (kind == 2 && !bias) ||
+        (kind == 3 && !res) || (!res && (fq_points & (FQ_RES_A | FQ_RES_B))) || (res && !aligned16(res)) || !aligned16(x) ||
         !aligned16(y) ||
         (y_raw && !aligned16(y_raw)) ||
-        !aligned16(weight) || (bias && !aligned16(bias))) {
+        (weight && !aligned16(weight)) || (bias && !aligned16(bias))) {
         qt_set_error("qt_norm_fq: needs 16-byte aligned contiguous bf16 rows, cols %% 8 == 0, cols <= 8192 (got %zu), "
                      "kind 0 (RMSNorm) or 1 (LayerNorm)", cols);
         return QT_ERR_INVALID_ARGUMENT;
@@ -896,7 +938,7 @@ extern "C" int qt_norm_fq(const void *x, void *y, void *y_raw, size_t rows, size
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                              \
         auto kernel = scaled ? norm_fq_kernel<R, true, TPR, VPL> : norm_fq_kernel<R, false, TPR, VPL>;           \
         qt_launch(kernel, dim3(grid_for(ctas, ROW_MIN_CTAS * 2)), dim3(ROW_THREADS), R::kSmemBytes, st,                            \
-            static_cast<const uint4 *>(x), y, static_cast<uint4 *>(y_raw), out_type, rows, (int)cols, kind,      \
+            static_cast<const uint4 *>(x), static_cast<const uint4 *>(res), y, static_cast<uint4 *>(y_raw), out_type, rows, (int)cols, kind, \
             static_cast<const uint4 *>(weight), static_cast<const uint4 *>(bias), eps, fq_points, params,        \
             scale_pre, scale_post);                                                                              \
     } while (0)

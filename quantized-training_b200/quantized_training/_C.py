@@ -60,6 +60,10 @@ EXPORTS = {
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                   ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_void_p]),
+    "qt_add_norm_fq": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p]),
     "qt_act_mul_fq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_size_t] * 5 +
                       [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
                        ctypes.c_void_p, ctypes.c_void_p]),
@@ -469,9 +473,10 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
 
 # ---- fused ops (qt_fused.cu): thin wrappers; argument checking beyond dtype/device lives in the C library --------
 FQ_PRE, FQ_MID, FQ_POST = 1, 2, 4
+FQ_RES_A, FQ_RES_B = 32, 64
 SOFTMAX_CAUSAL = 16
 CAUSAL_OUT_LOWER, CAUSAL_A_LOWER = 1, 2
-NORM_RMS, NORM_LAYER, NORM_NONE = 0, 1, 2
+NORM_RMS, NORM_LAYER, NORM_NONE, NORM_IDENTITY = 0, 1, 2, 3
 OUT_BF16, OUT_E4M3, OUT_E5M2 = 0, 1, 2
 
 
@@ -547,6 +552,20 @@ def norm_fq(x, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale
         _check(lib().qt_norm_fq(x.data_ptr(), y.data_ptr(), _ptr(y_raw), x.numel() // cols, cols, kind, weight.data_ptr(),
                                 _ptr(bias), float(eps), fq_points, _resolve_out(y, fmt), ctypes.byref(fmt),
                                 _ptr(scale_pre), _ptr(scale_post), _ptr(lut), _stream(x)))
+
+
+def add_norm_fq(x, res, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale_post=None, lut=None, y_raw=None):
+    """y = fq_post(norm(fq_pre(bf16(fq_a(x) + fq_b(res)))))  (qt_add_norm_fq)."""
+    _bf16_cuda(x, "x")
+    _bf16_cuda(res, "res")
+    assert x.is_contiguous() and res.is_contiguous() and y.is_contiguous() and res.shape == x.shape and y.shape == x.shape
+    assert weight is None or (weight.is_contiguous() and weight.dtype == torch.bfloat16)
+    assert y_raw is None or (y_raw.is_contiguous() and y_raw.shape == x.shape and y_raw.dtype == torch.bfloat16)
+    cols = x.shape[-1]
+    with torch.cuda.device(x.device):
+        _check(lib().qt_add_norm_fq(x.data_ptr(), res.data_ptr(), y.data_ptr(), _ptr(y_raw), x.numel() // cols, cols, kind,
+                                    _ptr(weight), _ptr(bias), float(eps), fq_points, _resolve_out(y, fmt),
+                                    ctypes.byref(fmt), _ptr(scale_pre), _ptr(scale_post), _ptr(lut), _stream(x)))
 
 
 def act_mul_fq(gate, up, out, activation, fq_points, fmt, scale_post=None, lut=None):

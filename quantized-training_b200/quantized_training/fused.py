@@ -179,11 +179,38 @@ def softmax(scores, alpha, mask, pre, mid, post, codes=False, causal=False, caus
     return probs
 
 
-def act_mul(gate, up, activation, post, codes=False):
-    fmt, lut, (s_post,) = _spec(post)
+def act_mul(gate, up, activation, post, codes=False, pre=None):
+    """fq_post(act(fq_pre(gate)) * up); `pre` (the activation module's own input hook) must be a bare spec."""
+    fmt, lut, (_, s_post) = _spec(pre, post)
+    if pre is not None and pre.qscheme is not None:
+        raise _NotFusable
     out = _out_like(gate, codes)
-    _C.act_mul_fq(gate, up, out, activation, _flags(post=post), fmt, s_post, lut)
+    _C.act_mul_fq(gate, up, out, activation, _flags(pre=pre, post=post), fmt, s_post, lut)
     return out
+
+
+def add_norm(x2, res2, res_a, res_b, norm_mod, post, want_raw=True):
+    """fq_post(norm(fq_pre(bf16(fq_a(x2) + fq_b(res2))))) in one pass: the hooked residual add (AddFunctional), the
+    norm with its input hook and the consumer's input hook.  norm_mod None: the add alone."""
+    if norm_mod is None:
+        kind, pre, w, b, eps = _C.NORM_IDENTITY, None, None, None, 0.0
+    else:
+        kind = _C.NORM_LAYER if isinstance(norm_mod, nn.LayerNorm) else _C.NORM_NONE
+        if kind == _C.NORM_NONE and type(norm_mod).__name__ != "NoNorm":
+            raise _NotFusable
+        pre, w, b, eps = point(norm_mod), norm_mod.weight, norm_mod.bias, getattr(norm_mod, "eps", 0.0)
+    if any(f is not None and f.qscheme is not None for f in (res_a, res_b)):
+        raise _NotFusable   # the add's hooks run on the bare path of the kernel
+    fmt, lut, (_, _, s_pre, s_post) = _spec(res_a, res_b, pre, post)
+    if not res2.is_contiguous():
+        res2 = res2.contiguous()
+    y = torch.empty_like(x2)
+    raw = torch.empty_like(x2) if want_raw and post is not None else None
+    flags = _flags(pre=pre, post=post) | (_C.FQ_RES_A if res_a is not None else 0) | (_C.FQ_RES_B if res_b is not None else 0)
+    _C.add_norm_fq(x2, res2, y, kind, w, b, eps, flags, fmt, s_pre, s_post, lut, raw)
+    if want_raw:
+        return y, (raw if raw is not None else y)
+    return y
 
 
 def fake_quant(x2, post, codes=False):
@@ -499,12 +526,16 @@ def bert_layer_forward(layer, hidden_states, attention_mask):
         q4 = qk[:, :hidden].view(B, S, H, D).transpose(1, 2)
         k4 = qk[:, hidden:].view(B, S, H, D).transpose(1, 2)
         ctx2 = attention(q4, k4, vt, scaling, attention_mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c_o, B, S, H, D)
+        n1 = so.LayerNorm
         if res1 == (None, None):
             h1 = _C.gemm_nt(ctx2, w_o, bias=b_o, residual=x, operand_type=t_o)
+            a_q, a_raw = norm(h1, n1.weight, n1.bias, n1.eps, _C.NORM_LAYER, ln1_in, i_in, c_i, want_raw=True)
+        elif not c_i and all(f is None or f.qscheme is None for f in res1):
+            # hooked residual add + LayerNorm + both hooks around it: one pass
+            a_q, a_raw = add_norm(_C.gemm_nt(ctx2, w_o, bias=b_o, operand_type=t_o), x, res1[0], res1[1], n1, i_in)
         else:
             h1 = so.residual(_C.gemm_nt(ctx2, w_o, bias=b_o, operand_type=t_o), x)
-        n1 = so.LayerNorm
-        a_q, a_raw = norm(h1, n1.weight, n1.bias, n1.eps, _C.NORM_LAYER, ln1_in, i_in, c_i, want_raw=True)
+            a_q, a_raw = norm(h1, n1.weight, n1.bias, n1.eps, _C.NORM_LAYER, ln1_in, i_in, c_i, want_raw=True)
 
         # feed-forward
         if act_in is None:
@@ -512,12 +543,16 @@ def bert_layer_forward(layer, hidden_states, attention_mask):
         else:
             mid = act_mod(_C.gemm_nt(a_q, w_i, bias=b_i, operand_type=t_i))                # hooked activation module
         mid_q = fake_quant(mid, o2_in, c_o2)
+        n2 = out.LayerNorm
         if res2 == (None, None):
             h2 = _C.gemm_nt(mid_q, w_o2, bias=b_o2, residual=a_raw, operand_type=t_o2)
+            y = norm(h2, n2.weight, n2.bias, n2.eps, _C.NORM_LAYER, ln2_in, None)
+        elif all(f is None or f.qscheme is None for f in res2):
+            y = add_norm(_C.gemm_nt(mid_q, w_o2, bias=b_o2, operand_type=t_o2), a_raw, res2[0], res2[1], n2, None,
+                         want_raw=False)
         else:
             h2 = out.residual(_C.gemm_nt(mid_q, w_o2, bias=b_o2, operand_type=t_o2), a_raw)
-        n2 = out.LayerNorm
-        y = norm(h2, n2.weight, n2.bias, n2.eps, _C.NORM_LAYER, ln2_in, None)
+            y = norm(h2, n2.weight, n2.bias, n2.eps, _C.NORM_LAYER, ln2_in, None)
         return y.view(B, S, hidden)
     except (_NotReady, _NotFusable, AttributeError):
         _why("layer")
@@ -536,11 +571,8 @@ def _linear_block(owner, tag, x_q, in_fq, lin, res_mod=None, res=None, act=None,
     epi_act = act if (act is not None and (act_mod is None or point(act_mod) is None)) else None
     epi_res = res if (res is not None and (point(res_mod, "0"), point(res_mod, "1")) == (None, None)) else None
     y = _C.gemm_nt(x_q, w, bias=b, activation=epi_act, residual=epi_res, operand_type=t)
-    if act is not None and epi_act is None:
-        y = act_mod(y)                       # hooked activation module: its own fake quant, then the op
-    if res is not None and epi_res is None:
-        y = res_mod(y, res)                  # hooked AddFunctional: fake quant of both inputs, then the add
-    return y
+    # hooked activation / hooked residual add: left to the caller, which fuses them with what follows
+    return y, (act is not None and epi_act is None), (res is not None and epi_res is None)
 
 
 _FP8_TORCH = {"e4m3": torch.float8_e4m3fn, "e5m2": torch.float8_e5m2}
@@ -600,10 +632,10 @@ def mobilebert_layer_forward(layer, hidden_states, attention_mask):
         # the layer input feeds three Linears (bottleneck.input, bottleneck.attention, value): one fake quant
         x_in = same_points(point(bn.input.dense), point(bn.attention.dense), point(att.value))
         xq = x if x_in is None else x_in(x)
-        layer_in = _linear_block(layer, "bn_in", xq, x_in, bn.input.dense)
+        layer_in, _, _ = _linear_block(layer, "bn_in", xq, x_in, bn.input.dense)
         layer_in = _nonorm(bn.input.LayerNorm, layer_in, None, want_raw=False)              # residual of self-output
         qk_in = same_points(point(att.query), point(att.key))
-        shared = _linear_block(layer, "bn_att", xq, x_in, bn.attention.dense)
+        shared, _, _ = _linear_block(layer, "bn_att", xq, x_in, bn.attention.dense)
         shared_q = _nonorm(bn.attention.LayerNorm, shared, qk_in, want_raw=False)            # input of query and key
 
         # self-attention: query | key in one GEMM, value from the layer input
@@ -612,7 +644,7 @@ def mobilebert_layer_forward(layer, hidden_states, attention_mask):
         if c_qkp:
             shared_q = shared_q.to(_FP8_TORCH[qk_in.fp8_kind]).view(torch.uint8)
         qk = _C.gemm_nt(shared_q, w_qk, bias=b_qk, operand_type=t_qkp)                       # [T, 2 * H * D]
-        v = _linear_block(layer, "v", xq, x_in, att.value)                                   # [T, H * D]
+        v, _, _ = _linear_block(layer, "v", xq, x_in, att.value)                             # [T, H * D]
         q_in, k_in = point(att.qk_matmul, "0"), point(att.qk_matmul, "1")
         p_in, v_in = point(att.av_matmul, "0"), point(att.av_matmul, "1")
         sc_in, sm_in = point(att.attn_scaling), point(att.softmax)
@@ -632,29 +664,35 @@ def mobilebert_layer_forward(layer, hidden_states, attention_mask):
         scaling = getattr(att, "scaling", D ** -0.5)
         ctx2 = attention(q4, k4, vt, scaling, attention_mask, sc_in, sm_in, p_in, o_in, t_qk, t_pv, c_o, B, S, H, D)
 
+        def dense_res_norm(tag, x_q, in_fq, lin, res_mod, res, norm_mod, post, want_raw=True):
+            """dense (+ residual in its epilogue when the add is un-hooked) -> [hooked add +] NoNorm + hooks, one pass"""
+            y, _, hooked_add = _linear_block(layer, tag, x_q, in_fq, lin, res_mod, res)
+            if hooked_add:
+                return add_norm(y, res, point(res_mod, "0"), point(res_mod, "1"), norm_mod, post, want_raw)
+            return _nonorm(norm_mod, y, post, want_raw)
+
         # self-output: dense + residual(layer_in) + NoNorm
-        a = _linear_block(layer, "so", ctx2, o_in, so.dense, so.residual, layer_in)
         first_ffn = ffns[0].intermediate.dense if ffns else layer.intermediate.dense
-        a_q, a_raw = _nonorm(so.LayerNorm, a, point(first_ffn))
+        a_q, a_raw = dense_res_norm("so", ctx2, o_in, so.dense, so.residual, layer_in, so.LayerNorm, point(first_ffn))
 
         # feed-forward stacks: intermediate (dense + act) -> output dense + residual + NoNorm
         stacks = [(f.intermediate, f.output, f"ffn{i}") for i, f in enumerate(ffns)] + [(layer.intermediate, out, "ffn_last")]
         for i, (inter, outp, tag) in enumerate(stacks):
             act_name, act_mod = act_of(inter)
-            mid = _linear_block(layer, tag + "_i", a_q, point(inter.dense), inter.dense, act=act_name, act_mod=act_mod)
+            mid, hooked_act, _ = _linear_block(layer, tag + "_i", a_q, point(inter.dense), inter.dense, act=act_name,
+                                               act_mod=act_mod)
             o_fq = point(outp.dense)
-            mid_q = fake_quant(mid, o_fq, gemm_operands(o_fq, _weight_fq(outp.dense), mid.shape[1])[1])
-            h = _linear_block(layer, tag + "_o", mid_q, o_fq, outp.dense, outp.residual, a_raw)
-            if i + 1 < len(stacks):
-                nxt = point(stacks[i + 1][0].dense)
+            o_codes = gemm_operands(o_fq, _weight_fq(outp.dense), mid.shape[1])[1]
+            if hooked_act:   # act module's input hook + activation + the next Linear's input hook: one pass
+                mid_q = act_mul(mid, None, act_name, o_fq, o_codes, pre=point(act_mod))
             else:
-                nxt = point(out.bottleneck.dense)
-            a_q, a_raw = _nonorm(outp.LayerNorm, h, nxt)
+                mid_q = fake_quant(mid, o_fq, o_codes)
+            nxt = point(stacks[i + 1][0].dense) if i + 1 < len(stacks) else point(out.bottleneck.dense)
+            a_q, a_raw = dense_res_norm(tag + "_o", mid_q, o_fq, outp.dense, outp.residual, a_raw, outp.LayerNorm, nxt)
 
         # output bottleneck: dense (true hidden -> hidden) + residual(layer input) + NoNorm
         ob = out.bottleneck
-        y = _linear_block(layer, "ob", a_q, point(ob.dense), ob.dense, ob.residual, x)
-        y = _nonorm(ob.LayerNorm, y, None, want_raw=False)
+        y = dense_res_norm("ob", a_q, point(ob.dense), ob.dense, ob.residual, x, ob.LayerNorm, None, want_raw=False)
         return y.view(B, S, hidden)
     except (_NotReady, _NotFusable, AttributeError):
         _why("layer")

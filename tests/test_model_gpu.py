@@ -161,23 +161,30 @@ def test_bert_fused_layer_matches_module_by_module(spec, ops_str, monkeypatch):
     am = torch.ones(3, 64, device=DEV, dtype=torch.long)
     am[1, 40:] = 0
     calls = {"n": 0}
-    real = _C.norm_fq
+    real, real_add = _C.norm_fq, _C.add_norm_fq
 
     def counting(*a, **k):
         calls["n"] += 1
         return real(*a, **k)
 
+    def counting_add(*a, **k):            # hooked residual add + LayerNorm + hooks in one pass (residual group on)
+        calls["n"] += 1
+        return real_add(*a, **k)
+
     monkeypatch.setattr(_C, "norm_fq", counting)
+    monkeypatch.setattr(_C, "add_norm_fq", counting_add)
     with torch.no_grad():
         model(input_ids=ids, attention_mask=am)
         assert calls["n"] == 0
         got = model(input_ids=ids, attention_mask=am)
-        assert calls["n"] == 4                          # 2 layers x 2 LayerNorms through the fused kernel
+        assert calls["n"] == 4                          # 2 layers x 2 LayerNorms through the fused kernels
         fused.set_enabled(False)
         want = model(input_ids=ids, attention_mask=am)
         fused.set_enabled(True)
     assert rel_err(got.start_logits, want.start_logits) < 2e-2
     assert rel_err(got.end_logits, want.end_logits) < 2e-2
+    same = float((got.start_logits.view(torch.int16) == want.start_logits.view(torch.int16)).float().mean())
+    assert same >= 0.95, same
 
 
 def test_quantized_weight_cache_follows_recalibration():
