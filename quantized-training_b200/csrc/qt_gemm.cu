@@ -20,8 +20,13 @@
 //               -> TMA store of 32 x 64 boxes (full 128-byte rows), overlapped with the MMAs of the next tile
 //               through the second accumulator
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), bulk-store groups.
-// block_n (64 / 128 / 256) is chosen per problem on the host so that short-K batched products (attention
-// scores) and small-N layers fill the 148 SMs.
+// block_n (a multiple of 16 up to 256) is chosen per problem on the host so that short-K batched products (attention
+// scores), small-N layers and the M = 1024 Llama projections fill the 148 SMs in the fewest waves.
+//
+// Tried and removed in round 2 (profiles/gemm_bench_r02_c*.log): clusters of two CTAs sharing the B tile through TMA
+// multicast (leader fetches, both receive; empty barriers count both CTAs' MMA commits).  Correct on every test, but
+// 3 - 15 % SLOWER than independent CTAs on all shapes (1024 x 4096 x 4096: 31.3 vs 27.0 us): the pair runs in lockstep
+// and one TMA stream feeds two SMs, while L2 -> SM operand traffic was not the limiter it was assumed to be.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
@@ -68,7 +73,9 @@ struct GemmParams {
     uint32_t batch_inner;    // batch index b = outer * batch_inner + inner (e.g. outer = sequence, inner = head)
     int k_blocks;            // ceil(K * elem_bytes / 128)
     uint32_t m_tiles, n_tiles, num_tiles;  // < 2^31 (checked by the launcher)
-    int block_n;             // 64, 128 or 256
+    int block_n;             // tile width: 64 ... 256; multiples of 16 for the plain bf16 epilogue, else of 64
+    __nv_bfloat16 *c_ptr;    // C as a plain pointer (+ strides): the partial last 64-column chunk of a tile whose width
+    int64_t ldc, strideC_inner, strideC_outer;  // is not a multiple of 64 is stored with ordinary 16-byte stores
     const int32_t *causal_flag;  // device flag gating `causal` (null: unconditional)
     int causal;              // 0 off; 1: tiles strictly above the diagonal are skipped (scores of a causal attention);
                              // 2: A is lower triangular (its probabilities): the K loop of row tile mt stops at its diagonal
@@ -452,7 +459,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int e = warp - EPI_WARP0;
         const int quarter = warp & 3, half = e >> 2;
         const uint32_t buf = epi_base + (uint32_t)e * EPI_BUF_BYTES;
-        const int chunks = block_n / EPI_CHUNK_COLS;
+        const int chunks = (block_n + EPI_CHUNK_COLS - 1) / EPI_CHUNK_COLS;
+        const int tail_cols = block_n % EPI_CHUNK_COLS;   // != 0: the last chunk is partial (OUT_PLAIN only)
         int acc = 0, tslot = 0;
         uint32_t acc_phase = 0;
         for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -572,6 +580,23 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
                 if (warp == 2 && lane == 0) trace(p, 2, tslot);  // T2: math done
+                if constexpr (OUT == OUT_PLAIN) {
+                    if (tail_cols && oc == chunks - 1) {
+                        // Partial chunk of a tile whose width was chosen to fill the SMs in fewer waves (e.g. 240 columns
+                        // for N = 4096 on 148 SMs): a 64-column TMA box would spill into the next tile, so this thread
+                        // writes its row's valid 16-byte groups itself.
+                        if (row < p.M) {
+                            __nv_bfloat16 *crow = p.c_ptr + (int64_t)bo * p.strideC_outer + (int64_t)bi * p.strideC_inner +
+                                                  row * p.ldc + n0;
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                if (g * 8 < tail_cols && n0 + g * 8 < p.N)
+                                    *reinterpret_cast<uint4 *>(crow + g * 8) =
+                                        make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+                        }
+                        continue;
+                    }
+                }
                 // the previous store from this buffer must have finished READING it
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
@@ -641,12 +666,15 @@ uint32_t make_idesc(int a_fmt, int b_fmt, int block_n, int a_mn = 0, int b_mn = 
 // and its epilogue time, plus a per-tile hand-over.  Constants measured on B200 (scripts/bmm_probe.py):
 // an MMA instruction takes N/2 cycles at N = 256 but never less than ~96 (narrow tiles are bound by the
 // shared-memory reads of the A operand), the epilogue ~11.3 cycles per output column of a 128-row tile.
-int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int min_bn = 64)
+int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int min_bn = 64, int step = 64)
 {
     const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     int best = MAX_BLOCK_N;
     double best_cost = 0.0;
-    for (int bn = MAX_BLOCK_N; bn >= min_bn; bn >>= 1) {
+    // step 64: the 256 / 128 / 64 ladder (halving).  step 16: every multiple of 16 -- the width that puts the tiles on
+    // the 148 SMs in the fewest, fullest waves (N = 4096 at M = 1024: 240 columns = 144 tiles in one wave instead of
+    // 128 tiles of 256; N = 12288: 224 columns = 440 tiles = 3 waves of 224 instead of 3 of 256).
+    for (int bn = MAX_BLOCK_N; bn >= min_bn; bn = (step == 64 ? bn >> 1 : bn - step)) {
         const int64_t tiles = m_tiles * ((N + bn - 1) / bn) * batch;
         const double rounds = (double)((tiles + sms - 1) / sms);
         const double mma = (double)k_blocks * 4.0 * (bn / 2.0 > 96.0 ? bn / 2.0 : 96.0);
@@ -803,13 +831,23 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.strideB_outer_c = outer > 1 ? d->strideB_outer : 0;
     p.code_lut = static_cast<const uint16_t *>(d->code_lut);
     // an MN-major B tile is made of boxes of 128 bytes of rows: 64 bf16 rows, 128 fp8 rows
-    p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, (glu || (b_mn && fp8)) ? 128 : 64);
+    // any multiple of 16 for the plain bf16 epilogue with a K-major B; the other variants keep whole 64-column chunks
+    const bool fine_bn = !glu && !requant && !b_mn && !b_code && !(getenv("QT_GEMM_COARSE_TILES") != nullptr);
+    p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, (glu || (b_mn && fp8)) ? 128 : 64, fine_bn ? 16 : 64);
+    p.c_ptr = static_cast<__nv_bfloat16 *>(d->C);
+    p.ldc = d->ldc;
+    p.strideC_inner = inner > 1 ? d->strideC_inner : 0;
+    p.strideC_outer = outer > 1 ? d->strideC_outer : 0;
     p.causal = d->causal;
     p.causal_flag = d->causal_flag;
     if (p.causal < 0 || p.causal > 2 || (p.causal == 1 && M != N) || (p.causal == 2 && M != K)) {
         qt_set_error("qt_gemm_nt: causal = 1 needs a square output (M == N), causal = 2 a square A (M == K); got "
                      "causal=%d M=%lld N=%lld K=%lld", p.causal, (long long)M, (long long)N, (long long)K);
         return QT_ERR_INVALID_ARGUMENT;
+    }
+    if (const char *bn = getenv("QT_GEMM_BN")) {  // tests: force a tile width (multiple of 16) where the epilogue allows it
+        const int v = atoi(bn);
+        if (fine_bn && v >= 16 && v <= MAX_BLOCK_N && v % 16 == 0) p.block_n = v;
     }
     if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
         p.debug = atoi(dbg);

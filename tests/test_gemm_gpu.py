@@ -394,3 +394,32 @@ def test_code8_batched_and_residual():
     want = _C.gemm_nt(x, fqm(w), residual=res)
     got = _C.gemm_nt(x, wc, residual=res, operand_type=_C.GEMM_CODE8_B, code_lut=lut)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("bn", [16, 48, 80, 112, 144, 176, 208, 224, 240])
+def test_tile_widths_that_are_not_multiples_of_64(bn, monkeypatch):
+    """The tile width is any multiple of 16 (chosen so that the tiles fill the 148 SMs in the fewest waves): the partial
+    last 64-column chunk of such a tile is written with plain 16-byte stores instead of a TMA box.  Forced here through
+    QT_GEMM_BN on ragged shapes, every epilogue variant of the plain bf16 output, bf16 and fp8 operands."""
+    monkeypatch.setenv("QT_GEMM_BN", str(bn))
+    gen = torch.Generator().manual_seed(bn)
+    for (M, N, K) in [(300, 1000, 136), (128, 8 * bn + 8, 64), (257, 2 * bn, 200)]:
+        a = quantized_operand((M, K), "e4m3", gen)
+        w = quantized_operand((N, K), "e4m3", gen, 0.05)
+        bias = torch.randn(N, generator=gen).to(torch.bfloat16).to(DEV)
+        res = torch.randn(M, N, generator=gen).to(torch.bfloat16).to(DEV)
+        base = a.double() @ w.double().t()
+        r16 = lambda x: x.to(torch.bfloat16).double()
+        big = torch.full((M + 3, N + 16), 7.0, dtype=torch.bfloat16, device=DEV)
+        _C.gemm_nt(a, w, out=big[:M, :N])
+        check(big[:M, :N], base)
+        assert bool((big[M:] == 7.0).all()) and bool((big[:, N:] == 7.0).all())      # nothing outside C is touched
+        check(_C.gemm_nt(a, w, bias=bias, activation="gelu", residual=res),
+              r16(torch.nn.functional.gelu(r16(base + bias.double()))) + res.double())
+        if K % 16 == 0:
+            c8 = lambda t: t.to(torch.float8_e4m3fn).view(torch.uint8)
+            check(_C.gemm_nt(c8(a), c8(w), operand_type=_C.GEMM_E4M3, alpha=0.5), base * 0.5)
+    B, Mb, Nb, Kb = 3, 130, 3 * bn + 24, 72
+    ab = quantized_operand((B, Mb, Kb), "e4m3", gen)
+    wb = quantized_operand((B, Nb, Kb), "e4m3", gen, 0.1)
+    check(_C.gemm_nt(ab, wb), ab.double() @ wb.double().transpose(-1, -2))
