@@ -285,6 +285,32 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank to the host cores of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated
+    (first touch decides where the pages live): with one process per GPU the host <-> device legs then stay on the
+    GPU's own socket instead of all ranks sharing node 0's memory controllers.  Returns a short description."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return f"gpu {local} ({bdf}): no NUMA affinity reported"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return f"gpu {local} ({bdf}) -> NUMA node {node}, {len(allowed)} cores"
+    except Exception as e:  # sysfs layout differs, container without the files, ...: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def run_gpu(args):
     import torch
     import quantized_training as qt
@@ -293,6 +319,7 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    numa = bind_to_gpu_numa(local) if world > 1 else "single process: unbound"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -500,7 +527,7 @@ def run_gpu(args):
                          "per_spec_GBps": {s: bytes_per_launch / (ms * 1e-3) / 1e9 for s, ms in zip(SWEEP, per_spec_ms)}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * ne,
-                    "d2h_bytes_per_step": 2 * ne * len(SWEEP), "log2_numel": ne.bit_length() - 1,
+                    "d2h_bytes_per_step": 2 * ne * len(SWEEP), "log2_numel": ne.bit_length() - 1, "host_affinity_rank0": numa,
                     "api": "quantized_training.host_io.HostPipeline.run_many(8 modules, pinned host tensor, 8 pinned "
                            f"host results): {2 << (args.e2e_log2_chunk - 20)} MB chunks, each uploaded once, H2D / "
                            "8 kernels / 8 D2H overlapped on 4 streams; value counts the algorithmic read+write bytes "

@@ -143,9 +143,11 @@ def table_host(fmt):
 
 
 def lut_host(fmt):
-    """float32[2048] CPU tensor with the fast-path constants of `fmt` (512 x {p1, p2, d, l}), or None for
-    formats that run on the direct path (int / uint / native dtypes)."""
-    out = torch.empty(QT_LUT_BYTES // 4, dtype=torch.float32)
+    """int32[2048] CPU tensor holding the fast-path constants of `fmt` (512 x {p1, p2, d, l} as float32 BIT PATTERNS),
+    or None for formats that run on the direct path (int / uint / native dtypes).  Integer on purpose: the table is a
+    module buffer, and model.bfloat16() / .half() / .to(dtype) cast every floating-point buffer -- which would turn raw
+    rounding constants into garbage -- but leave integer buffers alone."""
+    out = torch.empty(QT_LUT_BYTES // 4, dtype=torch.int32)
     rc = lib().qt_lut_build_host(ctypes.byref(fmt), out.data_ptr())
     if rc == QT_NO_LUT:
         return None
@@ -183,7 +185,7 @@ def fq_forward(x, y, outer, channels, inner, fmt, scale=None, amax_out=None, lut
     if amax_out is not None:
         assert amax_out.dtype == torch.float32 and amax_out.device == x.device and amax_out.numel() >= channels
     if lut is not None:
-        assert lut.dtype == torch.float32 and lut.device == x.device and lut.numel() * 4 == QT_LUT_BYTES \
+        assert lut.dtype in (torch.int32, torch.float32) and lut.device == x.device and lut.numel() * 4 == QT_LUT_BYTES \
             and lut.is_contiguous()
     with torch.cuda.device(x.device):
         _check(lib().qt_fq_forward(x.data_ptr(), y.data_ptr(), outer, channels, inner, _elem_type(x),

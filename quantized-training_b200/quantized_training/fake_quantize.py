@@ -281,6 +281,21 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
             self._flag_versions = versions
         return self._observe, self._quantize
 
+    def _apply(self, fn, *args, **kwargs):
+        """model.bfloat16() / .half() / .to(dtype) cast every floating-point buffer.  The observer state (`scale`,
+        `amax_history`, `zero_point`, `histogram`) is fp32 by definition -- the kernels read it through raw pointers --
+        so a dtype cast is undone here (device moves are kept); the reference tolerates such casts because its buffers
+        only ever meet torch ops."""
+        keep = {n: getattr(self, n).detach().clone() for n in ("scale", "amax_history", "zero_point", "histogram")
+                if getattr(self, n, None) is not None}
+        out = super()._apply(fn, *args, **kwargs)
+        for n, old in keep.items():
+            cur = getattr(self, n)
+            if cur.dtype != torch.float32:
+                self._buffers[n] = old.to(device=cur.device, dtype=torch.float32)
+        self._flag_versions = None
+        return out
+
     def state_key(self):
         """Hashable token that changes whenever the function this module computes may have changed: the observer
         updated the scale (epoch), the scale buffer was written or replaced by torch (version / storage), or the

@@ -275,3 +275,27 @@ def test_mobilebert_fused_layer_matches_module_by_module(spec, ops_str, monkeypa
     for g, w in ((got.start_logits, want.start_logits), (got.end_logits, want.end_logits)):
         same = float((g.view(torch.int16) == w.view(torch.int16)).float().mean())
         assert rel_err(g, w) < 1e-2 and same >= 0.98, (rel_err(g, w), same)
+
+
+def test_dtype_casts_after_quantize_do_not_touch_the_observer_state():
+    """model.bfloat16() / .half() issued AFTER quantize() (HF bf16_full_eval does this) casts every floating-point
+    buffer; the fake-quantizers keep `scale` / `amax_history` in fp32 and the rounding table as an integer buffer, so
+    the next forward computes exactly what it did before the cast."""
+    torch.manual_seed(3)
+    model = nn.Sequential(nn.Linear(64, 64), nn.GELU(), nn.Linear(64, 32)).to(DEV)
+    qt.quantize(model, parse("--activation", "posit8_1,qs=per_tensor_symmetric,qmax=64", "--weight", "posit8_1", "--bf16"))
+    x = torch.randn(8, 64, device=DEV).bfloat16()
+    with torch.no_grad():
+        model(x); model(x)
+        fqs = [m for m in model.modules() if isinstance(m, qt.FusedAmaxObsFakeQuantize)]
+        for m in fqs:
+            m.disable_observer()
+        want = model(x)
+        scales = [m.scale.clone() for m in fqs]
+        model.half()
+        model.bfloat16()
+        for m, s in zip(fqs, scales):
+            assert m.scale.dtype == torch.float32 and m.amax_history.dtype == torch.float32 and torch.equal(m.scale, s)
+            assert m.lut is None or m.lut.dtype == torch.int32
+        got = model(x)
+    assert torch.equal(got, want)
