@@ -27,6 +27,9 @@
 // multicast (leader fetches, both receive; empty barriers count both CTAs' MMA commits).  Correct on every test, but
 // 3 - 15 % SLOWER than independent CTAs on all shapes (1024 x 4096 x 4096: 31.3 vs 27.0 us): the pair runs in lockstep
 // and one TMA stream feeds two SMs, while L2 -> SM operand traffic was not the limiter it was assumed to be.
+// Also tried and removed: a ring whose depth grows for narrow tiles (8 stages of 24 KB for 64 columns out of the same
+// 192 KB).  No shape got faster and the short-K ones got much slower (BERT qkv 8.8 -> 11.1 us, QK^T 14.2 -> 22.7 us,
+// profiles/gemm_bench_r02_d*.log): a producer that runs many tiles ahead competes with the epilogue's stores.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
