@@ -169,8 +169,45 @@ def _require_cuda(t, what):
             f"{what} is on {t.device}: the B200 build of quantized_training runs on CUDA only (no CPU fallback)")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_dev = getattr(torch._C, "_cuda_getDevice", None)
+_set_dev = getattr(torch._C, "_cuda_setDevice", None)
+
+
 def _stream(t):
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    """cudaStream_t of torch's current stream on t's device (the raw getter: no Stream object per call -- these
+    wrappers run ~600 times per fine-tune step when a model executes eagerly)."""
+    if _raw_stream is not None:
+        return _raw_stream(t.device.index)
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _on:
+    """`with torch.cuda.device(t.device)` without its cost when t already lives on the current device."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = -1
+
+    def __enter__(self):
+        if _get_dev is None:
+            self.prev = torch.cuda.current_device()
+            if self.prev != self.idx:
+                torch.cuda.set_device(self.idx)
+            else:
+                self.prev = -1
+            return self
+        cur = _get_dev()
+        if cur != self.idx:
+            self.prev = cur
+            _set_dev(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            (_set_dev or torch.cuda.set_device)(self.prev)
+        return False
 
 
 def fq_forward(x, y, outer, channels, inner, fmt, scale=None, amax_out=None, lut=None):
@@ -187,7 +224,7 @@ def fq_forward(x, y, outer, channels, inner, fmt, scale=None, amax_out=None, lut
     if lut is not None:
         assert lut.dtype in (torch.int32, torch.float32) and lut.device == x.device and lut.numel() * 4 == QT_LUT_BYTES \
             and lut.is_contiguous()
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_fq_forward(x.data_ptr(), y.data_ptr(), outer, channels, inner, _elem_type(x),
                                    ctypes.byref(fmt), scale.data_ptr() if scale is not None else None,
                                    amax_out.data_ptr() if amax_out is not None else None,
@@ -199,7 +236,7 @@ def quantize_codes(x, codes, fmt, scale=None, amax_out=None, lut=None):
     _require_cuda(x, "input")
     assert x.is_contiguous() and codes.is_contiguous() and codes.dtype == torch.uint8 and codes.numel() == x.numel()
     assert lut is not None and lut.device == x.device
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_quantize_codes(x.data_ptr(), codes.data_ptr(), x.numel(), _elem_type(x), ctypes.byref(fmt),
                                        scale.data_ptr() if scale is not None else None,
                                        amax_out.data_ptr() if amax_out is not None else None, lut.data_ptr(),
@@ -228,7 +265,7 @@ def quantize_codes8(x, codes, fmt, code_kind=CODE_NATIVE, scale=None, amax_out=N
     """codes (uint8, same numel) = encode(round_fmt(x / s)) for any <= 8-bit format; per tensor."""
     _require_cuda(x, "input")
     assert x.is_contiguous() and codes.is_contiguous() and codes.dtype == torch.uint8 and codes.numel() == x.numel()
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_quantize_codes8(x.data_ptr(), codes.data_ptr(), x.numel(), _elem_type(x), ctypes.byref(fmt),
                                         int(code_kind), _ptr_or_none(scale), _ptr_or_none(amax_out), _stream(x)))
     return codes
@@ -237,7 +274,7 @@ def quantize_codes8(x, codes, fmt, code_kind=CODE_NATIVE, scale=None, amax_out=N
 def amax(x, outer, channels, inner, amax_out):
     _require_cuda(x, "input")
     assert x.is_contiguous() and amax_out.dtype == torch.float32 and amax_out.device == x.device
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_amax(x.data_ptr(), outer, channels, inner, _elem_type(x), amax_out.data_ptr(), _stream(x)))
 
 
@@ -245,7 +282,7 @@ def scale_update(history, ahl, channels, scale, quant_max, force_pow2):
     _require_cuda(history, "amax_history")
     assert history.dtype == torch.float32 and scale.dtype == torch.float32 and history.is_contiguous()
     assert history.numel() == ahl * channels and scale.numel() == channels and scale.device == history.device
-    with torch.cuda.device(history.device):
+    with _on(history):
         _check(lib().qt_scale_update(history.data_ptr(), ahl, channels, scale.data_ptr(), float(quant_max),
                                      int(bool(force_pow2)), _stream(history)))
 
@@ -310,7 +347,7 @@ def fq_block(x, y, dims, block_size, block_axis2, qscheme, quant_min, quant_max,
         d.pow2_table = pow2_table.data_ptr()
     d.scale = scale.data_ptr()
     d.zero_point = zero_point.data_ptr() if zero_point is not None else None
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_fq_block(ctypes.byref(d), _stream(x)))
 
 
@@ -351,7 +388,7 @@ def table_op(op, x, y, dims, block_size, block_axis2, scale, zero_point=None, ta
     d.scale = scale.data_ptr()
     d.zero_point = _ptr_or_none(zero_point)
     d.table_a, d.table_b = _ptr_or_none(table_a), _ptr_or_none(table_b)
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_table_op(ctypes.byref(d), _stream(x)))
 
 
@@ -468,7 +505,7 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
         if r4.dtype != torch.bfloat16:
             raise TypeError("residual must be bf16")
         d.residual, d.ldr, d.strideR_outer, d.strideR_inner = r4.data_ptr(), r4.stride(2), r4.stride(0), r4.stride(1)
-    with torch.cuda.device(a.device):
+    with _on(a):
         _check(lib().qt_gemm_nt_ex(ctypes.addressof(d), _stream(a)))
     return out
 
@@ -526,7 +563,7 @@ def causal_mask_check(mask3, flag=None):
     assert mask3.is_contiguous() and mask3.dim() == 3 and mask3.shape[1] == mask3.shape[2]
     if flag is None:
         flag = torch.empty(1, dtype=torch.int32, device=mask3.device)
-    with torch.cuda.device(mask3.device):
+    with _on(mask3):
         _check(lib().qt_causal_mask_check(mask3.data_ptr(), mask3.shape[0], mask3.shape[1], flag.data_ptr(),
                                           _stream(mask3)))
     return flag
@@ -537,7 +574,7 @@ def softmax_fq(scores, probs, alpha, mask, rows_per_batch, mask_rows, mask_batch
     _bf16_cuda(scores, "scores")
     assert scores.is_contiguous() and probs.is_contiguous() and probs.shape == scores.shape
     cols = scores.shape[-1]
-    with torch.cuda.device(scores.device):
+    with _on(scores):
         _check(lib().qt_softmax_fq(scores.data_ptr(), probs.data_ptr(), scores.numel() // cols, cols, float(alpha),
                                    _ptr(mask), rows_per_batch, mask_rows, mask_batches, fq_points,
                                    _resolve_out(probs, fmt), ctypes.byref(fmt), _ptr(scale_pre), _ptr(scale_mid),
@@ -550,7 +587,7 @@ def norm_fq(x, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=None, scale
     assert y.shape == x.shape
     assert y_raw is None or (y_raw.is_contiguous() and y_raw.shape == x.shape and y_raw.dtype == torch.bfloat16)
     cols = x.shape[-1]
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_norm_fq(x.data_ptr(), y.data_ptr(), _ptr(y_raw), x.numel() // cols, cols, kind, weight.data_ptr(),
                                 _ptr(bias), float(eps), fq_points, _resolve_out(y, fmt), ctypes.byref(fmt),
                                 _ptr(scale_pre), _ptr(scale_post), _ptr(lut), _stream(x)))
@@ -564,7 +601,7 @@ def add_norm_fq(x, res, y, kind, weight, bias, eps, fq_points, fmt, scale_pre=No
     assert weight is None or (weight.is_contiguous() and weight.dtype == torch.bfloat16)
     assert y_raw is None or (y_raw.is_contiguous() and y_raw.shape == x.shape and y_raw.dtype == torch.bfloat16)
     cols = x.shape[-1]
-    with torch.cuda.device(x.device):
+    with _on(x):
         _check(lib().qt_add_norm_fq(x.data_ptr(), res.data_ptr(), y.data_ptr(), _ptr(y_raw), x.numel() // cols, cols, kind,
                                     _ptr(weight), _ptr(bias), float(eps), fq_points, _resolve_out(y, fmt),
                                     ctypes.byref(fmt), _ptr(scale_pre), _ptr(scale_post), _ptr(lut), _stream(x)))
@@ -575,7 +612,7 @@ def act_mul_fq(gate, up, out, activation, fq_points, fmt, scale_post=None, lut=N
     _bf16_cuda(gate, "gate")
     assert gate.dim() == 2 and out.shape == gate.shape and gate.stride(1) == 1 and out.stride(1) == 1
     assert up is None or (up.shape == gate.shape and up.stride(1) == 1)
-    with torch.cuda.device(gate.device):
+    with _on(gate):
         _check(lib().qt_act_mul_fq(gate.data_ptr(), _ptr(up), out.data_ptr(), gate.shape[0], gate.shape[1],
                                    gate.stride(0), up.stride(0) if up is not None else 0, out.stride(0),
                                    ACTIVATIONS[activation], fq_points, _resolve_out(out, fmt), ctypes.byref(fmt),
@@ -590,7 +627,7 @@ def lora_merge_fq(w, a, b, out, scaling, fq_points, fmt, scale_post=None, lut=No
     n, k = w.shape
     r = a.shape[0]
     assert a.shape == (r, k) and b.shape == (n, r) and out.shape == w.shape
-    with torch.cuda.device(w.device):
+    with _on(w):
         _check(lib().qt_lora_merge_fq(w.data_ptr(), a.data_ptr(), b.data_ptr(), out.data_ptr(), n, k, r, float(scaling),
                                       int(fq_points), ctypes.byref(fmt), _ptr(scale_post), _ptr(lut), _stream(w)))
     return out
@@ -607,7 +644,7 @@ def rope_fq(q, q_out, k, k_out, cos, sin, fq_points, fmt, scale_q=None, scale_k=
         kh = k.shape[1]
         assert k.shape[0] == tokens and k.stride(2) == 1 and k.stride(1) == d and k_out.stride(1) == d
         assert k_out.dtype == q_out.dtype
-    with torch.cuda.device(q.device):
+    with _on(q):
         _check(lib().qt_rope_fq(q.data_ptr(), q_out.data_ptr(), q.stride(0), q_out.stride(0), qh,
                                 _ptr(k), _ptr(k_out), k.stride(0) if k is not None else 0,
                                 k_out.stride(0) if k is not None else 0, kh, tokens, d, cos.data_ptr(), sin.data_ptr(),
@@ -620,7 +657,7 @@ def fq_transpose(v, out, fq_points, fmt, scale_post=None, lut=None):
     _bf16_cuda(v, "v")
     b, s_, h, d = v.shape
     assert v.stride(3) == 1 and v.stride(2) == d and out.is_contiguous() and tuple(out.shape) == (b, h, d, s_)
-    with torch.cuda.device(v.device):
+    with _on(v):
         _check(lib().qt_fq_transpose(v.data_ptr(), out.data_ptr(), b, s_, h, d, v.stride(1), v.stride(0), fq_points,
                                      _resolve_out(out, fmt), ctypes.byref(fmt), _ptr(scale_post), _ptr(lut),
                                      _stream(v)))

@@ -362,6 +362,10 @@ class FusedAmaxObsFakeQuantize(FakeQuantizeBase):
         if self.record_histogram:
             mag = X.detach().float().abs()
             self.histogram += torch.histc(torch.log2(mag).floor(), bins=254, min=-126, max=127)
+        if not (X.requires_grad and torch.is_grad_enabled()):
+            # nothing to differentiate (inference, frozen activations, gradient hooks in backward): skip the
+            # autograd.Function round trip -- ~5 us of host time per call, ~600 calls per eager fine-tune step
+            return _run_block(self, X) if self.is_block_scaled else _run(self, X)
         if self.is_block_scaled:
             return BlockScaledFakeQuantFunction.apply(X, self)
         return FusedAmaxObsFakeQuantFunction.apply(X, self)
