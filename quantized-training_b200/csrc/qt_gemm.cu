@@ -473,7 +473,11 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (tile_skipped(causal, mt, nt, block_n)) continue;
             const int64_t row0 = (int64_t)mt * BLOCK_M + quarter * 32;
             const int64_t row = row0 + lane;
-            mbar_wait(tmem_full_bar(acc), acc_phase);
+            // the longest wait of the kernel (a whole K loop): parked, not spinning (QT_GEMM_DEBUG & 2048: spin, for A/B)
+            if (p.debug & 2048)
+                mbar_wait(tmem_full_bar(acc), acc_phase);
+            else
+                mbar_wait_parked(tmem_full_bar(acc), acc_phase, 20000u);
             if (warp == 2 && lane == 0) trace(p, 2, tslot);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;

@@ -29,6 +29,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// The same wait with a suspend-time hint: the hardware may park the thread for up to `hint_ns` (it is woken when the
+// phase completes).  Without the hint try_wait returns almost at once and the loop spins at full issue rate -- ncu showed
+// 37 % of all warp samples of the CODE8 GEMM in these loops (profiles/ncu_r02_code8.txt).  For LONG waits only
+// (an epilogue warp waiting for a whole K loop).
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, uint32_t hint_ns)
+{
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 24)) __trap();
+    }
+}
 // Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
