@@ -3,7 +3,7 @@
 * DEFAULT_QAT_MODULE_MAPPINGS   float module  -> QAT module (weight fake-quant inside)
 * TRANSFORMER_MODULE_MAPPINGS   HF block      -> quantizable block (hookable matmul/mul/add/softmax)
 * QCONFIG_PROPAGATE_MODULE_CLASS_LIST  op-group name (--quantize_forward / --quantize_backprop) -> classes
-The Llama entry is enabled (commented out at the reference's HEAD).  Conv, DistilBERT, GPT-2 and
+The Llama entry is enabled (commented out at the reference's HEAD).  ConvBn fusions, DistilBERT, GPT-2 and
 Whisper entries belong to model families outside this build's scope.
 """
 from typing import Any, Callable, Dict
@@ -18,6 +18,8 @@ from .modules import qat as nnqat
 from .modules import quantizable
 
 DEFAULT_QAT_MODULE_MAPPINGS: Dict[Callable, Any] = {
+    nn.Conv2d: nnqat.Conv2d,
+    nn.Conv3d: nnqat.Conv3d,
     nn.Linear: nnqat.Linear,
     _lora.LoraLinear: nnqat.LoraLinear,
 }

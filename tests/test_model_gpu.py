@@ -299,3 +299,54 @@ def test_dtype_casts_after_quantize_do_not_touch_the_observer_state():
             assert m.lut is None or m.lut.dtype == torch.int32
         got = model(x)
     assert torch.equal(got, want)
+
+
+def test_qat_conv2d_and_checkpoint_resume(oracle, tmp_path):
+    """reference modules/qat/conv.py:41-42 (`_conv_forward(input, weight_fake_quant(weight), bias)`) with the input
+    hook in front: bit-identical to cuDNN on table-quantized operands; STE gradients reach weight and input.  Then the
+    calibrated model is checkpointed (run_qa_no_trainer.py:961-990 layout) and a second, freshly calibrated model takes
+    the state and reproduces the outputs bit for bit."""
+    from quantized_training import checkpoint as ck
+    from quantized_training.modules import qat
+
+    def make(seed):
+        torch.manual_seed(seed)
+        net = nn.Sequential(nn.Conv2d(16, 32, 3, padding=1), nn.ReLU(), nn.Conv2d(32, 8, 1, bias=False)).to(DEV).bfloat16()
+        qt.quantize(net, parse("--activation", "posit8_1", "--weight", "posit8_1", "--error", "posit8_1",
+                               "--quantize_forward", "gemm", "--quantize_backprop", "gemm", "--bf16"))
+        return net
+
+    net = make(0)
+    assert isinstance(net[0], qat.Conv2d) and isinstance(net[2], qat.Conv2d)
+    x = torch.randn(2, 16, 20, 20, device=DEV).bfloat16().requires_grad_()
+    y = net(x)
+    fq = table_fq(oracle, "posit8_1")
+    h = torch.relu(torch.nn.functional.conv2d(fq(x.detach()), fq(net[0].weight.detach()), net[0].bias, padding=1))
+    ref = torch.nn.functional.conv2d(fq(h), fq(net[2].weight.detach()))
+    assert torch.equal(y, ref)
+    y.backward(torch.randn_like(y))
+    assert x.grad is not None and net[0].weight.grad is not None and net[2].weight.grad.abs().sum() > 0
+
+    # per-tensor scaled spec: calibrate, checkpoint, restore into another model whose quantizers saw different data
+    def make_scaled(seed, data_scale):
+        torch.manual_seed(seed)
+        m = nn.Sequential(nn.Conv2d(16, 8, 3), nn.Flatten(), nn.Linear(8 * 18 * 18, 4)).to(DEV).bfloat16()
+        qt.quantize(m, parse("--activation", "int8,qs=per_tensor_symmetric,ahl=4", "--weight",
+                             "int8,qs=per_channel_symmetric,ax=0", "--quantize_forward", "gemm", "--bf16"))
+        with torch.no_grad():
+            m(torch.randn(2, 16, 20, 20, device=DEV).bfloat16() * data_scale)
+        return m
+
+    a, b = make_scaled(1, 1.0), make_scaled(2, 7.0)
+    xs = torch.randn(2, 16, 20, 20, device=DEV).bfloat16()
+    a.eval(), b.eval()
+    for m in (a, b):
+        for mod in m.modules():
+            if isinstance(mod, qt.FusedAmaxObsFakeQuantize):
+                mod.disable_observer()
+    with torch.no_grad():
+        want = a(xs)
+        assert not torch.equal(b(xs), want)
+        ck.save_state(tmp_path / "epoch_0", a, best_metric={"f1": 1.0})
+        assert ck.load_state(tmp_path / "epoch_0", b, map_location=DEV)["best_metric"] == {"f1": 1.0}
+        assert torch.equal(b(xs), want)

@@ -166,3 +166,72 @@ def test_llama_and_mobilebert_hook_points():
                  "attention.output.LayerNorm", "ffn.0.output.residual", "output.residual", "output.bottleneck.residual",
                  "output.bottleneck.dense", "bottleneck.input.dense", "bottleneck.input.LayerNorm"]:
         assert L0 + leaf in names, leaf
+
+
+class _ConvNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 8, 3, stride=2, padding=1)
+        self.conv3 = nn.Conv3d(2, 4, (1, 3, 3), bias=False)
+        self.head = nn.Linear(8, 4)
+
+
+def test_conv_modules_become_qat_and_back():
+    """reference quantization_mappings.py:17-18 + modules/qat/conv.py: Conv2d / Conv3d are swapped for weight-quantized
+    subclasses that share the float Parameters, and `to_float` undoes it."""
+    net = _ConvNet()
+    w = net.conv.weight
+    qt.quantize(net, parse("--weight", "int8,qs=per_channel_symmetric,ax=0", "--activation", "int8,qs=per_tensor_symmetric",
+                           "--quantize_forward", "gemm"))
+    assert isinstance(net.conv, qat.Conv2d) and isinstance(net.conv, nn.Conv2d)
+    assert isinstance(net.conv3, qat.Conv3d) and net.conv3.bias is None
+    assert net.conv.weight is w and net.conv.stride == (2, 2) and net.conv.padding == (1, 1)
+    assert net.conv.weight_fake_quant.is_per_channel and net.conv.weight_fake_quant.ch_axis == 0
+    assert "conv" in hooked(net) and "conv3" in hooked(net)  # inputs are hooked like any gemm-group module
+    back = net.conv.to_float()
+    assert type(back) is nn.Conv2d and torch.equal(back.weight, w) and back.kernel_size == (3, 3)
+    with pytest.raises(AssertionError, match="only works for Conv2d"):
+        qat.Conv2d.from_float(nn.Conv1d(1, 1, 1))
+
+
+def test_checkpoint_tar_round_trip(tmp_path):
+    """reference run_qa_no_trainer.py:961-990 / :1021-1056: checkpoint.tar layout, resume bookkeeping, and a freshly
+    prepared model taking quantizer buffers that were shaped after the checkpointed run's calibration."""
+    from quantized_training import checkpoint as ck
+
+    def make():
+        torch.manual_seed(0)
+        m = nn.Sequential(nn.Linear(8, 8), nn.ReLU(), nn.Linear(8, 2))
+        qt.quantize(m, parse("--weight", "int8,qs=per_channel_symmetric,ax=0", "--activation",
+                             "int8,qs=per_tensor_symmetric,ahl=4", "--quantize_forward", "gemm"))
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+        return m, opt, torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+
+    m, opt, sch = make()
+    with torch.no_grad():  # stand-in for a calibrated + trained state (the kernels themselves need a GPU)
+        m[0].weight_fake_quant.scale = torch.rand(8, 1) + 0.5
+        m[0].weight_fake_quant.amax_history = torch.full((4, 8), 3.0)
+        m[0].weight.add_(1.0)
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step(), sch.step()
+    path = ck.save_state(tmp_path / "step_30", m, opt, sch, best_metric={"f1": 88.5}, run_id="abc")
+    assert path.endswith("step_30/checkpoint.tar")
+    raw = torch.load(path, weights_only=False)
+    assert set(raw) == {"model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "best_metric", "run_id"}
+
+    m2, opt2, sch2 = make()
+    got = ck.load_state(tmp_path / "step_30", m2, opt2, sch2)
+    assert got["best_metric"] == {"f1": 88.5} and got["run_id"] == "abc"
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert a.shape == b.shape and torch.equal(a, b), k
+    assert m2[0].weight_fake_quant.scale.shape == (8, 1) and sch2.last_epoch == 1
+    assert opt2.state_dict()["state"][0]["step"] == opt.state_dict()["state"][0]["step"]
+
+    ck.save_state(tmp_path / "epoch_0", m, opt, sch)
+    assert ck.find_latest(tmp_path).endswith("epoch_0")
+    # 100 batches per epoch, 4-batch accumulation: step_30 = 120 batches in = epoch 1, 20 batches to skip
+    assert ck.parse_resume(tmp_path / "step_30", 100, 4) == (1, 20, 30)
+    assert ck.parse_resume(tmp_path / "epoch_2", 100, 4) == (3, None, 75)
+    with pytest.raises(ValueError):
+        ck.parse_resume(tmp_path / "final", 100)
