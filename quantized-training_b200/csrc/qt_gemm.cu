@@ -19,6 +19,10 @@
 //   warps 2-9   epilogue: tcgen05.ld (32 lanes x 64 columns) -> registers -> fp32 math -> bf16 -> swizzled smem
 //               -> TMA store of 32 x 64 boxes (full 128-byte rows), overlapped with the MMAs of the next tile
 //               through the second accumulator
+// Long problems (>= 6000 k-block units of 256 x 256 x 64) run as CTA PAIRS instead (template PAIR): clusters of two CTAs on
+// the two SMs of a TPC, one tcgen05.mma.cta_group::2 of 256 rows per instruction, each CTA holding its 128 rows of A and
+// HALF of the B tile (six 32 KB stages).  +4 ... +8 % on the Llama projections (profiles/gemm_pair_r02.log).
+// Tiles are walked in bands of 2048 rows so that the tiles in flight share operands in L2 (8192^3: +12 %).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), bulk-store groups.
 // block_n (a multiple of 16 up to 256) is chosen per problem on the host so that short-K batched products (attention
 // scores), small-N layers and the M = 1024 Llama projections fill the 148 SMs in the fewest waves.
@@ -51,6 +55,9 @@ constexpr int BASE_STAGES = 4;
 constexpr int A_STAGE_BYTES = BLOCK_M * ROW_BYTES;  // 16 KB
 constexpr int B_STAGE_BYTES = MAX_BLOCK_N * ROW_BYTES;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+// CTA pairs hold half of the B tile each: 32 KB stages, six of them in the same 192 KB
+constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES / 2;
+constexpr int PAIR_STAGES = 6;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter, splitting the tile's 64-column chunks between them
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
@@ -75,7 +82,8 @@ struct GemmParams {
     int64_t M, N, K;         // K in elements
     uint32_t batch_inner;    // batch index b = outer * batch_inner + inner (e.g. outer = sequence, inner = head)
     int k_blocks;            // ceil(K * elem_bytes / 128)
-    uint32_t m_tiles, n_tiles, num_tiles;  // < 2^31 (checked by the launcher)
+    uint32_t m_tiles, n_tiles, num_tiles;  // < 2^31 (checked by the launcher); PAIR: m_tiles counts 256-row pairs
+    uint32_t group_m;        // row tiles per band of the tile walk (see tile_coord)
     int block_n;             // tile width: 64 ... 256; multiples of 16 for the plain bf16 epilogue, else of 64
     __nv_bfloat16 *c_ptr;    // C as a plain pointer (+ strides): the partial last 64-column chunk of a tile whose width
     int64_t ldc, strideC_inner, strideC_outer;  // is not a multiple of 64 is stored with ordinary 16-byte stores
@@ -180,13 +188,20 @@ __device__ __forceinline__ void trace(const GemmParams &, int, int &) {}
 // ACT: activation; AUX: the problem has a bias and / or a residual (pointers checked at run time);
 // OUT: OUT_PLAIN bf16 result | OUT_FQ result fake-quantized (bf16 values or fp8 codes) | OUT_GLU act(gate) * up of a
 // column-interleaved gate|up projection (64 gate columns, then the 64 up columns of the same features), fake-quantized.
-template <bool FP8, int ACT, bool AUX, int OUT, bool CODE = false>
+// PAIR: clusters of two CTAs (the two SMs of a TPC) run one 256 x block_n tile with cta_group::2 MMAs.  Each CTA loads
+// its own 128 rows of A and HALF of the B tile, so the tensor core of each SM reads half the B bytes from shared
+// memory per instruction (at 128 x 256 x 16 a single-CTA MMA reads 12 KB per 128 cycles, close to the 128 B / clk port).
+// Rank 0 issues the MMAs; TMA bytes of both CTAs are counted on its full barriers; its commits are multicast to both
+// CTAs' empty / tmem_full barriers; both CTAs' epilogue warps hand accumulators back on its tmem_empty barriers.
+template <bool FP8, int ACT, bool AUX, int OUT, bool CODE = false, bool PAIR = false>
 __global__ void __launch_bounds__(CODE ? CODE_NUM_THREADS : NUM_THREADS, 1)
 qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p)
 {
     extern __shared__ unsigned char smem_raw[];
-    constexpr int STAGES = CODE ? CODE_STAGES : BASE_STAGES;
+    static_assert(!(CODE && PAIR), "the decode variant runs single CTAs");
+    constexpr int STAGES = CODE ? CODE_STAGES : PAIR ? PAIR_STAGES : BASE_STAGES;
+    constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : (A_STAGE_BYTES + B_STAGE_BYTES);
     constexpr int EPI_WARP0 = CODE ? 4 : 2;                              // first epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;         // EPI_WARPS x 4 KB store staging
@@ -201,6 +216,24 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int block_n = p.block_n;
+    // PAIR: the cluster walks tiles of 256 rows (p.m_tiles counts row PAIRS); this CTA owns row tile 2 * pair + rank and
+    // rows [rank * block_n / 2, (rank + 1) * block_n / 2) of the B tile
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const uint32_t tile0 = PAIR ? blockIdx.x >> 1 : blockIdx.x, tile_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+    // tile index -> (row tile of THIS CTA, column tile, batch).  Inside a batch the tiles are walked in bands of
+    // p.group_m row tiles (row tile fastest, then the column tile, then the next band): the ~148 tiles in flight then
+    // cover a near-square patch of C and re-read few distinct A rows / B rows from L2 instead of all of A per wave.
+    auto tile_coord = [&](uint32_t tile, uint32_t &mt, uint32_t &nt, uint32_t &b) {
+        const uint32_t per_batch = p.m_tiles * p.n_tiles;
+        b = tile / per_batch;
+        const uint32_t t = tile - b * per_batch, band = p.group_m * p.n_tiles;
+        const uint32_t g = t / band, r = t - g * band;
+        const uint32_t rows = min(p.group_m, p.m_tiles - g * p.group_m);
+        const uint32_t m = g * p.group_m + r % rows;
+        nt = r / rows;
+        mt = PAIR ? m * 2u + cta_rank : m;
+    };
+    const int b_rows = PAIR ? block_n >> 1 : block_n;   // B rows in this CTA's shared memory
     // MN-major operand tiles: one TMA box = 128 bytes of rows (64 bf16 / 128 fp8) x the K lines of a k-block
     constexpr int MN_BOX_ROWS = FP8 ? 128 : 64;
     constexpr int MN_BOX_BYTES = (FP8 ? 128 : 64) * ROW_BYTES;        // K lines per k-block x 128 bytes
@@ -213,7 +246,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), EPI_WARPS);
+            mbar_init(tmem_empty_bar(a), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -221,13 +254,25 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"((uint32_t)TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {  // the same warp of both CTAs: the columns are allocated in both SMs' TMEM
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) {
+        if (cluster_nctarank() != 2u) __trap();  // launched without the cluster attribute: the protocol below would hang
+        cluster_sync_all();                      // both CTAs' barriers exist before either signals the other
+    } else {
+        __syncthreads();
+    }
     tcgen05_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -267,8 +312,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         };
         auto load = [&](const It &it, uint4 (&v)[MAXV]) {
-            const uint32_t mt = it.tile % p.m_tiles, rest = it.tile / p.m_tiles;
-            const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
+            uint32_t mt, nt, b;
+            tile_coord(it.tile, mt, nt, b);
             const int64_t bi = b % p.batch_inner, bo = b / p.batch_inner;
             const int64_t k0 = (int64_t)it.kb * 64;
 #pragma unroll
@@ -365,16 +410,49 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0, tslot = 0;
             uint32_t phase = 0;
             const uint32_t stage_tx = CODE ? (uint32_t)((p.a_code ? 0 : A_STAGE_BYTES) + (p.b_code ? 0 : block_n * ROW_BYTES))
-                                           : (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES);
-            for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const uint32_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
-                const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
+                                           : (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES);  // PAIR: both CTAs' bytes
+            for (uint32_t tile = tile0; tile < p.num_tiles; tile += tile_step) {
+                uint32_t mt, nt, b;
+                tile_coord(tile, mt, nt, b);
                 const int bi = (int)(b % p.batch_inner), bo = (int)(b / p.batch_inner);
                 if (tile_skipped(causal, mt, nt, block_n)) continue;
                 const int kbn = tile_k_blocks<FP8>(p, causal, mt);
                 for (int kb = 0; kb < kbn; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     trace(p, 0, tslot);
+                    if constexpr (PAIR) {
+                        // 2 x (A tile + half B tile) land on the leader's barrier; the peer's bytes may arrive before the
+                        // leader's expect_tx (the pending arrival keeps the phase open)
+                        // timing experiments (results are wrong): & 1 no B loads, & 2 no loads at all
+                        const bool no_a = p.debug & 2, no_b = p.debug & 3;
+                        if (cta_rank == 0)
+                            mbar_arrive_expect_tx(full_bar(stage), (no_a ? 0u : 2u * A_STAGE_BYTES) +
+                                                                       (no_b ? 0u : (uint32_t)block_n * ROW_BYTES));
+                        const uint32_t lbar = mapa_u32(full_bar(stage), 0u);
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                        const int kcoord = kb * (FP8 ? ROW_BYTES : ROW_BYTES / 2);
+                        const int brow0 = (int)(nt * block_n) + (int)cta_rank * b_rows;
+                        if (no_a) {
+                        } else if (!p.a_mn) {
+                            tma_load_4d_pair(sa, &map_a, lbar, kcoord, (int)(mt * BLOCK_M), bi, bo);
+                        } else {
+                            for (int j = 0; j < BLOCK_M / MN_BOX_ROWS; ++j)
+                                tma_load_4d_pair(sa + j * MN_BOX_BYTES, &map_a, lbar, (int)(mt * BLOCK_M) + j * MN_BOX_ROWS,
+                                                 kcoord, bi, bo);
+                        }
+                        if (no_b) {
+                        } else if (!p.b_mn) {
+                            tma_load_4d_pair(sb, &map_b, lbar, kcoord, brow0, bi, bo);
+                        } else {
+                            for (int j = 0; j < b_rows / MN_BOX_ROWS; ++j)
+                                tma_load_4d_pair(sb + j * MN_BOX_BYTES, &map_b, lbar, brow0 + j * MN_BOX_ROWS, kcoord, bi, bo);
+                        }
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(full_bar(stage), stage_tx);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     const int kcoord = kb * (FP8 ? ROW_BYTES : ROW_BYTES / 2);
@@ -411,13 +489,14 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (lane == 0 && cta_rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0, tslot = 0;
             uint32_t acc_phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const uint32_t mt = tile % p.m_tiles, nt = (tile / p.m_tiles) % p.n_tiles;
+            for (uint32_t tile = tile0; tile < p.num_tiles; tile += tile_step) {
+                uint32_t mt, nt, b_unused;
+                tile_coord(tile, mt, nt, b_unused);
                 if (tile_skipped(causal, mt, nt, block_n)) continue;
                 const int kbn = tile_k_blocks<FP8>(p, causal, mt);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
@@ -436,15 +515,23 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint64_t ka = p.a_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
                     const uint64_t kbs = p.b_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k)
-                        tcgen05_mma<FP8>(tmem_d, da + k * ka, db + k * kbs, p.idesc, (kb | k) != 0);
-                    tcgen05_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+                    for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k) {
+                        if constexpr (PAIR)
+                            tcgen05_mma_pair<FP8>(tmem_d, da + k * ka, db + k * kbs, p.idesc, (kb | k) != 0);
+                        else
+                            tcgen05_mma<FP8>(tmem_d, da + k * ka, db + k * kbs, p.idesc, (kb | k) != 0);
+                    }
+                    // frees the smem slot once these MMAs have read it (PAIR: in both CTAs)
+                    if constexpr (PAIR) tcgen05_commit_pair(empty_bar(stage), (uint16_t)3);
+                    else tcgen05_commit(empty_bar(stage));
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                tcgen05_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (PAIR: each CTA's warps read their own 128 lanes)
+                if constexpr (PAIR) tcgen05_commit_pair(tmem_full_bar(acc), (uint16_t)3);
+                else tcgen05_commit(tmem_full_bar(acc));
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1u;
@@ -466,9 +553,14 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int tail_cols = block_n % EPI_CHUNK_COLS;   // != 0: the last chunk is partial (OUT_PLAIN only)
         int acc = 0, tslot = 0;
         uint32_t acc_phase = 0;
-        for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const uint32_t mt = tile % p.m_tiles, rest = tile / p.m_tiles;
-            const uint32_t nt = rest % p.n_tiles, b = rest / p.n_tiles;
+        // hand-back of an accumulator: PAIR -> the leader's barrier (it counts both CTAs' epilogue warps)
+        auto release_acc = [&](int a) {
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(a), 0u));
+            else mbar_arrive(tmem_empty_bar(a));
+        };
+        for (uint32_t tile = tile0; tile < p.num_tiles; tile += tile_step) {
+            uint32_t mt, nt, b;
+            tile_coord(tile, mt, nt, b);
             const int bi = (int)(b % p.batch_inner), bo = (int)(b / p.batch_inner);
             if (tile_skipped(causal, mt, nt, block_n)) continue;
             const int64_t row0 = (int64_t)mt * BLOCK_M + quarter * 32;
@@ -492,7 +584,17 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (half >= out_chunks) {  // narrow tiles: the second warp of the quarter has no chunk, only the hand-back
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                if (lane == 0) release_acc(acc);
+            }
+            if (p.debug & 8192) {  // timing experiment: no epilogue work, only the hand-back
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0 && half < out_chunks) release_acc(acc);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+                continue;
             }
             for (int oc = half; oc < out_chunks; oc += 2) {
                 const int c = OUT == OUT_GLU ? 2 * oc : oc;  // first accumulator chunk
@@ -505,7 +607,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (OUT != OUT_GLU && last) {  // last TMEM read of this warp for this tile: hand the accumulator back
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                    if (lane == 0) release_acc(acc);
                 }
                 const int64_t n_in0 = (int64_t)nt * block_n + c * EPI_CHUNK_COLS;     // accumulator / bias column
                 const int64_t n0 = (int64_t)nt * out_block_n + oc * EPI_CHUNK_COLS;   // output column
@@ -531,7 +633,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (last) {
                         tcgen05_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                        if (lane == 0) release_acc(acc);
                     }
                 }
                 uint32_t packed[32];  // bf16: 64 values; codes: the first 16 words
@@ -651,11 +753,16 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and signal its barriers
+    else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                     : "memory");
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                         : "memory");
     }
 }
 
@@ -663,19 +770,21 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): D = F32 [4,6) = 1;
 // A/B format [7,10) / [10,13): kind::f16 BF16 = 1, kind::f8f6f4 E4M3 = 0 / E5M2 = 1; both K-major;
 // A / B major-ness at bit 15 / 16 (0 K-major, 1 MN-major); N >> 3 at [17,23); M >> 4 at [24,29).
-uint32_t make_idesc(int a_fmt, int b_fmt, int block_n, int a_mn = 0, int b_mn = 0)
+uint32_t make_idesc(int a_fmt, int b_fmt, int block_n, int a_mn = 0, int b_mn = 0, bool pair = false)
 {
     return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(a_mn != 0) << 15) |
-           ((uint32_t)(b_mn != 0) << 16) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+           ((uint32_t)(b_mn != 0) << 16) | ((uint32_t)(block_n >> 3) << 17) |
+           ((uint32_t)((pair ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);   // cta_group::2: M = 256 across the pair
 }
 
 // Tile width.  The persistent grid runs ceil(tiles / SMs) rounds; a round costs the larger of the tile's MMA time
 // and its epilogue time, plus a per-tile hand-over.  Constants measured on B200 (scripts/bmm_probe.py):
 // an MMA instruction takes N/2 cycles at N = 256 but never less than ~96 (narrow tiles are bound by the
 // shared-memory reads of the A operand), the epilogue ~11.3 cycles per output column of a 128-row tile.
-int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int min_bn = 64, int step = 64)
+int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int min_bn = 64, int step = 64,
+                 int tile_m = BLOCK_M)
 {
-    const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const int64_t m_tiles = (M + tile_m - 1) / tile_m;
     int best = MAX_BLOCK_N;
     double best_cost = 0.0;
     // step 64: the 256 / 128 / 64 ladder (halving).  step 16: every multiple of 16 -- the width that puts the tiles on
@@ -695,19 +804,36 @@ int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int
     return best;
 }
 
+thread_local bool g_pair = false;  // set by qt_gemm_nt_ex (same thread) before it dispatches: launch the CTA-pair kernel
+
+template <bool FP8, int ACT, bool AUX, int OUT, bool CODE, bool PAIR>
+void launch_kernel(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
+                   const CUtensorMap &map_c, const GemmParams &p)
+{
+    static bool done[64] = {};
+    constexpr size_t smem = CODE ? CODE_SMEM_BYTES : SMEM_BYTES;
+    static_assert((size_t)PAIR_STAGES * PAIR_STAGE_BYTES <= (size_t)BASE_STAGES * STAGE_BYTES, "pair ring fits the same smem");
+    if (dev >= 64 || !done[dev]) {
+        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        if (dev < 64) done[dev] = true;
+    }
+    if (PAIR)
+        qt_launch_cluster(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR>, dim3(grid), dim3(NUM_THREADS), smem, st, 2u, map_a,
+                          map_b, map_c, p);
+    else
+        qt_launch(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR>, dim3(grid), dim3(CODE ? CODE_NUM_THREADS : NUM_THREADS), smem,
+                  st, map_a, map_b, map_c, p);
+}
+
 template <bool FP8, int ACT, bool AUX, int OUT = OUT_PLAIN, bool CODE = false>
 void launch_variant(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
                     const CUtensorMap &map_c, const GemmParams &p)
 {
-    static bool done[64] = {};
-    constexpr size_t smem = CODE ? CODE_SMEM_BYTES : SMEM_BYTES;
-    if (dev >= 64 || !done[dev]) {
-        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-        if (dev < 64) done[dev] = true;
+    if constexpr (!CODE) {
+        if (g_pair) return launch_kernel<FP8, ACT, AUX, OUT, false, true>(dev, grid, st, map_a, map_b, map_c, p);
     }
-    qt_launch(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE>, dim3(grid), dim3(CODE ? CODE_NUM_THREADS : NUM_THREADS), smem, st,
-              map_a, map_b, map_c, p);
+    launch_kernel<FP8, ACT, AUX, OUT, CODE, false>(dev, grid, st, map_a, map_b, map_c, p);
 }
 
 }  // namespace
@@ -840,6 +966,20 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     // an MN-major B tile is made of boxes of 128 bytes of rows: 64 bf16 rows, 128 fp8 rows
     // any multiple of 16 for the plain bf16 epilogue with a K-major B; the other variants keep whole 64-column chunks
     const bool fine_bn = !glu && !requant && !b_mn && !b_code && !(getenv("QT_GEMM_COARSE_TILES") != nullptr);
+    // CTA pairs (cta_group::2): 256-row tiles on the two SMs of a TPC.  Measured on B200 (profiles/gemm_pair_r02.log):
+    // +4 ... +8 % on the long problems (Llama qkv / down / lm_head), -2 ... -5 % on problems that last under ~30 us (cluster
+    // launch and the two cluster-wide syncs are a fixed cost), so the choice is by work: 256 x 256 x 64 k-block units.
+    // The causal schedules and the decode variant stay on single CTAs.  QT_GEMM_PAIR=0 / 1 forces the choice (A/B, tests).
+    const bool pair_ok = !b_code && !d->causal && sms % 2 == 0;
+    const int64_t pairs256 = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + MAX_BLOCK_N - 1) / MAX_BLOCK_N) * batch;
+    bool pair = pair_ok && M > BLOCK_M && pairs256 * p.k_blocks >= 6000;
+    if (const char *pe = getenv("QT_GEMM_PAIR")) pair = pair_ok && pe[0] == '1';
+    g_pair = pair;
+    if (pair) {
+        // each CTA holds block_n / 2 rows of B: whole 128-byte row boxes for an MN-major B (64 bf16 / 128 fp8 rows)
+        const int min_bn = b_mn ? (fp8 ? 256 : 128) : glu ? 128 : 64;
+        p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms / 2, min_bn, fine_bn ? 16 : 64, 2 * BLOCK_M);
+    } else
     p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, (glu || (b_mn && fp8)) ? 128 : 64, fine_bn ? 16 : 64);
     p.c_ptr = static_cast<__nv_bfloat16 *>(d->C);
     p.ldc = d->ldc;
@@ -858,11 +998,12 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     }
     if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
         p.debug = atoi(dbg);
-        if (p.debug & 4) p.block_n = 128;
-        if ((p.debug & 8) && !glu && !(b_mn && fp8)) p.block_n = 64;
+        if ((p.debug & 4) && !(pair && b_mn && fp8)) p.block_n = 128;
+        if ((p.debug & 8) && !glu && !(b_mn && (fp8 || pair))) p.block_n = 64;
         if (p.debug & 16) p.block_n = 256;
     }
-    const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + p.block_n - 1) / p.block_n;
+    const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;   // p.m_tiles counts row pairs in pair mode
+    const int64_t m_tiles = (M + tile_m - 1) / tile_m, n_tiles = (N + p.block_n - 1) / p.block_n;
     if (m_tiles * n_tiles * batch >= (int64_t)1 << 31 || M >= (int64_t)1 << 31 || N >= (int64_t)1 << 31 ||
         inner >= (int64_t)1 << 31 || outer >= (int64_t)1 << 31) {
         qt_set_error("qt_gemm_nt: problem too large (%lld tiles)", (long long)(m_tiles * n_tiles * batch));
@@ -871,6 +1012,9 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     p.m_tiles = (uint32_t)m_tiles;
     p.n_tiles = (uint32_t)n_tiles;
     p.num_tiles = (uint32_t)(m_tiles * n_tiles * batch);
+    p.group_m = (uint32_t)(2048 / tile_m);   // bands of 2048 rows; QT_GEMM_GROUP_M overrides (tile rows; 0 = one band)
+    if (const char *gm = getenv("QT_GEMM_GROUP_M")) p.group_m = (uint32_t)atoi(gm);
+    if (p.group_m == 0 || p.group_m > p.m_tiles) p.group_m = p.m_tiles;
 
     CUtensorMap map_a, map_b, map_c;
     // K-major: [rows, K] boxes of rows x 128 bytes of K.  MN-major: [K, rows] boxes of one k-block of K lines x 128
@@ -896,7 +1040,8 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     }
     if (!b_code) {
         rc = b_mn ? make_map(&map_b, d->B, fp8, N, K, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, k_lines)
-                  : make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer, p.block_n);
+                  : make_map(&map_b, d->B, fp8, K, N, inner, outer, d->ldb, d->strideB_inner, d->strideB_outer,
+                             pair ? p.block_n / 2 : p.block_n);
         if (rc != QT_OK) return rc;
     }
 
@@ -910,13 +1055,14 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     switch (operand_type) {
     case QT_GEMM_BF16:
     case QT_GEMM_CODE8_B:
-    case QT_GEMM_CODE8_AB: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn); break;
-    case QT_GEMM_E4M3: p.idesc = make_idesc(0, 0, p.block_n, a_mn, b_mn); break;
-    case QT_GEMM_E5M2: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn); break;
-    case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1, p.block_n, a_mn, b_mn); break;
-    default: p.idesc = make_idesc(1, 0, p.block_n, a_mn, b_mn); break;  // QT_GEMM_E5M2_E4M3
+    case QT_GEMM_CODE8_AB: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn, pair); break;
+    case QT_GEMM_E4M3: p.idesc = make_idesc(0, 0, p.block_n, a_mn, b_mn, pair); break;
+    case QT_GEMM_E5M2: p.idesc = make_idesc(1, 1, p.block_n, a_mn, b_mn, pair); break;
+    case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1, p.block_n, a_mn, b_mn, pair); break;
+    default: p.idesc = make_idesc(1, 0, p.block_n, a_mn, b_mn, pair); break;  // QT_GEMM_E5M2_E4M3
     }
-    const unsigned grid = p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms;
+    const unsigned grid = pair ? 2u * (p.num_tiles < (uint32_t)(sms / 2) ? p.num_tiles : (unsigned)(sms / 2))
+                               : (p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool aux = d->bias != nullptr || d->residual != nullptr;
     if (b_code || ((p.debug & 4096) && operand_type == QT_GEMM_BF16 && !glu && !requant && d->activation == ACT_NONE)) {

@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "qt_internal.h"
 
@@ -90,6 +91,69 @@ __device__ __forceinline__ void tcgen05_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ----- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE 256-row MMA.  Each holds its own
+// 128 rows of A, half of the B tile and its 128 lanes of the accumulator; the leader (cluster rank 0) issues.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `local` (a shared::cta offset of this kernel's layout) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA's share of a pair's stage: data into THIS CTA's shared memory, bytes counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1,
+                                                 int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// arrives on the barrier at the same offset in every CTA of `mask` once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+template <bool FP8>
+__device__ __forceinline__ void tcgen05_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate)
+{
+    if (FP8)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
 template <bool FP8>
 __device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate)
@@ -172,6 +236,18 @@ EncodeTiledFn encode_tiled()
     return fn;
 }
 
+// QT_TMA_L2PROMO = 0 / 1 / 2 / 3: none / 64 B / 128 B / 256 B (default) L2 promotion of the maps (A/B runs)
+inline CUtensorMapL2promotion l2_promotion()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("QT_TMA_L2PROMO");
+        v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+    }
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // [outer, inner, rows, cols] tensor with a unit-stride last axis and arbitrary (16-byte aligned) strides on the other
 // three: dims {cols, rows, inner, outer}, box {box_cols, box_rows, 1, 1}, 128-byte swizzle (box_cols * esz == 128).
 // Loads: out-of-bounds elements (K tail, row tail) are filled with zeros.  Stores: they are not written.
@@ -207,7 +283,7 @@ int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int
     CUresult r = fn(map, one_byte ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         qt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld batch=%lldx%lld ld=%lld "
                      "strides=%lld,%lld)", (int)r, (long long)cols, (long long)rows, (long long)outer, (long long)inner,

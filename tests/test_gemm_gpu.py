@@ -14,6 +14,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["auto", "pair"])
+def cta_pairs(request, monkeypatch):
+    """Every test of this file runs twice: with the launcher's own choice between single CTAs and CTA pairs
+    (cta_group::2, 256-row tiles), and with pairs forced wherever the kernel has them (everything but the causal
+    schedules and the one-byte-code operands) -- including shapes with an odd number of row tiles or a single one,
+    where the second CTA of a pair works on rows outside the problem."""
+    if request.param == "pair":
+        monkeypatch.setenv("QT_GEMM_PAIR", "1")
+    yield request.param
+
+
 def check(got, ref):
     ref = ref.double()
     err = (got.double() - ref).abs()
