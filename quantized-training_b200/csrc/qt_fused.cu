@@ -242,8 +242,11 @@ __device__ __forceinline__ float row_reduce(float v)
 //   s = qk_matmul(q, k^T); [s = fq(s)]; s = s * scaling; s = s + mask; [s = fq(s)]; p = softmax(s, -1); [p = fq(p)]
 // Which steps exist is a run-time mask tested once per 8-element vector (a per-element test multiplies the
 // unrolled code by the number of combinations and thrashes the instruction cache).
-template <class R, bool SCALED, int TPR, int VPL>
-__global__ void __launch_bounds__(ROW_THREADS, ROW_MIN_CTAS)
+// SIMPLE: the step set of a gemm-only model (Llama perplexity, BASELINE configs[1]) -- no hook on the scores and no mid
+// point: those branches and the prefetched mask registers are compiled out
+// and the kernel keeps its row in registers without spills (the general kernel is capped at 64 registers).
+template <class R, bool SCALED, int TPR, int VPL, bool SIMPLE = false>
+__global__ void __launch_bounds__(ROW_THREADS, SIMPLE ? 3 : ROW_MIN_CTAS)
 softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, int out_type, size_t rows, int cols, float alpha,
                   int has_alpha, const uint4 *__restrict__ mask, size_t rows_per_batch, size_t mask_rows,
                   size_t mask_batch_stride_vec, int flags, const __grid_constant__ typename R::Params params,
@@ -270,14 +273,15 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
         const uint4 *srow = scores + (live ? row : 0) * nvec;
         const uint4 *mrow = nullptr;
         if (mask && live) mrow = mask + (row / rows_per_batch) * mask_batch_stride_vec + (row % mask_rows) * (size_t)nvec;
-        uint4 raw[VPL], mraw[VPL];
+        uint4 raw[VPL], mraw[SIMPLE ? 1 : VPL];
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {  // all loads first: VPL (x2 with a mask) 16-byte requests in flight per thread
             const int i = lane + TPR * j;
             const bool in = i < nvec && live && i * 8 <= r_seq;
             raw[j] = in ? __ldcs(srow + i) : make_uint4(0u, 0u, 0u, 0u);
             // causal by contract: the mask is known (0 up to the diagonal, finfo.min above it) and is not read
-            mraw[j] = (in && mrow && !(flags & FQ_CAUSAL)) ? __ldg(mrow + i) : make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (!SIMPLE)
+                mraw[j] = (in && mrow && !(flags & FQ_CAUSAL)) ? __ldg(mrow + i) : make_uint4(0u, 0u, 0u, 0u);
         }
         float f[VPL][8];
         float mx = -INFINITY;
@@ -286,7 +290,7 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
             const int i = lane + TPR * j;
             if (i < nvec && live && i * 8 <= r_seq) {
                 unpack8(raw[j], f[j]);
-                if (flags & FQ_PRE) fq8<R, SCALED>(round, f[j], pre);
+                if (!SIMPLE && (flags & FQ_PRE)) fq8<R, SCALED>(round, f[j], pre);
                 if (has_alpha) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[j][k] *= alpha;
@@ -302,12 +306,13 @@ softmax_fq_kernel(const uint4 *__restrict__ scores, void *__restrict__ probs, in
                     }
                 } else if (mrow) {
                     float m8[8];
-                    unpack8(mraw[j], m8);
+                    // SIMPLE: a mask that turned out not to be causal (device flag) is read here, unprefetched
+                    unpack8(SIMPLE ? __ldg(mrow + i) : mraw[SIMPLE ? 0 : j], m8);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[j][k] += m8[k];
                     round8(f[j]);
                 }
-                if (flags & FQ_MID) fq8<R, SCALED>(round, f[j], mid);
+                if (!SIMPLE && (flags & FQ_MID)) fq8<R, SCALED>(round, f[j], mid);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) mx = fmaxf(mx, f[j][k]);
             } else {
@@ -870,12 +875,16 @@ extern "C" int qt_softmax_fq(const void *scores, void *probs, size_t rows, size_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int has_alpha = alpha != 1.0f;
     const bool scaled = scale_pre || scale_mid || scale_post;
+    const bool simple = !(fq_points & (FQ_PRE | FQ_MID)) && getenv("QT_SOFTMAX_GENERAL") == nullptr;
     rc = dispatch_fused(P, lut, [&](auto tag, const auto &params) {
         using R = typename decltype(tag)::type;
 #define QT_SOFTMAX_LAUNCH(TPR, VPL)                                                                                  \
     do {                                                                                                             \
         const size_t ctas = (rows + (ROW_THREADS / TPR) - 1) / (ROW_THREADS / TPR);                                  \
         auto kernel = scaled ? softmax_fq_kernel<R, true, TPR, VPL> : softmax_fq_kernel<R, false, TPR, VPL>;         \
+        if (simple && TPR == 32 && VPL >= 2)                                                                         \
+            kernel = scaled ? softmax_fq_kernel<R, true, TPR, (VPL >= 2 ? VPL : 2), true>                            \
+                            : softmax_fq_kernel<R, false, TPR, (VPL >= 2 ? VPL : 2), true>;                          \
         qt_launch(kernel, dim3(grid_for(ctas, ROW_MIN_CTAS * 2)), dim3(ROW_THREADS), R::kSmemBytes, st,                                \
             static_cast<const uint4 *>(scores), probs, out_type, rows, (int)cols, alpha, has_alpha,                  \
             static_cast<const uint4 *>(mask), rows_per_batch, mask_rows, mask_batch_stride_vec, fq_points, params,   \
