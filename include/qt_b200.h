@@ -324,12 +324,27 @@ typedef struct qt_gemm_desc {
      * B needs N tiles of 128 rows (chosen automatically).  The causal schedules take K-major operands. */
     int32_t a_major, b_major;
     const void *code_lut; /* QT_GEMM_CODE8*: device uint16[256], bf16 bits of decode(byte) */
+    /* Block-scaled operands (OCP microscaling: one power-of-two scale per 32 elements along K), fp8 operand types
+     * only: C = sum over blocks of (a_block . b_block) * 2^(ea - 127) * 2^(eb - 127) on tcgen05.mma kind::mxf8f6f4
+     * .block_scale -- the product the reference's linear_mx forms by dequantizing both operands first
+     * (decomposed.py:311-331).  sf_a / sf_b: UE8M0 exponent bytes packed by qt_mx_pack_scales ([K / 128][32][rows_pad /
+     * 32][4]), sf_rows_a / sf_rows_b their padded row counts (multiples of 128).  NULL: plain fp8 product.
+     * K-major operands, no batch, plain epilogue (alpha, bias, residual). */
+    const void *sf_a, *sf_b;
+    int64_t sf_rows_a, sf_rows_b;
 } qt_gemm_desc_t;
 #define QT_MAJOR_K 0
 #define QT_MAJOR_MN 1
 #define QT_CAUSAL_OUT_LOWER 1
 #define QT_CAUSAL_A_LOWER 2
 int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
+
+/* Scales of one block-scaled operand, fp32 [rows, kblocks32] (kblocks32 = ceil(K / 32), every entry a power of two
+ * 2^e with -126 <= e <= 127), to the byte layout the block-scaled MMA path loads: out[kb][m0][g][j] (uint8) = biased
+ * exponent of scale[g * 32 + m0][kb * 4 + j], kb < ceil(kblocks32 / 4), m0 < 32, g < rows_pad / 32, j < 4; rows_pad =
+ * rows rounded up to 128; entries outside the matrix are 0.  out holds ceil(kblocks32 / 4) * rows_pad * 4 bytes.
+ * *ok_out (device int32, may be NULL) is AND-ed with "every scale is such a power of two". */
+int qt_mx_pack_scales(const float *scale, int64_t rows, int64_t kblocks32, void *out, int32_t *ok_out, void *stream);
 
 /* ---- ops between the GEMMs, fused with the fake-quant steps around them (qt_fused.cu) -------------------------
  * All tensors bf16 on the device, 16-byte aligned, column counts multiples of 8.  `fmt` / `lut` as in qt_fq_forward.

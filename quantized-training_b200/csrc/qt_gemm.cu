@@ -58,6 +58,14 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 // CTA pairs hold half of the B tile each: 32 KB stages, six of them in the same 192 KB
 constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES / 2;
 constexpr int PAIR_STAGES = 6;
+// Block-scaled (MX) variant: tiles of at most 192 columns, so that the scale-factor columns fit into TMEM between the two
+// accumulators (columns 192 ... 239: per ring stage 4 columns for A's 128 rows and 8 for B's <= 256).  Stage layout:
+// A 16 KB | B 24 KB | scale factors of A 512 B | of B 1 KB | pad.
+constexpr int MX_BLOCK_N = 192;
+constexpr int MX_SF_OFFSET = A_STAGE_BYTES + MX_BLOCK_N * ROW_BYTES;  // 40 KB
+constexpr int MX_STAGE_BYTES = MX_SF_OFFSET + 2048;                   // 42 KB (1024-byte multiple)
+constexpr int MX_SF_TMEM_COL = MX_BLOCK_N;
+constexpr int MX_SF_COLS_PER_STAGE = 12;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter, splitting the tile's 64-column chunks between them
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
@@ -193,15 +201,20 @@ __device__ __forceinline__ void trace(const GemmParams &, int, int &) {}
 // memory per instruction (at 128 x 256 x 16 a single-CTA MMA reads 12 KB per 128 cycles, close to the 128 B / clk port).
 // Rank 0 issues the MMAs; TMA bytes of both CTAs are counted on its full barriers; its commits are multicast to both
 // CTAs' empty / tmem_full barriers; both CTAs' epilogue warps hand accumulators back on its tmem_empty barriers.
-template <bool FP8, int ACT, bool AUX, int OUT, bool CODE = false, bool PAIR = false>
+// MX: fp8 operands with one UE8M0 scale per 32 K elements (kind::mxf8f6f4.block_scale).  The producer also loads the
+// k-block's scale-factor boxes; the MMA thread copies them into TMEM (tcgen05.cp) in front of the four MMAs that use
+// them, each selecting its byte of the scale columns through the descriptor's sf ids.
+template <bool FP8, int ACT, bool AUX, int OUT, bool CODE = false, bool PAIR = false, bool MX = false>
 __global__ void __launch_bounds__(CODE ? CODE_NUM_THREADS : NUM_THREADS, 1)
 qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p)
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p,
+               const __grid_constant__ CUtensorMap map_sfa, const __grid_constant__ CUtensorMap map_sfb)
 {
     extern __shared__ unsigned char smem_raw[];
     static_assert(!(CODE && PAIR), "the decode variant runs single CTAs");
+    static_assert(!MX || (FP8 && !CODE && !PAIR), "block scaling: fp8 operands, single CTAs");
     constexpr int STAGES = CODE ? CODE_STAGES : PAIR ? PAIR_STAGES : BASE_STAGES;
-    constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : (A_STAGE_BYTES + B_STAGE_BYTES);
+    constexpr int STAGE_BYTES = MX ? MX_STAGE_BYTES : PAIR ? PAIR_STAGE_BYTES : (A_STAGE_BYTES + B_STAGE_BYTES);
     constexpr int EPI_WARP0 = CODE ? 4 : 2;                              // first epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;         // EPI_WARPS x 4 KB store staging
@@ -410,7 +423,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0, tslot = 0;
             uint32_t phase = 0;
             const uint32_t stage_tx = CODE ? (uint32_t)((p.a_code ? 0 : A_STAGE_BYTES) + (p.b_code ? 0 : block_n * ROW_BYTES))
-                                           : (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES);  // PAIR: both CTAs' bytes
+                                           : (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES) +
+                                                 (MX ? 512u * (1u + (uint32_t)((block_n + 127) >> 7)) : 0u);
             for (uint32_t tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 uint32_t mt, nt, b;
                 tile_coord(tile, mt, nt, b);
@@ -470,6 +484,16 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             tma_load_4d(sa + j * MN_BOX_BYTES, &map_a, full_bar(stage),
                                         (int)(mt * BLOCK_M) + j * MN_BOX_ROWS, kcoord, bi, bo);
                     }
+                    if constexpr (MX) {
+                        // scale factors of this k-block: 32 x 16-byte boxes = four 32-row groups each
+                        tma_load_3d(sa + MX_SF_OFFSET, &map_sfa, full_bar(stage), (int)(mt * 16), 0, kb);
+                        // B's first 32-row group is nt * block_n / 32; a box must start on a multiple of four groups (16
+                        // bytes), so the load starts up to two groups early and the MMA skips those columns
+                        const uint32_t g_al = (nt * (uint32_t)(block_n >> 5)) & ~3u;
+                        for (int j = 0; j < (block_n + 127) >> 7; ++j)
+                            tma_load_3d(sa + MX_SF_OFFSET + 512 + 512 * j, &map_sfb, full_bar(stage), (int)((g_al + 4u * j) * 4u),
+                                        0, kb);
+                    }
                     if (CODE && p.b_code) {
                         if (kb + CODE_PREFETCH < kbn && !(p.debug & 1024))
                             tma_prefetch_4d(&map_b, (kb + CODE_PREFETCH) * 64, (int)(nt * block_n), bi, bo);
@@ -514,8 +538,23 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // a K-major tile; 16 (bf16) / 32 (fp8) K lines of 128 bytes in an MN-major tile
                     const uint64_t ka = p.a_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
                     const uint64_t kbs = p.b_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
+                    if constexpr (MX) {
+                        const uint32_t sfa_t = tmem_base + MX_SF_TMEM_COL + (uint32_t)stage * MX_SF_COLS_PER_STAGE;
+                        const uint32_t sfb_t = sfa_t + 4u;
+                        const uint32_t sfb_mma = sfb_t + ((nt * (uint32_t)(block_n >> 5)) & 3u);  // see the producer
+                        if (!(p.debug & 16384)) {
+                        tcgen05_cp_32x128b_warpx4(sfa_t, sa + MX_SF_OFFSET);
+                        for (int j = 0; j < (block_n + 127) >> 7; ++j)
+                            tcgen05_cp_32x128b_warpx4(sfb_t + 4u * j, sa + MX_SF_OFFSET + 512 + 512 * j);
+                        }
 #pragma unroll
-                    for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k) {
+                        for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k)  // sf ids: byte k of the scale columns
+                            if (!(p.debug & 32768))
+                            tcgen05_mma_mx(tmem_d, da + k * ka, db + k * kbs, p.idesc | ((uint32_t)k << 29) | ((uint32_t)k << 4),
+                                           sfa_t, sfb_mma, (kb | k) != 0);
+                    }
+#pragma unroll
+                    for (int k = 0; !MX && k < ROW_BYTES / MMA_K_BYTES; ++k) {
                         if constexpr (PAIR)
                             tcgen05_mma_pair<FP8>(tmem_d, da + k * ka, db + k * kbs, p.idesc, (kb | k) != 0);
                         else
@@ -805,8 +844,9 @@ int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int
 }
 
 thread_local bool g_pair = false;  // set by qt_gemm_nt_ex (same thread) before it dispatches: launch the CTA-pair kernel
+thread_local const CUtensorMap *g_map_sfa = nullptr, *g_map_sfb = nullptr;  // block-scaled launches: scale-factor maps
 
-template <bool FP8, int ACT, bool AUX, int OUT, bool CODE, bool PAIR>
+template <bool FP8, int ACT, bool AUX, int OUT, bool CODE, bool PAIR, bool MX = false>
 void launch_kernel(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
                    const CUtensorMap &map_c, const GemmParams &p)
 {
@@ -814,16 +854,19 @@ void launch_kernel(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &m
     constexpr size_t smem = CODE ? CODE_SMEM_BYTES : SMEM_BYTES;
     static_assert((size_t)PAIR_STAGES * PAIR_STAGE_BYTES <= (size_t)BASE_STAGES * STAGE_BYTES, "pair ring fits the same smem");
     if (dev >= 64 || !done[dev]) {
-        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR, MX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
         if (dev < 64) done[dev] = true;
     }
+    static_assert((size_t)BASE_STAGES * MX_STAGE_BYTES <= (size_t)BASE_STAGES * STAGE_BYTES, "MX ring fits the same smem");
+    // the scale-factor maps exist only for block-scaled launches; the other variants never touch the parameters
+    const CUtensorMap &sfa = MX ? *g_map_sfa : map_c, &sfb = MX ? *g_map_sfb : map_c;
     if (PAIR)
-        qt_launch_cluster(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR>, dim3(grid), dim3(NUM_THREADS), smem, st, 2u, map_a,
-                          map_b, map_c, p);
+        qt_launch_cluster(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR, MX>, dim3(grid), dim3(NUM_THREADS), smem, st, 2u,
+                          map_a, map_b, map_c, p, sfa, sfb);
     else
-        qt_launch(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR>, dim3(grid), dim3(CODE ? CODE_NUM_THREADS : NUM_THREADS), smem,
-                  st, map_a, map_b, map_c, p);
+        qt_launch(qt_gemm_kernel<FP8, ACT, AUX, OUT, CODE, PAIR, MX>, dim3(grid),
+                  dim3(CODE ? CODE_NUM_THREADS : NUM_THREADS), smem, st, map_a, map_b, map_c, p, sfa, sfb);
 }
 
 template <bool FP8, int ACT, bool AUX, int OUT = OUT_PLAIN, bool CODE = false>
@@ -877,6 +920,16 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
             d->activation != ACT_NONE) {
             qt_set_error("qt_gemm_nt: QT_GEMM_CODE8* needs code_lut (qt_code_table_host on the device), K-major code "
                          "operands with K and every stride a multiple of 16, and the plain epilogue (alpha, bias, residual)");
+            return QT_ERR_INVALID_ARGUMENT;
+        }
+    }
+    const bool mx = d->sf_a != nullptr || d->sf_b != nullptr;
+    if (mx) {
+        if (!d->sf_a || !d->sf_b || !fp8 || a_mn || b_mn || inner * outer != 1 || d->causal || d->fq_fmt || d->glu ||
+            d->activation != ACT_NONE || d->sf_rows_a % 128 || d->sf_rows_b % 128 || d->sf_rows_a < M || d->sf_rows_b < N ||
+            (reinterpret_cast<uintptr_t>(d->sf_a) | reinterpret_cast<uintptr_t>(d->sf_b)) & 15u) {
+            qt_set_error("qt_gemm_nt: block-scaled products take fp8 K-major operands without batch, both scale arrays "
+                         "(qt_mx_pack_scales, row counts padded to 128) and the plain epilogue (alpha, bias, residual)");
             return QT_ERR_INVALID_ARGUMENT;
         }
     }
@@ -970,7 +1023,7 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     // +4 ... +8 % on the long problems (Llama qkv / down / lm_head), -2 ... -5 % on problems that last under ~30 us (cluster
     // launch and the two cluster-wide syncs are a fixed cost), so the choice is by work: 256 x 256 x 64 k-block units.
     // The causal schedules and the decode variant stay on single CTAs.  QT_GEMM_PAIR=0 / 1 forces the choice (A/B, tests).
-    const bool pair_ok = !b_code && !d->causal && sms % 2 == 0;
+    const bool pair_ok = !b_code && !d->causal && sms % 2 == 0 && !mx;
     const int64_t pairs256 = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + MAX_BLOCK_N - 1) / MAX_BLOCK_N) * batch;
     bool pair = pair_ok && M > BLOCK_M && pairs256 * p.k_blocks >= 6000;
     if (const char *pe = getenv("QT_GEMM_PAIR")) pair = pair_ok && pe[0] == '1';
@@ -981,6 +1034,19 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
         p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms / 2, min_bn, fine_bn ? 16 : 64, 2 * BLOCK_M);
     } else
     p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, (glu || (b_mn && fp8)) ? 128 : 64, fine_bn ? 16 : 64);
+    if (mx) {  // 192 / 128 / 64 columns: the same cost model on the widths the scale-factor columns leave room for
+        const int64_t m_t = (M + BLOCK_M - 1) / BLOCK_M;
+        double best_cost = 0.0;
+        for (int bn = MX_BLOCK_N; bn >= 64; bn -= 64) {
+            const double rounds = (double)((m_t * ((N + bn - 1) / bn) + sms - 1) / sms);
+            const double mma = (double)p.k_blocks * 4.0 * (bn / 2.0 > 96.0 ? bn / 2.0 : 96.0), epi = 11.3 * bn;
+            const double cost = rounds * ((mma > epi ? mma : epi) + 500.0) + epi;
+            if (bn == MX_BLOCK_N || cost < best_cost * 0.97) {
+                p.block_n = bn;
+                best_cost = cost;
+            }
+        }
+    }
     p.c_ptr = static_cast<__nv_bfloat16 *>(d->C);
     p.ldc = d->ldc;
     p.strideC_inner = inner > 1 ? d->strideC_inner : 0;
@@ -994,13 +1060,14 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     }
     if (const char *bn = getenv("QT_GEMM_BN")) {  // tests: force a tile width (multiple of 16) where the epilogue allows it
         const int v = atoi(bn);
-        if (fine_bn && v >= 16 && v <= MAX_BLOCK_N && v % 16 == 0) p.block_n = v;
+        if (fine_bn && !mx && v >= 16 && v <= MAX_BLOCK_N && v % 16 == 0) p.block_n = v;
+        if (mx && (v == 64 || v == 128 || v == 192)) p.block_n = v;
     }
     if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
         p.debug = atoi(dbg);
         if ((p.debug & 4) && !(pair && b_mn && fp8)) p.block_n = 128;
         if ((p.debug & 8) && !glu && !(b_mn && (fp8 || pair))) p.block_n = 64;
-        if (p.debug & 16) p.block_n = 256;
+        if ((p.debug & 16) && !mx) p.block_n = 256;
     }
     const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;   // p.m_tiles counts row pairs in pair mode
     const int64_t m_tiles = (M + tile_m - 1) / tile_m, n_tiles = (N + p.block_n - 1) / p.block_n;
@@ -1045,6 +1112,15 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
         if (rc != QT_OK) return rc;
     }
 
+    CUtensorMap map_sfa, map_sfb;
+    if (mx) {
+        const int64_t k128 = (K + 127) / 128;
+        rc = make_sf_map(&map_sfa, d->sf_a, d->sf_rows_a, k128);
+        if (rc == QT_OK) rc = make_sf_map(&map_sfb, d->sf_b, d->sf_rows_b, k128);
+        if (rc != QT_OK) return rc;
+        g_map_sfa = &map_sfa;
+        g_map_sfb = &map_sfb;
+    }
     p.bias = static_cast<const __nv_bfloat16 *>(d->bias);
     p.residual = static_cast<const __nv_bfloat16 *>(d->residual);
     p.ldr = d->ldr;
@@ -1061,11 +1137,16 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     case QT_GEMM_E4M3_E5M2: p.idesc = make_idesc(0, 1, p.block_n, a_mn, b_mn, pair); break;
     default: p.idesc = make_idesc(1, 0, p.block_n, a_mn, b_mn, pair); break;  // QT_GEMM_E5M2_E4M3
     }
+    if (mx)  // block-scaled descriptor: no accumulator-format field (bits 4-5 are B's sf id), scale format E8M0 at bit 23
+        p.idesc = (p.idesc & ~(3u << 4)) | (1u << 23);
     const unsigned grid = pair ? 2u * (p.num_tiles < (uint32_t)(sms / 2) ? p.num_tiles : (unsigned)(sms / 2))
                                : (p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool aux = d->bias != nullptr || d->residual != nullptr;
-    if (b_code || ((p.debug & 4096) && operand_type == QT_GEMM_BF16 && !glu && !requant && d->activation == ACT_NONE)) {
+    if (mx) {
+        aux ? launch_kernel<true, ACT_NONE, true, OUT_PLAIN, false, false, true>(dev, grid, st, map_a, map_b, map_c, p)
+            : launch_kernel<true, ACT_NONE, false, OUT_PLAIN, false, false, true>(dev, grid, st, map_a, map_b, map_c, p);
+    } else if (b_code || ((p.debug & 4096) && operand_type == QT_GEMM_BF16 && !glu && !requant && d->activation == ACT_NONE)) {
         aux ? launch_variant<false, ACT_NONE, true, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p)
             : launch_variant<false, ACT_NONE, false, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p);
     } else if (glu) {

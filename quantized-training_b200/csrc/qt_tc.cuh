@@ -154,6 +154,38 @@ __device__ __forceinline__ void tcgen05_mma_pair(uint32_t tmem_d, uint64_t desc_
             "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
             : "memory");
 }
+// ----- block-scaled fp8 (kind::mxf8f6f4.block_scale): one UE8M0 scale per 32 K elements of a row, held in TMEM.
+// Scale factors of a 128-element k-block: a 32-bit TMEM column per group of 32 rows (lane = row % 32, replicated over
+// the four lane quarters), byte j = the j-th 32-element block; the instruction descriptor's sf ids pick the byte.
+template <int DUMMY = 0>
+__device__ __forceinline__ void tcgen05_mma_mx(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+// 32 rows x 16 bytes of shared memory (rows 16 bytes apart) -> 4 TMEM columns, broadcast to the four lane quarters
+__device__ __forceinline__ void tcgen05_cp_32x128b_warpx4(uint32_t tmem_dst, uint32_t smem_addr)
+{
+    // no-swizzle K-major matrix descriptor: core matrices of 8 rows x 16 bytes, 128 bytes apart (SBO); version 1
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(d) : "memory");
+}
+// 3-D tiled load without swizzle (scale-factor boxes)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 template <bool FP8>
 __device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate)
@@ -288,6 +320,31 @@ int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int
         qt_set_error("cuTensorMapEncodeTiled failed with CUresult %d (cols=%lld rows=%lld batch=%lldx%lld ld=%lld "
                      "strides=%lld,%lld)", (int)r, (long long)cols, (long long)rows, (long long)outer, (long long)inner,
                      (long long)ld, (long long)stride_inner, (long long)stride_outer);
+        return QT_ERR_INVALID_ARGUMENT;
+    }
+    return QT_OK;
+}
+
+// Packed scale factors of one operand (qt_mx_pack_scales): bytes [K128][32][groups * 4]; a box is 32 rows x 16 bytes
+// (four 32-row groups) of one 128-element k-block -- exactly the 32x128b source of tcgen05.cp.
+int make_sf_map(CUtensorMap *map, const void *ptr, int64_t rows_pad, int64_t k128)
+{
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) {
+        qt_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return QT_ERR_CUDA;
+    }
+    const cuuint64_t inner = (cuuint64_t)(rows_pad / 32) * 4;
+    cuuint64_t dims[3] = {inner, 32, (cuuint64_t)k128};
+    cuuint64_t strides[2] = {inner, inner * 32};
+    cuuint32_t box[3] = {16, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        qt_set_error("cuTensorMapEncodeTiled (scale factors) failed with CUresult %d (rows_pad=%lld k128=%lld)", (int)r,
+                     (long long)rows_pad, (long long)k128);
         return QT_ERR_INVALID_ARGUMENT;
     }
     return QT_OK;

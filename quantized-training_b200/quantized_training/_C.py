@@ -42,6 +42,8 @@ EXPORTS = {
     "qt_fq_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                      ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(QtFormat), ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "qt_mx_pack_scales": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]),
     "qt_quantize_codes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                          ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p]),
@@ -413,6 +415,7 @@ class QtGemmDesc(ctypes.Structure):
         ("out_type", ctypes.c_int32), ("glu", ctypes.c_int32),
         ("causal", ctypes.c_int32), ("reserved", ctypes.c_int32), ("causal_flag", ctypes.c_void_p),
         ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32), ("code_lut", ctypes.c_void_p),
+        ("sf_a", ctypes.c_void_p), ("sf_b", ctypes.c_void_p), ("sf_rows_a", ctypes.c_int64), ("sf_rows_b", ctypes.c_int64),
     ]
 
 
@@ -432,7 +435,8 @@ def _as4d(t, name, align):
 
 
 def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None,
-            fq=None, out_codes=False, glu=False, causal=0, causal_flag=None, a_mn=False, b_mn=False, code_lut=None):
+            fq=None, out_codes=False, glu=False, causal=0, causal_flag=None, a_mn=False, b_mn=False, code_lut=None,
+            sf_a=None, sf_b=None):
     """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
     a, b: bf16 (GEMM_BF16) or uint8 fp8 codes, up to two leading batch dimensions with arbitrary strides;
     bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional destination (any 16-byte
@@ -488,6 +492,12 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     d.a_major, d.b_major = int(bool(a_mn)), int(bool(b_mn))
     if code_lut is not None:
         d.code_lut = code_lut.data_ptr()
+    if sf_a is not None or sf_b is not None:
+        # block-scaled fp8 product: packed UE8M0 scale factors of both operands (mx_pack_scales)
+        assert sf_a.dtype == torch.uint8 and sf_b.dtype == torch.uint8 and sf_a.device == a.device == sf_b.device
+        k128 = (K + 127) // 128
+        d.sf_a, d.sf_b = sf_a.data_ptr(), sf_b.data_ptr()
+        d.sf_rows_a, d.sf_rows_b = sf_a.numel() // (4 * k128), sf_b.numel() // (4 * k128)
     if causal_flag is not None:
         assert causal_flag.dtype == torch.int32 and causal_flag.device == a.device
         d.causal_flag = causal_flag.data_ptr()
@@ -507,6 +517,21 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
         d.residual, d.ldr, d.strideR_outer, d.strideR_inner = r4.data_ptr(), r4.stride(2), r4.stride(0), r4.stride(1)
     with _on(a):
         _check(lib().qt_gemm_nt_ex(ctypes.addressof(d), _stream(a)))
+    return out
+
+
+def mx_pack_scales(scale, ok=None):
+    """fp32 [rows, K / 32] power-of-two block scales -> the packed UE8M0 bytes of the block-scaled GEMM
+    (qt_mx_pack_scales); `ok` (int32[1] on the device, preset to 1) is cleared if a scale is not such a power of two."""
+    _require_cuda(scale, "scale")
+    assert scale.dtype == torch.float32 and scale.dim() == 2 and scale.is_contiguous()
+    rows, kb32 = scale.shape
+    rows_pad, k128 = (rows + 127) // 128 * 128, (kb32 + 3) // 4
+    out = torch.empty(k128 * rows_pad * 4, dtype=torch.uint8, device=scale.device)
+    if ok is not None:
+        assert ok.dtype == torch.int32 and ok.device == scale.device
+    with _on(scale):
+        _check(lib().qt_mx_pack_scales(scale.data_ptr(), rows, kb32, out.data_ptr(), _ptr(ok), _stream(scale)))
     return out
 
 

@@ -10,6 +10,9 @@ codebook; these ops therefore gather from the caller's table (``qt_table_op``) i
 of the module path.  Type promotion follows torch: ``input / scale`` of a bf16 tensor and a multi-element fp32 scale
 is fp32 (and the lookup then truncates with round-to-odd, decomposed.py:151-153); 0-dim operands do not promote.
 """
+import os
+import weakref
+
 import torch
 
 from . import _C
@@ -164,10 +167,93 @@ def _decode(t, scale, block_size, code):
     return t
 
 
+# ---- block-scaled tensor-core route of linear_mx ----------------------------------------------------------------
+# OCP microscaling operands (fp8 / fp6 / fp4 element values, one power-of-two scale per 32 elements of K) are what
+# tcgen05.mma kind::mxf8f6f4.block_scale multiplies natively: the elements travel as one-byte fp8 codes (fp6 / fp4 values
+# are exact e4m3 values), the scales as UE8M0 exponent bytes in TMEM, and nothing is dequantized to bf16 in HBM.
+# Whether a call qualifies is a property of its DATA (element values on an fp8 grid, scales powers of two), so it is
+# checked on the device and read back once per call; QT_MX_TENSOR_CORES=0 turns the route off, =assume skips the check of
+# the activations (the caller guarantees MX-formatted operands; also the only mode usable under CUDA-graph capture).
+MX_TENSOR_CORES = os.environ.get("QT_MX_TENSOR_CORES", "1")
+_MX_WEIGHTS = {}
+_F8 = ((torch.float8_e4m3fn, "e4m3"), (torch.float8_e5m2, "e5m2"))
+_MX_TYPES = {("e4m3", "e4m3"): _C.GEMM_E4M3, ("e5m2", "e5m2"): _C.GEMM_E5M2, ("e4m3", "e5m2"): _C.GEMM_E4M3_E5M2,
+             ("e5m2", "e4m3"): _C.GEMM_E5M2_E4M3}
+
+
+def _mx_operand(t2, scale2):
+    """(codes per fp8 type, 'fits' flags, packed scales, scale flag) of one [rows, K] operand -- all on the device."""
+    ok = torch.ones(1, dtype=torch.int32, device=t2.device)
+    packed = _C.mx_pack_scales(scale2.float().contiguous(), ok)
+    codes, fits = [], []
+    for dt, _ in _F8:
+        c = t2.to(dt)
+        codes.append(c.view(torch.uint8))
+        fits.append((c.to(t2.dtype) == t2).all())
+    return codes, fits, packed, ok
+
+
+def _linear_mx_tensor_cores(input, weight, bias, input_scale, weight_scale, block_size):
+    """The block-scaled product, or None when the call does not qualify (the caller then dequantizes)."""
+    mode = MX_TENSOR_CORES
+    if mode == "0" or block_size != 32 or input_scale is None or weight_scale is None:
+        return None
+    if not (input.is_cuda and input.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.dim() == 2):
+        return None
+    N, K = weight.shape
+    kb = (K + 31) // 32
+    if K % 16 or N % 8 or input.shape[-1] != K or input.numel() == 0:
+        return None
+    if tuple(weight_scale.shape) != (N, kb) or tuple(input_scale.shape) != (*input.shape[:-1], kb):
+        return None
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing and mode != "assume":
+        return None
+    x2 = input.reshape(-1, K)
+    # cached per weight OBJECT (weak references: an address alone may be reused by a different tensor after a free)
+    key = (id(weight), id(weight_scale))
+    w = _MX_WEIGHTS.get(key)
+    if w is not None and not (w[3]() is weight and w[4]() is weight_scale and
+                              w[5] == (weight._version, weight_scale._version, weight.data_ptr(), weight_scale.data_ptr())):
+        w = None
+    if w is None:
+        if capturing:
+            return None
+        codes, fits, packed, ok = _mx_operand(weight, weight_scale)
+        flags = torch.stack([fits[0], fits[1], ok[0] != 0]).tolist()      # one read-back per weight, then cached
+        kind = "e4m3" if flags[0] else "e5m2" if flags[1] else None
+        w = (codes[0] if flags[0] else codes[1], kind if flags[2] else None, packed, weakref.ref(weight),
+             weakref.ref(weight_scale), (weight._version, weight_scale._version, weight.data_ptr(), weight_scale.data_ptr()))
+        if len(_MX_WEIGHTS) >= 256:
+            _MX_WEIGHTS.clear()
+        _MX_WEIGHTS[key] = w
+    w_codes, w_kind, w_sf = w[:3]
+    if w_kind is None:
+        return None
+    codes, fits, packed, ok = _mx_operand(x2, input_scale.reshape(-1, kb))
+    if mode == "assume":
+        a_kind, a_codes = "e4m3", codes[0]
+    else:
+        flags = torch.stack([fits[0], fits[1], ok[0] != 0]).tolist()      # the per-call read-back
+        if not flags[2] or not (flags[0] or flags[1]):
+            return None
+        a_kind, a_codes = ("e4m3", codes[0]) if flags[0] else ("e5m2", codes[1])
+    if bias is not None:
+        bias = bias.to(torch.bfloat16).contiguous()
+    y = _C.gemm_nt(a_codes, w_codes, operand_type=_MX_TYPES[(a_kind, w_kind)], bias=bias, sf_a=packed, sf_b=w_sf)
+    return y.reshape(*input.shape[:-1], N)
+
+
 def linear_mx(input, weight, bias=None, *, input_scale=None, weight_scale=None, block_size=None, input_code=None,
               weight_code=None):
-    """F.linear on the dequantized operands (decomposed.py:311-331); the product runs on the tcgen05 GEMM."""
+    """F.linear on the dequantized operands (decomposed.py:311-331).  Microscaling operands (block_size 32, power-of-two
+    scales, fp8-representable elements) are multiplied by the block-scaled tensor-core instruction without being
+    dequantized; everything else is dequantized first and runs on the bf16 tcgen05 GEMM."""
     from . import ops
+    if input_code is None and weight_code is None:
+        y = _linear_mx_tensor_cores(input, weight, bias, input_scale, weight_scale, block_size)
+        if y is not None:
+            return y
     return ops.linear(_decode(input, input_scale, block_size, input_code),
                       _decode(weight, weight_scale, block_size, weight_code), bias)
 

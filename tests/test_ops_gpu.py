@@ -138,3 +138,49 @@ def test_linear_and_matmul_mx_ops():
     got = torch.ops.quantized_ops.matmul_mx(a, b, input_scale=sa, weight_scale=sb, block_size=32)
     want = torch.matmul((a * expand(sa, a.shape, 32)).float(), (b * expand(sb, b.shape, 32)).float())
     assert float((got.float() - want).norm() / want.norm()) <= 2 ** -7
+
+
+@pytest.mark.parametrize("xe,we", [("fp8_e4m3", "fp8_e4m3"), ("fp4_e2m1", "fp4_e2m1"), ("fp8_e5m2", "fp6_e3m2"),
+                                   ("fp6_e2m3", "fp8_e5m2")])
+@pytest.mark.parametrize("shape,N", [((256, 512), 384), ((4, 100, 4096), 1024), ((130, 160), 200)])
+def test_linear_mx_on_the_block_scaled_tensor_cores(xe, we, shape, N, monkeypatch):
+    """Microscaling operands made by the reference's own recipe (quantize_mx: block 32 along K, power-of-two scales)
+    go to tcgen05.mma kind::mxf8f6f4.block_scale as one-byte codes + UE8M0 scale bytes -- nothing is dequantized in
+    HBM.  Checked against the reference formula (decomposed.py:311-331: dequantize, F.linear) in fp64 at the GEMM
+    tolerance of test_gemm_gpu.py, and against the dequantizing route of this library; operands that do not qualify
+    (scales that are not powers of two, integer elements outside every fp8 grid) silently take the old route."""
+    from quantized_training import _C, decomposed
+    from quantized_training.decomposed import expand
+    from quantized_training.quantizer import get_quant_min_max
+    torch.manual_seed(21)
+    K = shape[-1]
+
+    def mx(t, element, pow2=True):
+        qmax = float(get_quant_min_max(element)[1])
+        return torch.ops.quantized_ops.quantize_mx(t, qt.get_quantization_map(element, DEV), [-1], 32, qmax, pow2, None)
+
+    x = (torch.randn(shape, device=DEV) * torch.exp2(torch.randint(-4, 5, (*shape[:-1], 1), device=DEV).float())).bfloat16()
+    w = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV).bfloat16()
+    (xs, xq), (ws, wq) = mx(x, xe), mx(w, we)
+    taken = []
+    real = _C.gemm_nt
+    monkeypatch.setattr(_C, "gemm_nt", lambda *a, **k: (taken.append(k.get("sf_a") is not None), real(*a, **k))[1])
+    got = torch.ops.quantized_ops.linear_mx(xq, wq, bias, input_scale=xs, weight_scale=ws, block_size=32)
+    assert taken == [True] and got.dtype == torch.bfloat16 and got.shape == (*shape[:-1], N)
+    ref = (xq.double() * expand(xs, xq.shape, 32).double()).reshape(-1, K) @ (wq.double() * expand(ws, wq.shape, 32).double()).t()
+    ref = (ref + bias.double()).reshape(got.shape)
+    err = (got.double() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2.0 ** -8 * ref.pow(2).mean().sqrt()
+    assert not (err > tol).any(), f"{int((err > tol).sum())} of {err.numel()} outside tolerance"
+    monkeypatch.setattr(decomposed, "MX_TENSOR_CORES", "0")
+    old = torch.ops.quantized_ops.linear_mx(xq, wq, bias, input_scale=xs, weight_scale=ws, block_size=32)
+    assert taken == [True, False]
+    assert float((got.float() - old.float()).norm() / old.float().norm()) < 2 ** -7
+    # not microscaling data: amax / qmax scales (not powers of two) -> the dequantizing route, same numbers as before
+    monkeypatch.setattr(decomposed, "MX_TENSOR_CORES", "1")
+    (xs2, xq2) = mx(x, xe, pow2=False)
+    got2 = torch.ops.quantized_ops.linear_mx(xq2, wq, bias, input_scale=xs2, weight_scale=ws, block_size=32)
+    assert taken[-1] is False
+    ref2 = (xq2.double() * expand(xs2, xq2.shape, 32).double()).reshape(-1, K) @ (wq.double() * expand(ws, wq.shape, 32).double()).t()
+    assert float((got2.double().reshape(-1, N) - ref2 - bias.double()).norm() / ref2.norm()) < 2 ** -7
