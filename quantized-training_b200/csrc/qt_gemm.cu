@@ -542,14 +542,18 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint32_t sfa_t = tmem_base + MX_SF_TMEM_COL + (uint32_t)stage * MX_SF_COLS_PER_STAGE;
                         const uint32_t sfb_t = sfa_t + 4u;
                         const uint32_t sfb_mma = sfb_t + ((nt * (uint32_t)(block_n >> 5)) & 3u);  // see the producer
-                        if (!(p.debug & 16384)) {
-                        tcgen05_cp_32x128b_warpx4(sfa_t, sa + MX_SF_OFFSET);
-                        for (int j = 0; j < (block_n + 127) >> 7; ++j)
-                            tcgen05_cp_32x128b_warpx4(sfb_t + 4u * j, sa + MX_SF_OFFSET + 512 + 512 * j);
-                        }
+                        // shared memory -> TMEM copy of a stage's scale factors (its own 12 columns)
+                        auto copy_sf = [&](int st) {
+                            const uint32_t base = smem_base + st * STAGE_BYTES + MX_SF_OFFSET;
+                            const uint32_t t = tmem_base + MX_SF_TMEM_COL + (uint32_t)st * MX_SF_COLS_PER_STAGE;
+                            tcgen05_cp_32x128b_warpx4(t, base);
+                            for (int j = 0; j < (block_n + 127) >> 7; ++j)
+                                tcgen05_cp_32x128b_warpx4(t + 4u + 4u * j, base + 512 + 512 * j);
+                        };
+                        // (copying the NEXT k-block's scale factors in front of this k-block's MMAs was tried: slower)
+                        if (!((p.debug & 16384) && kb != 0)) copy_sf(stage);  // debug: timing without the per-k-block copies
 #pragma unroll
                         for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k)  // sf ids: byte k of the scale columns
-                            if (!(p.debug & 32768))
                             tcgen05_mma_mx(tmem_d, da + k * ka, db + k * kbs, p.idesc | ((uint32_t)k << 29) | ((uint32_t)k << 4),
                                            sfa_t, sfb_mma, (kb | k) != 0);
                     }

@@ -51,6 +51,21 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity, 
         if (spins > (1u << 24)) __trap();
     }
 }
+// non-blocking: has the phase of this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 // Bounded wait: a protocol bug must surface as a trap (launch failure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {

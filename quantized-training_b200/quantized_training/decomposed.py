@@ -181,16 +181,21 @@ _MX_TYPES = {("e4m3", "e4m3"): _C.GEMM_E4M3, ("e5m2", "e5m2"): _C.GEMM_E5M2, ("e
              ("e5m2", "e4m3"): _C.GEMM_E5M2_E4M3}
 
 
-def _mx_operand(t2, scale2):
-    """(codes per fp8 type, 'fits' flags, packed scales, scale flag) of one [rows, K] operand -- all on the device."""
+def _mx_operand(t2, scale2, check=True):
+    """One [rows, K] operand as (fp8 kind, one-byte codes, packed scales), or None when its elements are on neither fp8
+    grid or a scale is not a power of two.  check=False: e4m3 codes without looking (the caller's guarantee)."""
     ok = torch.ones(1, dtype=torch.int32, device=t2.device)
     packed = _C.mx_pack_scales(scale2.float().contiguous(), ok)
-    codes, fits = [], []
-    for dt, _ in _F8:
+    for dt, kind in _F8:
         c = t2.to(dt)
-        codes.append(c.view(torch.uint8))
-        fits.append((c.to(t2.dtype) == t2).all())
-    return codes, fits, packed, ok
+        if not check:
+            return kind, c.view(torch.uint8), packed
+        fits, scales_ok = torch.stack([(c.to(t2.dtype) == t2).all(), ok[0] != 0]).tolist()   # the read-back
+        if not scales_ok:
+            return None
+        if fits:
+            return kind, c.view(torch.uint8), packed
+    return None
 
 
 def _linear_mx_tensor_cores(input, weight, bias, input_scale, weight_scale, block_size):
@@ -219,25 +224,18 @@ def _linear_mx_tensor_cores(input, weight, bias, input_scale, weight_scale, bloc
     if w is None:
         if capturing:
             return None
-        codes, fits, packed, ok = _mx_operand(weight, weight_scale)
-        flags = torch.stack([fits[0], fits[1], ok[0] != 0]).tolist()      # one read-back per weight, then cached
-        kind = "e4m3" if flags[0] else "e5m2" if flags[1] else None
-        w = (codes[0] if flags[0] else codes[1], kind if flags[2] else None, packed, weakref.ref(weight),
-             weakref.ref(weight_scale), (weight._version, weight_scale._version, weight.data_ptr(), weight_scale.data_ptr()))
+        w = (_mx_operand(weight, weight_scale), None, None, weakref.ref(weight), weakref.ref(weight_scale),
+             (weight._version, weight_scale._version, weight.data_ptr(), weight_scale.data_ptr()))
         if len(_MX_WEIGHTS) >= 256:
             _MX_WEIGHTS.clear()
         _MX_WEIGHTS[key] = w
-    w_codes, w_kind, w_sf = w[:3]
-    if w_kind is None:
+    if w[0] is None:
         return None
-    codes, fits, packed, ok = _mx_operand(x2, input_scale.reshape(-1, kb))
-    if mode == "assume":
-        a_kind, a_codes = "e4m3", codes[0]
-    else:
-        flags = torch.stack([fits[0], fits[1], ok[0] != 0]).tolist()      # the per-call read-back
-        if not flags[2] or not (flags[0] or flags[1]):
-            return None
-        a_kind, a_codes = ("e4m3", codes[0]) if flags[0] else ("e5m2", codes[1])
+    w_kind, w_codes, w_sf = w[0]
+    a = _mx_operand(x2, input_scale.reshape(-1, kb), check=mode != "assume")
+    if a is None:
+        return None
+    a_kind, a_codes, packed = a
     if bias is not None:
         bias = bias.to(torch.bfloat16).contiguous()
     y = _C.gemm_nt(a_codes, w_codes, operand_type=_MX_TYPES[(a_kind, w_kind)], bias=bias, sf_a=packed, sf_b=w_sf)

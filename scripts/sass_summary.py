@@ -1,5 +1,5 @@
 """Per-kernel SASS evidence of the Blackwell-native paths in libqt_b200.so (no GPU needed):
-counts of UTC*MMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG / UTMAPF (TMA load / store /
+counts of UTC*MMA (tcgen05.mma; .2CTA = cta_group::2; with a tmem scale operand = block_scale), UTCCP (tcgen05.cp), LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG / UTMAPF (TMA load / store /
 prefetch), SYNCS (mbarrier), USETMAXREG (setmaxnreg), HMMA (legacy mma.sync -- must be 0), and registers per kernel.
     python scripts/sass_summary.py > profiles/sass_summary_r02.txt"""
 import collections, os, re, subprocess, sys
@@ -7,7 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "quantized-training_b200", "quantized_training", "_lib", "libqt_b200.so")
 PAT = {"UTCMMA": r"\bUTC[A-Z]*MMA", "LDTM": r"\bLDTM", "STTM": r"\bSTTM", "UTMALDG": r"\bUTMALDG", "UTMASTG": r"\bUTMASTG",
        "UTMAPF": r"\bUTMAPF", "SYNCS": r"\bSYNCS", "USETMAXREG": r"\bUSETMAXREG", "HMMA": r"\bHMMA", "LDGSTS": r"\bLDGSTS",
-       "REDUX": r"\bREDUX", "MUFU.EX2": r"MUFU\.EX2"}
+       "REDUX": r"\bREDUX", "MUFU.EX2": r"MUFU\.EX2", "UTCMMA.2CTA": r"\bUTC[A-Z]*MMA\.2CTA",
+       "UTCMMA.blockscale": r"\bUTC[A-Z]*MMA gdesc.*idesc\[UR\d+\], tmem", "UTCCP": r"\bUTCCP", "UTMALDG.2CTA": r"\bUTMALDG\.\dD\.2CTA",
+       "UTCBAR.MULTICAST": r"\bUTCBAR\.2CTA\.MULTICAST"}
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 res = subprocess.run(["cuobjdump", "--dump-resource-usage", LIB], capture_output=True, text=True).stdout
 regs = {}
