@@ -185,6 +185,8 @@ def run_gemm(dev):
         shapes[name] = {"qt_bf16_TFLOPs": round(r["qt_bf16_TF"], 1), "cublas_bf16_TFLOPs": round(r["cublas_bf16_TF"], 1),
                         "qt_fp8_TFLOPs": round(r["qt_fp8_TF"], 1), "frac_bf16": r["qt_bf16_TF"] / peak,
                         "frac_fp8_of_2x": r["qt_fp8_TF"] / (2 * peak), "vs_cublas_bf16": r["qt_bf16_TF"] / r["cublas_bf16_TF"]}
+        if "qt_mxfp8_TF" in r:   # block-scaled fp8 (kind::mxf8f6f4.block_scale), the linear_mx product
+            shapes[name]["qt_mxfp8_TFLOPs"] = round(r["qt_mxfp8_TF"], 1)
     return {"bound": "tensor", "unit": "TFLOP/s", "peak_bf16": peak, "peak_source": src,
             "timing": "20 launches per CUDA-graph replay, CUDA events, operands rotate through L2-resident buffers "
                       "(GEMM operands are re-read from L2 by design)", "shapes": shapes}

@@ -69,8 +69,15 @@ def _run(dev, quick):
         out[name] = {"qt_bf16_TF": fl / ms_q / 1e9, "cublas_bf16_TF": fl / ms_c / 1e9, "qt_fp8_TF": fl / ms_8 / 1e9,
                      "qt_bf16_us": ms_q * 1e3, "cublas_bf16_us": ms_c * 1e3, "qt_fp8_us": ms_8 * 1e3,
                      "out_GBps_qt_bf16": 2.0 * b * M * N / ms_q / 1e6}
+        mx = ""
+        if b == 1 and K % 128 == 0:   # block-scaled fp8 (microscaling: one UE8M0 scale per 32 K elements)
+            sa = _C.mx_pack_scales(torch.exp2(torch.randint(-3, 4, (M, K // 32), device=dev).float()))
+            sw = _C.mx_pack_scales(torch.exp2(torch.randint(-3, 4, (N, K // 32), device=dev).float()))
+            ms_x = timed(lambda: _C.gemm_nt(a8[0], w8[0], operand_type=_C.GEMM_E4M3, sf_a=sa, sf_b=sw, out=c[0]))
+            out[name]["qt_mxfp8_TF"], out[name]["qt_mxfp8_us"] = fl / ms_x / 1e9, ms_x * 1e3
+            mx = f" | qt mxfp8 {fl/ms_x/1e9:6.0f} TF {ms_x*1e3:7.1f} us"
         say(f"{name:38s} qt bf16 {fl/ms_q/1e9:6.0f} TF {ms_q*1e3:7.1f} us | cuBLAS bf16 {fl/ms_c/1e9:6.0f} TF {ms_c*1e3:7.1f} us | "
-              f"qt fp8 {fl/ms_8/1e9:6.0f} TF {ms_8*1e3:7.1f} us", flush=True)
+              f"qt fp8 {fl/ms_8/1e9:6.0f} TF {ms_8*1e3:7.1f} us" + mx, flush=True)
     # backward products (MN-major operands) vs the torch.matmul calls autograd would issue
     bwd = [("roberta 2048x768x768", 2048, 768, 768), ("roberta ffn1 2048x3072x768", 2048, 3072, 768),
            ("roberta ffn2 2048x768x3072", 2048, 768, 3072), ("llama o 1024x4096x4096", 1024, 4096, 4096),
