@@ -792,7 +792,9 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 acc_phase ^= 1u;
             }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+        // the staging buffers must outlive the stores' READS; the writes themselves complete with the grid (what a
+        // dependent kernel's griddepcontrol.wait / the stream order waits for), so the tail does not wait for them
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 
     tcgen05_fence_before();
