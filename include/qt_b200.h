@@ -329,9 +329,13 @@ typedef struct qt_gemm_desc {
      * .block_scale -- the product the reference's linear_mx forms by dequantizing both operands first
      * (decomposed.py:311-331).  sf_a / sf_b: UE8M0 exponent bytes packed by qt_mx_pack_scales ([K / 128][32][rows_pad /
      * 32][4]), sf_rows_a / sf_rows_b their padded row counts (multiples of 128).  NULL: plain fp8 product.
-     * K-major operands, no batch, plain epilogue (alpha, bias, residual). */
+     * A K-major; B K-major or MN-major (the second operand of torch.matmul as stored: tiles of 128 columns); plain
+     * epilogue (alpha, bias, residual). */
     const void *sf_a, *sf_b;
     int64_t sf_rows_a, sf_rows_b;
+    /* batched products (torch.matmul of matmul_mx, decomposed.py:341-363): non-zero = the operand's scale array holds
+     * one packed set per batch entry, entry = outer * batch_inner + inner; zero = one set shared by the batch. */
+    int32_t sf_a_batched, sf_b_batched;
 } qt_gemm_desc_t;
 #define QT_MAJOR_K 0
 #define QT_MAJOR_MN 1
@@ -345,6 +349,10 @@ int qt_gemm_nt_ex(const qt_gemm_desc_t *desc, void *stream);
  * rows rounded up to 128; entries outside the matrix are 0.  out holds ceil(kblocks32 / 4) * rows_pad * 4 bytes.
  * *ok_out (device int32, may be NULL) is AND-ed with "every scale is such a power of two". */
 int qt_mx_pack_scales(const float *scale, int64_t rows, int64_t kblocks32, void *out, int32_t *ok_out, void *stream);
+/* The same for `batch` matrices laid end to end (out: batch packed sets, each as above); transposed != 0: each scale
+ * matrix is stored [kblocks32, rows] (the second operand of matmul_mx, scaled along its first matrix axis). */
+int qt_mx_pack_scales_ex(const float *scale, int64_t batch, int64_t rows, int64_t kblocks32, int transposed, void *out,
+                         int32_t *ok_out, void *stream);
 
 /* ---- ops between the GEMMs, fused with the fake-quant steps around them (qt_fused.cu) -------------------------
  * All tensors bf16 on the device, 16-byte aligned, column counts multiples of 8.  `fmt` / `lut` as in qt_fq_forward.

@@ -214,42 +214,49 @@ extern "C" int qt_quantize_codes8(const void *x, void *codes, size_t n, int elem
 
 // ----------------------------------------------------------------------------- block-scale packing (qt_mx_pack_scales)
 namespace {
-__global__ void mx_pack_scales_kernel(const float *__restrict__ scale, long long rows, long long kblocks32,
-                                      uint8_t *__restrict__ out, long long total, long long groups,
+__global__ void mx_pack_scales_kernel(const float *__restrict__ scale, long long rows, long long kblocks32, int transposed,
+                                      uint8_t *__restrict__ out, long long per_entry, long long total, long long groups,
                                       int32_t *__restrict__ ok_out)
 {
     bool ok = true;
-    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i / per_entry, o = i - e * per_entry;
         const long long j = o & 3, g = (o >> 2) % groups, m0 = ((o >> 2) / groups) & 31, kb = (o >> 2) / groups >> 5;
         const long long r = g * 32 + m0, c = kb * 4 + j;
-        uint8_t e = 0;
+        uint8_t v = 0;
         if (r < rows && c < kblocks32) {
-            const uint32_t b = __float_as_uint(scale[r * kblocks32 + c]);
+            const float *m = scale + e * rows * kblocks32;
+            const uint32_t b = __float_as_uint(transposed ? m[c * rows + r] : m[r * kblocks32 + c]);
             const uint32_t ex = b >> 23;  // sign bit included: a negative scale fails the range test
             ok = ok && (b & 0x007FFFFFu) == 0u && ex >= 1u && ex <= 254u;
-            e = (uint8_t)ex;
+            v = (uint8_t)ex;
         }
-        out[o] = e;
+        out[i] = v;
     }
     if (ok_out && !ok) atomicAnd(ok_out, 0);
 }
 }  // namespace
 
-extern "C" int qt_mx_pack_scales(const float *scale, int64_t rows, int64_t kblocks32, void *out, int32_t *ok_out,
-                                 void *stream)
+extern "C" int qt_mx_pack_scales_ex(const float *scale, int64_t batch, int64_t rows, int64_t kblocks32, int transposed,
+                                    void *out, int32_t *ok_out, void *stream)
 {
-    if (!scale || !out || rows < 1 || kblocks32 < 1) {
+    if (!scale || !out || batch < 1 || rows < 1 || kblocks32 < 1) {
         qt_set_error("qt_mx_pack_scales: NULL argument or empty scale matrix");
         return QT_ERR_INVALID_ARGUMENT;
     }
     if (num_sms() == 0) return no_device();
     const long long rows_pad = (rows + 127) / 128 * 128, k128 = (kblocks32 + 3) / 4;
-    const long long total = k128 * rows_pad * 4;
+    const long long per_entry = k128 * rows_pad * 4, total = per_entry * batch;
     const unsigned grid = grid_for((size_t)((total + 255) / 256), 8);
-    mx_pack_scales_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(scale, rows, kblocks32,
-                                                                              static_cast<uint8_t *>(out), total,
-                                                                              rows_pad / 32, ok_out);
+    mx_pack_scales_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        scale, rows, kblocks32, transposed, static_cast<uint8_t *>(out), per_entry, total, rows_pad / 32, ok_out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "mx_pack_scales kernel launch");
     return QT_OK;
+}
+
+extern "C" int qt_mx_pack_scales(const float *scale, int64_t rows, int64_t kblocks32, void *out, int32_t *ok_out,
+                                 void *stream)
+{
+    return qt_mx_pack_scales_ex(scale, 1, rows, kblocks32, 0, out, ok_out, stream);
 }

@@ -99,6 +99,7 @@ struct GemmParams {
     int causal;              // 0 off; 1: tiles strictly above the diagonal are skipped (scores of a causal attention);
                              // 2: A is lower triangular (its probabilities): the K loop of row tile mt stops at its diagonal
     int debug;               // QT_GEMM_DEBUG bit mask (timing experiments only; results are wrong when set)
+    int sf_a_batched, sf_b_batched;  // MX: the operand's scale factors have one set per batch entry (else one shared set)
     int a_mn, b_mn;          // operand is MN-major: stored [K, rows] with a unit-stride row axis (backward products)
     // QT_GEMM_CODE8*: operands held as one-byte codes (K-major, strides in bytes), decoded through code_lut
     int a_code, b_code;
@@ -486,13 +487,14 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     if constexpr (MX) {
                         // scale factors of this k-block: 32 x 16-byte boxes = four 32-row groups each
-                        tma_load_3d(sa + MX_SF_OFFSET, &map_sfa, full_bar(stage), (int)(mt * 16), 0, kb);
+                        tma_load_5d(sa + MX_SF_OFFSET, &map_sfa, full_bar(stage), (int)(mt * 16), 0, kb,
+                                    p.sf_a_batched ? bi : 0, p.sf_a_batched ? bo : 0);
                         // B's first 32-row group is nt * block_n / 32; a box must start on a multiple of four groups (16
                         // bytes), so the load starts up to two groups early and the MMA skips those columns
                         const uint32_t g_al = (nt * (uint32_t)(block_n >> 5)) & ~3u;
                         for (int j = 0; j < (block_n + 127) >> 7; ++j)
-                            tma_load_3d(sa + MX_SF_OFFSET + 512 + 512 * j, &map_sfb, full_bar(stage), (int)((g_al + 4u * j) * 4u),
-                                        0, kb);
+                            tma_load_5d(sa + MX_SF_OFFSET + 512 + 512 * j, &map_sfb, full_bar(stage), (int)((g_al + 4u * j) * 4u),
+                                        0, kb, p.sf_b_batched ? bi : 0, p.sf_b_batched ? bo : 0);
                     }
                     if (CODE && p.b_code) {
                         if (kb + CODE_PREFETCH < kbn && !(p.debug & 1024))
@@ -931,10 +933,10 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     }
     const bool mx = d->sf_a != nullptr || d->sf_b != nullptr;
     if (mx) {
-        if (!d->sf_a || !d->sf_b || !fp8 || a_mn || b_mn || inner * outer != 1 || d->causal || d->fq_fmt || d->glu ||
+        if (!d->sf_a || !d->sf_b || !fp8 || a_mn || d->causal || d->fq_fmt || d->glu ||
             d->activation != ACT_NONE || d->sf_rows_a % 128 || d->sf_rows_b % 128 || d->sf_rows_a < M || d->sf_rows_b < N ||
             (reinterpret_cast<uintptr_t>(d->sf_a) | reinterpret_cast<uintptr_t>(d->sf_b)) & 15u) {
-            qt_set_error("qt_gemm_nt: block-scaled products take fp8 K-major operands without batch, both scale arrays "
+            qt_set_error("qt_gemm_nt: block-scaled products take fp8 operands (A K-major), both scale arrays "
                          "(qt_mx_pack_scales, row counts padded to 128) and the plain epilogue (alpha, bias, residual)");
             return QT_ERR_INVALID_ARGUMENT;
         }
@@ -1043,11 +1045,11 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     if (mx) {  // 192 / 128 / 64 columns: the same cost model on the widths the scale-factor columns leave room for
         const int64_t m_t = (M + BLOCK_M - 1) / BLOCK_M;
         double best_cost = 0.0;
-        for (int bn = MX_BLOCK_N; bn >= 64; bn -= 64) {
-            const double rounds = (double)((m_t * ((N + bn - 1) / bn) + sms - 1) / sms);
+        for (int bn = b_mn ? 128 : MX_BLOCK_N; bn >= (b_mn ? 128 : 64); bn -= 64) {  // MN-major fp8 B: 128-row boxes
+            const double rounds = (double)((m_t * ((N + bn - 1) / bn) * batch + sms - 1) / sms);
             const double mma = (double)p.k_blocks * 4.0 * (bn / 2.0 > 96.0 ? bn / 2.0 : 96.0), epi = 11.3 * bn;
             const double cost = rounds * ((mma > epi ? mma : epi) + 500.0) + epi;
-            if (bn == MX_BLOCK_N || cost < best_cost * 0.97) {
+            if (best_cost == 0.0 || cost < best_cost * 0.97) {
                 p.block_n = bn;
                 best_cost = cost;
             }
@@ -1067,7 +1069,7 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     if (const char *bn = getenv("QT_GEMM_BN")) {  // tests: force a tile width (multiple of 16) where the epilogue allows it
         const int v = atoi(bn);
         if (fine_bn && !mx && v >= 16 && v <= MAX_BLOCK_N && v % 16 == 0) p.block_n = v;
-        if (mx && (v == 64 || v == 128 || v == 192)) p.block_n = v;
+        if (mx && !b_mn && (v == 64 || v == 128 || v == 192)) p.block_n = v;
     }
     if (const char *dbg = getenv("QT_GEMM_DEBUG")) {  // timing experiments: 4 / 8 / 16 force the tile width
         p.debug = atoi(dbg);
@@ -1121,8 +1123,11 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     CUtensorMap map_sfa, map_sfb;
     if (mx) {
         const int64_t k128 = (K + 127) / 128;
-        rc = make_sf_map(&map_sfa, d->sf_a, d->sf_rows_a, k128);
-        if (rc == QT_OK) rc = make_sf_map(&map_sfb, d->sf_b, d->sf_rows_b, k128);
+        // sf_batched_*: one scale set per batch entry (activations / both operands of a batched matmul) or one shared
+        p.sf_a_batched = d->sf_a_batched != 0 && batch > 1;
+        p.sf_b_batched = d->sf_b_batched != 0 && batch > 1;
+        rc = make_sf_map(&map_sfa, d->sf_a, d->sf_rows_a, k128, inner, outer, p.sf_a_batched != 0);
+        if (rc == QT_OK) rc = make_sf_map(&map_sfb, d->sf_b, d->sf_rows_b, k128, inner, outer, p.sf_b_batched != 0);
         if (rc != QT_OK) return rc;
         g_map_sfa = &map_sfa;
         g_map_sfb = &map_sfb;

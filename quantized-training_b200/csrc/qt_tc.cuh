@@ -193,12 +193,14 @@ __device__ __forceinline__ void tcgen05_cp_32x128b_warpx4(uint32_t tmem_dst, uin
     d |= (uint64_t)1 << 46;
     asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(d) : "memory");
 }
-// 3-D tiled load without swizzle (scale-factor boxes)
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+// 5-D tiled load without swizzle (scale-factor boxes: bytes, row in group, k-block, batch inner, batch outer)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+            "r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 template <bool FP8>
@@ -340,9 +342,12 @@ int make_map(CUtensorMap *map, const void *ptr, bool one_byte, int64_t cols, int
     return QT_OK;
 }
 
-// Packed scale factors of one operand (qt_mx_pack_scales): bytes [K128][32][groups * 4]; a box is 32 rows x 16 bytes
-// (four 32-row groups) of one 128-element k-block -- exactly the 32x128b source of tcgen05.cp.
-int make_sf_map(CUtensorMap *map, const void *ptr, int64_t rows_pad, int64_t k128)
+// Packed scale factors of one operand (qt_mx_pack_scales): bytes [batch][K128][32][groups * 4]; a box is 32 rows x 16
+// bytes (four 32-row groups) of one 128-element k-block -- exactly the 32x128b source of tcgen05.cp.  The batch is
+// inner-major like the operands (entry = outer * inner_count + inner); an operand shared by the whole batch (the weight
+// of a Linear) has batched = false and ignores the batch coordinates.
+int make_sf_map(CUtensorMap *map, const void *ptr, int64_t rows_pad, int64_t k128, int64_t inner_count, int64_t outer_count,
+                bool batched)
 {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) {
@@ -350,11 +355,15 @@ int make_sf_map(CUtensorMap *map, const void *ptr, int64_t rows_pad, int64_t k12
         return QT_ERR_CUDA;
     }
     const cuuint64_t inner = (cuuint64_t)(rows_pad / 32) * 4;
-    cuuint64_t dims[3] = {inner, 32, (cuuint64_t)k128};
-    cuuint64_t strides[2] = {inner, inner * 32};
-    cuuint32_t box[3] = {16, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(ptr), dims, strides, box, estr,
+    const cuuint64_t per_entry = inner * 32 * (cuuint64_t)k128;
+    cuuint64_t dims[5] = {inner, 32, (cuuint64_t)k128, (cuuint64_t)inner_count, (cuuint64_t)outer_count};
+    // a shared operand has batch extents 1 (the kernel then passes batch coordinates 0); strides stay valid multiples of 16
+    cuuint64_t strides[4] = {inner, inner * 32, batched ? per_entry : inner * 32,
+                             batched ? per_entry * (cuuint64_t)inner_count : inner * 32};
+    if (!batched) dims[3] = dims[4] = 1;
+    cuuint32_t box[5] = {16, 32, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void *>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {

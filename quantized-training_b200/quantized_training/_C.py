@@ -44,6 +44,8 @@ EXPORTS = {
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qt_mx_pack_scales": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p]),
+    "qt_mx_pack_scales_ex": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "qt_quantize_codes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                          ctypes.POINTER(QtFormat), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p]),
@@ -416,6 +418,7 @@ class QtGemmDesc(ctypes.Structure):
         ("causal", ctypes.c_int32), ("reserved", ctypes.c_int32), ("causal_flag", ctypes.c_void_p),
         ("a_major", ctypes.c_int32), ("b_major", ctypes.c_int32), ("code_lut", ctypes.c_void_p),
         ("sf_a", ctypes.c_void_p), ("sf_b", ctypes.c_void_p), ("sf_rows_a", ctypes.c_int64), ("sf_rows_b", ctypes.c_int64),
+        ("sf_a_batched", ctypes.c_int32), ("sf_b_batched", ctypes.c_int32),
     ]
 
 
@@ -436,7 +439,7 @@ def _as4d(t, name, align):
 
 def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_type=GEMM_BF16, out=None,
             fq=None, out_codes=False, glu=False, causal=0, causal_flag=None, a_mn=False, b_mn=False, code_lut=None,
-            sf_a=None, sf_b=None):
+            sf_a=None, sf_b=None, sf_batched=(False, False)):
     """out[..., m, n] = epilogue(alpha * sum_k a[..., m, k] * b[..., n, k]) on the tcgen05 kernel.
     a, b: bf16 (GEMM_BF16) or uint8 fp8 codes, up to two leading batch dimensions with arbitrary strides;
     bias bf16 [n]; residual bf16 broadcastable to out's shape; out: optional destination (any 16-byte
@@ -495,9 +498,12 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     if sf_a is not None or sf_b is not None:
         # block-scaled fp8 product: packed UE8M0 scale factors of both operands (mx_pack_scales)
         assert sf_a.dtype == torch.uint8 and sf_b.dtype == torch.uint8 and sf_a.device == a.device == sf_b.device
-        k128 = (K + 127) // 128
+        # sf_batched: (a, b) -- the operand's scales come one packed set per batch entry (else one set for all)
+        k128, nb = (K + 127) // 128, inner * outer
         d.sf_a, d.sf_b = sf_a.data_ptr(), sf_b.data_ptr()
-        d.sf_rows_a, d.sf_rows_b = sf_a.numel() // (4 * k128), sf_b.numel() // (4 * k128)
+        d.sf_a_batched, d.sf_b_batched = int(bool(sf_batched[0])), int(bool(sf_batched[1]))
+        d.sf_rows_a = sf_a.numel() // (4 * k128 * (nb if sf_batched[0] else 1))
+        d.sf_rows_b = sf_b.numel() // (4 * k128 * (nb if sf_batched[1] else 1))
     if causal_flag is not None:
         assert causal_flag.dtype == torch.int32 and causal_flag.device == a.device
         d.causal_flag = causal_flag.data_ptr()
@@ -520,18 +526,21 @@ def gemm_nt(a, b, alpha=1.0, bias=None, activation=None, residual=None, operand_
     return out
 
 
-def mx_pack_scales(scale, ok=None):
-    """fp32 [rows, K / 32] power-of-two block scales -> the packed UE8M0 bytes of the block-scaled GEMM
-    (qt_mx_pack_scales); `ok` (int32[1] on the device, preset to 1) is cleared if a scale is not such a power of two."""
+def mx_pack_scales(scale, ok=None, transposed=False):
+    """fp32 [rows, K / 32] (or a batch [..., rows, K / 32]) power-of-two block scales -> the packed UE8M0 bytes of the
+    block-scaled GEMM (qt_mx_pack_scales_ex), one set per batch entry; transposed: the matrices are [K / 32, rows].
+    `ok` (int32[1] on the device, preset to 1) is cleared if a scale is not such a power of two."""
     _require_cuda(scale, "scale")
-    assert scale.dtype == torch.float32 and scale.dim() == 2 and scale.is_contiguous()
-    rows, kb32 = scale.shape
+    assert scale.dtype == torch.float32 and scale.dim() >= 2 and scale.is_contiguous()
+    rows, kb32 = (scale.shape[-1], scale.shape[-2]) if transposed else (scale.shape[-2], scale.shape[-1])
+    batch = scale.numel() // (rows * kb32)
     rows_pad, k128 = (rows + 127) // 128 * 128, (kb32 + 3) // 4
-    out = torch.empty(k128 * rows_pad * 4, dtype=torch.uint8, device=scale.device)
+    out = torch.empty(batch * k128 * rows_pad * 4, dtype=torch.uint8, device=scale.device)
     if ok is not None:
         assert ok.dtype == torch.int32 and ok.device == scale.device
     with _on(scale):
-        _check(lib().qt_mx_pack_scales(scale.data_ptr(), rows, kb32, out.data_ptr(), _ptr(ok), _stream(scale)))
+        _check(lib().qt_mx_pack_scales_ex(scale.data_ptr(), batch, rows, kb32, int(bool(transposed)), out.data_ptr(),
+                                          _ptr(ok), _stream(scale)))
     return out
 
 

@@ -18,7 +18,8 @@ import torch
 from . import _C
 from .fake_quantize import _block_view
 
-__all__ = ["vmap", "quantize", "dequantize", "expand", "calculate_mx_qparam", "quantize_mx", "linear_mx", "matmul_mx"]
+__all__ = ["vmap", "quantize", "dequantize", "expand", "calculate_mx_qparam", "quantize_mx", "linear_mx", "matmul_mx",
+           "conv2d_mx"]
 
 _lib = torch.library.Library("quantized_ops", "DEF")
 _lib.define("vmap(Tensor self, Tensor other) -> Tensor")
@@ -33,6 +34,9 @@ _lib.define("quantize_mx(Tensor self, Tensor qmap, SymInt[] axes, int block_size
 _lib.define("linear_mx(Tensor input, Tensor weight, Tensor? bias=None, *, Tensor? input_scale=None, "
             "Tensor? weight_scale=None, int? block_size=None, Tensor? input_code=None, "
             "Tensor? weight_code=None) -> Tensor")
+_lib.define("conv2d_mx(Tensor input, Tensor weight, Tensor? bias=None, SymInt[2] stride=1, SymInt[2] padding=0, "
+            "SymInt[2] dilation=1, SymInt groups=1, *, Tensor? input_scale=None, Tensor? weight_scale=None, "
+            "int? block_size=None, Tensor? input_code=None, Tensor? weight_code=None) -> Tensor")
 _lib.define("matmul_mx(Tensor self, Tensor other, *, Tensor? input_scale=None, Tensor? weight_scale=None, "
             "int? block_size=None, Tensor? input_code=None, Tensor? weight_code=None) -> Tensor")
 
@@ -181,11 +185,12 @@ _MX_TYPES = {("e4m3", "e4m3"): _C.GEMM_E4M3, ("e5m2", "e5m2"): _C.GEMM_E5M2, ("e
              ("e5m2", "e4m3"): _C.GEMM_E5M2_E4M3}
 
 
-def _mx_operand(t2, scale2, check=True):
-    """One [rows, K] operand as (fp8 kind, one-byte codes, packed scales), or None when its elements are on neither fp8
-    grid or a scale is not a power of two.  check=False: e4m3 codes without looking (the caller's guarantee)."""
+def _mx_operand(t2, scale2, check=True, transposed=False):
+    """One operand ([rows, K], or a batch [..., rows, K]; transposed: [..., K, rows] with scales [..., K / 32, rows]) as
+    (fp8 kind, one-byte codes in the same layout, packed scales), or None when its elements are on neither fp8 grid or a
+    scale is not a power of two.  check=False: e4m3 codes without looking (the caller's guarantee)."""
     ok = torch.ones(1, dtype=torch.int32, device=t2.device)
-    packed = _C.mx_pack_scales(scale2.float().contiguous(), ok)
+    packed = _C.mx_pack_scales(scale2.float().contiguous(), ok, transposed)
     for dt, kind in _F8:
         c = t2.to(dt)
         if not check:
@@ -256,10 +261,43 @@ def linear_mx(input, weight, bias=None, *, input_scale=None, weight_scale=None, 
                       _decode(weight, weight_scale, block_size, weight_code), bias)
 
 
+def _matmul_mx_tensor_cores(a, b, a_scale, b_scale, block_size):
+    """a [..., M, K] @ b [..., K, N] with scales [..., M, K / 32] and [..., K / 32, N] as ONE batched block-scaled product
+    (b is read as stored, MN-major), or None when the call does not qualify."""
+    mode = MX_TENSOR_CORES
+    if mode == "0" or block_size != 32 or a_scale is None or b_scale is None:
+        return None
+    if not (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() >= 2 and a.dim() == b.dim()
+            and a.dim() <= 4 and a.shape[:-2] == b.shape[:-2]):
+        return None
+    M, K, N = a.shape[-2], a.shape[-1], b.shape[-1]
+    kb = (K + 31) // 32
+    if b.shape[-2] != K or K % 16 or N % 16 or a.numel() == 0 or b.numel() == 0:
+        return None
+    if tuple(a_scale.shape) != (*a.shape[:-2], M, kb) or tuple(b_scale.shape) != (*b.shape[:-2], kb, N):
+        return None
+    if torch.cuda.is_current_stream_capturing() and mode != "assume":
+        return None
+    check = mode != "assume"
+    oa = _mx_operand(a.contiguous(), a_scale, check)
+    if oa is None:
+        return None
+    ob = _mx_operand(b.contiguous(), b_scale, check, transposed=True)
+    if ob is None:
+        return None
+    return _C.gemm_nt(oa[1], ob[1], operand_type=_MX_TYPES[(oa[0], ob[0])], b_mn=True, sf_a=oa[2], sf_b=ob[2],
+                      sf_batched=(True, True))
+
+
 def matmul_mx(self, other, *, input_scale=None, weight_scale=None, block_size=None, input_code=None,
               weight_code=None):
-    """torch.matmul on the dequantized operands (decomposed.py:341-363)."""
+    """torch.matmul on the dequantized operands (decomposed.py:341-363); microscaling operands (see linear_mx) are
+    multiplied by the block-scaled tensor-core instruction, the second one read as it is stored."""
     from . import ops
+    if input_code is None and weight_code is None:
+        y = _matmul_mx_tensor_cores(self, other, input_scale, weight_scale, block_size)
+        if y is not None:
+            return y
     return ops.matmul(_decode(self, input_scale, block_size, input_code),
                       _decode(other, weight_scale, block_size, weight_code))
 
@@ -267,7 +305,17 @@ def matmul_mx(self, other, *, input_scale=None, weight_scale=None, block_size=No
 _lib.impl("calculate_mx_qparam", calculate_mx_qparam, "CUDA")
 _lib.impl("quantize_mx", quantize_mx, "CUDA")
 _lib.impl("linear_mx", linear_mx, "CUDA")
+def conv2d_mx(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, *, input_scale=None,
+              weight_scale=None, block_size=None, input_code=None, weight_code=None):
+    """F.conv2d on the dequantized operands (decomposed.py:273-300): codebook decode and block scales by this library's
+    table kernel, the convolution itself by the library call the reference makes too (cuDNN)."""
+    return torch.nn.functional.conv2d(_decode(input, input_scale, block_size, input_code),
+                                      _decode(weight, weight_scale, block_size, weight_code), bias, stride, padding,
+                                      dilation, groups)
+
+
 _lib.impl("matmul_mx", matmul_mx, "CUDA")
+_lib.impl("conv2d_mx", conv2d_mx, "CUDA")
 _lib.impl("vmap", vmap, "CUDA")
 _lib.impl("quantize", quantize, "CUDA")
 _lib.impl("dequantize", dequantize, "CUDA")

@@ -184,3 +184,49 @@ def test_linear_mx_on_the_block_scaled_tensor_cores(xe, we, shape, N, monkeypatc
     assert taken[-1] is False
     ref2 = (xq2.double() * expand(xs2, xq2.shape, 32).double()).reshape(-1, K) @ (wq.double() * expand(ws, wq.shape, 32).double()).t()
     assert float((got2.double().reshape(-1, N) - ref2 - bias.double()).norm() / ref2.norm()) < 2 ** -7
+
+
+def test_conv2d_mx_op():
+    """conv2d_mx = dequantize both operands (block scales along the channel axis, expand semantics) + F.conv2d
+    (decomposed.py:273-300): identical to the reference formula evaluated with torch ops on the same device."""
+    from quantized_training.decomposed import expand
+    torch.manual_seed(3)
+    x = torch.randint(-7, 8, (2, 64, 12, 12), device=DEV).bfloat16()
+    w = torch.randint(-7, 8, (16, 64, 3, 3), device=DEV).bfloat16()
+    xs = torch.exp2(torch.randint(-3, 3, (2, 2, 12, 12), device=DEV).float()).bfloat16()     # 32 channels per block
+    ws = torch.exp2(torch.randint(-3, 3, (16, 2, 3, 3), device=DEV).float()).bfloat16()
+    bias = torch.randn(16, device=DEV).bfloat16()
+    got = torch.ops.quantized_ops.conv2d_mx(x, w, bias, [1, 1], [1, 1], [1, 1], 1, input_scale=xs, weight_scale=ws,
+                                            block_size=32)
+    want = torch.nn.functional.conv2d(x * expand(xs, x.shape, 32), w * expand(ws, w.shape, 32), bias, 1, 1, 1, 1)
+    assert got.shape == (2, 16, 12, 12) and torch.equal(got, want)
+
+
+@pytest.mark.parametrize("shape_a,shape_b", [((2, 4, 256, 128), (2, 4, 128, 256)), ((3, 130, 160), (3, 160, 208)),
+                                             ((192, 256), (256, 384)), ((1, 8, 384, 64), (1, 8, 64, 384))])
+@pytest.mark.parametrize("ea,eb", [("fp8_e4m3", "fp8_e4m3"), ("fp4_e2m1", "fp8_e5m2")])
+def test_matmul_mx_on_the_block_scaled_tensor_cores(shape_a, shape_b, ea, eb, monkeypatch):
+    """matmul_mx (decomposed.py:341-363) with microscaling operands -- `self` scaled along its last axis, `other` along
+    its second to last -- as ONE batched block-scaled product: other is read as it is stored (MN-major fp8 tiles), its
+    scales are packed from the [K / 32, N] matrices.  Against the reference formula in fp64 at the GEMM tolerance."""
+    from quantized_training import _C
+    from quantized_training.decomposed import expand
+    from quantized_training.quantizer import get_quant_min_max
+    torch.manual_seed(33)
+
+    def mx(t, element, axis):
+        qmax = float(get_quant_min_max(element)[1])
+        return torch.ops.quantized_ops.quantize_mx(t, qt.get_quantization_map(element, DEV), [axis], 32, qmax, True, None)
+
+    a = (torch.randn(shape_a, device=DEV) * 2).bfloat16()
+    b = (torch.randn(shape_b, device=DEV) * 0.1).bfloat16()
+    (sa, aq), (sb, bq) = mx(a, ea, -1), mx(b, eb, -2)
+    taken = []
+    real = _C.gemm_nt
+    monkeypatch.setattr(_C, "gemm_nt", lambda *x, **k: (taken.append(k.get("sf_a") is not None), real(*x, **k))[1])
+    got = torch.ops.quantized_ops.matmul_mx(aq, bq, input_scale=sa, weight_scale=sb, block_size=32)
+    assert taken == [True] and got.dtype == torch.bfloat16 and got.shape == (*shape_a[:-1], shape_b[-1])
+    ref = torch.matmul(aq.double() * expand(sa, aq.shape, 32).double(), bq.double() * expand(sb, bq.shape, 32).double())
+    err = (got.double() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2.0 ** -8 * ref.pow(2).mean().sqrt()
+    assert not (err > tol).any(), f"{int((err > tol).sum())} of {err.numel()} outside tolerance"
