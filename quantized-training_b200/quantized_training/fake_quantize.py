@@ -60,6 +60,10 @@ def _run(mod, x, emit_codes=False):
         raise RuntimeError(
             f"FusedAmaxObsFakeQuantize got a tensor on {x.device}: the B200 build runs on CUDA only "
             "(no CPU fallback)")
+    if x.dtype == torch.float16:
+        if emit_codes:
+            raise TypeError("fp8 codes are produced from bfloat16 / float32 tensors")
+        return _run_half(mod, x, observe, quantize)
     xd = x.detach()
     perm = None
     if mod.preserve_strides and not xd.is_contiguous() and not mod.is_per_channel and xd.dim() > 1:
@@ -113,6 +117,38 @@ def _run(mod, x, emit_codes=False):
         y = torch.empty_like(xc)
         _C.fq_forward(xc, y, outer, channels, inner, mod._fmt, scale, amax_slot, mod.lut)
     return y if perm is None else y.permute(perm)
+
+
+def _run_half(mod, x, observe, quantize):
+    """float16 tensors.  The reference's arithmetic is dtype-generic (fake_quantize.py:217-246): amax of the fp16
+    tensor, `scale.to(float16)`, an fp16 division, the table lookup through an exact fp32 widening with round-to-odd
+    truncation (decomposed.py:150-153), the table value narrowed to fp16, an fp16 multiply.  The observer and the
+    lookup run on the fp32 kernels (widening fp16 is exact); the two fp16 roundings of the scaled path are torch's own
+    division and multiplication, which is where the reference gets them too.  A compatibility path: five passes
+    instead of one (the models of the BASELINE configs are bf16)."""
+    xc = x.detach().contiguous()
+    x32 = xc.float()
+    if observe:
+        if xc.numel() == 0:
+            raise RuntimeError("amax(): cannot observe an empty tensor")
+        outer, channels, inner, stat_shape = (_channel_view(tuple(xc.shape), mod.ch_axis) if mod.is_per_channel
+                                              else (1, 1, xc.numel(), ()))
+        if mod.amax_history.numel() == 0:
+            mod.amax_history.resize_((mod.amax_history_len,) + stat_shape).fill_(0.0)
+            mod.scale.resize_(stat_shape).fill_(1.0)
+        _C.scale_update(mod.amax_history, mod.amax_history_len, channels, mod.scale, mod.quant_max,
+                        mod.force_scale_power_of_two)
+        mod._scale_epoch += 1
+        _C.amax(x32, outer, channels, inner, mod.amax_history)
+    if not quantize:
+        return x
+    s16 = mod.scale.to(torch.float16)
+    if s16.numel() > 1 and s16.dim() != xc.dim():
+        raise RuntimeError(f"scale of shape {tuple(s16.shape)} does not broadcast over input {tuple(xc.shape)}")
+    t32 = (xc / s16).float().contiguous()
+    q32 = torch.empty_like(t32)
+    _C.fq_forward(t32, q32, 1, 1, t32.numel(), mod._fmt, None, None, mod.lut)
+    return q32.to(torch.float16) * s16
 
 
 def _block_view(shape, axes, block_size):

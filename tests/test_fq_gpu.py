@@ -150,7 +150,7 @@ def test_edge_cases(oracle):
     want = oracle.vmap(bits_of(xt.contiguous()), oracle.qmap("posit8_1"))
     assert nan_eq16(bits_of(y), want).all()
     with pytest.raises(TypeError):
-        mod(x.to(torch.float16))
+        mod(x.to(torch.float64))                                      # float16 has its own path (test below)
     # observer on, fake quant off: statistics move, tensor passes through
     obs.disable_fake_quant()
     x32 = torch.randn(1000, device=DEV) * 7
@@ -278,3 +278,44 @@ def test_more_than_four_giga_elements():
     want = mx(blk)
     assert torch.equal(y.view(reps, -1).view(torch.int16), want.view(torch.int16).expand(reps, -1))
     assert torch.equal(s_all.view(reps, -1), mx.scale.view(1, -1).expand(reps, -1))
+
+
+@pytest.mark.parametrize("spec", ["posit8_1", "e4m3", "int8,qs=per_tensor_symmetric,ahl=4",
+                                  "fp8_e4m3,qs=per_channel_symmetric,ax=0,ahl=2", "fp6_e3m2,qs=per_tensor_symmetric,ahl=1"])
+def test_float16_tensors_follow_the_reference_arithmetic(oracle, spec):
+    """float16 inputs (compatibility path): the reference's dtype-generic chain restated with torch ops on the device --
+    amax of the fp16 tensor into the fp32 history, delayed scale, `scale.to(fp16)`, fp16 division, lookup of the
+    round-to-odd-truncated fp32 widening in the oracle's table, narrowing to fp16, fp16 multiply
+    (fake_quantize.py:217-246, decomposed.py:147-163) -- bit for bit over a sequence of calls."""
+    mod, qs = module_for(spec)
+    table = torch.from_numpy(oracle.qmap(qs.dtype).view(np.int16)).view(torch.bfloat16).to(DEV)
+    g = torch.Generator().manual_seed(17)
+    hist = scale = None
+    for call in range(4):
+        x = (torch.randn(48, 520, generator=g) * (4.0 ** call)).to(torch.float16).to(DEV)
+        if call == 2:
+            x[0, :4] = torch.tensor([float("inf"), float("nan"), 6e-8, -0.0], dtype=torch.float16)
+        want = x
+        if qs.qscheme is not None:
+            cur = x.abs().amax(dim=1, keepdim=True) if qs.ch_axis is not None else x.abs().amax()
+            if hist is None:
+                hist = torch.zeros((qs.amax_history_len,) + tuple(cur.shape), device=DEV)
+                scale = torch.ones(tuple(cur.shape), device=DEV)
+            amax = hist.amax(dim=0)
+            if hist.shape[0] > 1:
+                hist = torch.roll(hist, -1, 0)
+            hist[0] = cur
+            sf = amax / torch.full_like(amax, qs.quant_max)   # a tensor divisor: true division (a python scalar is
+            scale = torch.where((amax > 0) & torch.isfinite(amax), sf, scale)   # multiplied by its reciprocal on CUDA)
+        s16 = (scale if scale is not None else torch.ones((), device=DEV)).to(torch.float16)
+        bits = (x / s16).float().view(torch.int32)
+        idx = ((bits >> 16) & 0xFFFF) | ((bits & 0xFFFF) != 0).to(torch.int32)
+        want = table[idx].to(torch.float16) * s16
+        got = mod(x)
+        assert got.dtype == torch.float16
+        a, b = got.view(torch.int16).cpu().numpy().view(np.uint16), want.view(torch.int16).cpu().numpy().view(np.uint16)
+        same = (a == b) | (((a & 0x7FFF) > 0x7C00) & ((b & 0x7FFF) > 0x7C00))
+        assert same.all(), f"call {call}: {int((~same).sum())} mismatches"
+        if hist is not None:
+            assert nan_eq32(bits_of(mod.amax_history.reshape(hist.shape)), bits_of(hist)).all()
+            assert nan_eq32(bits_of(mod.scale.reshape(scale.shape)), bits_of(scale)).all()
