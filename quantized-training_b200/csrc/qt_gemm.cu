@@ -19,7 +19,7 @@
 //   warps 2-9   epilogue: tcgen05.ld (32 lanes x 64 columns) -> registers -> fp32 math -> bf16 -> swizzled smem
 //               -> TMA store of 32 x 64 boxes (full 128-byte rows), overlapped with the MMAs of the next tile
 //               through the second accumulator
-// Long problems (>= 6000 k-block units of 256 x 256 x 64) run as CTA PAIRS instead (template PAIR): clusters of two CTAs on
+// Long problems (>= 5000 k-block units of 256 x 256 x 128 B) run as CTA PAIRS instead (template PAIR): clusters of two CTAs on
 // the two SMs of a TPC, one tcgen05.mma.cta_group::2 of 256 rows per instruction, each CTA holding its 128 rows of A and
 // HALF of the B tile (six 32 KB stages).  +4 ... +8 % on the Llama projections (profiles/gemm_pair_r02.log).
 // Tiles are walked in bands of 2048 rows so that the tiles in flight share operands in L2 (8192^3: +12 %).
@@ -1033,7 +1033,7 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
     // The causal schedules and the decode variant stay on single CTAs.  QT_GEMM_PAIR=0 / 1 forces the choice (A/B, tests).
     const bool pair_ok = !b_code && !d->causal && sms % 2 == 0 && !mx;
     const int64_t pairs256 = ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + MAX_BLOCK_N - 1) / MAX_BLOCK_N) * batch;
-    bool pair = pair_ok && M > BLOCK_M && pairs256 * p.k_blocks >= 6000;
+    bool pair = pair_ok && M > BLOCK_M && pairs256 * p.k_blocks >= 5000;  // measured: 4096 units (o-proj) lose 3-5 %, 5504 (fp8 down-proj) gain 6 %
     if (const char *pe = getenv("QT_GEMM_PAIR")) pair = pair_ok && pe[0] == '1';
     g_pair = pair;
     if (pair) {
