@@ -66,6 +66,13 @@ constexpr int MX_SF_OFFSET = A_STAGE_BYTES + MX_BLOCK_N * ROW_BYTES;  // 40 KB
 constexpr int MX_STAGE_BYTES = MX_SF_OFFSET + 2048;                   // 42 KB (1024-byte multiple)
 constexpr int MX_SF_TMEM_COL = MX_BLOCK_N;
 constexpr int MX_SF_COLS_PER_STAGE = 12;
+// MX = 2: the CTA computes TWO row tiles (256 x block_n) against one B tile -- 30 % fewer operand bytes per flop, which is
+// what bounds this variant.  Both TMEM accumulators belong to the tile (no epilogue overlap: ~3 % of a K = 4096 tile);
+// three stages of A 32 KB | B 24 KB | scale boxes 2 KB; 16 scale columns per stage (A 8, B 8).
+constexpr int MX2_STAGES = 3;
+constexpr int MX2_SF_OFFSET = 2 * A_STAGE_BYTES + MX_BLOCK_N * ROW_BYTES;  // 56 KB
+constexpr int MX2_STAGE_BYTES = MX2_SF_OFFSET + 2048;                      // 58 KB
+constexpr int MX2_SF_COLS_PER_STAGE = 16;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;  // two per TMEM lane quarter, splitting the tile's 64-column chunks between them
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
@@ -205,7 +212,7 @@ __device__ __forceinline__ void trace(const GemmParams &, int, int &) {}
 // MX: fp8 operands with one UE8M0 scale per 32 K elements (kind::mxf8f6f4.block_scale).  The producer also loads the
 // k-block's scale-factor boxes; the MMA thread copies them into TMEM (tcgen05.cp) in front of the four MMAs that use
 // them, each selecting its byte of the scale columns through the descriptor's sf ids.
-template <bool FP8, int ACT, bool AUX, int OUT, bool CODE = false, bool PAIR = false, bool MX = false>
+template <bool FP8, int ACT, bool AUX, int OUT, bool CODE = false, bool PAIR = false, int MX = 0>
 __global__ void __launch_bounds__(CODE ? CODE_NUM_THREADS : NUM_THREADS, 1)
 qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ GemmParams p,
@@ -214,8 +221,13 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     extern __shared__ unsigned char smem_raw[];
     static_assert(!(CODE && PAIR), "the decode variant runs single CTAs");
     static_assert(!MX || (FP8 && !CODE && !PAIR), "block scaling: fp8 operands, single CTAs");
-    constexpr int STAGES = CODE ? CODE_STAGES : PAIR ? PAIR_STAGES : BASE_STAGES;
-    constexpr int STAGE_BYTES = MX ? MX_STAGE_BYTES : PAIR ? PAIR_STAGE_BYTES : (A_STAGE_BYTES + B_STAGE_BYTES);
+    constexpr int STAGES = CODE ? CODE_STAGES : PAIR ? PAIR_STAGES : MX == 2 ? MX2_STAGES : BASE_STAGES;
+    constexpr int STAGE_BYTES = MX == 2 ? MX2_STAGE_BYTES : MX ? MX_STAGE_BYTES : PAIR ? PAIR_STAGE_BYTES
+                                                                                   : (A_STAGE_BYTES + B_STAGE_BYTES);
+    constexpr int A_BYTES = MX == 2 ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;          // A part of a stage
+    constexpr int SF_OFFSET = MX == 2 ? MX2_SF_OFFSET : MX_SF_OFFSET;             // MX: scale boxes of a stage
+    constexpr int SF_A_BYTES = MX == 2 ? 1024 : 512;
+    constexpr int SF_COLS = MX == 2 ? MX2_SF_COLS_PER_STAGE : MX_SF_COLS_PER_STAGE;
     constexpr int EPI_WARP0 = CODE ? 4 : 2;                              // first epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;         // EPI_WARPS x 4 KB store staging
@@ -245,7 +257,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t rows = min(p.group_m, p.m_tiles - g * p.group_m);
         const uint32_t m = g * p.group_m + r % rows;
         nt = r / rows;
-        mt = PAIR ? m * 2u + cta_rank : m;
+        mt = PAIR ? m * 2u + cta_rank : MX == 2 ? m * 2u : m;   // MX == 2: the first of the tile's two row tiles
     };
     const int b_rows = PAIR ? block_n >> 1 : block_n;   // B rows in this CTA's shared memory
     // MN-major operand tiles: one TMA box = 128 bytes of rows (64 bf16 / 128 fp8) x the K lines of a k-block
@@ -425,7 +437,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint32_t phase = 0;
             const uint32_t stage_tx = CODE ? (uint32_t)((p.a_code ? 0 : A_STAGE_BYTES) + (p.b_code ? 0 : block_n * ROW_BYTES))
                                            : (uint32_t)(A_STAGE_BYTES + block_n * ROW_BYTES) +
-                                                 (MX ? 512u * (1u + (uint32_t)((block_n + 127) >> 7)) : 0u);
+                                                 (MX ? (uint32_t)SF_A_BYTES + 512u * (uint32_t)((block_n + 127) >> 7) : 0u) +
+                                                 (MX == 2 ? (uint32_t)A_STAGE_BYTES : 0u);
             for (uint32_t tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 uint32_t mt, nt, b;
                 tile_coord(tile, mt, nt, b);
@@ -469,8 +482,10 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         continue;
                     }
                     mbar_arrive_expect_tx(full_bar(stage), stage_tx);
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     const int kcoord = kb * (FP8 ? ROW_BYTES : ROW_BYTES / 2);
+                    if constexpr (MX == 2)  // the tile's second row tile (K-major A: checked by the launcher)
+                        tma_load_4d(sa + A_STAGE_BYTES, &map_a, full_bar(stage), kcoord, (int)((mt + 1) * BLOCK_M), bi, bo);
                     // K-major operand: one box, rows x 128 bytes of K.  MN-major operand: boxes of 128 bytes of rows
                     // x one k-block of K lines (64 bf16 / 128 fp8), side by side: the canonical MN-major layout
                     if (CODE && p.a_code) {
@@ -487,13 +502,14 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     if constexpr (MX) {
                         // scale factors of this k-block: 32 x 16-byte boxes = four 32-row groups each
-                        tma_load_5d(sa + MX_SF_OFFSET, &map_sfa, full_bar(stage), (int)(mt * 16), 0, kb,
-                                    p.sf_a_batched ? bi : 0, p.sf_a_batched ? bo : 0);
+                        for (int j = 0; j < (MX == 2 ? 2 : 1); ++j)
+                            tma_load_5d(sa + SF_OFFSET + 512 * j, &map_sfa, full_bar(stage), (int)((mt + j) * 16), 0, kb,
+                                        p.sf_a_batched ? bi : 0, p.sf_a_batched ? bo : 0);
                         // B's first 32-row group is nt * block_n / 32; a box must start on a multiple of four groups (16
                         // bytes), so the load starts up to two groups early and the MMA skips those columns
                         const uint32_t g_al = (nt * (uint32_t)(block_n >> 5)) & ~3u;
                         for (int j = 0; j < (block_n + 127) >> 7; ++j)
-                            tma_load_5d(sa + MX_SF_OFFSET + 512 + 512 * j, &map_sfb, full_bar(stage), (int)((g_al + 4u * j) * 4u),
+                            tma_load_5d(sa + SF_OFFSET + SF_A_BYTES + 512 * j, &map_sfb, full_bar(stage), (int)((g_al + 4u * j) * 4u),
                                         0, kb, p.sf_b_batched ? bi : 0, p.sf_b_batched ? bo : 0);
                     }
                     if (CODE && p.b_code) {
@@ -528,36 +544,38 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
                 trace(p, 1, tslot);
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;   // MX == 2: acc stays 0, both halves used
                 for (int kb = 0; kb < kbn; ++kb) {
                     mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
                     trace(p, 1, tslot);
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     const uint64_t da = p.a_mn ? make_smem_desc_mn(sa, MN_BOX_BYTES) : make_smem_desc(sa);
                     const uint64_t db = p.b_mn ? make_smem_desc_mn(sb, MN_BOX_BYTES) : make_smem_desc(sb);
                     // advancing K = advancing the start address (16-byte units): 32 bytes inside the swizzle atom of
                     // a K-major tile; 16 (bf16) / 32 (fp8) K lines of 128 bytes in an MN-major tile
                     const uint64_t ka = p.a_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
                     const uint64_t kbs = p.b_mn ? (uint64_t)(MN_K_STEP_BYTES >> 4) : (uint64_t)(MMA_K_BYTES >> 4);
-                    if constexpr (MX) {
-                        const uint32_t sfa_t = tmem_base + MX_SF_TMEM_COL + (uint32_t)stage * MX_SF_COLS_PER_STAGE;
-                        const uint32_t sfb_t = sfa_t + 4u;
+                    if constexpr (MX != 0) {
+                        // scale columns of this stage: A's (4 per row tile), then B's (4 per 128 rows)
+                        const uint32_t sfa_t = tmem_base + MX_SF_TMEM_COL + (uint32_t)stage * SF_COLS;
+                        const uint32_t sfb_t = sfa_t + (MX == 2 ? 8u : 4u);
                         const uint32_t sfb_mma = sfb_t + ((nt * (uint32_t)(block_n >> 5)) & 3u);  // see the producer
-                        // shared memory -> TMEM copy of a stage's scale factors (its own 12 columns)
-                        auto copy_sf = [&](int st) {
-                            const uint32_t base = smem_base + st * STAGE_BYTES + MX_SF_OFFSET;
-                            const uint32_t t = tmem_base + MX_SF_TMEM_COL + (uint32_t)st * MX_SF_COLS_PER_STAGE;
-                            tcgen05_cp_32x128b_warpx4(t, base);
-                            for (int j = 0; j < (block_n + 127) >> 7; ++j)
-                                tcgen05_cp_32x128b_warpx4(t + 4u + 4u * j, base + 512 + 512 * j);
-                        };
+                        const uint32_t sf_smem = sa + SF_OFFSET;
                         // (copying the NEXT k-block's scale factors in front of this k-block's MMAs was tried: slower)
-                        if (!((p.debug & 16384) && kb != 0)) copy_sf(stage);  // debug: timing without the per-k-block copies
+                        if (!((p.debug & 16384) && kb != 0)) {  // debug: timing without the per-k-block copies
+                            for (int j = 0; j < (MX == 2 ? 2 : 1); ++j) tcgen05_cp_32x128b_warpx4(sfa_t + 4u * j, sf_smem + 512 * j);
+                            for (int j = 0; j < (block_n + 127) >> 7; ++j)
+                                tcgen05_cp_32x128b_warpx4(sfb_t + 4u * j, sf_smem + SF_A_BYTES + 512 * j);
+                        }
 #pragma unroll
-                        for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k)  // sf ids: byte k of the scale columns
-                            tcgen05_mma_mx(tmem_d, da + k * ka, db + k * kbs, p.idesc | ((uint32_t)k << 29) | ((uint32_t)k << 4),
-                                           sfa_t, sfb_mma, (kb | k) != 0);
+                        for (int k = 0; k < ROW_BYTES / MMA_K_BYTES; ++k) {  // sf ids: byte k of the scale columns
+                            const uint32_t idk = p.idesc | ((uint32_t)k << 29) | ((uint32_t)k << 4);
+                            tcgen05_mma_mx(tmem_d, da + k * ka, db + k * kbs, idk, sfa_t, sfb_mma, (kb | k) != 0);
+                            if constexpr (MX == 2)   // second row tile: A 16 KB further, accumulator 256 columns further
+                                tcgen05_mma_mx(tmem_d + MAX_BLOCK_N, da + (A_STAGE_BYTES >> 4) + k * ka, db + k * kbs, idk,
+                                               sfa_t + 4u, sfb_mma, (kb | k) != 0);
+                        }
                     }
 #pragma unroll
                     for (int k = 0; !MX && k < ROW_BYTES / MMA_K_BYTES; ++k) {
@@ -577,7 +595,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // accumulator complete -> epilogue (PAIR: each CTA's warps read their own 128 lanes)
                 if constexpr (PAIR) tcgen05_commit_pair(tmem_full_bar(acc), (uint16_t)3);
                 else tcgen05_commit(tmem_full_bar(acc));
-                if (++acc == 2) {
+                if (MX == 2 || ++acc == 2) {   // MX == 2: one accumulator set, its barriers alternate phase every tile
                     acc = 0;
                     acc_phase ^= 1u;
                 }
@@ -608,7 +626,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tile_coord(tile, mt, nt, b);
             const int bi = (int)(b % p.batch_inner), bo = (int)(b / p.batch_inner);
             if (tile_skipped(causal, mt, nt, block_n)) continue;
-            const int64_t row0 = (int64_t)mt * BLOCK_M + quarter * 32;
+            // MX == 2: the two warps of a lane quarter take one row tile (= one accumulator half) each, all of its chunks
+            const int64_t row0 = (int64_t)(mt + (MX == 2 ? half : 0)) * BLOCK_M + quarter * 32;
             const int64_t row = row0 + lane;
             // the longest wait of the kernel (a whole K loop): parked, not spinning (QT_GEMM_DEBUG & 2048: spin, for A/B)
             if (p.debug & 2048)
@@ -617,7 +636,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait_parked(tmem_full_bar(acc), acc_phase, 20000u);
             if (warp == 2 && lane == 0) trace(p, 2, tslot);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                   (uint32_t)(MX == 2 ? half : acc) * MAX_BLOCK_N;
             const __nv_bfloat16 *rrow =
                 (AUX && p.residual && row < p.M)
                     ? p.residual + (int64_t)bo * p.strideR_outer + (int64_t)bi * p.strideR_inner + row * p.ldr
@@ -626,7 +646,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int out_chunks = OUT == OUT_GLU ? chunks >> 1 : chunks;
             const int out_block_n = OUT == OUT_GLU ? block_n >> 1 : block_n;
             const int64_t n_out_total = OUT == OUT_GLU ? p.N >> 1 : p.N;
-            if (half >= out_chunks) {  // narrow tiles: the second warp of the quarter has no chunk, only the hand-back
+            if (MX != 2 && half >= out_chunks) {  // narrow tiles: the second warp of the quarter has no chunk, only the hand-back
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) release_acc(acc);
@@ -634,16 +654,17 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.debug & 8192) {  // timing experiment: no epilogue work, only the hand-back
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0 && half < out_chunks) release_acc(acc);
-                if (++acc == 2) {
+                if (lane == 0 && (MX == 2 || half < out_chunks)) release_acc(acc);
+                if (MX == 2 || ++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1u;
                 }
                 continue;
             }
-            for (int oc = half; oc < out_chunks; oc += 2) {
+            constexpr int OC_STEP = MX == 2 ? 1 : 2;
+            for (int oc = MX == 2 ? 0 : half; oc < out_chunks; oc += OC_STEP) {
                 const int c = OUT == OUT_GLU ? 2 * oc : oc;  // first accumulator chunk
-                const bool last = oc + 2 >= out_chunks;
+                const bool last = oc + OC_STEP >= out_chunks;
                 uint32_t v[64];
                 tmem_ld_32x32_nowait(taddr + c * EPI_CHUNK_COLS, v);
                 tmem_ld_32x32_nowait(taddr + c * EPI_CHUNK_COLS + 32, v + 32);
@@ -789,7 +810,7 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 if (warp == 2 && lane == 0) trace(p, 2, tslot);
             }
-            if (++acc == 2) {
+            if (MX == 2 || ++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;
             }
@@ -854,7 +875,7 @@ int pick_block_n(int64_t batch, int64_t M, int64_t N, int k_blocks, int sms, int
 thread_local bool g_pair = false;  // set by qt_gemm_nt_ex (same thread) before it dispatches: launch the CTA-pair kernel
 thread_local const CUtensorMap *g_map_sfa = nullptr, *g_map_sfb = nullptr;  // block-scaled launches: scale-factor maps
 
-template <bool FP8, int ACT, bool AUX, int OUT, bool CODE, bool PAIR, bool MX = false>
+template <bool FP8, int ACT, bool AUX, int OUT, bool CODE, bool PAIR, int MX = 0>
 void launch_kernel(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &map_a, const CUtensorMap &map_b,
                    const CUtensorMap &map_c, const GemmParams &p)
 {
@@ -866,7 +887,8 @@ void launch_kernel(int dev, unsigned grid, cudaStream_t st, const CUtensorMap &m
                              (int)smem);
         if (dev < 64) done[dev] = true;
     }
-    static_assert((size_t)BASE_STAGES * MX_STAGE_BYTES <= (size_t)BASE_STAGES * STAGE_BYTES, "MX ring fits the same smem");
+    static_assert((size_t)BASE_STAGES * MX_STAGE_BYTES <= (size_t)BASE_STAGES * STAGE_BYTES &&
+                  (size_t)MX2_STAGES * MX2_STAGE_BYTES <= (size_t)BASE_STAGES * STAGE_BYTES, "MX rings fit the same smem");
     // the scale-factor maps exist only for block-scaled launches; the other variants never touch the parameters
     const CUtensorMap &sfa = MX ? *g_map_sfa : map_c, &sfb = MX ? *g_map_sfb : map_c;
     if (PAIR)
@@ -1042,13 +1064,16 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
         p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms / 2, min_bn, fine_bn ? 16 : 64, 2 * BLOCK_M);
     } else
     p.block_n = pick_block_n(batch, M, N, p.k_blocks, sms, (glu || (b_mn && fp8)) ? 128 : 64, fine_bn ? 16 : 64);
+    // two row tiles per CTA (MX = 2) whenever the problem has them: fewer operand bytes per flop (QT_GEMM_MX1=1: old form)
+    const bool mx2 = mx && M > BLOCK_M && getenv("QT_GEMM_MX1") == nullptr;
     if (mx) {  // 192 / 128 / 64 columns: the same cost model on the widths the scale-factor columns leave room for
-        const int64_t m_t = (M + BLOCK_M - 1) / BLOCK_M;
+        const int64_t m_t = (M + (mx2 ? 2 : 1) * BLOCK_M - 1) / ((mx2 ? 2 : 1) * BLOCK_M);
         double best_cost = 0.0;
         for (int bn = b_mn ? 128 : MX_BLOCK_N; bn >= (b_mn ? 128 : 64); bn -= 64) {  // MN-major fp8 B: 128-row boxes
             const double rounds = (double)((m_t * ((N + bn - 1) / bn) * batch + sms - 1) / sms);
-            const double mma = (double)p.k_blocks * 4.0 * (bn / 2.0 > 96.0 ? bn / 2.0 : 96.0), epi = 11.3 * bn;
-            const double cost = rounds * ((mma > epi ? mma : epi) + 500.0) + epi;
+            const double mma = (mx2 ? 2.0 : 1.0) * (double)p.k_blocks * 4.0 * (bn / 2.0 > 96.0 ? bn / 2.0 : 96.0);
+            const double epi = 11.3 * bn;
+            const double cost = mx2 ? rounds * (mma + epi + 500.0) : rounds * ((mma > epi ? mma : epi) + 500.0) + epi;
             if (best_cost == 0.0 || cost < best_cost * 0.97) {
                 p.block_n = bn;
                 best_cost = cost;
@@ -1077,7 +1102,7 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
         if ((p.debug & 8) && !glu && !(b_mn && (fp8 || pair))) p.block_n = 64;
         if ((p.debug & 16) && !mx) p.block_n = 256;
     }
-    const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;   // p.m_tiles counts row pairs in pair mode
+    const int tile_m = (pair || mx2) ? 2 * BLOCK_M : BLOCK_M;   // p.m_tiles counts 256-row tiles in pair / MX = 2 mode
     const int64_t m_tiles = (M + tile_m - 1) / tile_m, n_tiles = (N + p.block_n - 1) / p.block_n;
     if (m_tiles * n_tiles * batch >= (int64_t)1 << 31 || M >= (int64_t)1 << 31 || N >= (int64_t)1 << 31 ||
         inner >= (int64_t)1 << 31 || outer >= (int64_t)1 << 31) {
@@ -1154,9 +1179,12 @@ extern "C" int qt_gemm_nt_ex(const qt_gemm_desc_t *d, void *stream)
                                : (p.num_tiles < (uint32_t)sms ? p.num_tiles : (unsigned)sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool aux = d->bias != nullptr || d->residual != nullptr;
-    if (mx) {
-        aux ? launch_kernel<true, ACT_NONE, true, OUT_PLAIN, false, false, true>(dev, grid, st, map_a, map_b, map_c, p)
-            : launch_kernel<true, ACT_NONE, false, OUT_PLAIN, false, false, true>(dev, grid, st, map_a, map_b, map_c, p);
+    if (mx2) {
+        aux ? launch_kernel<true, ACT_NONE, true, OUT_PLAIN, false, false, 2>(dev, grid, st, map_a, map_b, map_c, p)
+            : launch_kernel<true, ACT_NONE, false, OUT_PLAIN, false, false, 2>(dev, grid, st, map_a, map_b, map_c, p);
+    } else if (mx) {
+        aux ? launch_kernel<true, ACT_NONE, true, OUT_PLAIN, false, false, 1>(dev, grid, st, map_a, map_b, map_c, p)
+            : launch_kernel<true, ACT_NONE, false, OUT_PLAIN, false, false, 1>(dev, grid, st, map_a, map_b, map_c, p);
     } else if (b_code || ((p.debug & 4096) && operand_type == QT_GEMM_BF16 && !glu && !requant && d->activation == ACT_NONE)) {
         aux ? launch_variant<false, ACT_NONE, true, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p)
             : launch_variant<false, ACT_NONE, false, OUT_PLAIN, true>(dev, grid, st, map_a, map_b, map_c, p);
