@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libqt_b200.so")
+# QT_B200_LIB: load another build of the library (A/B runs of kernel changes on the same box)
+LIB_PATH = os.environ.get("QT_B200_LIB") or os.path.join(_HERE, "_lib", "libqt_b200.so")
 
 QT_BF16, QT_F32 = 0, 1
 QT_NO_LUT = 5
