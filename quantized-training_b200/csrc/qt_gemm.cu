@@ -531,7 +531,8 @@ qt_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0 && cta_rank == 0) {
+        // the whole warp runs this loop in converged code; the tcgen05 wrappers elect the lane that issues (qt_tc.cuh)
+        if (cta_rank == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0, tslot = 0;

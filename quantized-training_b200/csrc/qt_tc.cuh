@@ -104,7 +104,13 @@ __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.f
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    // Executed by the WHOLE MMA warp in converged code; one elected lane issues.  (A loop body under `if (lane == 0)`
+    // made every operand a per-thread register that has to be broadcast into uniform registers inside a divergence loop
+    // -- ELECT / R2UR.BROADCAST / BRA.U.ANY, ~25 instructions per MMA on the single thread that paces the tensor pipe.)
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar)
+        : "memory");
 }
 // ----- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE 256-row MMA.  Each holds its own
 // 128 rows of A, half of the B tile and its 128 lanes of the accumulator; the leader (cluster rank 0) issues.
@@ -148,9 +154,11 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
 // arrives on the barrier at the same offset in every CTA of `mask` once the pair's MMAs issued so far have completed
 __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar, uint16_t mask)
 {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(mask)
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(bar),
+        "h"(mask)
+        : "memory");
 }
 template <bool FP8>
 __device__ __forceinline__ void tcgen05_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -158,14 +166,14 @@ __device__ __forceinline__ void tcgen05_mma_pair(uint32_t tmem_d, uint64_t desc_
 {
     if (FP8)
         asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
             "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
             : "memory");
     else
         asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
             "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
             : "memory");
 }
@@ -177,8 +185,8 @@ __device__ __forceinline__ void tcgen05_mma_mx(uint32_t tmem_d, uint64_t desc_a,
                                                uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
         : "memory");
 }
@@ -191,7 +199,9 @@ __device__ __forceinline__ void tcgen05_cp_32x128b_warpx4(uint32_t tmem_dst, uin
     d |= (uint64_t)(128 >> 4) << 16;
     d |= (uint64_t)(128 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(d) : "memory");
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;\n\t}\n" ::"r"(tmem_dst),
+                 "l"(d)
+                 : "memory");
 }
 // 5-D tiled load without swizzle (scale-factor boxes: bytes, row in group, k-block, batch inner, batch outer)
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
@@ -209,14 +219,14 @@ __device__ __forceinline__ void tcgen05_mma(uint32_t tmem_d, uint64_t desc_a, ui
 {
     if (FP8)
         asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
             "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
             : "memory");
     else
         asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+            "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
             "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
             : "memory");
 }
